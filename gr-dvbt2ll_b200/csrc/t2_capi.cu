@@ -1,0 +1,792 @@
+// C ABI of libdvbt2ll_cuda.so (declared in include/dvbt2ll_cuda.h): handles own the host plan, the
+// device copies of its tables, a CUDA stream and scratch buffers.  There is no CPU fallback: every
+// *_work() call needs a CUDA device and fails with DVBT2LL_ERR_CUDA otherwise.
+#include "../../include/dvbt2ll_cuda.h"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "t2_kernels.cuh"
+#include "t2_plan.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg) { g_err = msg; return code; }
+
+#define CK(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t e_ = (call);                                                                      \
+    if (e_ != cudaSuccess)                                                                        \
+      return fail(DVBT2LL_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));          \
+  } while (0)
+
+struct DevBuf {
+  void *p; size_t cap;
+  DevBuf() : p(0), cap(0) {}
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t ensure(size_t n)
+  {
+    if (n <= cap) return cudaSuccess;
+    if (p) { cudaFree(p); p = 0; cap = 0; }
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+template <class T>
+cudaError_t upload(DevBuf &b, const std::vector<T> &v)
+{
+  cudaError_t e = b.ensure(v.size() * sizeof(T) + 16);
+  if (e != cudaSuccess) return e;
+  return cudaMemcpy(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+inline int align16(int n) { return (n + 15) & ~15; }
+
+std::vector<t2::cfloat> make_twiddles(int n, int count)
+{
+  std::vector<t2::cfloat> w(count);
+  const double k2pi = 6.283185307179586476925286766559;
+  for (int i = 0; i < count; i++) {
+    w[i].re = (float)std::cos(k2pi * i / n);
+    w[i].im = (float)std::sin(k2pi * i / n);
+  }
+  return w;
+}
+
+} // namespace
+
+// ------------------------------------------------------------------------------------------------
+struct dvbt2ll_handle {
+  enum Kind { BB, LDPC, MAP, FRAME, OFDM, CHAIN } kind;
+  cudaStream_t stream;
+  bool dev_ready;
+  int warnings;
+  DevBuf stage_in, stage_out;   // device staging for host-buffer work()
+  explicit dvbt2ll_handle(Kind k) : kind(k), stream(0), dev_ready(false), warnings(0) {}
+  virtual ~dvbt2ll_handle() { if (stream) cudaStreamDestroy(stream); }
+  virtual int output_multiple() const = 0;
+  virtual int forecast(int noutput) const = 0;
+  virtual int in_item() const = 0;
+  virtual int out_item() const = 0;
+  virtual int dev_init() = 0;
+  // device-resident work on the given stream
+  virtual int work_device(const void *d_in, int ninput, void *d_out, int noutput, int *consumed, cudaStream_t s) = 0;
+  // host-side staging hooks: items that must be copied in for noutput outputs (default = forecast)
+  virtual long long plan_get(const char *name, void *out, long long cap) const = 0;
+
+  int ensure_device()
+  {
+    if (dev_ready) return 0;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n < 1) {
+      cudaGetLastError();
+      return fail(DVBT2LL_ERR_CUDA, "no CUDA device available (libdvbt2ll_cuda has no CPU fallback)");
+    }
+    if (!stream) CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    int r = dev_init();
+    if (r) return r;
+    dev_ready = true;
+    return 0;
+  }
+};
+
+namespace {
+
+long long copy_out(const void *src, size_t bytes, void *out, long long cap)
+{
+  if (out && cap > 0) std::memcpy(out, src, (size_t)cap < bytes ? (size_t)cap : bytes);
+  return (long long)bytes;
+}
+template <class T>
+long long copy_vec(const std::vector<T> &v, void *out, long long cap) { return copy_out(v.data(), v.size() * sizeof(T), out, cap); }
+
+long long dims_get(const t2::OfdmDims &d, void *out, long long cap)
+{
+  const int v[16] = { d.fft_n, d.fft_index, d.miso, d.n_p2, d.c_p2, d.c_data, d.n_fc, d.c_fc, d.c_ps, d.k_ext,
+                      d.k_offset, d.dx, d.dy, d.gi, d.num_symbols, d.active_items };
+  return copy_out(v, sizeof(v), out, cap);
+}
+
+// ================================================================================================
+struct BbHandle : dvbt2ll_handle {
+  t2::BbPlan plan;
+  DevBuf d_scr, d_crc, d_tab, d_cols, d_ib, d_ts, d_packed, d_err;
+  // streaming state (reference: count, crc via history, fec_block)
+  int count, fec_block;
+  std::vector<uint8_t> history;   // last 187 TS bytes
+  int reported_errors;
+  BbHandle() : dvbt2ll_handle(BB), count(0), fec_block(0), history(187, 0), reported_errors(0) {}
+
+  int output_multiple() const { return plan.fec.nbch; }
+  int in_item() const { return 1; }
+  int out_item() const { return 1; }
+  int forecast(int noutput) const
+  {
+    // reference :207-216
+    const int base = (noutput - 80 - (plan.fec.nbch - plan.fec.kbch)) / 8;
+    return plan.mode == t2::INPUTMODE_NORMAL ? base : base + ((plan.fec.kbch - 80) / 8) / 187 + 1;
+  }
+  int dev_init()
+  {
+    CK(upload(d_scr, plan.scramble));
+    std::vector<uint8_t> crc(plan.crc8_tab, plan.crc8_tab + 256);
+    CK(upload(d_crc, crc));
+    CK(upload(d_tab, plan.bch_byte_tab));
+    CK(upload(d_cols, plan.bch_shift_cols));
+    CK(upload(d_ib, plan.inband_bytes));
+    CK(d_err.ensure(16));
+    CK(cudaMemset(d_err.p, 0, 16));
+    return 0;
+  }
+  // payload bytes of `frames` FECFRAMEs starting at in-band phase fb0
+  long long payload_bytes(int frames, int fb0) const
+  {
+    long long nb = 0;
+    if (plan.inband) nb = (fb0 + frames + plan.fecblocks - 1) / plan.fecblocks - (fb0 + plan.fecblocks - 1) / plan.fecblocks;
+    return (long long)frames * plan.payload_bytes - 13 * nb;
+  }
+  long long ts_needed(int frames) const
+  {
+    const long long P = payload_bytes(frames, fec_block);
+    if (plan.mode == t2::INPUTMODE_NORMAL || P == 0) return P;
+    const int t0 = (188 - count) % 188;
+    const long long last = P - 1;
+    return (last < t0 ? last : t0 + 1 + (last - t0) + (last - t0) / 187) + 1;
+  }
+  void fill_args(t2k::BbArgs &a, const uint8_t *d_ts_ptr, long long pitch, int channels, int frames, int count0,
+                 int fb0, int hist_valid, uint8_t *d_out, int out_pitch)
+  {
+    a.ts = d_ts_ptr; a.ts_pitch = pitch; a.hist_valid = hist_valid; a.n_channels = channels; a.frames = frames;
+    a.count0 = count0; a.fec_block0 = fb0;
+    a.kbch = plan.fec.kbch; a.nbch = plan.fec.nbch; a.bch_r = plan.fec.bch_r; a.payload_bytes = plan.payload_bytes;
+    a.mode = plan.mode; a.inband = plan.inband ? 1 : 0; a.fecblocks = plan.fecblocks;
+    a.chunk_bytes = plan.chunk_bytes; a.lead_zero_bytes = plan.lead_zero_bytes;
+    a.scramble = d_scr.as<uint8_t>(); a.crc8_tab = d_crc.as<uint8_t>(); a.bch_tab = d_tab.as<uint32_t>();
+    a.bch_cols = d_cols.as<uint32_t>(); a.inband_bytes = d_ib.as<uint8_t>();
+    a.out = d_out; a.out_pitch = out_pitch; a.sync_errors = d_err.as<int>();
+  }
+  // d_in must be preceded by 187 bytes of valid history on the device (work() arranges that)
+  int work_device(const void *d_in, int ninput, void *d_out, int noutput, int *consumed, cudaStream_t s)
+  {
+    const int frames = noutput / plan.fec.nbch;
+    if (consumed) *consumed = 0;
+    if (frames < 1) return 0;
+    const long long need = ts_needed(frames);
+    if (ninput < need) return fail(DVBT2LL_ERR_SHORT, "bbheaderbch_bb: not enough input items");
+    const int pitch = align16(plan.fec.nbch / 8);
+    CK(d_packed.ensure((size_t)frames * pitch));
+    t2k::BbArgs a;
+    fill_args(a, (const uint8_t *)d_in, 0, 1, frames, count, fec_block, hist_on_device, d_packed.as<uint8_t>(), pitch);
+    t2k::launch_bb_bch(a, s);
+    t2k::launch_unpack_bits(d_packed.as<uint8_t>(), pitch, plan.fec.nbch, (uint8_t *)d_out, frames, s);
+    CK(cudaGetLastError());
+    count = (int)((count + need) % 188);
+    if (plan.inband) fec_block = (fec_block + frames) % plan.fecblocks;
+    if (consumed) *consumed = (int)need;
+    return frames * plan.fec.nbch;
+  }
+  int hist_on_device = 0;
+  long long plan_get(const char *name, void *out, long long cap) const
+  {
+    std::string n(name);
+    if (n == "bb.scramble") return copy_vec(plan.scramble, out, cap);
+    if (n == "bb.crc8") return copy_out(plan.crc8_tab, 256, out, cap);
+    if (n == "bb.bch_tab") return copy_vec(plan.bch_byte_tab, out, cap);
+    if (n == "bb.bch_cols") return copy_vec(plan.bch_shift_cols, out, cap);
+    if (n == "bb.inband") return copy_vec(plan.inband_bytes, out, cap);
+    if (n == "bb.dims") {
+      const int v[8] = { plan.fec.kbch, plan.fec.nbch, plan.fec.q, plan.fec.bch_r, plan.payload_bytes,
+                         plan.chunk_bytes, plan.lead_zero_bytes, plan.fec.nldpc };
+      return copy_out(v, sizeof(v), out, cap);
+    }
+    return -1;
+  }
+};
+
+// ================================================================================================
+struct LdpcHandle : dvbt2ll_handle {
+  t2::LdpcPlan plan;
+  DevBuf d_rowptr, d_entries, d_in_packed, d_out_packed;
+  LdpcHandle() : dvbt2ll_handle(LDPC) {}
+  int output_multiple() const { return plan.fec.nldpc; }
+  int in_item() const { return 1; }
+  int out_item() const { return 1; }
+  int forecast(int noutput) const { return (noutput / plan.fec.nldpc) * plan.fec.nbch; }
+  int dev_init()
+  {
+    CK(upload(d_rowptr, plan.row_ptr));
+    CK(upload(d_entries, plan.entries));
+    return 0;
+  }
+  void fill_args(t2k::LdpcArgs &a, const uint8_t *in, int in_pitch, uint8_t *out, int out_pitch, int frames)
+  {
+    a.in = in; a.in_pitch = in_pitch; a.out = out; a.out_pitch = out_pitch; a.frames = frames;
+    a.nbch = plan.fec.nbch; a.nldpc = plan.fec.nldpc; a.q = plan.fec.q; a.groups = plan.groups;
+    a.row_ptr = d_rowptr.as<uint16_t>(); a.entries = d_entries.as<uint32_t>();
+  }
+  int work_device(const void *d_in, int ninput, void *d_out, int noutput, int *consumed, cudaStream_t s)
+  {
+    const int frames = noutput / plan.fec.nldpc;
+    if (consumed) *consumed = 0;
+    if (frames < 1) return 0;
+    if (ninput < frames * plan.fec.nbch) return fail(DVBT2LL_ERR_SHORT, "ldpc: not enough input items");
+    const int ip = align16(plan.fec.nbch / 8), op = align16(plan.fec.nldpc / 8);
+    CK(d_in_packed.ensure((size_t)frames * ip + 16));
+    CK(d_out_packed.ensure((size_t)frames * op + 16));
+    t2k::launch_pack_bits((const uint8_t *)d_in, plan.fec.nbch, d_in_packed.as<uint8_t>(), ip, frames, s);
+    t2k::LdpcArgs a;
+    fill_args(a, d_in_packed.as<uint8_t>(), ip, d_out_packed.as<uint8_t>(), op, frames);
+    t2k::launch_ldpc(a, s);
+    t2k::launch_unpack_ldpc(d_out_packed.as<uint8_t>(), op, plan.fec.nbch, plan.fec.nldpc, plan.fec.q, (uint8_t *)d_out, frames, s);
+    CK(cudaGetLastError());
+    if (consumed) *consumed = frames * plan.fec.nbch;
+    return frames * plan.fec.nldpc;
+  }
+  long long plan_get(const char *name, void *out, long long cap) const
+  {
+    std::string n(name);
+    if (n == "ldpc.row_ptr") return copy_vec(plan.row_ptr, out, cap);
+    if (n == "ldpc.entries") return copy_vec(plan.entries, out, cap);
+    return -1;
+  }
+};
+
+// ================================================================================================
+struct MapHandle : dvbt2ll_handle {
+  t2::MapPlan plan;
+  DevBuf d_bitsrc, d_lut, d_packed;
+  MapHandle() : dvbt2ll_handle(MAP) {}
+  int output_multiple() const { return plan.cell_size; }
+  int in_item() const { return 1; }
+  int out_item() const { return 8; }
+  int forecast(int noutput) const { return (noutput / plan.cell_size) * plan.fec.nldpc; }
+  int dev_init()
+  {
+    CK(upload(d_bitsrc, plan.bit_src));
+    CK(upload(d_lut, plan.lut));
+    return 0;
+  }
+  void fill_args(t2k::MapArgs &a, const uint8_t *in, int in_pitch, float2 *out, int frames)
+  {
+    a.in = in; a.in_pitch = in_pitch; a.out = out; a.frames = frames;
+    a.nldpc = plan.fec.nldpc; a.mod = plan.mod; a.cell_size = plan.cell_size; a.cyclic_delay = plan.cyclic_delay;
+    a.bit_src = d_bitsrc.as<uint16_t>(); a.lut = d_lut.as<float2>();
+  }
+  int work_device(const void *d_in, int ninput, void *d_out, int noutput, int *consumed, cudaStream_t s)
+  {
+    const int frames = noutput / plan.cell_size;
+    if (consumed) *consumed = 0;
+    if (frames < 1) return 0;
+    if (ninput < frames * plan.fec.nldpc) return fail(DVBT2LL_ERR_SHORT, "interleavermod_bc: not enough input items");
+    const int ip = align16(plan.fec.nldpc / 8);
+    CK(d_packed.ensure((size_t)frames * ip + 16));
+    t2k::launch_pack_ldpc((const uint8_t *)d_in, plan.fec.nbch, plan.fec.nldpc, plan.fec.q, d_packed.as<uint8_t>(), ip, frames, s);
+    t2k::MapArgs a;
+    fill_args(a, d_packed.as<uint8_t>(), ip, (float2 *)d_out, frames);
+    t2k::launch_map(a, s);
+    CK(cudaGetLastError());
+    if (consumed) *consumed = frames * plan.fec.nldpc;
+    return frames * plan.cell_size;
+  }
+  long long plan_get(const char *name, void *out, long long cap) const
+  {
+    std::string n(name);
+    if (n == "map.bit_src") return copy_vec(plan.bit_src, out, cap);
+    if (n == "map.lut") return copy_vec(plan.lut, out, cap);
+    return -1;
+  }
+};
+
+// ================================================================================================
+struct FrameHandle : dvbt2ll_handle {
+  t2::FramePlan plan;
+  DevBuf d_code, d_pool;
+  int t2_frame_num;
+  FrameHandle() : dvbt2ll_handle(FRAME), t2_frame_num(0) {}
+  int output_multiple() const { return plan.mapped_items; }
+  int in_item() const { return 8; }
+  int out_item() const { return 8; }
+  int forecast(int noutput) const { return plan.stream_items * (noutput / plan.mapped_items); }
+  int dev_init()
+  {
+    CK(upload(d_code, plan.code));
+    CK(upload(d_pool, plan.pool.cells));
+    return 0;
+  }
+  int work_device(const void *d_in, int ninput, void *d_out, int noutput, int *consumed, cudaStream_t s)
+  {
+    const int frames = noutput / plan.mapped_items;
+    if (consumed) *consumed = 0;
+    if (frames < 1) return 0;
+    if ((long long)ninput < (long long)frames * plan.stream_items)
+      return fail(DVBT2LL_ERR_SHORT, "framemapperfint_cc: not enough input items");
+    t2k::GatherArgs a;
+    a.in = (const float2 *)d_in; a.in_stride = plan.stream_items;
+    a.out = (float2 *)d_out; a.out_stride = plan.mapped_items;
+    a.code = d_code.as<int32_t>(); a.n = plan.mapped_items; a.pool = d_pool.as<float2>();
+    a.l1post_base = plan.pool.l1post_base; a.l1post_cells = plan.pool.l1post_cells; a.l1post_variants = plan.pool.l1post_variants;
+    a.frames = frames; a.frame_idx0 = t2_frame_num;
+    t2k::launch_gather(a, s);
+    CK(cudaGetLastError());
+    t2_frame_num = (t2_frame_num + frames) % plan.prm.t2frames;
+    if (consumed) *consumed = frames * plan.stream_items;
+    return frames * plan.mapped_items;
+  }
+  long long plan_get(const char *name, void *out, long long cap) const
+  {
+    std::string n(name);
+    if (n == "frame.code") return copy_vec(plan.code, out, cap);
+    if (n == "frame.pool") return copy_vec(plan.pool.cells, out, cap);
+    if (n == "frame.cell_perm") return copy_vec(plan.cell_perm, out, cap);
+    if (n == "frame.fec_shift") return copy_vec(plan.fec_shift, out, cap);
+    if (n == "frame.ti_src") return copy_vec(plan.ti_src, out, cap);
+    if (n == "frame.dims") return dims_get(plan.dims, out, cap);
+    if (n == "frame.info") {
+      const int v[12] = { plan.cell_size, plan.stream_items, plan.mapped_items, plan.eta_mod, plan.n_post, plan.n_punc,
+                          plan.dummy_cells, plan.pool.l1post_base, plan.pool.l1post_cells, plan.pool.l1post_variants,
+                          plan.pool_dummy, plan.pool_zero };
+      return copy_out(v, sizeof(v), out, cap);
+    }
+    return -1;
+  }
+};
+
+// ================================================================================================
+struct OfdmDevice {
+  DevBuf d_code, d_pool, d_p1, d_sinc, d_tw, d_tw_split;
+  int log2_m, split;
+  int init(const std::vector<int32_t> &code, const t2::CellPool &pool, const t2::OfdmPlan &op)
+  {
+    CK(upload(d_code, code));
+    CK(upload(d_pool, pool.cells));
+    CK(upload(d_p1, op.p1));
+    if (!op.inv_sinc.empty()) CK(upload(d_sinc, op.inv_sinc));
+    const int N = op.dims.fft_n;
+    split = N > 16384 ? 2 : 1;
+    const int M = N / split;
+    log2_m = 0;
+    while ((1 << log2_m) < M) log2_m++;
+    CK(upload(d_tw, make_twiddles(M, M)));
+    if (split == 2) CK(upload(d_tw_split, make_twiddles(N, M)));
+    return 0;
+  }
+  void fill(t2k::OfdmArgs &a, const t2::OfdmPlan &op, const t2::CellPool &pool) const
+  {
+    a.code = d_code.as<int32_t>(); a.pool = d_pool.as<float2>();
+    a.l1post_base = pool.l1post_base; a.l1post_cells = pool.l1post_cells; a.l1post_variants = pool.l1post_variants;
+    a.p1 = d_p1.as<float2>(); a.inv_sinc = op.inv_sinc.empty() ? 0 : d_sinc.as<float>();
+    a.tw = d_tw.as<float2>(); a.tw_split = split == 2 ? d_tw_split.as<float2>() : 0;
+    a.fft_n = op.dims.fft_n; a.log2_m = log2_m; a.split = split;
+    a.c_ps = op.dims.c_ps; a.left_nulls = op.left_nulls; a.gi = op.dims.gi; a.num_symbols = op.dims.num_symbols;
+    a.norm = op.normalization;
+  }
+};
+
+struct OfdmHandle : dvbt2ll_handle {
+  t2::OfdmPlan plan;
+  OfdmDevice dev;
+  OfdmHandle() : dvbt2ll_handle(OFDM) {}
+  int output_multiple() const { return plan.samples_per_frame; }
+  int in_item() const { return 8; }
+  int out_item() const { return 8; }
+  int forecast(int noutput) const { return plan.dims.active_items * (noutput / plan.samples_per_frame); }
+  int dev_init() { return dev.init(plan.code, plan.pool, plan); }
+  int work_device(const void *d_in, int ninput, void *d_out, int noutput, int *consumed, cudaStream_t s)
+  {
+    const int frames = noutput / plan.samples_per_frame;
+    if (consumed) *consumed = 0;
+    if (frames < 1) return 0;
+    if ((long long)ninput < (long long)frames * plan.dims.active_items)
+      return fail(DVBT2LL_ERR_SHORT, "pilotgenp1insert_cc: not enough input items");
+    t2k::OfdmArgs a;
+    dev.fill(a, plan, plan.pool);
+    a.cells = (const float2 *)d_in; a.cells_stride = plan.dims.active_items;
+    a.out = (float2 *)d_out; a.out_stride = plan.samples_per_frame;
+    a.frames = frames; a.frame_idx0 = 0; a.frames_per_channel = frames;
+    t2k::launch_ofdm(a, s);
+    CK(cudaGetLastError());
+    if (consumed) *consumed = frames * plan.dims.active_items;
+    return frames * plan.samples_per_frame;
+  }
+  long long plan_get(const char *name, void *out, long long cap) const
+  {
+    std::string n(name);
+    if (n == "ofdm.code") return copy_vec(plan.code, out, cap);
+    if (n == "ofdm.pool") return copy_vec(plan.pool.cells, out, cap);
+    if (n == "ofdm.p1") return copy_vec(plan.p1, out, cap);
+    if (n == "ofdm.carrier_type") return copy_vec(plan.carrier_type, out, cap);
+    if (n == "ofdm.inv_sinc") return copy_vec(plan.inv_sinc, out, cap);
+    if (n == "ofdm.sym_data_start") return copy_vec(plan.sym_data_start, out, cap);
+    if (n == "ofdm.dims") return dims_get(plan.dims, out, cap);
+    if (n == "ofdm.info") {
+      int v[4] = { plan.left_nulls, plan.samples_per_frame, 0, 0 };
+      std::memcpy(&v[2], &plan.normalization, 4);
+      return copy_out(v, sizeof(v), out, cap);
+    }
+    return -1;
+  }
+};
+
+// ================================================================================================
+struct ChainHandle : dvbt2ll_handle {
+  BbHandle bb;
+  LdpcHandle ldpc;
+  MapHandle map;
+  t2::FramePlan fplan;
+  t2::OfdmPlan oplan;
+  t2::ChainTables tables;
+  OfdmDevice odev;
+  DevBuf d_bch, d_fec, d_cells, d_ts_stage, d_out_stage;
+  int max_frames, device;
+  int last_frames;
+  bool timing;
+  cudaEvent_t ev[5];
+  float stage_ms[5];
+  ChainHandle() : dvbt2ll_handle(CHAIN), max_frames(0), device(0), last_frames(0), timing(false)
+  {
+    for (int i = 0; i < 5; i++) { ev[i] = 0; stage_ms[i] = 0.f; }
+  }
+  ~ChainHandle() { for (int i = 0; i < 5; i++) if (ev[i]) cudaEventDestroy(ev[i]); }
+  int F() const { return fplan.prm.fecblocks; }
+  long long ts_per_frame() const { return bb.payload_bytes(F(), 0); }
+  int output_multiple() const { return oplan.samples_per_frame; }
+  int in_item() const { return 1; }
+  int out_item() const { return 8; }
+  int forecast(int noutput) const { return (int)(ts_per_frame() * (noutput / oplan.samples_per_frame)); }
+  int dev_init()
+  {
+    bb.stream = 0; ldpc.stream = 0; map.stream = 0;
+    int r;
+    if ((r = bb.dev_init())) return r;
+    if ((r = ldpc.dev_init())) return r;
+    if ((r = map.dev_init())) return r;
+    if ((r = odev.init(tables.code, tables.pool, oplan))) return r;
+    const size_t nfec = (size_t)max_frames * F();
+    CK(d_bch.ensure(nfec * align16(bb.plan.fec.nbch / 8) + 64));
+    CK(d_fec.ensure(nfec * align16(bb.plan.fec.nldpc / 8) + 64));
+    CK(d_cells.ensure(nfec * map.plan.cell_size * sizeof(float2)));
+    for (int i = 0; i < 5; i++) CK(cudaEventCreate(&ev[i]));
+    return 0;
+  }
+  int run(const void *d_ts, long long ts_pitch, int n_channels, int n_frames, long long first_frame, void *d_out, cudaStream_t s)
+  {
+    const int frames = n_channels * n_frames;
+    if (frames < 1) return 0;
+    if (frames > max_frames) return fail(DVBT2LL_ERR_INVALID, "chain: batch larger than max_frames given at create");
+    const int nfec = frames * F();
+    const int bp = align16(bb.plan.fec.nbch / 8), fp = align16(bb.plan.fec.nldpc / 8);
+    // stream position of the batch start (streams begin on a packet boundary at frame 0)
+    const long long j0 = first_frame * F();
+    const int fb0 = bb.plan.inband ? (int)(j0 % bb.plan.fecblocks) : 0;
+    long long nb0 = 0;
+    if (bb.plan.inband) nb0 = (j0 + bb.plan.fecblocks - 1) / bb.plan.fecblocks;
+    const long long p_before = j0 * bb.plan.payload_bytes - 13 * nb0;
+    const int count0 = (int)(p_before % 188);
+
+    if (timing) cudaEventRecord(ev[0], s);
+    t2k::BbArgs ba;
+    bb.fill_args(ba, (const uint8_t *)d_ts, ts_pitch, n_channels, n_frames * F(), count0, fb0, first_frame > 0 ? 1 : 0,
+                 d_bch.as<uint8_t>(), bp);
+    t2k::launch_bb_bch(ba, s);
+    if (timing) cudaEventRecord(ev[1], s);
+    t2k::LdpcArgs la;
+    ldpc.fill_args(la, d_bch.as<uint8_t>(), bp, d_fec.as<uint8_t>(), fp, nfec);
+    t2k::launch_ldpc(la, s);
+    if (timing) cudaEventRecord(ev[2], s);
+    t2k::MapArgs ma;
+    map.fill_args(ma, d_fec.as<uint8_t>(), fp, d_cells.as<float2>(), nfec);
+    t2k::launch_map(ma, s);
+    if (timing) cudaEventRecord(ev[3], s);
+    t2k::OfdmArgs oa;
+    odev.fill(oa, oplan, tables.pool);
+    oa.cells = d_cells.as<float2>(); oa.cells_stride = (long long)F() * map.plan.cell_size;
+    oa.out = (float2 *)d_out; oa.out_stride = oplan.samples_per_frame;
+    oa.frames = frames; oa.frame_idx0 = first_frame; oa.frames_per_channel = n_frames;
+    t2k::launch_ofdm(oa, s);
+    if (timing) cudaEventRecord(ev[4], s);
+    CK(cudaGetLastError());
+    last_frames = frames;
+    return frames;
+  }
+  int work_device(const void *d_in, int ninput, void *d_out, int noutput, int *consumed, cudaStream_t s)
+  {
+    const int frames = noutput / oplan.samples_per_frame;
+    if (consumed) *consumed = 0;
+    if (frames < 1) return 0;
+    if ((long long)ninput < ts_per_frame() * frames) return fail(DVBT2LL_ERR_SHORT, "chain: not enough input items");
+    int r = run(d_in, 0, 1, frames, 0, d_out, s);
+    if (r < 0) return r;
+    if (consumed) *consumed = (int)(ts_per_frame() * frames);
+    return frames * oplan.samples_per_frame;
+  }
+  long long plan_get(const char *name, void *out, long long cap) const
+  {
+    std::string n(name);
+    if (n == "chain.code") return copy_vec(tables.code, out, cap);
+    if (n == "chain.pool") return copy_vec(tables.pool.cells, out, cap);
+    long long r;
+    if ((r = bb.plan_get(name, out, cap)) >= 0) return r;
+    if ((r = ldpc.plan_get(name, out, cap)) >= 0) return r;
+    if ((r = map.plan_get(name, out, cap)) >= 0) return r;
+    if (n == "frame.code") return copy_vec(fplan.code, out, cap);
+    if (n == "ofdm.code") return copy_vec(oplan.code, out, cap);
+    if (n == "ofdm.dims") return dims_get(oplan.dims, out, cap);
+    return -1;
+  }
+};
+
+} // namespace
+
+// ================================================================================================
+extern "C" {
+
+const char *dvbt2ll_last_error(void) { return g_err.c_str(); }
+const char *dvbt2ll_version(void) { return "dvbt2ll-b200 0.1 (sm_100a)"; }
+long long dvbt2ll_kernel_launches(void) { return t2k::kernel_launch_count(); }
+
+int dvbt2ll_device_available(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n > 0;
+}
+
+int dvbt2ll_output_multiple(const dvbt2ll_handle *h) { return h ? h->output_multiple() : DVBT2LL_ERR_INVALID; }
+int dvbt2ll_forecast(const dvbt2ll_handle *h, int noutput) { return h ? h->forecast(noutput) : DVBT2LL_ERR_INVALID; }
+int dvbt2ll_warnings(const dvbt2ll_handle *h) { return h ? h->warnings : 0; }
+void dvbt2ll_destroy(dvbt2ll_handle *h) { delete h; }
+
+long long dvbt2ll_plan_get(const dvbt2ll_handle *h, const char *name, void *out, long long cap)
+{
+  if (!h || !name) return -1;
+  return h->plan_get(name, out, cap);
+}
+
+int dvbt2ll_work_device(dvbt2ll_handle *h, const void *d_in, int ninput, void *d_out, int noutput, int *consumed, void *stream)
+{
+  if (!h) return fail(DVBT2LL_ERR_INVALID, "null handle");
+  int r = h->ensure_device();
+  if (r) return r;
+  if (h->kind == dvbt2ll_handle::BB) {
+    // device-resident callers must keep 187 bytes of history in front of d_in themselves
+    static_cast<BbHandle *>(h)->hist_on_device = 0;
+  }
+  cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+  r = h->work_device(d_in, ninput, d_out, noutput, consumed, s);
+  if (r >= 0 && !stream) CK(cudaStreamSynchronize(s));
+  return r;
+}
+
+int dvbt2ll_work(dvbt2ll_handle *h, const void *in, int ninput, void *out, int noutput, int *consumed)
+{
+  if (!h) return fail(DVBT2LL_ERR_INVALID, "null handle");
+  if (consumed) *consumed = 0;
+  int r = h->ensure_device();
+  if (r) return r;
+  const int om = h->output_multiple();
+  const int frames = noutput / om;
+  if (frames < 1) return 0;
+  const int nout = frames * om;
+  // items to stage in
+  long long need;
+  if (h->kind == dvbt2ll_handle::BB) need = static_cast<BbHandle *>(h)->ts_needed(frames);
+  else if (h->kind == dvbt2ll_handle::CHAIN) need = static_cast<ChainHandle *>(h)->ts_per_frame() * frames;
+  else need = (long long)h->forecast(nout);
+  if (ninput < need) return fail(DVBT2LL_ERR_SHORT, "not enough input items for the requested output");
+  DevBuf &d_in = h->stage_in, &d_out = h->stage_out;
+  const size_t in_bytes = (size_t)need * h->in_item(), out_bytes = (size_t)nout * h->out_item();
+  const size_t prefix = 192;
+  CK(d_in.ensure(prefix + in_bytes + 256));
+  CK(d_out.ensure(out_bytes + 256));
+  uint8_t *din = d_in.as<uint8_t>() + prefix;
+  cudaStream_t s = h->stream;
+  if (h->kind == dvbt2ll_handle::BB) {
+    BbHandle *b = static_cast<BbHandle *>(h);
+    CK(cudaMemcpyAsync(din - 187, b->history.data(), 187, cudaMemcpyHostToDevice, s));
+    b->hist_on_device = 1;
+  }
+  CK(cudaMemcpyAsync(din, in, in_bytes, cudaMemcpyHostToDevice, s));
+  int used = 0;
+  r = h->work_device(din, (int)need, d_out.p, nout, &used, s);
+  if (r < 0) return r;
+  CK(cudaMemcpyAsync(out, d_out.p, out_bytes, cudaMemcpyDeviceToHost, s));
+  if (h->kind == dvbt2ll_handle::BB) {
+    BbHandle *b = static_cast<BbHandle *>(h);
+    int errs = 0;
+    CK(cudaMemcpyAsync(&errs, b->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    h->warnings = errs;
+    // keep the last 187 consumed bytes as history for the CRC-8 of the packet in flight
+    std::vector<uint8_t> joined(b->history);
+    joined.insert(joined.end(), (const uint8_t *)in, (const uint8_t *)in + used);
+    b->history.assign(joined.end() - 187, joined.end());
+  }
+  else CK(cudaStreamSynchronize(s));
+  if (consumed) *consumed = used;
+  return r;
+}
+
+// ---- factories -----------------------------------------------------------------------------------
+dvbt2ll_handle *dvbt2ll_bbheaderbch_create(int framesize, int rate, int mode, int inband, int fecblocks, int tsrate)
+{
+  BbHandle *h = new BbHandle();
+  std::string err;
+  if (mode != t2::INPUTMODE_NORMAL && mode != t2::INPUTMODE_HIEFF) { delete h; fail(DVBT2LL_ERR_INVALID, "bbheaderbch_bb: unknown input mode"); return 0; }
+  if (!t2::build_bb_plan(framesize, rate, mode, inband, fecblocks, tsrate, &h->plan, &err)) { delete h; fail(DVBT2LL_ERR_INVALID, err); return 0; }
+  return h;
+}
+
+dvbt2ll_handle *dvbt2ll_ldpc_create(int framesize, int rate)
+{
+  LdpcHandle *h = new LdpcHandle();
+  std::string err;
+  if (!t2::build_ldpc_plan(framesize, rate, &h->plan, &err)) { delete h; fail(DVBT2LL_ERR_INVALID, err); return 0; }
+  return h;
+}
+
+dvbt2ll_handle *dvbt2ll_interleavermod_create(int framesize, int rate, int constellation, int rotation)
+{
+  MapHandle *h = new MapHandle();
+  std::string err;
+  if (!t2::build_map_plan(framesize, rate, constellation, rotation, &h->plan, &err)) { delete h; fail(DVBT2LL_ERR_INVALID, err); return 0; }
+  return h;
+}
+
+dvbt2ll_handle *dvbt2ll_framemapperfint_create(int framesize, int rate, int constellation, int rotation, int fecblocks,
+                                               int tiblocks, int carriermode, int fftsize, int guardinterval,
+                                               int l1constellation, int pilotpattern, int t2frames, int numdatasyms,
+                                               int paprmode, int version, int preamble, int inputmode,
+                                               int reservedbiasbits, int l1scrambled, int inband)
+{
+  FrameHandle *h = new FrameHandle();
+  std::string err;
+  t2::FrameParams p = { framesize, rate, constellation, rotation, fecblocks, tiblocks, carriermode, fftsize, guardinterval,
+                        l1constellation, pilotpattern, t2frames, numdatasyms, paprmode, version, preamble, inputmode,
+                        reservedbiasbits, l1scrambled, inband };
+  if (!t2::build_frame_plan(p, &h->plan, &err)) { delete h; fail(DVBT2LL_ERR_INVALID, err); return 0; }
+  return h;
+}
+
+dvbt2ll_handle *dvbt2ll_pilotgenp1insert_create(int carriermode, int fftsize, int pilotpattern, int guardinterval,
+                                                int numdatasyms, int paprmode, int version, int preamble,
+                                                int misogroup, int equalization, int bandwidth, int vlength)
+{
+  OfdmHandle *h = new OfdmHandle();
+  std::string err;
+  t2::OfdmParams p = { carriermode, fftsize, pilotpattern, guardinterval, numdatasyms, paprmode, version, preamble,
+                       misogroup, equalization, bandwidth, vlength };
+  if (!t2::build_ofdm_plan(p, &h->plan, &err)) { delete h; fail(DVBT2LL_ERR_INVALID, err); return 0; }
+  return h;
+}
+
+dvbt2ll_handle *dvbt2ll_chain_create(const dvbt2ll_chain_params *c, int max_frames, int device)
+{
+  if (!c || max_frames < 1) { fail(DVBT2LL_ERR_INVALID, "chain: bad arguments"); return 0; }
+  ChainHandle *h = new ChainHandle();
+  std::string err;
+  h->max_frames = max_frames; h->device = device;
+  t2::FrameParams fp = { c->framesize, c->rate, c->constellation, c->rotation, c->fecblocks, c->tiblocks, c->carriermode,
+                         c->fftsize, c->guardinterval, c->l1constellation, c->pilotpattern, c->t2frames, c->numdatasyms,
+                         c->paprmode, c->version, c->preamble, c->inputmode, c->reservedbiasbits, c->l1scrambled, c->inband };
+  t2::OfdmParams op = { c->carriermode, c->fftsize, c->pilotpattern, c->guardinterval, c->numdatasyms, c->paprmode,
+                        c->version, c->preamble, c->misogroup, c->equalization, c->bandwidth, c->vlength };
+  bool ok = true;
+  if (c->inputmode != t2::INPUTMODE_NORMAL) { ok = false; err = "chain: only INPUTMODE_NORMAL is supported in chain mode (TS bytes per frame must be constant)"; }
+  ok = ok && t2::build_bb_plan(c->framesize, c->rate, c->inputmode, c->inband, c->fecblocks, c->tsrate, &h->bb.plan, &err);
+  ok = ok && t2::build_ldpc_plan(c->framesize, c->rate, &h->ldpc.plan, &err);
+  ok = ok && t2::build_map_plan(c->framesize, c->rate, c->constellation, c->rotation, &h->map.plan, &err);
+  ok = ok && t2::build_frame_plan(fp, &h->fplan, &err);
+  ok = ok && t2::build_ofdm_plan(op, &h->oplan, &err);
+  ok = ok && t2::compose_chain(h->fplan, h->oplan, &h->tables, &err);
+  if (!ok) { delete h; fail(DVBT2LL_ERR_INVALID, err); return 0; }
+  return h;
+}
+
+static ChainHandle *as_chain(const dvbt2ll_handle *h)
+{
+  return (h && h->kind == dvbt2ll_handle::CHAIN) ? static_cast<ChainHandle *>(const_cast<dvbt2ll_handle *>(h)) : 0;
+}
+
+long long dvbt2ll_chain_ts_bytes_per_frame(const dvbt2ll_handle *h) { ChainHandle *c = as_chain(h); return c ? c->ts_per_frame() : -1; }
+long long dvbt2ll_chain_samples_per_frame(const dvbt2ll_handle *h) { ChainHandle *c = as_chain(h); return c ? c->oplan.samples_per_frame : -1; }
+int dvbt2ll_chain_fecframes_per_frame(const dvbt2ll_handle *h) { ChainHandle *c = as_chain(h); return c ? c->F() : -1; }
+
+int dvbt2ll_chain_run_device(dvbt2ll_handle *h, const void *d_ts, long long ts_pitch, int n_channels, int n_frames,
+                             long long first_frame, void *d_out, void *stream)
+{
+  ChainHandle *c = as_chain(h);
+  if (!c) return fail(DVBT2LL_ERR_INVALID, "not a chain handle");
+  if (c->device >= 0 && !c->dev_ready) CK(cudaSetDevice(c->device));
+  int r = c->ensure_device();
+  if (r) return r;
+  return c->run(d_ts, ts_pitch, n_channels, n_frames, first_frame, d_out, stream ? (cudaStream_t)stream : c->stream);
+}
+
+int dvbt2ll_chain_run_host(dvbt2ll_handle *h, const void *ts, long long ts_pitch, int n_channels, int n_frames,
+                           long long first_frame, void *out)
+{
+  ChainHandle *c = as_chain(h);
+  if (!c) return fail(DVBT2LL_ERR_INVALID, "not a chain handle");
+  if (c->device >= 0 && !c->dev_ready) CK(cudaSetDevice(c->device));
+  int r = c->ensure_device();
+  if (r) return r;
+  const long long per = c->ts_per_frame() * n_frames;
+  const long long hist = first_frame > 0 ? 187 : 0;
+  const long long dpitch = (per + hist + 255) & ~255LL;
+  const size_t out_bytes = (size_t)n_channels * n_frames * c->oplan.samples_per_frame * sizeof(float2);
+  CK(c->d_ts_stage.ensure((size_t)n_channels * dpitch + 512));
+  CK(c->d_out_stage.ensure(out_bytes));
+  cudaStream_t s = c->stream;
+  uint8_t *base = c->d_ts_stage.as<uint8_t>() + 256;
+  // host layout: channel-major with pitch ts_pitch; when first_frame > 0 each channel pointer must be preceded by 187 history bytes
+  CK(cudaMemcpy2DAsync(base - hist, (size_t)dpitch, (const uint8_t *)ts - hist, (size_t)ts_pitch, (size_t)(per + hist),
+                       (size_t)n_channels, cudaMemcpyHostToDevice, s));
+  r = c->run(base, dpitch, n_channels, n_frames, first_frame, c->d_out_stage.p, s);
+  if (r < 0) return r;
+  CK(cudaMemcpyAsync(out, c->d_out_stage.p, out_bytes, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return r;
+}
+
+long long dvbt2ll_chain_tap(dvbt2ll_handle *h, const char *stage, void *out, long long cap)
+{
+  ChainHandle *c = as_chain(h);
+  if (!c || !stage) return fail(DVBT2LL_ERR_INVALID, "not a chain handle");
+  if (!c->dev_ready || c->last_frames < 1) return fail(DVBT2LL_ERR_INVALID, "chain: nothing has run yet");
+  const size_t nfec = (size_t)c->last_frames * c->F();
+  const void *src; size_t bytes;
+  std::string n(stage);
+  if (n == "bch") { src = c->d_bch.p; bytes = nfec * align16(c->bb.plan.fec.nbch / 8); }
+  else if (n == "fec") { src = c->d_fec.p; bytes = nfec * align16(c->bb.plan.fec.nldpc / 8); }
+  else if (n == "cells") { src = c->d_cells.p; bytes = nfec * c->map.plan.cell_size * sizeof(float2); }
+  else return fail(DVBT2LL_ERR_INVALID, "chain: unknown tap");
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaDeviceSynchronize());
+  if (out && cap > 0) CK(cudaMemcpy(out, src, (size_t)cap < bytes ? (size_t)cap : bytes, cudaMemcpyDeviceToHost));
+  return (long long)bytes;
+}
+
+void dvbt2ll_chain_enable_timing(dvbt2ll_handle *h, int on) { ChainHandle *c = as_chain(h); if (c) c->timing = on != 0; }
+
+int dvbt2ll_chain_stage_ms(dvbt2ll_handle *h, float *ms5)
+{
+  ChainHandle *c = as_chain(h);
+  if (!c || !ms5) return fail(DVBT2LL_ERR_INVALID, "not a chain handle");
+  if (!c->timing || !c->dev_ready) return fail(DVBT2LL_ERR_INVALID, "chain: timing not enabled");
+  CK(cudaEventSynchronize(c->ev[4]));
+  for (int i = 0; i < 4; i++) CK(cudaEventElapsedTime(&ms5[i], c->ev[i], c->ev[i + 1]));
+  CK(cudaEventElapsedTime(&ms5[4], c->ev[0], c->ev[4]));
+  return 0;
+}
+
+} // extern "C"

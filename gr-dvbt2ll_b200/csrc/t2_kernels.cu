@@ -1,0 +1,701 @@
+// Hand-written sm_100a kernels of the DVB-T2 modulator hot path.
+//
+//   k_bb_bch   warp per FECFRAME : BB header, TS payload with CRC-8 sync substitution, BB scrambler,
+//                                  BCH parity as GF(2) polynomial remainder (per-lane chunk remainders
+//                                  from a byte table, combined with a ballot-evaluated x^L multiply)
+//   k_ldpc     warp per FECFRAME : IRA parity as XOR of 360-bit cyclic rotations (funnel shifts on a
+//                                  wrap-extended copy of each info group), accumulator in closed form
+//   k_map      CTA per FECFRAME  : bit interleaver + demux (table driven bit gather from shared
+//                                  memory), constellation LUT, cyclic Q delay, coalesced float2 stores
+//   k_gather   grid-stride       : frame mapper as one static gather
+//   k_ofdm     CTA per OFDM symbol: carrier fill (gather + pilots), in-place shared-memory DIT FFT
+//                                  (radix 16/8/4/2 in registers, XOR-swizzled), scale, CP, P1
+//
+// None of the stages is a dense contraction, so no tensor-core path is used: the cell-domain
+// kernels are HBM/L2 bound, the bit-domain ones integer-pipe bound, the IFFT shared-memory bound.
+#include "t2_kernels.cuh"
+
+#include <atomic>
+
+namespace t2k {
+
+static std::atomic<long long> g_launches(0);
+long long kernel_launch_count() { return g_launches.load(); }
+static inline void count_launch() { g_launches.fetch_add(1); }
+
+static inline int sm_count()
+{
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+__device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
+// 32 stream bits starting at bit position p of a big-endian word array
+__device__ __forceinline__ uint32_t window32(const uint32_t *w, int p)
+{
+  const int k = p >> 5;
+  return __funnelshift_l(w[k + 1], w[k], p & 31);
+}
+
+// ================================================================================================
+// K1  BB framing + scrambler + BCH
+// ================================================================================================
+constexpr int BB_WARPS = 4;
+
+__device__ __forceinline__ int multiples_in(int a, int b, int m)   // multiples of m in [a, b), a,b >= 0
+{
+  return (b + m - 1) / m - (a + m - 1) / m;
+}
+
+// TS index of de-synced payload byte P in high-efficiency mode (sync bytes dropped), c0 = packet phase of ts[0]
+__device__ __forceinline__ long long hem_ts_index(long long P, int c0)
+{
+  const int t0 = (188 - c0) % 188;      // TS index of the first sync byte
+  if (P < t0) return P;
+  const long long pp = P - t0;
+  return t0 + 1 + pp + pp / 187;
+}
+
+__global__ void __launch_bounds__(BB_WARPS * 32) k_bb_bch(const BbArgs a)
+{
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  uint32_t *s_tab = reinterpret_cast<uint32_t *>(smem_raw);   // 256 * 6
+  uint32_t *s_cols = s_tab + 256 * 6;                         // 6 * 32 * 6
+  uint8_t *s_crc8 = reinterpret_cast<uint8_t *>(s_cols + 6 * 32 * 6);
+  uint8_t *s_buf = s_crc8 + 256;
+  const int nbytes = a.nbch / 8, msg_bytes = a.kbch / 8;
+  const int buf_pitch = (nbytes + 15) & ~15;
+
+  for (int i = threadIdx.x; i < 256 * 6; i += blockDim.x) s_tab[i] = a.bch_tab[i];
+  for (int i = threadIdx.x; i < 6 * 32 * 6; i += blockDim.x) s_cols[i] = a.bch_cols[i];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_crc8[i] = a.crc8_tab[i];
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t *buf = s_buf + warp * buf_pitch;
+  const int total = a.n_channels * a.frames;
+  const int D = a.payload_bytes;
+  const bool hem = a.mode != 0;
+
+  for (int job = blockIdx.x * BB_WARPS + warp; job < total; job += gridDim.x * BB_WARPS) {
+    const int c = job / a.frames, j = job - c * a.frames;
+    const uint8_t *ts = a.ts + (long long)c * a.ts_pitch;
+    const int nb = a.inband ? multiples_in(a.fec_block0, a.fec_block0 + j, a.fecblocks) : 0;
+    const bool ib = a.inband && ((a.fec_block0 + j) % a.fecblocks == 0);
+    const long long P0 = (long long)j * D - 13LL * nb;     // payload bytes before this frame
+    const int Dj = D - (ib ? 13 : 0);
+    // TS index at which the frame's read loop starts, and packet phase there
+    long long t_start;
+    if (!hem) t_start = P0;
+    else t_start = P0 == 0 ? 0 : hem_ts_index(P0 - 1, a.count0) + 1;
+    const int count = (int)((a.count0 + t_start) % 188);
+
+    // ---- BB header (EN 302 755 5.1.7): MATYPE, UPL, DFL, SYNC, SYNCD, CRC-8 (xor MODE)
+    if (lane == 0) {
+      uint8_t h[10];
+      h[0] = 0xF0;            // TS, SIS, CCM, no ISSY, no NPD, EXT 00
+      h[1] = 0x00;
+      const int upl = hem ? 0 : 188 * 8, dfl = a.kbch - 80 - (ib ? 104 : 0);
+      const int syncd = count ? (188 - count) * 8 : 0;
+      h[2] = (uint8_t)(upl >> 8); h[3] = (uint8_t)upl;
+      h[4] = (uint8_t)(dfl >> 8); h[5] = (uint8_t)dfl;
+      h[6] = hem ? 0x00 : 0x47;
+      h[7] = (uint8_t)(syncd >> 8); h[8] = (uint8_t)syncd;
+      uint8_t crc = 0;
+      for (int i = 0; i < 9; i++) crc = s_crc8[crc ^ h[i]];
+      h[9] = hem ? (crc ^ 1) : crc;
+      for (int i = 0; i < 10; i++) buf[i] = h[i] ^ a.scramble[i];
+    }
+    // ---- payload
+    if (!hem) {
+      for (int i = lane; i < Dj; i += 32) buf[10 + i] = ts[P0 + i] ^ a.scramble[10 + i];
+      // sync bytes: replaced by the CRC-8 of the previous packet's 187 bytes
+      const int i0 = (188 - count) % 188;
+      for (int si = i0 + 188 * lane; si < Dj; si += 188 * 32) {
+        const long long t = P0 + si;
+        if (ts[t] != 0x47) atomicAdd(a.sync_errors, 1);
+        uint8_t crc = 0;
+        long long lo = t - 187;
+        if (lo < 0 && !a.hist_valid) lo = 0;
+        for (long long u = lo; u < t; u++) crc = s_crc8[ts[u] ^ crc];
+        buf[10 + si] = crc ^ a.scramble[10 + si];
+      }
+    }
+    else {
+      for (int i = lane; i < Dj; i += 32) {
+        const long long t = hem_ts_index(P0 + i, a.count0);
+        buf[10 + i] = ts[t] ^ a.scramble[10 + i];
+      }
+      // sync bytes skipped by this frame: positions between t_start and the last payload byte
+      const long long t_end = hem_ts_index(P0 + Dj - 1, a.count0);
+      const int first = (int)((188 - (a.count0 + t_start) % 188) % 188);
+      for (long long t = t_start + first + 188LL * lane; t <= t_end; t += 188LL * 32)
+        if (ts[t] != 0x47) atomicAdd(a.sync_errors, 1);
+    }
+    if (ib)
+      for (int i = lane; i < 13; i += 32) buf[10 + Dj + i] = a.inband_bytes[i] ^ a.scramble[10 + Dj + i];
+    __syncwarp();
+
+    // ---- BCH: per-lane remainder of a chunk of the message (byte-table LFSR on a 192-bit register)
+    uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = 0, r4 = 0, r5 = 0;
+    {
+      int s = lane * a.chunk_bytes - a.lead_zero_bytes;
+      const int e = s + a.chunk_bytes;
+      if (s < 0) s = 0;
+      for (int i = s; i < e; i++) {
+        const uint32_t *T = s_tab + 6 * ((r0 >> 24) ^ buf[i]);
+        r0 = ((r0 << 8) | (r1 >> 24)) ^ T[0];
+        r1 = ((r1 << 8) | (r2 >> 24)) ^ T[1];
+        r2 = ((r2 << 8) | (r3 >> 24)) ^ T[2];
+        r3 = ((r3 << 8) | (r4 >> 24)) ^ T[3];
+        r4 = ((r4 << 8) | (r5 >> 24)) ^ T[4];
+        r5 = (r5 << 8) ^ T[5];
+      }
+    }
+    // ---- Horner combine: acc = acc * x^(8*chunk) + R_i, the multiply evaluated column-wise:
+    // lane l computes output bit (31 - l) of every word as parity(acc & column) and a ballot
+    // assembles the words, so acc stays warp-uniform.
+    uint32_t c0 = __shfl_sync(0xffffffffu, r0, 0), c1 = __shfl_sync(0xffffffffu, r1, 0),
+             c2 = __shfl_sync(0xffffffffu, r2, 0), c3 = __shfl_sync(0xffffffffu, r3, 0),
+             c4 = __shfl_sync(0xffffffffu, r4, 0), c5 = __shfl_sync(0xffffffffu, r5, 0);
+    for (int i = 1; i < 32; i++) {
+      uint32_t n[6];
+#pragma unroll
+      for (int w = 0; w < 6; w++) {
+        const uint32_t *col = s_cols + (w * 32 + lane) * 6;
+        const uint32_t x = (c0 & col[0]) ^ (c1 & col[1]) ^ (c2 & col[2]) ^ (c3 & col[3]) ^ (c4 & col[4]) ^ (c5 & col[5]);
+        n[w] = __ballot_sync(0xffffffffu, __popc(x) & 1);
+      }
+      c0 = n[0] ^ __shfl_sync(0xffffffffu, r0, i);
+      c1 = n[1] ^ __shfl_sync(0xffffffffu, r1, i);
+      c2 = n[2] ^ __shfl_sync(0xffffffffu, r2, i);
+      c3 = n[3] ^ __shfl_sync(0xffffffffu, r3, i);
+      c4 = n[4] ^ __shfl_sync(0xffffffffu, r4, i);
+      c5 = n[5] ^ __shfl_sync(0xffffffffu, r5, i);
+    }
+    if (lane < a.bch_r / 8) {
+      const uint32_t words[6] = { c0, c1, c2, c3, c4, c5 };
+      buf[msg_bytes + lane] = (uint8_t)(words[lane >> 2] >> (24 - 8 * (lane & 3)));
+    }
+    __syncwarp();
+    // ---- store the packed codeword
+    uint8_t *o = a.out + (long long)job * a.out_pitch;
+    const int nw = nbytes >> 2;
+    const uint32_t *bw = reinterpret_cast<const uint32_t *>(buf);
+    uint32_t *ow = reinterpret_cast<uint32_t *>(o);
+    for (int i = lane; i < nw; i += 32) ow[i] = bw[i];
+    for (int i = (nw << 2) + lane; i < nbytes; i += 32) o[i] = buf[i];
+    __syncwarp();
+  }
+}
+
+void launch_bb_bch(const BbArgs &a, cudaStream_t s)
+{
+  const int nbytes = a.nbch / 8;
+  const int buf_pitch = (nbytes + 15) & ~15;
+  const size_t smem = 256 * 6 * 4 + 6 * 32 * 6 * 4 + 256 + (size_t)BB_WARPS * buf_pitch;
+  const int total = a.n_channels * a.frames;
+  int blocks = (total + BB_WARPS - 1) / BB_WARPS;
+  const int cap = sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) return;
+  k_bb_bch<<<blocks, BB_WARPS * 32, smem, s>>>(a);
+  count_launch();
+}
+
+// ================================================================================================
+// K2  LDPC
+// ================================================================================================
+constexpr int LDPC_WARPS = 4;
+
+__global__ void __launch_bounds__(LDPC_WARPS * 32) k_ldpc(const LdpcArgs a, int cw_words, int warp_words)
+{
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  uint32_t *s_all = reinterpret_cast<uint32_t *>(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t *cw = s_all + warp * warp_words;       // [cw_words]  codeword info part, big-endian words
+  uint32_t *ext = cw + cw_words;                  // [groups][13]
+  uint32_t *rows = ext + a.groups * 13;           // [q][12]
+  const int q = a.q, G = a.groups;
+  const int info_bytes = a.nbch / 8;
+
+  for (int job = blockIdx.x * LDPC_WARPS + warp; job < a.frames; job += gridDim.x * LDPC_WARPS) {
+    const uint8_t *in = a.in + (long long)job * a.in_pitch;
+    uint8_t *out = a.out + (long long)job * a.out_pitch;
+    // ---- load info bits (and pass them through to the output)
+    {
+      const uint32_t *iw = reinterpret_cast<const uint32_t *>(in);
+      uint32_t *ow = reinterpret_cast<uint32_t *>(out);
+      const int nw = (info_bytes + 3) >> 2;
+      for (int i = lane; i < nw; i += 32) {
+        const uint32_t v = iw[i];
+        cw[i] = bswap32(v);
+        if (4 * i + 4 <= info_bytes) ow[i] = v;
+        else for (int b = 4 * i; b < info_bytes; b++) out[b] = in[b];
+      }
+      for (int i = nw + lane; i < cw_words; i += 32) cw[i] = 0;
+    }
+    __syncwarp();
+    // ---- wrap-extended groups: 13 words = circular bits [0, 416) of each 360-bit group
+    for (int idx = lane; idx < G * 13; idx += 32) {
+      const int g = idx / 13, w = idx - g * 13;
+      const int base = 360 * g;
+      uint32_t v;
+      if (w < 11) v = window32(cw, base + 32 * w);
+      else if (w == 11) v = (window32(cw, base + 352) & 0xFF000000u) | (window32(cw, base) >> 8);
+      else v = window32(cw, base + 24);
+      ext[idx] = v;
+    }
+    __syncwarp();
+    // ---- pre-accumulator parity rows: R_t = XOR of rotated info groups
+    for (int idx = lane; idx < q * 12; idx += 32) {
+      const int t = idx / 12, w = idx - t * 12;
+      uint32_t acc = 0;
+      const int e1 = a.row_ptr[t + 1];
+      for (int e = a.row_ptr[t]; e < e1; e++) {
+        const uint32_t en = __ldg(a.entries + e);
+        int p = 32 * w - (int)(en >> 16);
+        if (p < 0) p += 360;
+        acc ^= window32(ext + (en & 0xffffu) * 13, p);
+      }
+      if (w == 11) acc &= 0xFF000000u;
+      rows[idx] = acc;
+    }
+    __syncwarp();
+    // ---- accumulator, part 1: T_t = XOR_{t' <= t} R_t'  (prefix over rows, word-parallel)
+    if (lane < 12) {
+      uint32_t run = 0;
+      for (int t = 0; t < q; t++) { run ^= rows[t * 12 + lane]; rows[t * 12 + lane] = run; }
+    }
+    __syncwarp();
+    // ---- part 2: E = exclusive prefix-XOR along the 360 bit positions of T_{q-1}
+    uint32_t E = 0;
+    {
+      uint32_t x = lane < 12 ? rows[(q - 1) * 12 + lane] : 0;
+      x ^= x >> 1; x ^= x >> 2; x ^= x >> 4; x ^= x >> 8; x ^= x >> 16;   // inclusive, MSB first
+      // carry into word w = parity of all earlier words = XOR of their last inclusive bits
+      uint32_t par = x & 1u, carry = par;
+#pragma unroll
+      for (int d = 1; d < 16; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, carry, d);
+        if (lane >= d) carry ^= o;
+      }
+      carry ^= par;     // exclusive over words
+      E = (x >> 1) ^ (carry ? 0xFFFFFFFFu : 0u);
+      if (lane == 11) E &= 0xFF000000u;
+    }
+    if (lane < 12)
+      for (int t = 0; t < q; t++) rows[t * 12 + lane] ^= E;
+    __syncwarp();
+    // ---- store parity rows: row t occupies bytes [nbch/8 + 45 t, +45)
+    for (int idx = lane; idx < q * 45; idx += 32) {
+      const int t = idx / 45, b = idx - t * 45;
+      out[info_bytes + idx] = (uint8_t)(rows[t * 12 + (b >> 2)] >> (24 - 8 * (b & 3)));
+    }
+    __syncwarp();
+  }
+}
+
+void launch_ldpc(const LdpcArgs &a, cudaStream_t s)
+{
+  const int cw_words = ((a.nbch + 31) / 32 + 2 + 3) & ~3;
+  const int warp_words = cw_words + a.groups * 13 + a.q * 12 + 4;
+  const size_t smem = (size_t)LDPC_WARPS * warp_words * 4;
+  int blocks = (a.frames + LDPC_WARPS - 1) / LDPC_WARPS;
+  const int cap = sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) return;
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(k_ldpc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+  k_ldpc<<<blocks, LDPC_WARPS * 32, smem, s>>>(a, cw_words, warp_words);
+  count_launch();
+}
+
+// ================================================================================================
+// K3  bit interleaver + demux + mapper
+// ================================================================================================
+constexpr int MAP_THREADS = 256;
+
+__global__ void __launch_bounds__(MAP_THREADS) k_map(const MapArgs a)
+{
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int nwords = (a.nldpc + 31) / 32;
+  uint32_t *u = reinterpret_cast<uint32_t *>(smem_raw);                   // [nwords + 1]
+  float2 *lut = reinterpret_cast<float2 *>(u + ((nwords + 2) & ~1));      // [1 << mod]
+  uint8_t *cw = reinterpret_cast<uint8_t *>(lut + (1 << a.mod));          // [cell_size]
+  for (int i = threadIdx.x; i < (1 << a.mod); i += blockDim.x) lut[i] = a.lut[i];
+
+  for (int f = blockIdx.x; f < a.frames; f += gridDim.x) {
+    const uint32_t *in = reinterpret_cast<const uint32_t *>(a.in + (long long)f * a.in_pitch);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nwords; i += blockDim.x) u[i] = bswap32(in[i]);
+    __syncthreads();
+    const int mod = a.mod;
+    for (int c = threadIdx.x; c < a.cell_size; c += blockDim.x) {
+      const uint16_t *src = a.bit_src + c * mod;
+      uint32_t v = 0;
+      for (int b = 0; b < mod; b++) {
+        const int p = __ldg(src + b);
+        v = (v << 1) | ((u[p >> 5] >> (31 - (p & 31))) & 1u);
+      }
+      cw[c] = (uint8_t)v;
+    }
+    __syncthreads();
+    float2 *out = a.out + (long long)f * a.cell_size;
+    if (a.cyclic_delay) {
+      for (int c = threadIdx.x; c < a.cell_size; c += blockDim.x) {
+        const int pc = c == 0 ? a.cell_size - 1 : c - 1;
+        out[c] = make_float2(lut[cw[c]].x, lut[cw[pc]].y);
+      }
+    }
+    else {
+      for (int c = threadIdx.x; c < a.cell_size; c += blockDim.x) out[c] = lut[cw[c]];
+    }
+  }
+}
+
+void launch_map(const MapArgs &a, cudaStream_t s)
+{
+  const int nwords = (a.nldpc + 31) / 32;
+  const size_t smem = (size_t)((nwords + 2) & ~1) * 4 + (size_t)(1 << a.mod) * 8 + ((a.cell_size + 15) & ~15);
+  int blocks = a.frames;
+  const int cap = sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) return;
+  k_map<<<blocks, MAP_THREADS, smem, s>>>(a);
+  count_launch();
+}
+
+// ================================================================================================
+// bit format helpers
+// ================================================================================================
+__global__ void k_pack_bits(const uint8_t *in, int nbits, uint8_t *out, int out_pitch, int frames)
+{
+  const int nbytes = (nbits + 7) / 8;
+  const long long total = (long long)frames * nbytes;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(i / nbytes), b = (int)(i - (long long)f * nbytes);
+    const uint8_t *p = in + (long long)f * nbits + 8 * b;
+    uint32_t v = 0;
+    for (int k = 0; k < 8; k++) v = (v << 1) | ((8 * b + k < nbits) ? (p[k] & 1u) : 0u);
+    out[(long long)f * out_pitch + b] = (uint8_t)v;
+  }
+}
+
+__global__ void k_unpack_bits(const uint8_t *in, int in_pitch, int nbits, uint8_t *out, int frames)
+{
+  const long long total = (long long)frames * nbits;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(i / nbits), b = (int)(i - (long long)f * nbits);
+    out[i] = (in[(long long)f * in_pitch + (b >> 3)] >> (7 - (b & 7))) & 1u;
+  }
+}
+
+__global__ void k_unpack_ldpc(const uint8_t *in, int in_pitch, int nbch, int nldpc, int q, uint8_t *out, int frames)
+{
+  const long long total = (long long)frames * nldpc;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(i / nldpc), b = (int)(i - (long long)f * nldpc);
+    int p = b;
+    if (b >= nbch) { const int x = b - nbch; p = nbch + 360 * (x % q) + x / q; }
+    out[i] = (in[(long long)f * in_pitch + (p >> 3)] >> (7 - (p & 7))) & 1u;
+  }
+}
+
+__global__ void k_pack_ldpc(const uint8_t *in, int nbch, int nldpc, int q, uint8_t *out, int out_pitch, int frames)
+{
+  const int nbytes = nldpc / 8;
+  const long long total = (long long)frames * nbytes;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(i / nbytes), b = (int)(i - (long long)f * nbytes);
+    const uint8_t *fr = in + (long long)f * nldpc;
+    uint32_t v = 0;
+    for (int k = 0; k < 8; k++) {
+      const int p = 8 * b + k;          // position in "u" order
+      int n = p;                        // natural index
+      if (p >= nbch) { const int x = p - nbch; n = nbch + q * (x % 360) + x / 360; }
+      v = (v << 1) | (fr[n] & 1u);
+    }
+    out[(long long)f * out_pitch + b] = (uint8_t)v;
+  }
+}
+
+static inline int grid_for(long long total, int threads)
+{
+  long long b = (total + threads - 1) / threads;
+  const long long cap = (long long)sm_count() * 32;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+void launch_pack_bits(const uint8_t *in, int nbits, uint8_t *out, int out_pitch, int frames, cudaStream_t s)
+{
+  if (frames < 1) return;
+  k_pack_bits<<<grid_for((long long)frames * ((nbits + 7) / 8), 256), 256, 0, s>>>(in, nbits, out, out_pitch, frames);
+  count_launch();
+}
+void launch_unpack_bits(const uint8_t *in, int in_pitch, int nbits, uint8_t *out, int frames, cudaStream_t s)
+{
+  if (frames < 1) return;
+  k_unpack_bits<<<grid_for((long long)frames * nbits, 256), 256, 0, s>>>(in, in_pitch, nbits, out, frames);
+  count_launch();
+}
+void launch_unpack_ldpc(const uint8_t *in, int in_pitch, int nbch, int nldpc, int q, uint8_t *out, int frames, cudaStream_t s)
+{
+  if (frames < 1) return;
+  k_unpack_ldpc<<<grid_for((long long)frames * nldpc, 256), 256, 0, s>>>(in, in_pitch, nbch, nldpc, q, out, frames);
+  count_launch();
+}
+void launch_pack_ldpc(const uint8_t *in, int nbch, int nldpc, int q, uint8_t *out, int out_pitch, int frames, cudaStream_t s)
+{
+  if (frames < 1) return;
+  k_pack_ldpc<<<grid_for((long long)frames * (nldpc / 8), 256), 256, 0, s>>>(in, nbch, nldpc, q, out, out_pitch, frames);
+  count_launch();
+}
+
+// ================================================================================================
+// K4  frame mapper gather
+// ================================================================================================
+__device__ __forceinline__ float2 fetch_cell(int code, const float2 *__restrict__ cells, const float2 *__restrict__ pool,
+                                            int l1post_base, int l1post_cells, int variant)
+{
+  if (code >= 0) return __ldg(cells + code);
+  int idx = -(code + 1);
+  if ((unsigned)(idx - l1post_base) < (unsigned)l1post_cells) idx += variant * l1post_cells;
+  return __ldg(pool + idx);
+}
+
+__global__ void __launch_bounds__(256) k_gather(const GatherArgs a)
+{
+  const long long total = (long long)a.frames * a.n;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(i / a.n), j = (int)(i - (long long)f * a.n);
+    const int variant = (a.frame_idx0 + f) % a.l1post_variants;
+    a.out[(long long)f * a.out_stride + j] =
+        fetch_cell(__ldg(a.code + j), a.in + (long long)f * a.in_stride, a.pool, a.l1post_base, a.l1post_cells, variant);
+  }
+}
+
+void launch_gather(const GatherArgs &a, cudaStream_t s)
+{
+  if (a.frames < 1) return;
+  k_gather<<<grid_for((long long)a.frames * a.n, 256), 256, 0, s>>>(a);
+  count_launch();
+}
+
+// ================================================================================================
+// K5  OFDM symbol: carrier fill, IFFT, scale, guard interval, P1
+// ================================================================================================
+// In-place decimation-in-time FFT of M = 2^log2_m points in shared memory, backward sign
+// (x[t] = sum_b X_b e^{+j 2 pi b t / M}).  Pass j multiplies element q of each butterfly by
+// W_{n_j}^{i q}, does an R-point DFT in registers and writes back in place; inputs are stored at
+// digit-reversed positions by the carrier-fill stage so the result comes out in natural order.
+// Shared-memory index swizzle: the low nibble is XORed with the fold of the upper nibbles, which
+// makes every access pattern used below (unit stride, power-of-two strides of the butterflies and the
+// digit-reversed fill) conflict-free per half-warp for 8-byte elements.
+
+__device__ __forceinline__ int swz(int p) { return p ^ (((p >> 4) ^ (p >> 8) ^ (p >> 12)) & 15); }
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+
+// multiply by exp(+j 2 pi k / 16); k is a compile-time constant after unrolling
+__device__ __forceinline__ float2 tw16(float2 d, int k)
+{
+  const float h = 0.70710678118654752440f, c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f;
+  switch (k) {
+    case 0: return d;
+    case 1: return cmul(d, make_float2(c1, s1));
+    case 2: return make_float2(h * (d.x - d.y), h * (d.x + d.y));
+    case 3: return cmul(d, make_float2(s1, c1));
+    case 4: return make_float2(-d.y, d.x);
+    case 5: return cmul(d, make_float2(-s1, c1));
+    case 6: return make_float2(-h * (d.x + d.y), h * (d.x - d.y));
+    default: return cmul(d, make_float2(-c1, s1));
+  }
+}
+
+// R-point backward DFT in registers (radix-2 DIF, fully unrolled); output index k is left in v[bitrev(k)]
+template <int R>
+__device__ __forceinline__ void dft_reg(float2 (&v)[R])
+{
+#pragma unroll
+  for (int len = R; len >= 2; len >>= 1) {
+#pragma unroll
+    for (int base = 0; base < R; base += len) {
+#pragma unroll
+      for (int j = 0; j < len / 2; j++) {
+        const float2 p = v[base + j], q = v[base + j + len / 2];
+        v[base + j] = cadd(p, q);
+        v[base + j + len / 2] = tw16(csub(p, q), (j * 16) / len);
+      }
+    }
+  }
+}
+
+template <int R> __device__ __forceinline__ int bitrev_r(int k)
+{
+  int r = 0;
+#pragma unroll
+  for (int b = 1; b < R; b <<= 1) { r = (r << 1) | (k & 1); k >>= 1; }
+  return r;
+}
+
+// one in-place DIT pass of radix R; n_prev = length of the already transformed sub-blocks
+template <int R>
+__device__ __forceinline__ void fft_pass(float2 *x, int M, int n_prev, const float2 *__restrict__ tw)
+{
+  const int nb = M / R;
+  const int tw_step = M / (n_prev * R);
+  for (int u = threadIdx.x; u < nb; u += blockDim.x) {
+    const int i = u & (n_prev - 1);
+    const int base = (u - i) * R + i;
+    float2 v[R];
+#pragma unroll
+    for (int qd = 0; qd < R; qd++) v[qd] = x[swz(base + qd * n_prev)];
+    if (n_prev > 1) {
+      // twiddles W_{n}^{i q}: w1 from the table, powers by a short product tree
+      float2 w[R];
+      w[1] = __ldg(tw + i * tw_step);
+#pragma unroll
+      for (int qd = 2; qd < R; qd++) w[qd] = (qd & 1) ? cmul(w[qd - 1], w[1]) : cmul(w[qd >> 1], w[qd >> 1]);
+#pragma unroll
+      for (int qd = 1; qd < R; qd++) v[qd] = cmul(v[qd], w[qd]);
+    }
+    dft_reg<R>(v);
+#pragma unroll
+    for (int k = 0; k < R; k++) x[swz(base + k * n_prev)] = v[bitrev_r<R>(k)];
+  }
+}
+
+struct FftShape { int nr; int lg[4]; };   // radices as log2, first pass first
+
+__host__ __device__ inline FftShape fft_shape(int log2_m)
+{
+  FftShape s;
+  // last passes radix 16; the first pass takes the remainder (10 -> 2,4,4; 11 -> 3,4,4; 12 -> 4,4,4; 13 -> 1,4,4,4; 14 -> 2,4,4,4)
+  int rem = log2_m;
+  int n16 = rem / 4;
+  int first = rem - 4 * n16;
+  s.nr = 0;
+  if (first) s.lg[s.nr++] = first;
+  for (int i = 0; i < n16; i++) s.lg[s.nr++] = 4;
+  return s;
+}
+
+// position of input bin b: digits of b taken from the most significant end go to the least significant end
+__device__ __forceinline__ int digit_reverse(int b, int log2_m, const FftShape &sh)
+{
+  int p = 0, shift_out = 0, rem = log2_m;
+  for (int j = 0; j < sh.nr; j++) {
+    rem -= sh.lg[j];
+    const int d = (b >> rem) & ((1 << sh.lg[j]) - 1);
+    p |= d << shift_out;
+    shift_out += sh.lg[j];
+  }
+  return p;
+}
+
+__global__ void __launch_bounds__(512) k_ofdm(const OfdmArgs a)
+{
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  float2 *x = reinterpret_cast<float2 *>(smem_raw);
+  const int M = 1 << a.log2_m, N = a.fft_n;
+  const FftShape sh = fft_shape(a.log2_m);
+  const int units = a.frames * a.num_symbols;
+
+  for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+    const int f = unit / a.num_symbols, l = unit - f * a.num_symbols;
+    const int variant = (int)((a.frame_idx0 + (f % a.frames_per_channel)) % a.l1post_variants);
+    const float2 *cells = a.cells + (long long)f * a.cells_stride;
+    const int32_t *code = a.code + (long long)l * a.c_ps;
+    float2 *out = a.out + (long long)f * a.out_stride;
+    float2 *sym = out + 2048 + (long long)l * (N + a.gi);
+
+    if (l == 0)
+      for (int i = threadIdx.x; i < 2048; i += blockDim.x) out[i] = __ldg(a.p1 + i);
+
+    for (int phase = 0; phase < a.split; phase++) {
+      __syncthreads();
+      // ---- carrier fill: bin b of the sub-transform
+      for (int b = threadIdx.x; b < M; b += blockDim.x) {
+        float2 v;
+        if (a.split == 1) {
+          const int m = (b + N / 2) & (N - 1);
+          const int k = m - a.left_nulls;
+          v = make_float2(0.f, 0.f);
+          if ((unsigned)k < (unsigned)a.c_ps) {
+            v = fetch_cell(__ldg(code + k), cells, a.pool, a.l1post_base, a.l1post_cells, variant);
+            if (a.inv_sinc) { const float g = __ldg(a.inv_sinc + m); v.x *= g; v.y *= g; }
+          }
+        }
+        else {
+          // N = 2 M: X_b = C[b + N/2], X_{b+N/2} = C[b]; even samples need X_b + X_{b+M}, odd ones (X_b - X_{b+M}) W_N^b
+          const int k_hi = b + M - a.left_nulls, k_lo = b - a.left_nulls;
+          float2 hi = make_float2(0.f, 0.f), lo = make_float2(0.f, 0.f);
+          if ((unsigned)k_hi < (unsigned)a.c_ps) {
+            hi = fetch_cell(__ldg(code + k_hi), cells, a.pool, a.l1post_base, a.l1post_cells, variant);
+            if (a.inv_sinc) { const float g = __ldg(a.inv_sinc + b + M); hi.x *= g; hi.y *= g; }
+          }
+          if ((unsigned)k_lo < (unsigned)a.c_ps) {
+            lo = fetch_cell(__ldg(code + k_lo), cells, a.pool, a.l1post_base, a.l1post_cells, variant);
+            if (a.inv_sinc) { const float g = __ldg(a.inv_sinc + b); lo.x *= g; lo.y *= g; }
+          }
+          v = phase == 0 ? cadd(hi, lo) : cmul(csub(hi, lo), __ldg(a.tw_split + b));
+        }
+        x[swz(digit_reverse(b, a.log2_m, sh))] = v;
+      }
+      __syncthreads();
+      // ---- FFT passes
+      int n_prev = 1;
+      for (int j = 0; j < sh.nr; j++) {
+        switch (sh.lg[j]) {
+          case 1: fft_pass<2>(x, M, n_prev, a.tw); break;
+          case 2: fft_pass<4>(x, M, n_prev, a.tw); break;
+          case 3: fft_pass<8>(x, M, n_prev, a.tw); break;
+          default: fft_pass<16>(x, M, n_prev, a.tw); break;
+        }
+        n_prev <<= sh.lg[j];
+        __syncthreads();
+      }
+      // ---- scale, store symbol and cyclic prefix
+      const int cp_from = N - a.gi;
+      for (int t = threadIdx.x; t < M; t += blockDim.x) {
+        float2 v = x[swz(t)];
+        v.x *= a.norm; v.y *= a.norm;
+        const int T = a.split == 1 ? t : 2 * t + phase;
+        sym[a.gi + T] = v;
+        if (T >= cp_from) sym[T - cp_from] = v;
+      }
+    }
+  }
+}
+
+void launch_ofdm(const OfdmArgs &a, cudaStream_t s)
+{
+  const int M = 1 << a.log2_m;
+  const size_t smem = (size_t)M * sizeof(float2);
+  const int units = a.frames * a.num_symbols;
+  if (units < 1) return;
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(k_ofdm, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+  int threads = M >= 8192 ? 512 : 256;
+  // resident CTAs per SM limited by shared memory (227 KB usable)
+  int per_sm = (int)((227 * 1024) / (smem + 1024));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 2048 / threads) per_sm = 2048 / threads;
+  int blocks = sm_count() * per_sm;
+  if (blocks > units) blocks = units;
+  k_ofdm<<<blocks, threads, smem, s>>>(a);
+  count_launch();
+}
+
+} // namespace t2k

@@ -1,0 +1,98 @@
+// Device-side argument blocks and launch wrappers of the sm_100a kernels (t2_kernels.cu).
+#ifndef T2_KERNELS_CUH
+#define T2_KERNELS_CUH
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace t2k {
+
+// ---- K1: BB header + payload + CRC-8 sync substitution + scrambler + BCH -----------------------
+struct BbArgs {
+  const uint8_t *ts;          // channel-major TS bytes; ts + c * ts_pitch = first byte of this call
+  long long ts_pitch;
+  int hist_valid;             // 1: the 187 bytes before ts are valid stream history
+  int n_channels, frames;     // FECFRAMEs per channel in this call
+  int count0;                 // packet phase (0..187) of ts[0]
+  int fec_block0;             // in-band type B phase of the first FECFRAME
+  int kbch, nbch, bch_r, payload_bytes, mode, inband, fecblocks;
+  int chunk_bytes, lead_zero_bytes;
+  const uint8_t *scramble;    // kbch / 8
+  const uint8_t *crc8_tab;    // 256
+  const uint32_t *bch_tab;    // 256 * 6
+  const uint32_t *bch_cols;   // 6 * 32 * 6
+  const uint8_t *inband_bytes;// 13
+  uint8_t *out;               // packed codewords, pitch out_pitch bytes per FECFRAME
+  int out_pitch;
+  int *sync_errors;           // counter of payload sync bytes != 0x47 (reference logs a warning)
+};
+void launch_bb_bch(const BbArgs &a, cudaStream_t s);
+
+// ---- K2: LDPC (IRA) ------------------------------------------------------------------------------
+struct LdpcArgs {
+  const uint8_t *in;  int in_pitch;    // packed BCH codewords
+  uint8_t *out;       int out_pitch;   // packed: info bits then q rows of 360 parity bits ("u" order)
+  int frames;
+  int nbch, nldpc, q, groups;
+  const uint16_t *row_ptr;   // q + 1
+  const uint32_t *entries;   // (shift << 16) | group
+};
+void launch_ldpc(const LdpcArgs &a, cudaStream_t s);
+
+// ---- K3: bit interleaver + demux + constellation mapping (+ cyclic Q delay) -----------------------
+struct MapArgs {
+  const uint8_t *in;  int in_pitch;    // packed "u" codewords
+  float2 *out;                         // frames * cell_size cells
+  int frames;
+  int nldpc, mod, cell_size, cyclic_delay;
+  const uint16_t *bit_src;   // nldpc
+  const float2 *lut;         // 1 << mod
+};
+void launch_map(const MapArgs &a, cudaStream_t s);
+
+// ---- bit format helpers for the drop-in blocks (1 bit per byte <-> packed) ------------------------
+// pack: in = frames * nbits bytes (0/1) -> out packed with pitch
+void launch_pack_bits(const uint8_t *in, int nbits, uint8_t *out, int out_pitch, int frames, cudaStream_t s);
+// unpack first nbits of each packed frame
+void launch_unpack_bits(const uint8_t *in, int in_pitch, int nbits, uint8_t *out, int frames, cudaStream_t s);
+// LDPC drop-in output: packed "u" order -> 1 bit/byte natural order (parity index q*s + t <- row t, bit s)
+void launch_unpack_ldpc(const uint8_t *in, int in_pitch, int nbch, int nldpc, int q, uint8_t *out, int frames,
+                        cudaStream_t s);
+// interleavermod drop-in input: 1 bit/byte natural-order codeword -> packed "u" order
+void launch_pack_ldpc(const uint8_t *in, int nbch, int nldpc, int q, uint8_t *out, int out_pitch, int frames,
+                      cudaStream_t s);
+
+// ---- K4: frame mapper gather (cell int + time int + L1 + frame + frequency int composed) ----------
+struct GatherArgs {
+  const float2 *in;  long long in_stride;    // cells per T2 frame in
+  float2 *out;       long long out_stride;   // cells per T2 frame out (= n codes)
+  const int32_t *code; int n;
+  const float2 *pool;
+  int l1post_base, l1post_cells, l1post_variants;
+  int frames; int frame_idx0;               // t2_frame_num of the first frame
+};
+void launch_gather(const GatherArgs &a, cudaStream_t s);
+
+// ---- K5: carrier fill + IFFT + normalisation + guard interval + P1 --------------------------------
+struct OfdmArgs {
+  const float2 *cells; long long cells_stride;   // per T2 frame
+  float2 *out;         long long out_stride;     // samples per T2 frame
+  const int32_t *code;       // [num_symbols * c_ps]
+  const float2 *pool;
+  int l1post_base, l1post_cells, l1post_variants;
+  const float2 *p1;          // 2048
+  const float *inv_sinc;     // fft_n or NULL
+  const float2 *tw;          // W_M^m, m < M  (M = sub-transform size)
+  const float2 *tw_split;    // W_N^b, b < N/2 (only when N = 2 M)
+  int fft_n, log2_m, split;  // M = 1 << log2_m, split = N / M (1 or 2)
+  int c_ps, left_nulls, gi, num_symbols;
+  float norm;
+  int frames; long long frame_idx0;   // t2 frame numbers: frame_idx0 + f (per channel layout below)
+  int frames_per_channel;    // frame f -> t2 frame number frame_idx0 + (f % frames_per_channel)
+};
+void launch_ofdm(const OfdmArgs &a, cudaStream_t s);
+
+long long kernel_launch_count();
+
+} // namespace t2k
+#endif

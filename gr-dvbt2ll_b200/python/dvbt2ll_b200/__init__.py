@@ -1,0 +1,268 @@
+"""dvbt2ll_b200 -- Python face of libdvbt2ll_cuda.so (ctypes over the C ABI in include/dvbt2ll_cuda.h).
+
+Mirrors the reference's Python surface (python/__init__.py:27-31 re-exports the SWIG module: the enum
+constants plus one factory per block, e.g. ``dvbt2ll.bbheaderbch_bb(framesize, rate, mode, inband,
+fecblocks, tsrate)``) with the same factory names, argument order and meaning.  Instead of being wired
+into a GNU Radio flowgraph the returned objects expose ``work()`` -- the block's general_work() on
+host buffers -- so the parity tests can drive them exactly like the reference blocks.
+
+There is no CPU fallback: work() raises if the CUDA library or a device is missing.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from .configs import *  # noqa: F401,F403  (enum constants, CONFIGS, make_ts)
+from . import configs
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "..", "libdvbt2ll_cuda.so"))
+
+_lib = None
+
+EXPORTED_SYMBOLS = [
+    "dvbt2ll_last_error", "dvbt2ll_version", "dvbt2ll_kernel_launches", "dvbt2ll_device_available",
+    "dvbt2ll_output_multiple", "dvbt2ll_forecast", "dvbt2ll_work", "dvbt2ll_work_device", "dvbt2ll_warnings",
+    "dvbt2ll_destroy", "dvbt2ll_plan_get", "dvbt2ll_bbheaderbch_create", "dvbt2ll_ldpc_create",
+    "dvbt2ll_interleavermod_create", "dvbt2ll_framemapperfint_create", "dvbt2ll_pilotgenp1insert_create",
+    "dvbt2ll_chain_create", "dvbt2ll_chain_ts_bytes_per_frame", "dvbt2ll_chain_samples_per_frame",
+    "dvbt2ll_chain_fecframes_per_frame", "dvbt2ll_chain_run_device", "dvbt2ll_chain_run_host",
+    "dvbt2ll_chain_tap", "dvbt2ll_chain_stage_ms", "dvbt2ll_chain_enable_timing",
+]
+
+
+class ChainParams(C.Structure):
+    _fields_ = [(n, C.c_int) for n in (
+        "framesize", "rate", "constellation", "rotation", "fecblocks", "tiblocks", "carriermode", "fftsize",
+        "guardinterval", "l1constellation", "pilotpattern", "t2frames", "numdatasyms", "paprmode", "version",
+        "preamble", "inputmode", "reservedbiasbits", "l1scrambled", "inband", "misogroup", "equalization",
+        "bandwidth", "vlength", "tsrate")]
+
+
+def lib():
+    """Load libdvbt2ll_cuda.so (built in-tree by gr-dvbt2ll_b200/csrc/Makefile); raises if missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("libdvbt2ll_cuda.so not built: run `make -C gr-dvbt2ll_b200/csrc` "
+                               "(or __graft_entry__.build()); there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        vp, ci, cll = C.c_void_p, C.c_int, C.c_longlong
+        L.dvbt2ll_last_error.restype = C.c_char_p
+        L.dvbt2ll_version.restype = C.c_char_p
+        L.dvbt2ll_kernel_launches.restype = cll
+        L.dvbt2ll_output_multiple.argtypes = [vp]
+        L.dvbt2ll_forecast.argtypes = [vp, ci]
+        L.dvbt2ll_work.argtypes = [vp, vp, ci, vp, ci, C.POINTER(ci)]
+        L.dvbt2ll_work_device.argtypes = [vp, vp, ci, vp, ci, C.POINTER(ci), vp]
+        L.dvbt2ll_warnings.argtypes = [vp]
+        L.dvbt2ll_destroy.argtypes = [vp]
+        L.dvbt2ll_plan_get.restype = cll
+        L.dvbt2ll_plan_get.argtypes = [vp, C.c_char_p, vp, cll]
+        for name, n in (("dvbt2ll_bbheaderbch_create", 6), ("dvbt2ll_ldpc_create", 2),
+                        ("dvbt2ll_interleavermod_create", 4), ("dvbt2ll_framemapperfint_create", 20),
+                        ("dvbt2ll_pilotgenp1insert_create", 12)):
+            f = getattr(L, name)
+            f.restype = vp
+            f.argtypes = [ci] * n
+        L.dvbt2ll_chain_create.restype = vp
+        L.dvbt2ll_chain_create.argtypes = [C.POINTER(ChainParams), ci, ci]
+        L.dvbt2ll_chain_ts_bytes_per_frame.restype = cll
+        L.dvbt2ll_chain_ts_bytes_per_frame.argtypes = [vp]
+        L.dvbt2ll_chain_samples_per_frame.restype = cll
+        L.dvbt2ll_chain_samples_per_frame.argtypes = [vp]
+        L.dvbt2ll_chain_fecframes_per_frame.argtypes = [vp]
+        L.dvbt2ll_chain_run_device.argtypes = [vp, vp, cll, ci, ci, cll, vp, vp]
+        L.dvbt2ll_chain_run_host.argtypes = [vp, vp, cll, ci, ci, cll, vp]
+        L.dvbt2ll_chain_tap.restype = cll
+        L.dvbt2ll_chain_tap.argtypes = [vp, C.c_char_p, vp, cll]
+        L.dvbt2ll_chain_stage_ms.argtypes = [vp, C.POINTER(C.c_float)]
+        L.dvbt2ll_chain_enable_timing.argtypes = [vp, ci]
+        _lib = L
+    return _lib
+
+
+def last_error():
+    return lib().dvbt2ll_last_error().decode()
+
+
+def device_available():
+    return bool(lib().dvbt2ll_device_available())
+
+
+def kernel_launches():
+    return int(lib().dvbt2ll_kernel_launches())
+
+
+class _Block(object):
+    in_dtype = np.uint8
+    out_dtype = np.uint8
+
+    def __init__(self, handle, what):
+        if not handle:
+            raise ValueError("%s: %s" % (what, last_error()))
+        self._h = C.c_void_p(handle)
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                lib().dvbt2ll_destroy(h)
+            except Exception:
+                pass
+
+    @property
+    def output_multiple(self):
+        return lib().dvbt2ll_output_multiple(self._h)
+
+    def forecast(self, noutput):
+        return lib().dvbt2ll_forecast(self._h, noutput)
+
+    @property
+    def warnings(self):
+        return lib().dvbt2ll_warnings(self._h)
+
+    def work(self, data, nframes):
+        """general_work() on host buffers for nframes frames of output. Returns (out, consumed)."""
+        data = np.ascontiguousarray(data, dtype=self.in_dtype)
+        nout = nframes * self.output_multiple
+        out = np.empty(nout, dtype=self.out_dtype)
+        consumed = C.c_int(0)
+        r = lib().dvbt2ll_work(self._h, data.ctypes.data, data.size, out.ctypes.data, nout, C.byref(consumed))
+        if r < 0:
+            raise RuntimeError("dvbt2ll_work failed (%d): %s" % (r, last_error()))
+        return out[:r], consumed.value
+
+    def plan(self, name, dtype):
+        """Host-side plan table by name (see dvbt2ll_plan_get)."""
+        n = lib().dvbt2ll_plan_get(self._h, name.encode(), None, 0)
+        if n < 0:
+            raise KeyError(name)
+        buf = np.empty(n, dtype=np.uint8)
+        lib().dvbt2ll_plan_get(self._h, name.encode(), buf.ctypes.data, n)
+        return buf.view(dtype)
+
+
+class bbheaderbch_bb(_Block):
+    """TS bytes -> BB header + scrambled BBFRAME + BCH parity, one bit per output byte."""
+
+    def __init__(self, framesize, rate, mode, inband, fecblocks, tsrate):
+        _Block.__init__(self, lib().dvbt2ll_bbheaderbch_create(framesize, rate, mode, inband, fecblocks, tsrate),
+                        "bbheaderbch_bb")
+
+
+class ldpc_bb(_Block):
+    """The LDPC stage the shipped flowgraph places after bbheaderbch_bb (dtv.dvb_ldpc_bb, DVB-T2 codes)."""
+
+    def __init__(self, framesize, rate):
+        _Block.__init__(self, lib().dvbt2ll_ldpc_create(framesize, rate), "ldpc_bb")
+
+
+class interleavermod_bc(_Block):
+    out_dtype = np.complex64
+
+    def __init__(self, framesize, rate, constellation, rotation):
+        _Block.__init__(self, lib().dvbt2ll_interleavermod_create(framesize, rate, constellation, rotation),
+                        "interleavermod_bc")
+
+
+class framemapperfint_cc(_Block):
+    in_dtype = np.complex64
+    out_dtype = np.complex64
+
+    def __init__(self, framesize, rate, constellation, rotation, fecblocks, tiblocks, carriermode, fftsize,
+                 guardinterval, l1constellation, pilotpattern, t2frames, numdatasyms, paprmode, version, preamble,
+                 inputmode, reservedbiasbits, l1scrambled, inband):
+        _Block.__init__(self, lib().dvbt2ll_framemapperfint_create(
+            framesize, rate, constellation, rotation, fecblocks, tiblocks, carriermode, fftsize, guardinterval,
+            l1constellation, pilotpattern, t2frames, numdatasyms, paprmode, version, preamble, inputmode,
+            reservedbiasbits, l1scrambled, inband), "framemapperfint_cc")
+
+
+class pilotgenp1insert_cc(_Block):
+    in_dtype = np.complex64
+    out_dtype = np.complex64
+
+    def __init__(self, carriermode, fftsize, pilotpattern, guardinterval, numdatasyms, paprmode, version, preamble,
+                 misogroup, equalization, bandwidth, vlength):
+        _Block.__init__(self, lib().dvbt2ll_pilotgenp1insert_create(
+            carriermode, fftsize, pilotpattern, guardinterval, numdatasyms, paprmode, version, preamble, misogroup,
+            equalization, bandwidth, vlength), "pilotgenp1insert_cc")
+
+
+def blocks_for(cfg):
+    """The five stages of the shipped flowgraph for a config dict (configs.resolve)."""
+    cfg = configs.resolve(cfg)
+    return dict(
+        bb=bbheaderbch_bb(cfg["framesize"], cfg["rate"], cfg["inputmode"], cfg["inband"], cfg["fecblocks"], cfg["tsrate"]),
+        ldpc=ldpc_bb(cfg["framesize"], cfg["rate"]),
+        im=interleavermod_bc(cfg["framesize"], cfg["rate"], cfg["constellation"], cfg["rotation"]),
+        fm=framemapperfint_cc(cfg["framesize"], cfg["rate"], cfg["constellation"], cfg["rotation"], cfg["fecblocks"],
+                              cfg["tiblocks"], cfg["carriermode"], cfg["fftsize"], cfg["guardinterval"],
+                              cfg["l1constellation"], cfg["pilotpattern"], cfg["t2frames"], cfg["numdatasyms"],
+                              cfg["paprmode"], cfg["version"], cfg["preamble"], cfg["inputmode"],
+                              cfg["reservedbiasbits"], cfg["l1scrambled"], cfg["inband"]),
+        pg=pilotgenp1insert_cc(cfg["carriermode"], cfg["fftsize"], cfg["pilotpattern"], cfg["guardinterval"],
+                               cfg["numdatasyms"], cfg["paprmode"], cfg["version"], cfg["preamble"], cfg["misogroup"],
+                               cfg["equalization"], cfg["bandwidth"], cfg["vlength"]))
+
+
+class Chain(_Block):
+    """Fused device-resident chain: TS bytes -> complex baseband, batching channels x T2 frames."""
+    out_dtype = np.complex64
+
+    def __init__(self, cfg, max_frames, device=-1):
+        cfg = configs.resolve(cfg)
+        self.cfg = cfg
+        p = ChainParams(**{n: int(cfg[n]) for n, _ in ChainParams._fields_})
+        _Block.__init__(self, lib().dvbt2ll_chain_create(C.byref(p), int(max_frames), int(device)), "chain")
+        self.max_frames = max_frames
+
+    @property
+    def ts_bytes_per_frame(self):
+        return int(lib().dvbt2ll_chain_ts_bytes_per_frame(self._h))
+
+    @property
+    def samples_per_frame(self):
+        return int(lib().dvbt2ll_chain_samples_per_frame(self._h))
+
+    @property
+    def fecframes_per_frame(self):
+        return int(lib().dvbt2ll_chain_fecframes_per_frame(self._h))
+
+    def run_host(self, ts, n_channels, n_frames, first_frame=0, out=None):
+        """ts: uint8 array [n_channels, >= n_frames*ts_bytes_per_frame] (host). Returns complex64 [n_channels, n_frames*samples]."""
+        ts = np.ascontiguousarray(ts, dtype=np.uint8).reshape(n_channels, -1)
+        if out is None:
+            out = np.empty((n_channels, n_frames * self.samples_per_frame), dtype=np.complex64)
+        r = lib().dvbt2ll_chain_run_host(self._h, ts.ctypes.data, ts.shape[1], n_channels, n_frames, first_frame,
+                                         out.ctypes.data)
+        if r < 0:
+            raise RuntimeError("dvbt2ll_chain_run_host failed (%d): %s" % (r, last_error()))
+        return out
+
+    def run_device(self, d_ts_ptr, ts_pitch, n_channels, n_frames, first_frame, d_out_ptr, stream_ptr):
+        r = lib().dvbt2ll_chain_run_device(self._h, d_ts_ptr, ts_pitch, n_channels, n_frames, first_frame, d_out_ptr,
+                                           stream_ptr)
+        if r < 0:
+            raise RuntimeError("dvbt2ll_chain_run_device failed (%d): %s" % (r, last_error()))
+        return r
+
+    def tap(self, stage, dtype=np.uint8):
+        n = lib().dvbt2ll_chain_tap(self._h, stage.encode(), None, 0)
+        if n < 0:
+            raise RuntimeError(last_error())
+        buf = np.empty(n, dtype=np.uint8)
+        lib().dvbt2ll_chain_tap(self._h, stage.encode(), buf.ctypes.data, n)
+        return buf.view(dtype)
+
+    def enable_timing(self, on=True):
+        lib().dvbt2ll_chain_enable_timing(self._h, 1 if on else 0)
+
+    def stage_ms(self):
+        ms = (C.c_float * 5)()
+        r = lib().dvbt2ll_chain_stage_ms(self._h, ms)
+        if r < 0:
+            raise RuntimeError(last_error())
+        return dict(zip(("bb_bch", "ldpc", "map", "ofdm", "total"), [float(x) for x in ms]))

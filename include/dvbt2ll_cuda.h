@@ -1,0 +1,130 @@
+/*
+ * dvbt2ll_cuda.h -- C ABI of libdvbt2ll_cuda.so, the B200 (sm_100a) implementation of the
+ * gr-dvbt2ll DVB-T2 modulator hot path.
+ *
+ * This is the drop-in boundary: each entry point is what a GNU Radio block's constructor /
+ * forecast() / general_work() / destructor calls.  Plain pointers and sizes only; buffers handed to
+ * *_work() are HOST memory owned by the caller (the GNU Radio scheduler); the call is synchronous.
+ * Handles are independent (no global mutable state; one CUDA stream per handle) and may be used
+ * from different threads, one thread per handle at a time -- the GNU Radio threading contract.
+ *
+ * Reference interfaces replaced (paths relative to the gr-dvbt2ll tree):
+ *   dvbt2ll_bbheaderbch_*      <- gr::dvbt2ll::bbheaderbch_bb       include/dvbt2ll/bbheaderbch_bb.h:49,
+ *                                 lib/bbheaderbch_bb_impl.cc:42-196 (ctor), :207-216 (forecast), :648-742 (work)
+ *   dvbt2ll_ldpc_*             <- gr::dtv::dvb_ldpc_bb (GNU Radio in-tree, wired in apps/vv009-4kshort.grc);
+ *                                 restated by the reference at lib/bbheaderbch_bb_impl.cc:533-646
+ *   dvbt2ll_interleavermod_*   <- gr::dvbt2ll::interleavermod_bc    include/dvbt2ll/interleavermod_bc.h:49,
+ *                                 lib/interleavermod_bc_impl.cc:42-255, :264-268, :270-704
+ *   dvbt2ll_framemapperfint_*  <- gr::dvbt2ll::framemapperfint_cc   include/dvbt2ll/framemapperfint_cc.h:49,
+ *                                 lib/framemapperfint_cc_impl.cc:41-1190, :1942-1946, :1948-2151
+ *   dvbt2ll_pilotgenp1insert_* <- gr::dvbt2ll::pilotgenp1insert_cc  include/dvbt2ll/pilotgenp1insert_cc.h:49,
+ *                                 lib/pilotgenp1insert_cc_impl.cc:43-1229, :1239-1243, :2784-2907
+ *   dvbt2ll_chain_*            <- new, additive: the five stages fused device-resident (what bench.py times)
+ *
+ * All integer parameters carry the enum VALUES of include/dvbt2ll/dvbt2ll_config.h:60-202.
+ *
+ * Return conventions: *_create() returns NULL on failure; *_work() returns the number of output
+ * items produced (>= 0) or a negative error code; dvbt2ll_last_error() returns a thread-local
+ * message for the most recent failure on the calling thread.
+ */
+#ifndef DVBT2LL_CUDA_H
+#define DVBT2LL_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DVBT2LL_API_EXPORT __attribute__((visibility("default")))
+
+#define DVBT2LL_ERR_INVALID   (-1)   /* bad argument / unsupported parameter combination */
+#define DVBT2LL_ERR_CUDA      (-2)   /* CUDA runtime error or no usable device (there is NO CPU fallback) */
+#define DVBT2LL_ERR_SHORT     (-3)   /* not enough input items for the requested output */
+
+typedef struct dvbt2ll_handle dvbt2ll_handle;   /* opaque */
+
+DVBT2LL_API_EXPORT const char *dvbt2ll_last_error(void);
+DVBT2LL_API_EXPORT const char *dvbt2ll_version(void);
+/* Number of kernel launches issued by this library in the calling process (all handles). */
+DVBT2LL_API_EXPORT long long dvbt2ll_kernel_launches(void);
+/* 1 when a CUDA device is usable. */
+DVBT2LL_API_EXPORT int dvbt2ll_device_available(void);
+
+/* ---- common to all block handles ------------------------------------------------------------- */
+/* set_output_multiple() value of the block: items of ONE frame of output. */
+DVBT2LL_API_EXPORT int dvbt2ll_output_multiple(const dvbt2ll_handle *h);
+/* forecast(): input items needed for noutput output items. */
+DVBT2LL_API_EXPORT int dvbt2ll_forecast(const dvbt2ll_handle *h, int noutput);
+/* general_work() on HOST buffers.  Processes floor(noutput / output_multiple) frames (any number,
+ * unlike the reference which is only correct for one), writes *consumed = input items used
+ * (the value the block passes to consume_each) and returns the output items produced. */
+DVBT2LL_API_EXPORT int dvbt2ll_work(dvbt2ll_handle *h, const void *in, int ninput, void *out, int noutput,
+                                    int *consumed);
+/* Same on DEVICE buffers (already resident in HBM), asynchronous on `stream` (a cudaStream_t, NULL =
+ * the handle's own stream followed by a synchronize). */
+DVBT2LL_API_EXPORT int dvbt2ll_work_device(dvbt2ll_handle *h, const void *d_in, int ninput, void *d_out,
+                                           int noutput, int *consumed, void *stream);
+/* Number of warnings the reference would have logged so far ("Transport Stream sync error!"). */
+DVBT2LL_API_EXPORT int dvbt2ll_warnings(const dvbt2ll_handle *h);
+DVBT2LL_API_EXPORT void dvbt2ll_destroy(dvbt2ll_handle *h);
+/* Host-side plan introspection (tables the kernels consume), for tests: copies at most cap bytes
+ * of the named table to out and returns the table size in bytes, or -1 for an unknown name. */
+DVBT2LL_API_EXPORT long long dvbt2ll_plan_get(const dvbt2ll_handle *h, const char *name, void *out, long long cap);
+
+/* ---- bbheaderbch_bb: TS bytes -> BBFRAME -> scrambled -> BCH codeword, 1 bit per output byte --- */
+DVBT2LL_API_EXPORT dvbt2ll_handle *dvbt2ll_bbheaderbch_create(int framesize, int rate, int mode, int inband,
+                                                              int fecblocks, int tsrate);
+
+/* ---- LDPC: nbch bits -> 64800 | 16200 bits (info then parity, natural order), 1 bit per byte --- */
+DVBT2LL_API_EXPORT dvbt2ll_handle *dvbt2ll_ldpc_create(int framesize, int rate);
+
+/* ---- interleavermod_bc: FECFRAME bits (1 per byte) -> cell_size complex64 cells ---------------- */
+DVBT2LL_API_EXPORT dvbt2ll_handle *dvbt2ll_interleavermod_create(int framesize, int rate, int constellation,
+                                                                 int rotation);
+
+/* ---- framemapperfint_cc: fecblocks*cell_size cells -> mapped_items cells per T2 frame ---------- */
+DVBT2LL_API_EXPORT dvbt2ll_handle *dvbt2ll_framemapperfint_create(
+    int framesize, int rate, int constellation, int rotation, int fecblocks, int tiblocks, int carriermode,
+    int fftsize, int guardinterval, int l1constellation, int pilotpattern, int t2frames, int numdatasyms,
+    int paprmode, int version, int preamble, int inputmode, int reservedbiasbits, int l1scrambled, int inband);
+
+/* ---- pilotgenp1insert_cc: active cells -> P1 + num_symbols * (N + GI) time samples ------------- */
+DVBT2LL_API_EXPORT dvbt2ll_handle *dvbt2ll_pilotgenp1insert_create(
+    int carriermode, int fftsize, int pilotpattern, int guardinterval, int numdatasyms, int paprmode,
+    int version, int preamble, int misogroup, int equalization, int bandwidth, int vlength);
+
+/* ---- fused device-resident chain (TS bytes -> baseband), batching channels x T2 frames --------- */
+typedef struct dvbt2ll_chain_params {
+  int framesize, rate, constellation, rotation, fecblocks, tiblocks, carriermode, fftsize, guardinterval,
+      l1constellation, pilotpattern, t2frames, numdatasyms, paprmode, version, preamble, inputmode,
+      reservedbiasbits, l1scrambled, inband, misogroup, equalization, bandwidth, vlength, tsrate;
+} dvbt2ll_chain_params;
+
+/* device < 0: current device.  max_frames = largest channels*frames batch a single run will be given. */
+DVBT2LL_API_EXPORT dvbt2ll_handle *dvbt2ll_chain_create(const dvbt2ll_chain_params *p, int max_frames, int device);
+DVBT2LL_API_EXPORT long long dvbt2ll_chain_ts_bytes_per_frame(const dvbt2ll_handle *h);
+DVBT2LL_API_EXPORT long long dvbt2ll_chain_samples_per_frame(const dvbt2ll_handle *h);
+DVBT2LL_API_EXPORT int dvbt2ll_chain_fecframes_per_frame(const dvbt2ll_handle *h);
+/* n_channels independent transport streams, each contributing n_frames consecutive T2 frames starting at
+ * its stream frame number first_frame (streams start on a packet boundary at frame 0).  d_ts: channel-major,
+ * n_frames*ts_bytes_per_frame (+ 0..187 trailing bytes ignored) bytes per channel with pitch ts_pitch.
+ * d_out: complex64, channel-major, n_frames*samples_per_frame per channel.  Asynchronous on `stream`. */
+DVBT2LL_API_EXPORT int dvbt2ll_chain_run_device(dvbt2ll_handle *h, const void *d_ts, long long ts_pitch,
+                                                int n_channels, int n_frames, long long first_frame,
+                                                void *d_out, void *stream);
+/* Same with HOST buffers: H2D copy, run, D2H copy, synchronize. */
+DVBT2LL_API_EXPORT int dvbt2ll_chain_run_host(dvbt2ll_handle *h, const void *ts, long long ts_pitch, int n_channels,
+                                              int n_frames, long long first_frame, void *out);
+/* Stage taps of the most recent chain run, for parity tests: "bch" (packed bits), "fec" (packed, parity
+ * in interleaved-row order), "cells" (complex64).  Copies to HOST; returns bytes or negative error. */
+DVBT2LL_API_EXPORT long long dvbt2ll_chain_tap(dvbt2ll_handle *h, const char *stage, void *out, long long cap);
+/* Device time in ms of each stage kernel of the most recent chain run (bb_bch, ldpc, map, ofdm, total). */
+DVBT2LL_API_EXPORT int dvbt2ll_chain_stage_ms(dvbt2ll_handle *h, float *ms5);
+DVBT2LL_API_EXPORT void dvbt2ll_chain_enable_timing(dvbt2ll_handle *h, int on);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DVBT2LL_CUDA_H */

@@ -76,16 +76,19 @@ void *ref_framemapper_new(int framesize, int rate, int constellation, int rotati
                           int paprmode, int version, int preamble, int inputmode,
                           int reservedbiasbits, int l1scrambled, int inband)
 {
-  return wrap(REF_FRAMEMAPPER,
-              framemapperfint_cc::make((dvbt2_framesize_t)framesize, (dvbt2_code_rate_t)rate,
+  boost::shared_ptr<framemapperfint_cc> blk = framemapperfint_cc::make((dvbt2_framesize_t)framesize, (dvbt2_code_rate_t)rate,
                   (dvbt2_constellation_t)constellation, (dvbt2_rotation_t)rotation, fecblocks, tiblocks,
                   (dvbt2_extended_carrier_t)carriermode, (dvbt2_fftsize_t)fftsize,
                   (dvbt2_guardinterval_t)guardinterval, (dvbt2_l1constellation_t)l1constellation,
                   (dvbt2_pilotpattern_t)pilotpattern, t2frames, numdatasyms, (dvbt2_papr_t)paprmode,
                   (dvbt2_version_t)version, (dvbt2_preamble_t)preamble, (dvbt2_inputmode_t)inputmode,
                   (dvbt2_reservedbiasbits_t)reservedbiasbits, (dvbt2_l1scrambled_t)l1scrambled,
-                  (dvbt2_inband_t)inband),
-              8, 8);
+                  (dvbt2_inband_t)inband);
+  /* The reference never initialises L1Post::plp_id_dynamic (framemapperfint_cc_impl.cc:240 assigns
+   * plp_id a second time instead), so the dynamic PLP_ID field of L1-post is whatever the heap held.
+   * The only PLP has PLP_ID 0; pin the field to that so the oracle is deterministic. */
+  dynamic_cast<framemapperfint_cc_impl *>(blk.get())->L1_Signalling[0].l1post_data.plp_id_dynamic = 0;
+  return wrap(REF_FRAMEMAPPER, blk, 8, 8);
 }
 
 void *ref_pilotgen_new(int carriermode, int fftsize, int pilotpattern, int guardinterval,

@@ -1,0 +1,252 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes), against the compiled unmodified
+reference (oracle/_ref) and the committed golden fixtures, on identical synthetic TS input.
+
+Bars (BASELINE.json north_star): BBFRAME/FECFRAME bits bit-exact; cells bit-exact (the LUT reproduces the
+reference's float arithmetic, so better than the 1-ulp bar); frame-mapper output bit-exact; time-domain
+baseband MER >= 90 dB and max error <= 1e-5 of RMS against the oracle's double-precision IFFT.
+"""
+import numpy as np
+import pytest
+
+import dvbt2ll_b200 as T
+from dvbt2ll_b200 import configs as K
+from common import bits_equal, cells_equal, mer_db, max_err_over_rms, load_golden, sha
+
+pytestmark = pytest.mark.gpu
+
+MER_MIN_DB = 90.0
+MAX_ERR_OVER_RMS = 1e-5
+
+
+def _ref_frames(reflib, cfg, ts, nframes):
+    ch = reflib.Chain(cfg)
+    return [ch.run_frame(ts) for _ in range(nframes)]
+
+
+@pytest.mark.parametrize("name", ["c1", "c2", "c3", "c4"])
+def test_blocks_match_reference(reflib, name):
+    """Each drop-in block driven like the flowgraph does, two T2 frames with state carried across."""
+    cfg = K.resolve(name)
+    nframes = 2
+    B = T.blocks_for(cfg)
+    F = cfg["fecblocks"]
+    n_ts = F * B["bb"].forecast(B["bb"].output_multiple)
+    ts = K.make_ts(nframes * n_ts + 1000)
+    refs = _ref_frames(reflib, cfg, ts, nframes)
+    pos = 0
+    for fr in range(nframes):
+        r = refs[fr]
+        bch, used = B["bb"].work(ts[pos:pos + n_ts + 400], F)
+        pos += used
+        assert used == r["ts_used"]
+        assert bits_equal(bch, r["bch"]), "BCH codewords differ"
+        fec, _ = B["ldpc"].work(bch, F)
+        assert bits_equal(fec, r["fec"]), "LDPC codewords differ"
+        cells, _ = B["im"].work(fec, F)
+        assert cells_equal(cells, r["cells"]), "cells differ"
+        mapped, _ = B["fm"].work(cells, 1)
+        assert cells_equal(mapped, r["mapped"]), "frame mapper output differs"
+        samples, _ = B["pg"].work(mapped, 1)
+        assert samples.shape == r["samples"].shape
+        assert mer_db(samples, r["samples"]) >= MER_MIN_DB
+        assert max_err_over_rms(samples, r["samples"]) <= MAX_ERR_OVER_RMS
+    assert B["bb"].warnings == 0
+
+
+@pytest.mark.parametrize("name", ["c1", "c2", "c3", "c4"])
+def test_blocks_match_golden(name):
+    """Same drive, checked against the committed fixtures (generated from the reference by tools/make_golden.py)."""
+    g = load_golden("chain_%s.json" % name)
+    cfg = K.resolve(name)
+    B = T.blocks_for(cfg)
+    F = cfg["fecblocks"]
+    n_ts = F * B["bb"].forecast(B["bb"].output_multiple)
+    ts = K.make_ts(2 * n_ts + 1000)
+    assert sha(ts[:4096]) == g["ts_head_sha256"]
+    pos = 0
+    for fr in range(2):
+        gf = g["frames"][fr]
+        bch, used = B["bb"].work(ts[pos:pos + n_ts + 400], F)
+        pos += used
+        assert sha(np.packbits(bch)) == gf["bch_sha256"]
+        fec, _ = B["ldpc"].work(bch, F)
+        assert sha(np.packbits(fec)) == gf["fec_sha256"]
+        cells, _ = B["im"].work(fec, F)
+        assert sha(cells) == gf["cells_sha256"]
+        mapped, _ = B["fm"].work(cells, 1)
+        assert sha(mapped) == gf["mapped_sha256"]
+        samples, _ = B["pg"].work(mapped, 1)
+        head = np.array(gf["samples_head"], dtype=np.float32).view(np.complex64)
+        rms = gf["samples_rms"]
+        assert np.abs(samples[:head.size] - head).max() <= MAX_ERR_OVER_RMS * rms
+        assert abs(np.sqrt(np.mean(np.abs(samples.astype(np.complex128)) ** 2)) - rms) <= 1e-5 * rms
+
+
+@pytest.mark.parametrize("name", ["c1", "c2", "c3", "c4"])
+def test_chain_matches_reference(reflib, name):
+    """Fused device-resident chain (what bench.py times) against the reference flowgraph."""
+    cfg = K.resolve(name)
+    nframes = 2
+    ch = T.Chain(cfg, max_frames=nframes)
+    n_ts = ch.ts_bytes_per_frame
+    ts = K.make_ts(nframes * n_ts + 1000)
+    refs = _ref_frames(reflib, cfg, ts, nframes)
+    assert refs[0]["ts_used"] == n_ts
+    out = ch.run_host(ts[:nframes * n_ts], 1, nframes)[0]
+    S = ch.samples_per_frame
+    F = cfg["fecblocks"]
+    nbch = refs[0]["bch"].size // F
+    nldpc = refs[0]["fec"].size // F
+    bch = ch.tap("bch").reshape(nframes * F, -1)
+    cells = ch.tap("cells", np.complex64)
+    for fr in range(nframes):
+        r = refs[fr]
+        got = np.unpackbits(bch[fr * F:(fr + 1) * F, :nbch // 8], axis=1).reshape(-1)
+        assert bits_equal(got, r["bch"])
+        assert cells_equal(cells[fr * r["cells"].size:(fr + 1) * r["cells"].size], r["cells"])
+        s = out[fr * S:(fr + 1) * S]
+        assert mer_db(s, r["samples"]) >= MER_MIN_DB
+        assert max_err_over_rms(s, r["samples"]) <= MAX_ERR_OVER_RMS
+
+
+def test_chain_multichannel_and_offset(reflib):
+    """c5-style batching: independent channels (seed + channel) in one launch, and a batch that starts at
+    T2 frame 1 (stream history in front of the pointer) equals the tail of a batch that starts at frame 0."""
+    cfg = K.resolve("c1")
+    nch, nframes = 3, 3
+    ch = T.Chain(cfg, max_frames=nch * nframes)
+    n_ts = ch.ts_bytes_per_frame
+    S = ch.samples_per_frame
+    ts = np.stack([K.make_ts(nframes * n_ts, seed=K.TS_SEED + c) for c in range(nch)])
+    out = ch.run_host(ts, nch, nframes)
+    for c in range(nch):
+        refs = _ref_frames(reflib, cfg, ts[c], nframes)
+        for fr in range(nframes):
+            s = out[c, fr * S:(fr + 1) * S]
+            assert mer_db(s, refs[fr]["samples"]) >= MER_MIN_DB
+            assert max_err_over_rms(s, refs[fr]["samples"]) <= MAX_ERR_OVER_RMS
+    # offset batch: frames 1..2 of channel 0, pointer advanced by one frame (history = previous bytes)
+    import ctypes as C
+    sub = np.ascontiguousarray(ts[0])
+    out2 = np.empty((1, 2 * S), dtype=np.complex64)
+    r = T.lib().dvbt2ll_chain_run_host(ch._h, sub.ctypes.data + n_ts, sub.size, 1, 2, 1, out2.ctypes.data)
+    assert r == 2, T.last_error()
+    assert max_err_over_rms(out2[0], out[0, S:3 * S]) <= 1e-6
+
+
+def test_ragged_and_empty_calls():
+    """noutput that is not a multiple of one frame produces floor() frames; zero output is a no-op;
+    too little input is an error, not a partial frame."""
+    cfg = K.resolve("c1")
+    B = T.blocks_for(cfg)
+    nbch = B["bb"].output_multiple
+    ts = K.make_ts(3 * B["bb"].forecast(nbch) + 10)
+    out = np.empty(nbch + 100, dtype=np.uint8)
+    import ctypes as C
+    consumed = C.c_int(0)
+    L = T.lib()
+    r = L.dvbt2ll_work(B["bb"]._h, ts.ctypes.data, ts.size, out.ctypes.data, nbch + 100, C.byref(consumed))
+    assert r == nbch and consumed.value == B["bb"].forecast(nbch)
+    r = L.dvbt2ll_work(B["bb"]._h, ts.ctypes.data, ts.size, out.ctypes.data, nbch - 1, C.byref(consumed))
+    assert r == 0 and consumed.value == 0
+    r = L.dvbt2ll_work(B["bb"]._h, ts.ctypes.data, 10, out.ctypes.data, nbch, C.byref(consumed))
+    assert r == -3
+
+
+def test_ts_sync_error_is_counted(reflib):
+    """A packet whose first byte is not 0x47 only raises a warning in the reference
+    (bbheaderbch_bb_impl.cc:703-705); output still follows the same rule (sync byte replaced by CRC-8)."""
+    cfg = K.resolve("c1")
+    bb = T.bbheaderbch_bb(cfg["framesize"], cfg["rate"], cfg["inputmode"], cfg["inband"], cfg["fecblocks"], cfg["tsrate"])
+    rb = reflib.bbheaderbch(cfg["framesize"], cfg["rate"], cfg["inputmode"], cfg["inband"], cfg["fecblocks"], cfg["tsrate"])
+    n = bb.forecast(bb.output_multiple)
+    ts = K.make_ts(2 * n + 10)
+    ts[188 * 3] = 0x00
+    a, _ = bb.work(ts, 2)
+    b, _ = rb.work(ts, 2)
+    assert bits_equal(a, b)
+    assert bb.warnings == 1 and rb.warnings == 1
+
+
+@pytest.mark.parametrize("mode,inband", [(1, 0), (0, 1), (1, 1)])
+def test_bbheader_hiefficiency_and_inband(reflib, mode, inband):
+    """INPUTMODE_HIEFF (sync bytes dropped, CRC-8 xor MODE) and in-band type B signalling."""
+    fs, rate, fecblocks, tsrate = K.FECFRAME_SHORT, K.C3_5, 3, 4000000
+    bb = T.bbheaderbch_bb(fs, rate, mode, inband, fecblocks, tsrate)
+    rb = reflib.bbheaderbch(fs, rate, mode, inband, fecblocks, tsrate)
+    nbch = bb.output_multiple
+    ts = K.make_ts(12 * (bb.forecast(nbch) + 8))
+    pos_a = pos_b = 0
+    for call_frames in (1, 4, 2):
+        a, ua = bb.work(ts[pos_a:], call_frames)
+        b, ub = rb.work(ts[pos_b:], call_frames)
+        assert ua == ub
+        assert bits_equal(a, b)
+        pos_a += ua
+        pos_b += ub
+
+
+@pytest.mark.parametrize("fs,rate,con,rot", [
+    (1, K.C1_2, K.MOD_QPSK, 1), (1, K.C3_5, K.MOD_16QAM, 0), (1, K.C3_4, K.MOD_64QAM, 1), (1, K.C5_6, K.MOD_256QAM, 0),
+    (0, K.C1_3, K.MOD_QPSK, 0), (0, K.C2_5, K.MOD_16QAM, 1), (0, K.C1_2, K.MOD_64QAM, 0), (0, K.C5_6, K.MOD_256QAM, 1),
+    (0, K.C1_3, K.MOD_256QAM, 1), (1, K.C4_5, K.MOD_16QAM, 1)])
+def test_ldpc_and_mapper_modes(reflib, fs, rate, con, rot):
+    """LDPC + bit interleaver/mapper over code rates, frame sizes and constellations beyond the five configs."""
+    rng = np.random.default_rng(fs * 100 + rate * 10 + con)
+    rbb = reflib.bbheaderbch(fs, rate, 0, 0, 1, 0)
+    nbch, N = rbb.get_int("nbch"), rbb.get_int("frame_size")
+    ld = T.ldpc_bb(fs, rate)
+    im = T.interleavermod_bc(fs, rate, con, rot)
+    rim = reflib.interleavermod(fs, rate, con, rot)
+    nfr = 3
+    info = rng.integers(0, 2, nfr * nbch, dtype=np.uint8)
+    fec, used = ld.work(info, nfr)
+    assert used == nfr * nbch
+    want = np.concatenate([rbb.ldpc(info[f * nbch:(f + 1) * nbch], N) for f in range(nfr)])
+    assert bits_equal(fec, want)
+    cells, _ = im.work(fec, nfr)
+    assert cells_equal(cells, rim.work(want, nfr)[0])
+
+
+def test_ldpc_parity_check_independent():
+    """Known-answer independent of the reference code: every parity check of the IRA code built straight
+    from the address table (check j: XOR of the info bits hitting row j, p[j] and p[j-1]) is satisfied."""
+    fs, rate = 1, K.C2_3
+    ld = T.ldpc_bb(fs, rate)
+    rng = np.random.default_rng(7)
+    nbch, N, q = 43200, 64800, 60
+    info = rng.integers(0, 2, nbch, dtype=np.uint8)
+    cw, _ = ld.work(info, 1)
+    P = N - nbch
+    row_ptr = ld.plan("ldpc.row_ptr", np.uint16).astype(int)
+    ent = ld.plan("ldpc.entries", np.uint32)
+    acc = np.zeros(P, dtype=np.uint8)
+    for t in range(q):
+        for e in range(row_ptr[t], row_ptr[t + 1]):
+            g, s = int(ent[e] & 0xFFFF), int(ent[e] >> 16)
+            n = np.arange(360)
+            acc[q * ((n + s) % 360) + t] ^= info[360 * g + n]
+    p = cw[nbch:]
+    prev = np.concatenate([[0], p[:-1]]).astype(np.uint8)
+    assert not np.any(acc ^ p ^ prev)
+
+
+def test_fft_sizes_parseval_and_reference(reflib):
+    """Every FFT size 1K..32K through block 5: against the reference, plus Parseval per symbol."""
+    rng = np.random.default_rng(3)
+    cases = [(K.FFTSIZE_1K, K.PILOT_PP1, K.GI_1_16, 0), (K.FFTSIZE_2K, K.PILOT_PP2, K.GI_1_8, 0),
+             (K.FFTSIZE_4K, K.PILOT_PP3, K.GI_1_4, 0), (K.FFTSIZE_8K, K.PILOT_PP4, K.GI_19_128, 1),
+             (K.FFTSIZE_16K, K.PILOT_PP5, K.GI_19_256, 1), (K.FFTSIZE_32K, K.PILOT_PP6, K.GI_1_32, 1),
+             (K.FFTSIZE_32K, K.PILOT_PP8, K.GI_1_16, 0)]
+    for fft, pp, gi, ext in cases:
+        args = (ext, fft, pp, gi, 5, K.PAPR_OFF, 0, K.PREAMBLE_T2_SISO, 0, K.EQUALIZATION_ON, K.BANDWIDTH_8_0_MHZ, K.VLENGTH[fft])
+        pg = T.pilotgenp1insert_cc(*args)
+        rp = reflib.pilotgen(*args)
+        n_in = pg.forecast(pg.output_multiple)
+        assert n_in == rp.forecast(rp.output_multiple)
+        x = (rng.standard_normal(2 * n_in) + 1j * rng.standard_normal(2 * n_in)).astype(np.complex64)
+        y, used = pg.work(x, 2)
+        want, _ = rp.work(x, 2)
+        assert used == 2 * n_in
+        assert mer_db(y, want) >= MER_MIN_DB, (fft, pp)
+        assert max_err_over_rms(y, want) <= MAX_ERR_OVER_RMS, (fft, pp)
