@@ -288,14 +288,15 @@ def run_ours(args):
     # ---- optional ordered gather of the finished frames to rank 0 (north_star: NCCL only for that)
     gather = None
     if world > 1:
-        bufs = [torch.empty_like(d_out) for _ in range(world)] if rank == 0 else None
+        d_real = torch.view_as_real(d_out)
+        bufs = [torch.empty_like(d_real) for _ in range(world)] if rank == 0 else None
         torch.cuda.synchronize(); dist.barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        dist.gather(d_out, bufs, dst=0)
+        dist.gather(d_real, bufs, dst=0)
         torch.cuda.synchronize(); dist.barrier()
         g0.record()
         for _ in range(3):
-            dist.gather(d_out, bufs, dst=0)
+            dist.gather(d_real, bufs, dst=0)
         g1.record()
         torch.cuda.synchronize()
         gather = {"ms_per_step": g0.elapsed_time(g1) / 3.0, "bytes_into_root": (world - 1) * d_out.numel() * 8,

@@ -281,6 +281,7 @@ struct MapHandle : dvbt2ll_handle {
     a.in = in; a.in_pitch = in_pitch; a.out = out; a.frames = frames;
     a.nldpc = plan.fec.nldpc; a.mod = plan.mod; a.cell_size = plan.cell_size; a.cyclic_delay = plan.cyclic_delay;
     a.bit_src = d_bitsrc.as<uint16_t>(); a.lut = d_lut.as<float2>();
+    a.ci_inv = 0; a.fec_shift = 0; a.fecblocks = 1;
   }
   int work_device(const void *d_in, int ninput, void *d_out, int noutput, int *consumed, cudaStream_t s)
   {
@@ -349,6 +350,7 @@ struct FrameHandle : dvbt2ll_handle {
     if (n == "frame.pool") return copy_vec(plan.pool.cells, out, cap);
     if (n == "frame.cell_perm") return copy_vec(plan.cell_perm, out, cap);
     if (n == "frame.fec_shift") return copy_vec(plan.fec_shift, out, cap);
+    if (n == "frame.ci_dst") return copy_vec(plan.ci_dst, out, cap);
     if (n == "frame.ti_src") return copy_vec(plan.ti_src, out, cap);
     if (n == "frame.dims") return dims_get(plan.dims, out, cap);
     if (n == "frame.info") {
@@ -367,24 +369,43 @@ struct OfdmDevice {
   int log2_m, split;
   int init(const std::vector<int32_t> &code, const t2::CellPool &pool, const t2::OfdmPlan &op)
   {
-    CK(upload(d_code, code));
     CK(upload(d_pool, pool.cells));
     CK(upload(d_p1, op.p1));
-    if (!op.inv_sinc.empty()) CK(upload(d_sinc, op.inv_sinc));
     const int N = op.dims.fft_n;
     split = N > 16384 ? 2 : 1;
     const int M = N / split;
     log2_m = 0;
     while ((1 << log2_m) < M) log2_m++;
+    // carrier codes re-laid out per (symbol, phase) in the shared-memory position order of the FFT kernel:
+    // sub-transform bin m of phase p is FFT bin b = split * m + p, i.e. centred spectrum index (b + N/2) mod N,
+    // i.e. carrier k = that - left_nulls (null carriers outside [0, C_PS) take pool cell 0 = zero).
+    const int L = op.dims.num_symbols, cps = op.dims.c_ps;
+    std::vector<int> pos(M);
+    for (int m = 0; m < M; m++) pos[m] = t2k::ofdm_position_of_bin(m, log2_m);
+    std::vector<int32_t> code_pos((size_t)L * N, -1);
+    for (int l = 0; l < L; l++)
+      for (int p = 0; p < split; p++)
+        for (int m = 0; m < M; m++) {
+          const int c = (split * m + p + N / 2) & (N - 1);
+          const int k = c - op.left_nulls;
+          code_pos[((size_t)l * split + p) * M + pos[m]] = (k >= 0 && k < cps) ? code[(size_t)l * cps + k] : -1;
+        }
+    CK(upload(d_code, code_pos));
+    if (!op.inv_sinc.empty()) {
+      std::vector<float> sinc_pos((size_t)N);
+      for (int p = 0; p < split; p++)
+        for (int m = 0; m < M; m++) sinc_pos[(size_t)p * M + pos[m]] = op.inv_sinc[(split * m + p + N / 2) & (N - 1)];
+      CK(upload(d_sinc, sinc_pos));
+    }
     CK(upload(d_tw, make_twiddles(M, M)));
     if (split == 2) CK(upload(d_tw_split, make_twiddles(N, M)));
     return 0;
   }
   void fill(t2k::OfdmArgs &a, const t2::OfdmPlan &op, const t2::CellPool &pool) const
   {
-    a.code = d_code.as<int32_t>(); a.pool = d_pool.as<float2>();
+    a.code_pos = d_code.as<int32_t>(); a.pool = d_pool.as<float2>();
     a.l1post_base = pool.l1post_base; a.l1post_cells = pool.l1post_cells; a.l1post_variants = pool.l1post_variants;
-    a.p1 = d_p1.as<float2>(); a.inv_sinc = op.inv_sinc.empty() ? 0 : d_sinc.as<float>();
+    a.p1 = d_p1.as<float2>(); a.sinc_pos = op.inv_sinc.empty() ? 0 : d_sinc.as<float>();
     a.tw = d_tw.as<float2>(); a.tw_split = split == 2 ? d_tw_split.as<float2>() : 0;
     a.fft_n = op.dims.fft_n; a.log2_m = log2_m; a.split = split;
     a.c_ps = op.dims.c_ps; a.left_nulls = op.left_nulls; a.gi = op.dims.gi; a.num_symbols = op.dims.num_symbols;
@@ -446,7 +467,7 @@ struct ChainHandle : dvbt2ll_handle {
   t2::OfdmPlan oplan;
   t2::ChainTables tables;
   OfdmDevice odev;
-  DevBuf d_bch, d_fec, d_cells, d_ts_stage, d_out_stage;
+  DevBuf d_bch, d_fec, d_cells, d_ts_stage, d_out_stage, d_ci_inv, d_fec_shift;
   int max_frames, device;
   int last_frames;
   bool timing;
@@ -471,6 +492,8 @@ struct ChainHandle : dvbt2ll_handle {
     if ((r = ldpc.dev_init())) return r;
     if ((r = map.dev_init())) return r;
     if ((r = odev.init(tables.code, tables.pool, oplan))) return r;
+    CK(upload(d_ci_inv, fplan.cell_perm_inv));
+    CK(upload(d_fec_shift, fplan.fec_shift));
     const size_t nfec = (size_t)max_frames * F();
     CK(d_bch.ensure(nfec * align16(bb.plan.fec.nbch / 8) + 64));
     CK(d_fec.ensure(nfec * align16(bb.plan.fec.nldpc / 8) + 64));
@@ -505,6 +528,7 @@ struct ChainHandle : dvbt2ll_handle {
     if (timing) cudaEventRecord(ev[2], s);
     t2k::MapArgs ma;
     map.fill_args(ma, d_fec.as<uint8_t>(), fp, d_cells.as<float2>(), nfec);
+    ma.ci_inv = d_ci_inv.as<uint16_t>(); ma.fec_shift = d_fec_shift.as<int32_t>(); ma.fecblocks = F();   // fused cell interleaver
     t2k::launch_map(ma, s);
     if (timing) cudaEventRecord(ev[3], s);
     t2k::OfdmArgs oa;
@@ -539,6 +563,7 @@ struct ChainHandle : dvbt2ll_handle {
     if ((r = ldpc.plan_get(name, out, cap)) >= 0) return r;
     if ((r = map.plan_get(name, out, cap)) >= 0) return r;
     if (n == "frame.code") return copy_vec(fplan.code, out, cap);
+    if (n == "frame.ci_dst") return copy_vec(fplan.ci_dst, out, cap);
     if (n == "ofdm.code") return copy_vec(oplan.code, out, cap);
     if (n == "ofdm.dims") return dims_get(oplan.dims, out, cap);
     return -1;
@@ -707,7 +732,7 @@ dvbt2ll_handle *dvbt2ll_chain_create(const dvbt2ll_chain_params *c, int max_fram
   ok = ok && t2::build_map_plan(c->framesize, c->rate, c->constellation, c->rotation, &h->map.plan, &err);
   ok = ok && t2::build_frame_plan(fp, &h->fplan, &err);
   ok = ok && t2::build_ofdm_plan(op, &h->oplan, &err);
-  ok = ok && t2::compose_chain(h->fplan, h->oplan, &h->tables, &err);
+  ok = ok && t2::compose_chain(h->fplan, h->oplan, true, &h->tables, &err);
   if (!ok) { delete h; fail(DVBT2LL_ERR_INVALID, err); return 0; }
   return h;
 }

@@ -348,14 +348,26 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map(const MapArgs a)
     }
     __syncthreads();
     float2 *out = a.out + (long long)f * a.cell_size;
-    if (a.cyclic_delay) {
-      for (int c = threadIdx.x; c < a.cell_size; c += blockDim.x) {
-        const int pc = c == 0 ? a.cell_size - 1 : c - 1;
+    const int Nc = a.cell_size;
+    if (a.ci_inv) {
+      // fused cell interleaver (chain mode): output position x holds cell ci_inv[(x - shift) mod Nc]
+      const int shift = a.fec_shift[f % a.fecblocks];
+      for (int xo = threadIdx.x; xo < Nc; xo += blockDim.x) {
+        int y = xo - shift;
+        if (y < 0) y += Nc;
+        const int c = __ldg(a.ci_inv + y);
+        const int pc = c == 0 ? Nc - 1 : c - 1;
+        out[xo] = make_float2(lut[cw[c]].x, lut[cw[a.cyclic_delay ? pc : c]].y);
+      }
+    }
+    else if (a.cyclic_delay) {
+      for (int c = threadIdx.x; c < Nc; c += blockDim.x) {
+        const int pc = c == 0 ? Nc - 1 : c - 1;
         out[c] = make_float2(lut[cw[c]].x, lut[cw[pc]].y);
       }
     }
     else {
-      for (int c = threadIdx.x; c < a.cell_size; c += blockDim.x) out[c] = lut[cw[c]];
+      for (int c = threadIdx.x; c < Nc; c += blockDim.x) out[c] = lut[cw[c]];
     }
   }
 }
@@ -493,15 +505,23 @@ void launch_gather(const GatherArgs &a, cudaStream_t s)
 // ================================================================================================
 // K5  OFDM symbol: carrier fill, IFFT, scale, guard interval, P1
 // ================================================================================================
-// In-place decimation-in-time FFT of M = 2^log2_m points in shared memory, backward sign
+// In-place decimation-in-time FFT of M = 2^LOG2M points in shared memory, backward sign
 // (x[t] = sum_b X_b e^{+j 2 pi b t / M}).  Pass j multiplies element q of each butterfly by
 // W_{n_j}^{i q}, does an R-point DFT in registers and writes back in place; inputs are stored at
-// digit-reversed positions by the carrier-fill stage so the result comes out in natural order.
+// digit-reversed positions so the result comes out in natural order.  The host lays the per-symbol
+// carrier code table out in POSITION order (t2k::ofdm_position_of_bin), so the fill stage reads the
+// table coalesced, writes shared memory linearly and never computes a digit reversal.
 // Shared-memory index swizzle: the low nibble is XORed with the fold of the upper nibbles, which
-// makes every access pattern used below (unit stride, power-of-two strides of the butterflies and the
-// digit-reversed fill) conflict-free per half-warp for 8-byte elements.
+// makes every access pattern used below (unit stride and the power-of-two strides of the butterflies)
+// conflict-free per half-warp for 8-byte elements.  swz() is XOR-linear, so inside a butterfly the
+// element addresses are swz(base) ^ constant.
+//
+// N = 32K does not fit (256 KB): it is split by bin parity (decimation in time at the top level):
+// phase 0 transforms the even bins and stores E[n] to out[n] and out[n + N/2]; phase 1 transforms the
+// odd bins and adds / subtracts W_N^n O[n] in place (the same thread re-reads what it wrote, from L2).
+// Each carrier is gathered exactly once and every global store is a full, contiguous line.
 
-__device__ __forceinline__ int swz(int p) { return p ^ (((p >> 4) ^ (p >> 8) ^ (p >> 12)) & 15); }
+__host__ __device__ constexpr int swz(int p) { return p ^ (((p >> 4) ^ (p >> 8) ^ (p >> 12)) & 15); }
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
@@ -541,30 +561,29 @@ __device__ __forceinline__ void dft_reg(float2 (&v)[R])
   }
 }
 
-template <int R> __device__ __forceinline__ int bitrev_r(int k)
+__host__ __device__ constexpr int bitrev_c(int k, int r)
 {
-  int r = 0;
-#pragma unroll
-  for (int b = 1; b < R; b <<= 1) { r = (r << 1) | (k & 1); k >>= 1; }
-  return r;
+  int out = 0;
+  for (int b = 1; b < r; b <<= 1) { out = (out << 1) | (k & 1); k >>= 1; }
+  return out;
 }
 
-// one in-place DIT pass of radix R; n_prev = length of the already transformed sub-blocks
-template <int R>
-__device__ __forceinline__ void fft_pass(float2 *x, int M, int n_prev, const float2 *__restrict__ tw)
+// one in-place DIT pass of radix R over M points; NPREV = length of the already transformed sub-blocks
+template <int R, int M, int NPREV>
+__device__ __forceinline__ void fft_pass(float2 *x, const float2 *__restrict__ tw)
 {
-  const int nb = M / R;
-  const int tw_step = M / (n_prev * R);
-  for (int u = threadIdx.x; u < nb; u += blockDim.x) {
-    const int i = u & (n_prev - 1);
-    const int base = (u - i) * R + i;
+  constexpr int NB = M / R;
+  constexpr int TW_STEP = M / (NPREV * R);
+  for (int u = threadIdx.x; u < NB; u += blockDim.x) {
+    const int i = u & (NPREV - 1);
+    const int sb = swz((u - i) * R + i);
     float2 v[R];
 #pragma unroll
-    for (int qd = 0; qd < R; qd++) v[qd] = x[swz(base + qd * n_prev)];
-    if (n_prev > 1) {
+    for (int qd = 0; qd < R; qd++) v[qd] = x[sb ^ swz(qd * NPREV)];
+    if (NPREV > 1) {
       // twiddles W_{n}^{i q}: w1 from the table, powers by a short product tree
       float2 w[R];
-      w[1] = __ldg(tw + i * tw_step);
+      w[1] = __ldg(tw + i * TW_STEP);
 #pragma unroll
       for (int qd = 2; qd < R; qd++) w[qd] = (qd & 1) ? cmul(w[qd - 1], w[1]) : cmul(w[qd >> 1], w[qd >> 1]);
 #pragma unroll
@@ -572,51 +591,59 @@ __device__ __forceinline__ void fft_pass(float2 *x, int M, int n_prev, const flo
     }
     dft_reg<R>(v);
 #pragma unroll
-    for (int k = 0; k < R; k++) x[swz(base + k * n_prev)] = v[bitrev_r<R>(k)];
+    for (int k = 0; k < R; k++) x[sb ^ swz(k * NPREV)] = v[bitrev_c(k, R)];
   }
 }
 
-struct FftShape { int nr; int lg[4]; };   // radices as log2, first pass first
-
-__host__ __device__ inline FftShape fft_shape(int log2_m)
+// pass schedule: the first pass takes the remainder (LOG2M mod 4 bits), the others are radix 16
+template <int LOG2M>
+__device__ __forceinline__ void fft_inplace(float2 *x, const float2 *__restrict__ tw)
 {
-  FftShape s;
-  // last passes radix 16; the first pass takes the remainder (10 -> 2,4,4; 11 -> 3,4,4; 12 -> 4,4,4; 13 -> 1,4,4,4; 14 -> 2,4,4,4)
-  int rem = log2_m;
-  int n16 = rem / 4;
-  int first = rem - 4 * n16;
-  s.nr = 0;
-  if (first) s.lg[s.nr++] = first;
-  for (int i = 0; i < n16; i++) s.lg[s.nr++] = 4;
-  return s;
+  constexpr int M = 1 << LOG2M;
+  constexpr int F = LOG2M & 3;          // log2 of the first radix (0 = none)
+  if (F == 1) fft_pass<2, M, 1>(x, tw);
+  if (F == 2) fft_pass<4, M, 1>(x, tw);
+  if (F == 3) fft_pass<8, M, 1>(x, tw);
+  if (F) __syncthreads();
+  constexpr int N0 = 1 << F;
+  fft_pass<16, M, N0>(x, tw);
+  __syncthreads();
+  if (LOG2M - F >= 8) { fft_pass<16, M, (N0 << 4 < M ? N0 << 4 : 1)>(x, tw); __syncthreads(); }
+  if (LOG2M - F >= 12) { fft_pass<16, M, (N0 << 8 < M ? N0 << 8 : 1)>(x, tw); __syncthreads(); }
 }
 
-// position of input bin b: digits of b taken from the most significant end go to the least significant end
-__device__ __forceinline__ int digit_reverse(int b, int log2_m, const FftShape &sh)
+int ofdm_position_of_bin(int m, int log2_m)
 {
-  int p = 0, shift_out = 0, rem = log2_m;
-  for (int j = 0; j < sh.nr; j++) {
-    rem -= sh.lg[j];
-    const int d = (b >> rem) & ((1 << sh.lg[j]) - 1);
-    p |= d << shift_out;
-    shift_out += sh.lg[j];
+  // digits of m taken from the most significant end go to the least significant end of the position
+  const int first = log2_m & 3;
+  int lg[4], nr = 0;
+  if (first) lg[nr++] = first;
+  for (int i = 0; i < log2_m / 4; i++) lg[nr++] = 4;
+  int p = 0, out_shift = 0, rem = log2_m;
+  for (int j = 0; j < nr; j++) {
+    rem -= lg[j];
+    p |= ((m >> rem) & ((1 << lg[j]) - 1)) << out_shift;
+    out_shift += lg[j];
   }
   return p;
 }
 
+constexpr int OFDM_FILL_UNROLL = 8;
+
+template <int LOG2M>
 __global__ void __launch_bounds__(512) k_ofdm(const OfdmArgs a)
 {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   float2 *x = reinterpret_cast<float2 *>(smem_raw);
-  const int M = 1 << a.log2_m, N = a.fft_n;
-  const FftShape sh = fft_shape(a.log2_m);
+  constexpr int M = 1 << LOG2M;
+  const int N = a.fft_n;
   const int units = a.frames * a.num_symbols;
 
   for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
     const int f = unit / a.num_symbols, l = unit - f * a.num_symbols;
     const int variant = (int)((a.frame_idx0 + (f % a.frames_per_channel)) % a.l1post_variants);
     const float2 *cells = a.cells + (long long)f * a.cells_stride;
-    const int32_t *code = a.code + (long long)l * a.c_ps;
+    const int l1_lo = a.l1post_base, l1_n = a.l1post_cells, l1_add = variant * a.l1post_cells;
     float2 *out = a.out + (long long)f * a.out_stride;
     float2 *sym = out + 2048 + (long long)l * (N + a.gi);
 
@@ -624,56 +651,67 @@ __global__ void __launch_bounds__(512) k_ofdm(const OfdmArgs a)
       for (int i = threadIdx.x; i < 2048; i += blockDim.x) out[i] = __ldg(a.p1 + i);
 
     for (int phase = 0; phase < a.split; phase++) {
+      const int32_t *code = a.code_pos + ((long long)l * a.split + phase) * M;
+      const float *sinc = a.sinc_pos ? a.sinc_pos + (long long)phase * M : nullptr;
       __syncthreads();
-      // ---- carrier fill: bin b of the sub-transform
-      for (int b = threadIdx.x; b < M; b += blockDim.x) {
-        float2 v;
-        if (a.split == 1) {
-          const int m = (b + N / 2) & (N - 1);
-          const int k = m - a.left_nulls;
-          v = make_float2(0.f, 0.f);
-          if ((unsigned)k < (unsigned)a.c_ps) {
-            v = fetch_cell(__ldg(code + k), cells, a.pool, a.l1post_base, a.l1post_cells, variant);
-            if (a.inv_sinc) { const float g = __ldg(a.inv_sinc + m); v.x *= g; v.y *= g; }
+      // ---- carrier fill: position q of the sub-transform (table is in position order)
+      for (int q0 = threadIdx.x; q0 < M; q0 += blockDim.x * OFDM_FILL_UNROLL) {
+        int c[OFDM_FILL_UNROLL];
+        const float2 *src[OFDM_FILL_UNROLL];
+        float2 v[OFDM_FILL_UNROLL];
+#pragma unroll
+        for (int u = 0; u < OFDM_FILL_UNROLL; u++) {
+          const int q = q0 + u * blockDim.x;
+          c[u] = q < M ? __ldg(code + q) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < OFDM_FILL_UNROLL; u++) {
+          int idx = -(c[u] + 1);
+          if ((unsigned)(idx - l1_lo) < (unsigned)l1_n) idx += l1_add;
+          src[u] = c[u] >= 0 ? cells + c[u] : a.pool + idx;
+        }
+#pragma unroll
+        for (int u = 0; u < OFDM_FILL_UNROLL; u++) v[u] = __ldg(src[u]);
+#pragma unroll
+        for (int u = 0; u < OFDM_FILL_UNROLL; u++) {
+          const int q = q0 + u * blockDim.x;
+          if (q < M) {
+            if (sinc) { const float g = __ldg(sinc + q); v[u].x *= g; v[u].y *= g; }
+            x[swz(q)] = v[u];
           }
         }
-        else {
-          // N = 2 M: X_b = C[b + N/2], X_{b+N/2} = C[b]; even samples need X_b + X_{b+M}, odd ones (X_b - X_{b+M}) W_N^b
-          const int k_hi = b + M - a.left_nulls, k_lo = b - a.left_nulls;
-          float2 hi = make_float2(0.f, 0.f), lo = make_float2(0.f, 0.f);
-          if ((unsigned)k_hi < (unsigned)a.c_ps) {
-            hi = fetch_cell(__ldg(code + k_hi), cells, a.pool, a.l1post_base, a.l1post_cells, variant);
-            if (a.inv_sinc) { const float g = __ldg(a.inv_sinc + b + M); hi.x *= g; hi.y *= g; }
-          }
-          if ((unsigned)k_lo < (unsigned)a.c_ps) {
-            lo = fetch_cell(__ldg(code + k_lo), cells, a.pool, a.l1post_base, a.l1post_cells, variant);
-            if (a.inv_sinc) { const float g = __ldg(a.inv_sinc + b); lo.x *= g; lo.y *= g; }
-          }
-          v = phase == 0 ? cadd(hi, lo) : cmul(csub(hi, lo), __ldg(a.tw_split + b));
-        }
-        x[swz(digit_reverse(b, a.log2_m, sh))] = v;
       }
       __syncthreads();
-      // ---- FFT passes
-      int n_prev = 1;
-      for (int j = 0; j < sh.nr; j++) {
-        switch (sh.lg[j]) {
-          case 1: fft_pass<2>(x, M, n_prev, a.tw); break;
-          case 2: fft_pass<4>(x, M, n_prev, a.tw); break;
-          case 3: fft_pass<8>(x, M, n_prev, a.tw); break;
-          default: fft_pass<16>(x, M, n_prev, a.tw); break;
-        }
-        n_prev <<= sh.lg[j];
-        __syncthreads();
-      }
+      fft_inplace<LOG2M>(x, a.tw);
       // ---- scale, store symbol and cyclic prefix
       const int cp_from = N - a.gi;
-      for (int t = threadIdx.x; t < M; t += blockDim.x) {
-        float2 v = x[swz(t)];
-        v.x *= a.norm; v.y *= a.norm;
-        const int T = a.split == 1 ? t : 2 * t + phase;
-        sym[a.gi + T] = v;
-        if (T >= cp_from) sym[T - cp_from] = v;
+      if (a.split == 1) {
+        for (int t = threadIdx.x; t < M; t += blockDim.x) {
+          float2 v = x[swz(t)];
+          v.x *= a.norm; v.y *= a.norm;
+          sym[a.gi + t] = v;
+          if (t >= cp_from) sym[t - cp_from] = v;
+        }
+      }
+      else if (phase == 0) {
+        for (int t = threadIdx.x; t < M; t += blockDim.x) {
+          float2 v = x[swz(t)];
+          v.x *= a.norm; v.y *= a.norm;
+          sym[a.gi + t] = v;
+          sym[a.gi + t + M] = v;
+          if (t + M >= cp_from) sym[t + M - cp_from] = v;
+        }
+      }
+      else {
+        for (int t = threadIdx.x; t < M; t += blockDim.x) {
+          float2 v = cmul(x[swz(t)], __ldg(a.tw_split + t));
+          v.x *= a.norm; v.y *= a.norm;
+          const float2 e = sym[a.gi + t];
+          sym[a.gi + t] = cadd(e, v);
+          const float2 hi = csub(e, v);
+          sym[a.gi + t + M] = hi;
+          if (t + M >= cp_from) sym[t + M - cp_from] = hi;
+        }
       }
     }
   }
@@ -685,8 +723,20 @@ void launch_ofdm(const OfdmArgs &a, cudaStream_t s)
   const size_t smem = (size_t)M * sizeof(float2);
   const int units = a.frames * a.num_symbols;
   if (units < 1) return;
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(k_ofdm, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+  void (*kern)(const OfdmArgs) = nullptr;
+  switch (a.log2_m) {
+    case 10: kern = k_ofdm<10>; break;
+    case 11: kern = k_ofdm<11>; break;
+    case 12: kern = k_ofdm<12>; break;
+    case 13: kern = k_ofdm<13>; break;
+    case 14: kern = k_ofdm<14>; break;
+    default: return;
+  }
+  static bool attr[16] = { false };
+  if (!attr[a.log2_m]) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr[a.log2_m] = true;
+  }
   int threads = M >= 8192 ? 512 : 256;
   // resident CTAs per SM limited by shared memory (227 KB usable)
   int per_sm = (int)((227 * 1024) / (smem + 1024));
@@ -694,7 +744,7 @@ void launch_ofdm(const OfdmArgs &a, cudaStream_t s)
   if (per_sm > 2048 / threads) per_sm = 2048 / threads;
   int blocks = sm_count() * per_sm;
   if (blocks > units) blocks = units;
-  k_ofdm<<<blocks, threads, smem, s>>>(a);
+  kern<<<blocks, threads, smem, s>>>(a);
   count_launch();
 }
 

@@ -47,6 +47,10 @@ struct MapArgs {
   int nldpc, mod, cell_size, cyclic_delay;
   const uint16_t *bit_src;   // nldpc
   const float2 *lut;         // 1 << mod
+  // optional fused cell interleaver (chain mode): out[(perm[c] + shift_r) % cell_size] = cell c of FEC block r
+  const uint16_t *ci_inv;    // inverse of the cell permutation, or NULL for natural order
+  const int32_t *fec_shift;  // [fecblocks] cyclic shift per FEC block of the T2 frame
+  int fecblocks;
 };
 void launch_map(const MapArgs &a, cudaStream_t s);
 
@@ -77,13 +81,13 @@ void launch_gather(const GatherArgs &a, cudaStream_t s);
 struct OfdmArgs {
   const float2 *cells; long long cells_stride;   // per T2 frame
   float2 *out;         long long out_stride;     // samples per T2 frame
-  const int32_t *code;       // [num_symbols * c_ps]
+  const int32_t *code_pos;   // [num_symbols][split][M] carrier codes in shared-memory POSITION order
   const float2 *pool;
   int l1post_base, l1post_cells, l1post_variants;
   const float2 *p1;          // 2048
-  const float *inv_sinc;     // fft_n or NULL
+  const float *sinc_pos;     // [split][M] inverse-sinc factors in position order, or NULL
   const float2 *tw;          // W_M^m, m < M  (M = sub-transform size)
-  const float2 *tw_split;    // W_N^b, b < N/2 (only when N = 2 M)
+  const float2 *tw_split;    // W_N^n, n < N/2 (only when N = 2 M): recombination of the even/odd-bin halves
   int fft_n, log2_m, split;  // M = 1 << log2_m, split = N / M (1 or 2)
   int c_ps, left_nulls, gi, num_symbols;
   float norm;
@@ -91,6 +95,9 @@ struct OfdmArgs {
   int frames_per_channel;    // frame f -> t2 frame number frame_idx0 + (f % frames_per_channel)
 };
 void launch_ofdm(const OfdmArgs &a, cudaStream_t s);
+// shared-memory position (before swizzle) at which the carrier-fill stage must store bin m of an
+// M = 2^log2_m point sub-transform (mixed-radix digit reversal matching the kernel's pass schedule)
+int ofdm_position_of_bin(int m, int log2_m);
 
 long long kernel_launch_count();
 

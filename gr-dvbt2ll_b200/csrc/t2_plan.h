@@ -146,7 +146,9 @@ struct FramePlan {
   bool overfull;                       // reference warns "too many FEC blocks in T2 frame"
   std::vector<int32_t> cell_perm;      // cell interleaver permutation (reference :1087-1107)
   std::vector<int32_t> fec_shift;      // per FEC block cyclic shift (reference :1981-1992)
-  std::vector<int32_t> ti_src;         // time-interleaver read-out: position -> cell-interleaved index
+  std::vector<int32_t> ti_src;         // time-interleaver read-out position -> input cell index (cell int. composed)
+  std::vector<int32_t> ci_dst;         // input cell index -> index in cell-interleaved memory
+  std::vector<uint16_t> cell_perm_inv; // inverse of cell_perm
   std::vector<int32_t> code;           // [mapped_items]
   CellPool pool;                       // [L1-pre 1840][L1-post x t2frames][dummy][zero]
   int pool_l1pre, pool_dummy, pool_zero;
@@ -182,7 +184,10 @@ struct ChainTables {
   std::vector<int32_t> code;   // [num_symbols * c_ps]
   CellPool pool;
 };
-bool compose_chain(const FramePlan &fp, const OfdmPlan &op, ChainTables *out, std::string *err);
+// cells_cell_interleaved: the mapper kernel already stored the cells in cell-interleaved order (fused), so
+// data codes index that memory instead of the natural-order cells.
+bool compose_chain(const FramePlan &fp, const OfdmPlan &op, bool cells_cell_interleaved, ChainTables *out,
+                   std::string *err);
 
 // small utilities
 void bb_prbs_bits(int n, uint8_t *out);          // 1 bit per byte; reference :357-369

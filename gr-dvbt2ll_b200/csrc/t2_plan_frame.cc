@@ -435,11 +435,17 @@ bool build_frame_plan(const FrameParams &prm, FramePlan *p, std::string *err)
     }
     if ((int)p->fec_shift.size() != F) { if (err) *err = "framemapperfint_cc: fecblocks/tiblocks combination leaves FEC blocks unassigned"; return false; }
 
-    // cell-interleaved memory index -> input index
+    // cell-interleaved memory index <-> input index
     std::vector<int32_t> ci_src((size_t)F * Nc);
+    p->ci_dst.assign((size_t)F * Nc, 0);
     for (int r = 0; r < F; r++)
-      for (int w = 0; w < Nc; w++)
-        ci_src[(size_t)r * Nc + (p->cell_perm[w] + p->fec_shift[r]) % Nc] = r * Nc + w;
+      for (int w = 0; w < Nc; w++) {
+        const int x = r * Nc + (p->cell_perm[w] + p->fec_shift[r]) % Nc;
+        ci_src[x] = r * Nc + w;
+        p->ci_dst[(size_t)r * Nc + w] = x;
+      }
+    p->cell_perm_inv.assign(Nc, 0);
+    for (int w = 0; w < Nc; w++) p->cell_perm_inv[p->cell_perm[w]] = (uint16_t)w;
 
     // time interleaver read-out (EN 302 755 6.5; reference :1999-2028)
     p->ti_src.assign((size_t)F * Nc, 0);

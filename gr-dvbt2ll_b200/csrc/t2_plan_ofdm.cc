@@ -288,7 +288,8 @@ bool build_ofdm_plan(const OfdmParams &prm, OfdmPlan *p, std::string *err)
   return true;
 }
 
-bool compose_chain(const FramePlan &fp, const OfdmPlan &op, ChainTables *out, std::string *err)
+bool compose_chain(const FramePlan &fp, const OfdmPlan &op, bool cells_cell_interleaved, ChainTables *out,
+                   std::string *err)
 {
   if (fp.mapped_items != op.dims.active_items || fp.dims.c_ps != op.dims.c_ps) {
     if (err) *err = "chain: frame mapper and pilot generator parameters do not describe the same frame";
@@ -305,7 +306,7 @@ bool compose_chain(const FramePlan &fp, const OfdmPlan &op, ChainTables *out, st
     const int32_t c = op.code[i];
     if (c < 0) { out->code[i] = c; continue; }
     const int32_t f = fp.code[c];
-    out->code[i] = f >= 0 ? f : -(1 + base + (-(f + 1)));
+    out->code[i] = f >= 0 ? (cells_cell_interleaved ? fp.ci_dst[f] : f) : -(1 + base + (-(f + 1)));
   }
   return true;
 }

@@ -1,0 +1,60 @@
+"""Multi-GPU sharding of the modulator chain (one process per GPU).
+
+T2 frames are independent once BB framing is done (the only carried state -- packet phase, CRC-8 of the
+packet in flight, in-band phase, L1 FRAME_IDX -- is a closed-form function of the stream position), so
+work is partitioned with NO data-path collective: whole channels per rank when there are at least as
+many channels as ranks (config 5), otherwise contiguous runs of T2 frames of a channel.  The only
+exchange step is the ordered reassembly of the finished frames on one rank, an NCCL gather.
+"""
+import numpy as np
+
+
+def channels_for_rank(n_channels, world, rank):
+    """Contiguous block of channel indices owned by `rank` (sizes differ by at most one)."""
+    base, extra = divmod(n_channels, world)
+    start = rank * base + min(rank, extra)
+    return list(range(start, start + base + (1 if rank < extra else 0)))
+
+
+def frames_for_rank(n_frames, world, rank):
+    """(first_frame, count) of the contiguous run of T2 frames of ONE channel owned by `rank`."""
+    base, extra = divmod(n_frames, world)
+    start = rank * base + min(rank, extra)
+    return start, base + (1 if rank < extra else 0)
+
+
+def ts_slice_for_frames(ts_bytes_per_frame, first_frame, count):
+    """Byte range of a channel's TS needed for frames [first_frame, first_frame + count): the payload bytes
+    plus up to 187 bytes of history for the CRC-8 that replaces the first sync byte."""
+    lo = first_frame * ts_bytes_per_frame
+    return max(0, lo - 187), lo + count * ts_bytes_per_frame
+
+
+def gather_frames(local, dst=0, group=None):
+    """Ordered reassembly on rank `dst`: returns the concatenation over ranks (rank order = channel / frame
+    order by construction of the partitions above) on dst, None elsewhere.  `local` is a torch tensor;
+    NCCL on GPUs, gloo in the CPU tests."""
+    import torch
+    import torch.distributed as dist
+    if local.is_complex():                      # collectives move real pairs (gloo has no complex types)
+        out = gather_frames(torch.view_as_real(local.contiguous()), dst=dst, group=group)
+        return None if out is None else torch.view_as_complex(out.reshape(-1, 2))
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=local.device) for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([local.numel()], dtype=torch.int64, device=local.device), group=group)
+    sizes = [int(s.item()) for s in sizes]
+    flat = local.reshape(-1)
+    if len(set(sizes)) == 1:
+        bufs = [torch.empty_like(flat) for _ in range(world)] if rank == dst else None
+        dist.gather(flat, bufs, dst=dst, group=group)
+        return torch.cat(bufs) if rank == dst else None
+    # ragged: pad to the maximum, trim on the root
+    mx = max(sizes)
+    pad = torch.zeros(mx, dtype=flat.dtype, device=flat.device)
+    pad[:flat.numel()] = flat
+    bufs = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
+    dist.gather(pad, bufs, dst=dst, group=group)
+    if rank != dst:
+        return None
+    return torch.cat([b[:n] for b, n in zip(bufs, sizes)])

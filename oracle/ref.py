@@ -17,6 +17,15 @@ LIB_PATH = os.path.join(_HERE, "_ref", "libdvbt2ll_ref.so")
 
 _lib = None
 
+# (framesize, rate) pairs for which the reference's own (dead-code) LDPC encoder is unusable: its lookup
+# table (LDPC_BF macro, lib/bbheaderbch_bb_impl.cc:533-561) reserves floor(edges*360/P)+2 slots per
+# parity bit, but for the irregular short codes 1/2, 3/4 and 5/6 some check nodes have more neighbours
+# than that, so ldpc_lookup_generate() overruns its rows (heap overflow already in the constructor) and
+# ldpc_calculate() returns garbage.  The live path (gr-dtv dvb_ldpc_bb) has no such limit; for these
+# codes the numpy oracle (scatter form straight from the address table, checked through H.c = 0) is the
+# only checker, and tests do not construct the reference's bbheaderbch block for them.
+REF_LDPC_BROKEN = {(0, 0), (0, 3), (0, 5)}
+
 
 def available():
     return os.path.exists(LIB_PATH)
@@ -140,6 +149,8 @@ class Block:
 
 
 def bbheaderbch(framesize, rate, mode, inband, fecblocks, tsrate):
+    if (framesize, rate) in REF_LDPC_BROKEN:
+        raise NotImplementedError("reference bbheaderbch_bb overruns its LDPC lookup table for this code (see REF_LDPC_BROKEN)")
     return Block(lib().ref_bbheaderbch_new(framesize, rate, mode, inband, fecblocks, tsrate),
                  np.uint8, np.uint8)
 

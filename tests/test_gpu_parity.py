@@ -99,11 +99,13 @@ def test_chain_matches_reference(reflib, name):
     nldpc = refs[0]["fec"].size // F
     bch = ch.tap("bch").reshape(nframes * F, -1)
     cells = ch.tap("cells", np.complex64)
+    ci_dst = ch.plan("frame.ci_dst", np.int32)     # the chain's mapper stores cells already cell-interleaved
     for fr in range(nframes):
         r = refs[fr]
         got = np.unpackbits(bch[fr * F:(fr + 1) * F, :nbch // 8], axis=1).reshape(-1)
         assert bits_equal(got, r["bch"])
-        assert cells_equal(cells[fr * r["cells"].size:(fr + 1) * r["cells"].size], r["cells"])
+        frame_cells = cells[fr * r["cells"].size:(fr + 1) * r["cells"].size]
+        assert cells_equal(frame_cells[ci_dst], r["cells"])
         s = out[fr * S:(fr + 1) * S]
         assert mer_db(s, r["samples"]) >= MER_MIN_DB
         assert max_err_over_rms(s, r["samples"]) <= MAX_ERR_OVER_RMS
@@ -192,9 +194,10 @@ def test_bbheader_hiefficiency_and_inband(reflib, mode, inband):
     (0, K.C1_3, K.MOD_256QAM, 1), (1, K.C4_5, K.MOD_16QAM, 1)])
 def test_ldpc_and_mapper_modes(reflib, fs, rate, con, rot):
     """LDPC + bit interleaver/mapper over code rates, frame sizes and constellations beyond the five configs."""
+    from oracle import t2oracle as O
     rng = np.random.default_rng(fs * 100 + rate * 10 + con)
-    rbb = reflib.bbheaderbch(fs, rate, 0, 0, 1, 0)
-    nbch, N = rbb.get_int("nbch"), rbb.get_int("frame_size")
+    p = O.fec_params(fs, rate)
+    nbch, N = p["nbch"], p["nldpc"]
     ld = T.ldpc_bb(fs, rate)
     im = T.interleavermod_bc(fs, rate, con, rot)
     rim = reflib.interleavermod(fs, rate, con, rot)
@@ -202,8 +205,11 @@ def test_ldpc_and_mapper_modes(reflib, fs, rate, con, rot):
     info = rng.integers(0, 2, nfr * nbch, dtype=np.uint8)
     fec, used = ld.work(info, nfr)
     assert used == nfr * nbch
-    want = np.concatenate([rbb.ldpc(info[f * nbch:(f + 1) * nbch], N) for f in range(nfr)])
+    want = O.ldpc_encode(info.reshape(nfr, nbch), fs, rate).reshape(-1)
     assert bits_equal(fec, want)
+    if (fs, rate) not in reflib.REF_LDPC_BROKEN:      # the reference's dead-code encoder overruns its LUT for 3 short codes
+        rbb = reflib.bbheaderbch(fs, rate, 0, 0, 1, 0)
+        assert bits_equal(want, np.concatenate([rbb.ldpc(info[f * nbch:(f + 1) * nbch], N) for f in range(nfr)]))
     cells, _ = im.work(fec, nfr)
     assert cells_equal(cells, rim.work(want, nfr)[0])
 
