@@ -71,7 +71,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -236,14 +236,21 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # clocks are sampled from before the warm-up until after the timed region (nvidia-smi needs ~0.1 s to
+    # start; the timed region itself can be shorter than one sampling period)
+    clocks = ClockSampler(local)
+    clocks.start()
     chain.enable_timing(False)
-    for _ in range(max(3, args.warmup)):
+    t_w = time.perf_counter()
+    n_w = 0
+    while n_w < max(3, args.warmup) or time.perf_counter() - t_w < 0.4:
         step()
+        n_w += 1
+        if n_w % 8 == 0:
+            torch.cuda.synchronize()
     barrier()
 
     # ---- timed region: K steps, CUDA events on the launching stream, max over ranks
-    clocks = ClockSampler(local)
-    clocks.start()
     chain.enable_timing(True)
     launches0 = T.kernel_launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

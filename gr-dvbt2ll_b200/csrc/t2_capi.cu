@@ -138,7 +138,9 @@ struct BbHandle : dvbt2ll_handle {
   }
   int dev_init()
   {
-    CK(upload(d_scr, plan.scramble));
+    std::vector<uint8_t> scr(plan.scramble);
+    scr.resize((scr.size() + 7) & ~(size_t)3, 0);      // kernel XORs the scrambler word-wise
+    CK(upload(d_scr, scr));
     std::vector<uint8_t> crc(plan.crc8_tab, plan.crc8_tab + 256);
     CK(upload(d_crc, crc));
     CK(upload(d_tab, plan.bch_byte_tab));
@@ -282,6 +284,9 @@ struct MapHandle : dvbt2ll_handle {
     a.nldpc = plan.fec.nldpc; a.mod = plan.mod; a.cell_size = plan.cell_size; a.cyclic_delay = plan.cyclic_delay;
     a.bit_src = d_bitsrc.as<uint16_t>(); a.lut = d_lut.as<float2>();
     a.ci_inv = 0; a.fec_shift = 0; a.fecblocks = 1;
+    a.ncol = plan.ncol;
+    std::memcpy(a.col_of_bit, plan.col_of_bit, 16);
+    std::memcpy(a.twist_of_col, plan.twist_of_col, 16);
   }
   int work_device(const void *d_in, int ninput, void *d_out, int noutput, int *consumed, cudaStream_t s)
   {

@@ -46,7 +46,7 @@ __device__ __forceinline__ uint32_t window32(const uint32_t *w, int p)
 // ================================================================================================
 // K1  BB framing + scrambler + BCH
 // ================================================================================================
-constexpr int BB_WARPS = 4;
+constexpr int BB_WARPS = 8;
 
 __device__ __forceinline__ int multiples_in(int a, int b, int m)   // multiples of m in [a, b), a,b >= 0
 {
@@ -60,6 +60,17 @@ __device__ __forceinline__ long long hem_ts_index(long long P, int c0)
   if (P < t0) return P;
   const long long pp = P - t0;
   return t0 + 1 + pp + pp / 187;
+}
+
+// 4 bytes at an arbitrary byte address, via aligned 32-bit loads (little endian)
+__device__ __forceinline__ uint32_t load_u32_unaligned(const uint8_t *p)
+{
+  const uintptr_t ad = reinterpret_cast<uintptr_t>(p);
+  const uint32_t *w = reinterpret_cast<const uint32_t *>(ad & ~(uintptr_t)3);
+  const int sh = (int)(ad & 3) * 8;
+  const uint32_t lo = __ldg(w);
+  if (sh == 0) return lo;
+  return __funnelshift_r(lo, __ldg(w + 1), sh);
 }
 
 __global__ void __launch_bounds__(BB_WARPS * 32) k_bb_bch(const BbArgs a)
@@ -79,9 +90,11 @@ __global__ void __launch_bounds__(BB_WARPS * 32) k_bb_bch(const BbArgs a)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t *buf = s_buf + warp * buf_pitch;
+  uint32_t *bufw = reinterpret_cast<uint32_t *>(buf);
   const int total = a.n_channels * a.frames;
   const int D = a.payload_bytes;
   const bool hem = a.mode != 0;
+  const uint32_t *scr32 = reinterpret_cast<const uint32_t *>(a.scramble);   // zero padded to a word multiple
 
   for (int job = blockIdx.x * BB_WARPS + warp; job < total; job += gridDim.x * BB_WARPS) {
     const int c = job / a.frames, j = job - c * a.frames;
@@ -96,6 +109,54 @@ __global__ void __launch_bounds__(BB_WARPS * 32) k_bb_bch(const BbArgs a)
     else t_start = P0 == 0 ? 0 : hem_ts_index(P0 - 1, a.count0) + 1;
     const int count = (int)((a.count0 + t_start) % 188);
 
+    // ---- stage the raw payload in shared memory (buf byte 10 + i = payload byte i)
+    if (!hem) {
+      const uint8_t *src = ts + P0;
+      if (lane < 2) buf[10 + lane] = src[lane];
+      const int w_end = (10 + Dj) >> 2;                    // words [3, w_end) lie completely inside the payload
+      for (int w = 3 + lane; w < w_end; w += 32) bufw[w] = load_u32_unaligned(src + 4 * w - 10);
+      for (int i = 4 * w_end - 10 + lane; i < Dj; i += 32) buf[10 + i] = src[i];
+    }
+    else {
+      for (int i = lane; i < Dj; i += 32) buf[10 + i] = ts[hem_ts_index(P0 + i, a.count0)];
+      // sync bytes skipped by this frame: positions between t_start and the last payload byte
+      const long long t_end = hem_ts_index(P0 + Dj - 1, a.count0);
+      const int first = (int)((188 - (a.count0 + t_start) % 188) % 188);
+      for (long long t = t_start + first + 188LL * lane; t <= t_end; t += 188LL * 32)
+        if (ts[t] != 0x47) atomicAdd(a.sync_errors, 1);
+    }
+    __syncwarp();
+    // ---- NORMAL mode: each sync byte is replaced by the CRC-8 of the previous packet's 187 bytes
+    // (bytes of this frame come from shared memory, earlier ones from the stream history in global memory)
+    uint8_t my_crc[2] = { 0, 0 };
+    const int i0 = (188 - count) % 188;
+    if (!hem) {
+#pragma unroll
+      for (int rnd = 0; rnd < 2; rnd++) {
+        const int si = i0 + 188 * (lane + 32 * rnd);
+        if (si < Dj) {
+          if (buf[10 + si] != 0x47) atomicAdd(a.sync_errors, 1);
+          uint8_t crc = 0;
+          int u = si - 187;
+          if (u < 0) {
+            long long g = P0 + u;
+            if (g < 0 && !a.hist_valid) g = 0;
+            for (; g < P0; g++) crc = s_crc8[ts[g] ^ crc];
+            u = 0;
+          }
+          for (; u < si; u++) crc = s_crc8[buf[10 + u] ^ crc];
+          my_crc[rnd] = crc;
+        }
+      }
+    }
+    __syncwarp();
+    if (!hem) {
+#pragma unroll
+      for (int rnd = 0; rnd < 2; rnd++) {
+        const int si = i0 + 188 * (lane + 32 * rnd);
+        if (si < Dj) buf[10 + si] = my_crc[rnd];
+      }
+    }
     // ---- BB header (EN 302 755 5.1.7): MATYPE, UPL, DFL, SYNC, SYNCD, CRC-8 (xor MODE)
     if (lane == 0) {
       uint8_t h[10];
@@ -110,36 +171,13 @@ __global__ void __launch_bounds__(BB_WARPS * 32) k_bb_bch(const BbArgs a)
       uint8_t crc = 0;
       for (int i = 0; i < 9; i++) crc = s_crc8[crc ^ h[i]];
       h[9] = hem ? (crc ^ 1) : crc;
-      for (int i = 0; i < 10; i++) buf[i] = h[i] ^ a.scramble[i];
-    }
-    // ---- payload
-    if (!hem) {
-      for (int i = lane; i < Dj; i += 32) buf[10 + i] = ts[P0 + i] ^ a.scramble[10 + i];
-      // sync bytes: replaced by the CRC-8 of the previous packet's 187 bytes
-      const int i0 = (188 - count) % 188;
-      for (int si = i0 + 188 * lane; si < Dj; si += 188 * 32) {
-        const long long t = P0 + si;
-        if (ts[t] != 0x47) atomicAdd(a.sync_errors, 1);
-        uint8_t crc = 0;
-        long long lo = t - 187;
-        if (lo < 0 && !a.hist_valid) lo = 0;
-        for (long long u = lo; u < t; u++) crc = s_crc8[ts[u] ^ crc];
-        buf[10 + si] = crc ^ a.scramble[10 + si];
-      }
-    }
-    else {
-      for (int i = lane; i < Dj; i += 32) {
-        const long long t = hem_ts_index(P0 + i, a.count0);
-        buf[10 + i] = ts[t] ^ a.scramble[10 + i];
-      }
-      // sync bytes skipped by this frame: positions between t_start and the last payload byte
-      const long long t_end = hem_ts_index(P0 + Dj - 1, a.count0);
-      const int first = (int)((188 - (a.count0 + t_start) % 188) % 188);
-      for (long long t = t_start + first + 188LL * lane; t <= t_end; t += 188LL * 32)
-        if (ts[t] != 0x47) atomicAdd(a.sync_errors, 1);
+      for (int i = 0; i < 10; i++) buf[i] = h[i];
     }
     if (ib)
-      for (int i = lane; i < 13; i += 32) buf[10 + Dj + i] = a.inband_bytes[i] ^ a.scramble[10 + Dj + i];
+      for (int i = lane; i < 13; i += 32) buf[10 + Dj + i] = a.inband_bytes[i];
+    __syncwarp();
+    // ---- BB scrambler, word-wise
+    for (int w = lane; w < (msg_bytes + 3) >> 2; w += 32) bufw[w] ^= __ldg(scr32 + w);
     __syncwarp();
 
     // ---- BCH: per-lane remainder of a chunk of the message (byte-table LFSR on a 192-bit register)
@@ -164,32 +202,39 @@ __global__ void __launch_bounds__(BB_WARPS * 32) k_bb_bch(const BbArgs a)
     uint32_t c0 = __shfl_sync(0xffffffffu, r0, 0), c1 = __shfl_sync(0xffffffffu, r1, 0),
              c2 = __shfl_sync(0xffffffffu, r2, 0), c3 = __shfl_sync(0xffffffffu, r3, 0),
              c4 = __shfl_sync(0xffffffffu, r4, 0), c5 = __shfl_sync(0xffffffffu, r5, 0);
-    for (int i = 1; i < 32; i++) {
-      uint32_t n[6];
+    {
+      // this lane's six column masks stay in registers for the whole combine
+      uint32_t col[6][6];
 #pragma unroll
-      for (int w = 0; w < 6; w++) {
-        const uint32_t *col = s_cols + (w * 32 + lane) * 6;
-        const uint32_t x = (c0 & col[0]) ^ (c1 & col[1]) ^ (c2 & col[2]) ^ (c3 & col[3]) ^ (c4 & col[4]) ^ (c5 & col[5]);
-        n[w] = __ballot_sync(0xffffffffu, __popc(x) & 1);
+      for (int w = 0; w < 6; w++)
+#pragma unroll
+        for (int k = 0; k < 6; k++) col[w][k] = s_cols[(w * 32 + lane) * 6 + k];
+      for (int i = 1; i < 32; i++) {
+        uint32_t n[6];
+#pragma unroll
+        for (int w = 0; w < 6; w++) {
+          const uint32_t x = (c0 & col[w][0]) ^ (c1 & col[w][1]) ^ (c2 & col[w][2]) ^ (c3 & col[w][3]) ^ (c4 & col[w][4]) ^ (c5 & col[w][5]);
+          n[w] = __ballot_sync(0xffffffffu, __popc(x) & 1);
+        }
+        c0 = n[0] ^ __shfl_sync(0xffffffffu, r0, i);
+        c1 = n[1] ^ __shfl_sync(0xffffffffu, r1, i);
+        c2 = n[2] ^ __shfl_sync(0xffffffffu, r2, i);
+        c3 = n[3] ^ __shfl_sync(0xffffffffu, r3, i);
+        c4 = n[4] ^ __shfl_sync(0xffffffffu, r4, i);
+        c5 = n[5] ^ __shfl_sync(0xffffffffu, r5, i);
       }
-      c0 = n[0] ^ __shfl_sync(0xffffffffu, r0, i);
-      c1 = n[1] ^ __shfl_sync(0xffffffffu, r1, i);
-      c2 = n[2] ^ __shfl_sync(0xffffffffu, r2, i);
-      c3 = n[3] ^ __shfl_sync(0xffffffffu, r3, i);
-      c4 = n[4] ^ __shfl_sync(0xffffffffu, r4, i);
-      c5 = n[5] ^ __shfl_sync(0xffffffffu, r5, i);
     }
     if (lane < a.bch_r / 8) {
-      const uint32_t words[6] = { c0, c1, c2, c3, c4, c5 };
-      buf[msg_bytes + lane] = (uint8_t)(words[lane >> 2] >> (24 - 8 * (lane & 3)));
+      const int wsel = lane >> 2;
+      const uint32_t word = wsel == 0 ? c0 : wsel == 1 ? c1 : wsel == 2 ? c2 : wsel == 3 ? c3 : wsel == 4 ? c4 : c5;
+      buf[msg_bytes + lane] = (uint8_t)(word >> (24 - 8 * (lane & 3)));
     }
     __syncwarp();
     // ---- store the packed codeword
     uint8_t *o = a.out + (long long)job * a.out_pitch;
     const int nw = nbytes >> 2;
-    const uint32_t *bw = reinterpret_cast<const uint32_t *>(buf);
     uint32_t *ow = reinterpret_cast<uint32_t *>(o);
-    for (int i = lane; i < nw; i += 32) ow[i] = bw[i];
+    for (int i = lane; i < nw; i += 32) ow[i] = bufw[i];
     for (int i = (nw << 2) + lane; i < nbytes; i += 32) o[i] = buf[i];
     __syncwarp();
   }
@@ -201,10 +246,15 @@ void launch_bb_bch(const BbArgs &a, cudaStream_t s)
   const int buf_pitch = (nbytes + 15) & ~15;
   const size_t smem = 256 * 6 * 4 + 6 * 32 * 6 * 4 + 256 + (size_t)BB_WARPS * buf_pitch;
   const int total = a.n_channels * a.frames;
+  if (total < 1) return;
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(k_bb_bch, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr = true; }
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bb_bch, BB_WARPS * 32, smem);
+  if (per_sm < 1) per_sm = 1;
   int blocks = (total + BB_WARPS - 1) / BB_WARPS;
-  const int cap = sm_count() * 8;
+  const int cap = sm_count() * per_sm;        // one resident wave; warps loop over the remaining FECFRAMEs
   if (blocks > cap) blocks = cap;
-  if (blocks < 1) return;
   k_bb_bch<<<blocks, BB_WARPS * 32, smem, s>>>(a);
   count_launch();
 }
@@ -320,35 +370,119 @@ void launch_ldpc(const LdpcArgs &a, cudaStream_t s)
 // ================================================================================================
 // K3  bit interleaver + demux + mapper
 // ================================================================================================
-constexpr int MAP_THREADS = 256;
+// QAM path (column twist + demux): for 32 consecutive rows d of the twist matrix, column c contributes the
+// 32 consecutive codeword bits u[rows*c + (d - twist[c]) mod rows] -- one funnel-shifted window of the
+// packed codeword per column.  The windows are loaded in OUTPUT-bit order (demux folded into which
+// column feeds which row), a 32x32 bit-matrix transpose in registers turns them into 32 cell-pair words,
+// and the cells go to shared memory as bytes.  QPSK (no twist / demux) uses the generic bit_src table.
+constexpr int MAP_THREADS = 128;
+
+template <int J>
+__device__ __forceinline__ void transpose32_stage(uint32_t (&A)[32])
+{
+  constexpr uint32_t m = J == 16 ? 0x0000FFFFu : J == 8 ? 0x00FF00FFu : J == 4 ? 0x0F0F0F0Fu : J == 2 ? 0x33333333u : 0x55555555u;
+#pragma unroll
+  for (int k = 0; k < 32; k++) {
+    if ((k & J) == 0) {
+      const uint32_t t = (A[k] ^ (A[k + J] >> J)) & m;
+      A[k] ^= t;
+      A[k + J] ^= t << J;
+    }
+  }
+}
+
+// in-place 32x32 bit-matrix transpose (recursive block swap) in (row, MSB-first column) coordinates
+__device__ __forceinline__ void transpose32(uint32_t (&A)[32])
+{
+  transpose32_stage<16>(A);
+  transpose32_stage<8>(A);
+  transpose32_stage<4>(A);
+  transpose32_stage<2>(A);
+  transpose32_stage<1>(A);
+}
 
 __global__ void __launch_bounds__(MAP_THREADS) k_map(const MapArgs a)
 {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int nwords = (a.nldpc + 31) / 32;
-  uint32_t *u = reinterpret_cast<uint32_t *>(smem_raw);                   // [nwords + 1]
-  float2 *lut = reinterpret_cast<float2 *>(u + ((nwords + 2) & ~1));      // [1 << mod]
-  uint8_t *cw = reinterpret_cast<uint8_t *>(lut + (1 << a.mod));          // [cell_size]
+  uint32_t *u = reinterpret_cast<uint32_t *>(smem_raw);                   // [nwords + 2]
+  float2 *lut = reinterpret_cast<float2 *>(u + ((nwords + 3) & ~1));      // [1 << mod]
+  uint8_t *cw = reinterpret_cast<uint8_t *>(lut + (1 << a.mod));          // [cell_size rounded up to 64]
   for (int i = threadIdx.x; i < (1 << a.mod); i += blockDim.x) lut[i] = a.lut[i];
+  const int mod = a.mod, Nc = a.cell_size;
+  __shared__ int s_base[16], s_twist[16];      // per output bit: first codeword bit of its column, twist
+  if (threadIdx.x < 16) {
+    const int rho = threadIdx.x;
+    int col = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) if (k == rho) col = a.col_of_bit[k];
+    int tw = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) if (k == col) tw = a.twist_of_col[k];
+    s_base[rho] = a.ncol ? (a.nldpc / a.ncol) * col : 0;
+    s_twist[rho] = tw;
+  }
 
   for (int f = blockIdx.x; f < a.frames; f += gridDim.x) {
     const uint32_t *in = reinterpret_cast<const uint32_t *>(a.in + (long long)f * a.in_pitch);
     __syncthreads();
-    for (int i = threadIdx.x; i < nwords; i += blockDim.x) u[i] = bswap32(in[i]);
+    for (int i = threadIdx.x; i < nwords + 2; i += blockDim.x) u[i] = i < nwords ? bswap32(in[i]) : 0u;
     __syncthreads();
-    const int mod = a.mod;
-    for (int c = threadIdx.x; c < a.cell_size; c += blockDim.x) {
-      const uint16_t *src = a.bit_src + c * mod;
-      uint32_t v = 0;
-      for (int b = 0; b < mod; b++) {
-        const int p = __ldg(src + b);
-        v = (v << 1) | ((u[p >> 5] >> (31 - (p & 31))) & 1u);
+    if (a.ncol) {
+      const int rows = a.nldpc / a.ncol;
+      const int groups = (rows + 31) >> 5;
+      for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+        const int d0 = g << 5;
+        uint32_t A[32];
+#pragma unroll
+        for (int y = 0; y < 32; y++) A[y] = 0;
+#pragma unroll
+        for (int y = 16; y < 32; y++) {
+          const int rho = y - (32 - a.ncol);     // output bit (0 = MSB of the ncol-bit demux word) held by row y
+          if (rho >= 0) {
+            int s0 = d0 - s_twist[rho];
+            if (s0 < 0) s0 += rows;
+            const int base = s_base[rho];
+            const int n1 = rows - s0;
+            uint32_t w = window32(u, base + s0);
+            if (n1 < 32) w = (w & ~(0xFFFFFFFFu >> n1)) | (window32(u, base) >> n1);
+            A[y] = w;
+          }
+        }
+        transpose32(A);
+        // transpose32 uses (row, MSB-first column) coordinates: window bit i (from the MSB) of row y moves to
+        // bit y (from the MSB) of A[i], so A[i] is the ncol-bit word of row d0 + i of the twist matrix.
+        // Emit cells (two per word when ncol = 2 mod, else one) as packed bytes.
+        const uint32_t mask = (1u << mod) - 1u;
+        if (a.ncol == 2 * mod) {
+          uint32_t *dst = reinterpret_cast<uint32_t *>(cw + 2 * d0);
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const uint32_t p0 = A[i], p1 = A[i + 1];
+            dst[i >> 1] = (p0 >> mod) | ((p0 & mask) << 8) | ((p1 >> mod) << 16) | ((p1 & mask) << 24);
+          }
+        }
+        else {
+          uint32_t *dst = reinterpret_cast<uint32_t *>(cw + d0);
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            dst[i >> 2] = (A[i] & mask) | ((A[i + 1] & mask) << 8) | ((A[i + 2] & mask) << 16) | ((A[i + 3] & mask) << 24);
+        }
       }
-      cw[c] = (uint8_t)v;
+    }
+    else {
+      for (int c = threadIdx.x; c < Nc; c += blockDim.x) {
+        const uint16_t *src = a.bit_src + c * mod;
+        uint32_t v = 0;
+        for (int b = 0; b < mod; b++) {
+          const int p = __ldg(src + b);
+          v = (v << 1) | ((u[p >> 5] >> (31 - (p & 31))) & 1u);
+        }
+        cw[c] = (uint8_t)v;
+      }
     }
     __syncthreads();
-    float2 *out = a.out + (long long)f * a.cell_size;
-    const int Nc = a.cell_size;
+    float2 *out = a.out + (long long)f * Nc;
     if (a.ci_inv) {
       // fused cell interleaver (chain mode): output position x holds cell ci_inv[(x - shift) mod Nc]
       const int shift = a.fec_shift[f % a.fecblocks];
@@ -375,7 +509,7 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map(const MapArgs a)
 void launch_map(const MapArgs &a, cudaStream_t s)
 {
   const int nwords = (a.nldpc + 31) / 32;
-  const size_t smem = (size_t)((nwords + 2) & ~1) * 4 + (size_t)(1 << a.mod) * 8 + ((a.cell_size + 15) & ~15);
+  const size_t smem = (size_t)((nwords + 3) & ~1) * 4 + (size_t)(1 << a.mod) * 8 + ((a.cell_size + 127) & ~63);
   int blocks = a.frames;
   const int cap = sm_count() * 16;
   if (blocks > cap) blocks = cap;

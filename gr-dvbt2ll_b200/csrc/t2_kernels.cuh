@@ -45,8 +45,13 @@ struct MapArgs {
   float2 *out;                         // frames * cell_size cells
   int frames;
   int nldpc, mod, cell_size, cyclic_delay;
-  const uint16_t *bit_src;   // nldpc
+  const uint16_t *bit_src;   // nldpc (generic path, used when ncol == 0: QPSK)
   const float2 *lut;         // 1 << mod
+  // QAM fast path: column-twist geometry; col_of_bit[p] = twist-matrix column feeding output bit p
+  // (p = 0 is the MSB of the ncol-bit demux word), twist_of_col[c] = start row of column c
+  int ncol;                  // 0 = use bit_src
+  uint8_t col_of_bit[16];
+  uint8_t twist_of_col[16];
   // optional fused cell interleaver (chain mode): out[(perm[c] + shift_r) % cell_size] = cell c of FEC block r
   const uint16_t *ci_inv;    // inverse of the cell permutation, or NULL for natural order
   const int32_t *fec_shift;  // [fecblocks] cyclic shift per FEC block of the T2 frame

@@ -103,6 +103,10 @@ struct MapPlan {
   std::vector<uint16_t> bit_src;      // [nldpc]
   std::vector<cfloat> lut;            // [1 << mod], rotated if rotation on (reference :169-253)
   int cyclic_delay;                   // 1: out[j] = (Re lut[c_j], Im lut[c_{j-1 mod cell_size}])
+  // column-twist geometry for the kernel's word-parallel path (0 columns for QPSK)
+  int ncol;
+  uint8_t col_of_bit[16];             // twist-matrix column feeding output bit p of the demux word (p = 0 MSB)
+  uint8_t twist_of_col[16];
 };
 bool build_map_plan(int framesize, int rate, int constellation, int rotation, MapPlan *p, std::string *err);
 

@@ -293,6 +293,9 @@ bool build_map_plan(int framesize, int rate, int constellation, int rotation, Ma
   p->cyclic_delay = rotation ? 1 : 0;
   const int N = f.nldpc, nbch = f.nbch, q = f.q;
   p->bit_src.assign(N, 0);
+  p->ncol = 0;
+  std::memset(p->col_of_bit, 0, sizeof(p->col_of_bit));
+  std::memset(p->twist_of_col, 0, sizeof(p->twist_of_col));
 
   if (constellation == MOD_QPSK) {
     // reference :289-314: parity interleaving only for short 1/3 and 2/5; otherwise cells are taken
@@ -330,6 +333,8 @@ bool build_map_plan(int framesize, int rate, int constellation, int rotation, Ma
       mux = (rate == C1_3) ? kDemux_256s_13 : (rate == C2_5) ? kDemux_256s_25 : kDemux_256s;
     }
     const int rows = N / ncol;
+    p->ncol = ncol;
+    for (int e = 0; e < ncol; e++) { p->col_of_bit[mux[e]] = (uint8_t)e; p->twist_of_col[e] = twist[e]; }
     // v[rows*c + (twist[c] + r) % rows] = u[rows*c + r]
     std::vector<int> vsrc(N);
     for (int c = 0; c < ncol; c++)
