@@ -264,13 +264,19 @@ void launch_bb_bch(const BbArgs &a, cudaStream_t s)
 // ================================================================================================
 constexpr int LDPC_WARPS = 4;
 
-__global__ void __launch_bounds__(LDPC_WARPS * 32) k_ldpc(const LdpcArgs a, int cw_words, int warp_words)
+// 32 stream bits starting at bit position p of a packed (byte stream) global buffer that is 4-byte aligned
+__device__ __forceinline__ uint32_t window32_global(const uint32_t *__restrict__ w, int p)
+{
+  const int k = p >> 5;
+  return __funnelshift_l(bswap32(__ldg(w + k + 1)), bswap32(__ldg(w + k)), p & 31);
+}
+
+__global__ void __launch_bounds__(LDPC_WARPS * 32) k_ldpc(const LdpcArgs a, int warp_words)
 {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint32_t *s_all = reinterpret_cast<uint32_t *>(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint32_t *cw = s_all + warp * warp_words;       // [cw_words]  codeword info part, big-endian words
-  uint32_t *ext = cw + cw_words;                  // [groups][13]
+  uint32_t *ext = s_all + warp * warp_words;      // [groups][13]
   uint32_t *rows = ext + a.groups * 13;           // [q][12]
   const int q = a.q, G = a.groups;
   const int info_bytes = a.nbch / 8;
@@ -278,28 +284,24 @@ __global__ void __launch_bounds__(LDPC_WARPS * 32) k_ldpc(const LdpcArgs a, int 
   for (int job = blockIdx.x * LDPC_WARPS + warp; job < a.frames; job += gridDim.x * LDPC_WARPS) {
     const uint8_t *in = a.in + (long long)job * a.in_pitch;
     uint8_t *out = a.out + (long long)job * a.out_pitch;
-    // ---- load info bits (and pass them through to the output)
+    const uint32_t *iw = reinterpret_cast<const uint32_t *>(in);
+    // ---- info bits pass through to the output
     {
-      const uint32_t *iw = reinterpret_cast<const uint32_t *>(in);
       uint32_t *ow = reinterpret_cast<uint32_t *>(out);
-      const int nw = (info_bytes + 3) >> 2;
-      for (int i = lane; i < nw; i += 32) {
-        const uint32_t v = iw[i];
-        cw[i] = bswap32(v);
-        if (4 * i + 4 <= info_bytes) ow[i] = v;
-        else for (int b = 4 * i; b < info_bytes; b++) out[b] = in[b];
-      }
-      for (int i = nw + lane; i < cw_words; i += 32) cw[i] = 0;
+      const int nw = info_bytes >> 2;
+      for (int i = lane; i < nw; i += 32) ow[i] = __ldg(iw + i);
+      for (int b = (nw << 2) + lane; b < info_bytes; b += 32) out[b] = in[b];
     }
-    __syncwarp();
     // ---- wrap-extended groups: 13 words = circular bits [0, 416) of each 360-bit group
+    // (windows are cut straight out of the packed codeword in global memory; bits past nbch never enter:
+    //  the last window of a group is masked / taken from the group's own start)
     for (int idx = lane; idx < G * 13; idx += 32) {
       const int g = idx / 13, w = idx - g * 13;
       const int base = 360 * g;
       uint32_t v;
-      if (w < 11) v = window32(cw, base + 32 * w);
-      else if (w == 11) v = (window32(cw, base + 352) & 0xFF000000u) | (window32(cw, base) >> 8);
-      else v = window32(cw, base + 24);
+      if (w < 11) v = window32_global(iw, base + 32 * w);
+      else if (w == 11) v = (window32_global(iw, base + 352) & 0xFF000000u) | (window32_global(iw, base) >> 8);
+      else v = window32_global(iw, base + 24);
       ext[idx] = v;
     }
     __syncwarp();
@@ -340,13 +342,14 @@ __global__ void __launch_bounds__(LDPC_WARPS * 32) k_ldpc(const LdpcArgs a, int 
       E = (x >> 1) ^ (carry ? 0xFFFFFFFFu : 0u);
       if (lane == 11) E &= 0xFF000000u;
     }
-    if (lane < 12)
-      for (int t = 0; t < q; t++) rows[t * 12 + lane] ^= E;
-    __syncwarp();
-    // ---- store parity rows: row t occupies bytes [nbch/8 + 45 t, +45)
-    for (int idx = lane; idx < q * 45; idx += 32) {
-      const int t = idx / 45, b = idx - t * 45;
-      out[info_bytes + idx] = (uint8_t)(rows[t * 12 + (b >> 2)] >> (24 - 8 * (b & 3)));
+    // ---- store parity rows (row t occupies bytes [nbch/8 + 45 t, +45)), applying E on the fly
+    for (int i0 = 0; i0 < q * 45; i0 += 32) {          // warp-uniform trip count (shuffle inside)
+      const int idx = i0 + lane;
+      const bool on = idx < q * 45;
+      const int t = on ? idx / 45 : 0, b = on ? idx - t * 45 : 0;
+      const int w = b >> 2;
+      const uint32_t ew = __shfl_sync(0xffffffffu, E, w);
+      if (on) out[info_bytes + idx] = (uint8_t)((rows[t * 12 + w] ^ ew) >> (24 - 8 * (b & 3)));
     }
     __syncwarp();
   }
@@ -354,16 +357,18 @@ __global__ void __launch_bounds__(LDPC_WARPS * 32) k_ldpc(const LdpcArgs a, int 
 
 void launch_ldpc(const LdpcArgs &a, cudaStream_t s)
 {
-  const int cw_words = ((a.nbch + 31) / 32 + 2 + 3) & ~3;
-  const int warp_words = cw_words + a.groups * 13 + a.q * 12 + 4;
+  const int warp_words = a.groups * 13 + a.q * 12 + 4;
   const size_t smem = (size_t)LDPC_WARPS * warp_words * 4;
-  int blocks = (a.frames + LDPC_WARPS - 1) / LDPC_WARPS;
-  const int cap = sm_count() * 8;
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) return;
+  if (a.frames < 1) return;
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(k_ldpc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
-  k_ldpc<<<blocks, LDPC_WARPS * 32, smem, s>>>(a, cw_words, warp_words);
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ldpc, LDPC_WARPS * 32, smem);
+  if (per_sm < 1) per_sm = 1;
+  int blocks = (a.frames + LDPC_WARPS - 1) / LDPC_WARPS;
+  const int cap = sm_count() * per_sm;
+  if (blocks > cap) blocks = cap;
+  k_ldpc<<<blocks, LDPC_WARPS * 32, smem, s>>>(a, warp_words);
   count_launch();
 }
 
@@ -455,7 +460,7 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map(const MapArgs a)
         // Emit cells (two per word when ncol = 2 mod, else one) as packed bytes.
         const uint32_t mask = (1u << mod) - 1u;
         if (a.ncol == 2 * mod) {
-          uint32_t *dst = reinterpret_cast<uint32_t *>(cw + 2 * d0);
+          uint32_t *dst = reinterpret_cast<uint32_t *>(cw + 2 * d0 + 4 * g);      // 64 cells + 1 pad word per thread
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
             const uint32_t p0 = A[i], p1 = A[i + 1];
@@ -463,7 +468,7 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map(const MapArgs a)
           }
         }
         else {
-          uint32_t *dst = reinterpret_cast<uint32_t *>(cw + d0);
+          uint32_t *dst = reinterpret_cast<uint32_t *>(cw + d0 + 4 * (g >> 1));   // 32 cells per thread, pad per 64
 #pragma unroll
           for (int i = 0; i < 32; i += 4)
             dst[i >> 2] = (A[i] & mask) | ((A[i + 1] & mask) << 8) | ((A[i + 2] & mask) << 16) | ((A[i + 3] & mask) << 24);
@@ -478,10 +483,11 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map(const MapArgs a)
           const int p = __ldg(src + b);
           v = (v << 1) | ((u[p >> 5] >> (31 - (p & 31))) & 1u);
         }
-        cw[c] = (uint8_t)v;
+        cw[c + ((c >> 6) << 2)] = (uint8_t)v;
       }
     }
     __syncthreads();
+    auto cell = [&](int c) -> int { return cw[c + ((c >> 6) << 2)]; };     // padded layout, see above
     float2 *out = a.out + (long long)f * Nc;
     if (a.ci_inv) {
       // fused cell interleaver (chain mode): output position x holds cell ci_inv[(x - shift) mod Nc]
@@ -491,17 +497,17 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map(const MapArgs a)
         if (y < 0) y += Nc;
         const int c = __ldg(a.ci_inv + y);
         const int pc = c == 0 ? Nc - 1 : c - 1;
-        out[xo] = make_float2(lut[cw[c]].x, lut[cw[a.cyclic_delay ? pc : c]].y);
+        out[xo] = make_float2(lut[cell(c)].x, lut[cell(a.cyclic_delay ? pc : c)].y);
       }
     }
     else if (a.cyclic_delay) {
       for (int c = threadIdx.x; c < Nc; c += blockDim.x) {
         const int pc = c == 0 ? Nc - 1 : c - 1;
-        out[c] = make_float2(lut[cw[c]].x, lut[cw[pc]].y);
+        out[c] = make_float2(lut[cell(c)].x, lut[cell(pc)].y);
       }
     }
     else {
-      for (int c = threadIdx.x; c < Nc; c += blockDim.x) out[c] = lut[cw[c]];
+      for (int c = threadIdx.x; c < Nc; c += blockDim.x) out[c] = lut[cell(c)];
     }
   }
 }
@@ -509,7 +515,7 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map(const MapArgs a)
 void launch_map(const MapArgs &a, cudaStream_t s)
 {
   const int nwords = (a.nldpc + 31) / 32;
-  const size_t smem = (size_t)((nwords + 3) & ~1) * 4 + (size_t)(1 << a.mod) * 8 + ((a.cell_size + 127) & ~63);
+  const size_t smem = (size_t)((nwords + 3) & ~1) * 4 + (size_t)(1 << a.mod) * 8 + ((a.cell_size + 127) & ~63) + 4 * (a.cell_size / 64 + 2);
   int blocks = a.frames;
   const int cap = sm_count() * 16;
   if (blocks > cap) blocks = cap;
@@ -765,7 +771,7 @@ int ofdm_position_of_bin(int m, int log2_m)
 constexpr int OFDM_FILL_UNROLL = 8;
 
 template <int LOG2M>
-__global__ void __launch_bounds__(512) k_ofdm(const OfdmArgs a)
+__global__ void __launch_bounds__(1024) k_ofdm(const OfdmArgs a)
 {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   float2 *x = reinterpret_cast<float2 *>(smem_raw);
@@ -837,14 +843,26 @@ __global__ void __launch_bounds__(512) k_ofdm(const OfdmArgs a)
         }
       }
       else {
-        for (int t = threadIdx.x; t < M; t += blockDim.x) {
-          float2 v = cmul(x[swz(t)], __ldg(a.tw_split + t));
-          v.x *= a.norm; v.y *= a.norm;
-          const float2 e = sym[a.gi + t];
-          sym[a.gi + t] = cadd(e, v);
-          const float2 hi = csub(e, v);
-          sym[a.gi + t + M] = hi;
-          if (t + M >= cp_from) sym[t + M - cp_from] = hi;
+        // odd-bin half: out[n] = E[n] + W_N^n O[n], out[n + N/2] = E[n] - W_N^n O[n]; loads batched 4 deep
+        for (int t0 = threadIdx.x; t0 < M; t0 += 4 * blockDim.x) {
+          float2 e[4], w[4];
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const int t = t0 + u * blockDim.x;
+            if (t < M) { e[u] = sym[a.gi + t]; w[u] = __ldg(a.tw_split + t); }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const int t = t0 + u * blockDim.x;
+            if (t < M) {
+              float2 v = cmul(x[swz(t)], w[u]);
+              v.x *= a.norm; v.y *= a.norm;
+              sym[a.gi + t] = cadd(e[u], v);
+              const float2 hi = csub(e[u], v);
+              sym[a.gi + t + M] = hi;
+              if (t + M >= cp_from) sym[t + M - cp_from] = hi;
+            }
+          }
         }
       }
     }
@@ -871,7 +889,7 @@ void launch_ofdm(const OfdmArgs &a, cudaStream_t s)
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr[a.log2_m] = true;
   }
-  int threads = M >= 8192 ? 512 : 256;
+  int threads = M >= 16384 ? 1024 : M >= 8192 ? 512 : 256;
   // resident CTAs per SM limited by shared memory (227 KB usable)
   int per_sm = (int)((227 * 1024) / (smem + 1024));
   if (per_sm < 1) per_sm = 1;

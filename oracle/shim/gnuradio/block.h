@@ -1,7 +1,7 @@
 /*
  * TEST INFRASTRUCTURE ONLY -- minimal stand-in for the GNU Radio 3.7 runtime
  * headers, just large enough to compile the UNMODIFIED reference sources
- * (/root/reference/lib/*_impl.cc) into oracle/_ref/ without GNU Radio, Boost,
+ * (/root/reference/lib/<block>_impl.cc) into oracle/_ref/ without GNU Radio, Boost,
  * FFTW or VOLK.  Nothing under oracle/ is linked into the product library.
  *
  * What the reference uses from <gnuradio/block.h> (see e.g.
