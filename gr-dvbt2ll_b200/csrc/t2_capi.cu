@@ -5,6 +5,7 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -372,9 +373,22 @@ struct FrameHandle : dvbt2ll_handle {
 struct OfdmDevice {
   DevBuf d_code, d_pool, d_p1, d_sinc, d_tw, d_tw_split;
   int log2_m, split;
+  long long pool_stride;
   int init(const std::vector<int32_t> &code, const t2::CellPool &pool, const t2::OfdmPlan &op)
   {
-    CK(upload(d_pool, pool.cells));
+    // one copy of the pool per L1-post variant: in copy v the L1-post slot holds variant v, so the kernel
+    // selects a pool base per frame instead of patching indices per cell
+    {
+      const int nv = pool.l1post_variants > 0 ? pool.l1post_variants : 1;
+      pool_stride = (long long)pool.cells.size();
+      std::vector<t2::cfloat> rep((size_t)nv * pool.cells.size());
+      for (int v = 0; v < nv; v++) {
+        std::copy(pool.cells.begin(), pool.cells.end(), rep.begin() + (size_t)v * pool.cells.size());
+        for (int i = 0; i < pool.l1post_cells; i++)
+          rep[(size_t)v * pool.cells.size() + pool.l1post_base + i] = pool.cells[pool.l1post_base + (size_t)v * pool.l1post_cells + i];
+      }
+      CK(upload(d_pool, rep));
+    }
     CK(upload(d_p1, op.p1));
     const int N = op.dims.fft_n;
     split = N > 16384 ? 2 : 1;
@@ -408,7 +422,7 @@ struct OfdmDevice {
   }
   void fill(t2k::OfdmArgs &a, const t2::OfdmPlan &op, const t2::CellPool &pool) const
   {
-    a.code_pos = d_code.as<int32_t>(); a.pool = d_pool.as<float2>();
+    a.code_pos = d_code.as<int32_t>(); a.pool = d_pool.as<float2>(); a.pool_stride = pool_stride;
     a.l1post_base = pool.l1post_base; a.l1post_cells = pool.l1post_cells; a.l1post_variants = pool.l1post_variants;
     a.p1 = d_p1.as<float2>(); a.sinc_pos = op.inv_sinc.empty() ? 0 : d_sinc.as<float>();
     a.tw = d_tw.as<float2>(); a.tw_split = split == 2 ? d_tw_split.as<float2>() : 0;

@@ -708,48 +708,60 @@ __host__ __device__ constexpr int bitrev_c(int k, int r)
   return out;
 }
 
-// one in-place DIT pass of radix R over M points; NPREV = length of the already transformed sub-blocks
-template <int R, int M, int NPREV>
-__device__ __forceinline__ void fft_pass(float2 *x, const float2 *__restrict__ tw)
+// twiddles W_{n}^{i q}, q = 1..R-1: w1 from the table, powers by a short product tree; applied to v
+template <int R>
+__device__ __forceinline__ void apply_twiddles(float2 (&v)[R], float2 w1)
 {
-  constexpr int NB = M / R;
-  constexpr int TW_STEP = M / (NPREV * R);
-  for (int u = threadIdx.x; u < NB; u += blockDim.x) {
+  float2 w[R];
+  w[1] = w1;
+#pragma unroll
+  for (int qd = 2; qd < R; qd++) w[qd] = (qd & 1) ? cmul(w[qd - 1], w[1]) : cmul(w[qd >> 1], w[qd >> 1]);
+#pragma unroll
+  for (int qd = 1; qd < R; qd++) v[qd] = cmul(v[qd], w[qd]);
+}
+
+// one in-place DIT pass of radix 16 over M points; NPREV = length of the already transformed sub-blocks
+template <int M, int NPREV, int T>
+__device__ __forceinline__ void fft_pass16(float2 *x, const float2 *__restrict__ tw)
+{
+  constexpr int NB = M / 16;
+  constexpr int TW_STEP = M / (NPREV * 16);
+#pragma unroll 1
+  for (int u = threadIdx.x; u < NB; u += T) {
     const int i = u & (NPREV - 1);
-    const int sb = swz((u - i) * R + i);
-    float2 v[R];
+    const int sb = swz((u - i) * 16 + i);
+    const float2 w1 = __ldg(tw + i * TW_STEP);
+    float2 v[16];
 #pragma unroll
-    for (int qd = 0; qd < R; qd++) v[qd] = x[sb ^ swz(qd * NPREV)];
-    if (NPREV > 1) {
-      // twiddles W_{n}^{i q}: w1 from the table, powers by a short product tree
-      float2 w[R];
-      w[1] = __ldg(tw + i * TW_STEP);
+    for (int qd = 0; qd < 16; qd++) v[qd] = x[sb ^ swz(qd * NPREV)];
+    apply_twiddles<16>(v, w1);
+    dft_reg<16>(v);
 #pragma unroll
-      for (int qd = 2; qd < R; qd++) w[qd] = (qd & 1) ? cmul(w[qd - 1], w[1]) : cmul(w[qd >> 1], w[qd >> 1]);
-#pragma unroll
-      for (int qd = 1; qd < R; qd++) v[qd] = cmul(v[qd], w[qd]);
-    }
-    dft_reg<R>(v);
-#pragma unroll
-    for (int k = 0; k < R; k++) x[sb ^ swz(k * NPREV)] = v[bitrev_c(k, R)];
+    for (int k = 0; k < 16; k++) x[sb ^ swz(k * NPREV)] = v[bitrev_c(k, 16)];
   }
 }
 
-// pass schedule: the first pass takes the remainder (LOG2M mod 4 bits), the others are radix 16
-template <int LOG2M>
-__device__ __forceinline__ void fft_inplace(float2 *x, const float2 *__restrict__ tw)
+// exp(+j 2 pi k / 32), k compile-time after unrolling
+__device__ __forceinline__ float2 w32(int k)
 {
-  constexpr int M = 1 << LOG2M;
-  constexpr int F = LOG2M & 3;          // log2 of the first radix (0 = none)
-  if (F == 1) fft_pass<2, M, 1>(x, tw);
-  if (F == 2) fft_pass<4, M, 1>(x, tw);
-  if (F == 3) fft_pass<8, M, 1>(x, tw);
-  if (F) __syncthreads();
-  constexpr int N0 = 1 << F;
-  fft_pass<16, M, N0>(x, tw);
-  __syncthreads();
-  if (LOG2M - F >= 8) { fft_pass<16, M, (N0 << 4 < M ? N0 << 4 : 1)>(x, tw); __syncthreads(); }
-  if (LOG2M - F >= 12) { fft_pass<16, M, (N0 << 8 < M ? N0 << 8 : 1)>(x, tw); __syncthreads(); }
+  switch (k) {
+    case 0: return make_float2(1.f, 0.f);
+    case 1: return make_float2(0.98078528040323043f, 0.19509032201612825f);
+    case 2: return make_float2(0.92387953251128674f, 0.38268343236508978f);
+    case 3: return make_float2(0.83146961230254524f, 0.55557023301960218f);
+    case 4: return make_float2(0.70710678118654757f, 0.70710678118654746f);
+    case 5: return make_float2(0.55557023301960229f, 0.83146961230254524f);
+    case 6: return make_float2(0.38268343236508984f, 0.92387953251128674f);
+    case 7: return make_float2(0.19509032201612833f, 0.98078528040323043f);
+    case 8: return make_float2(0.f, 1.f);
+    case 9: return make_float2(-0.19509032201612819f, 0.98078528040323043f);
+    case 10: return make_float2(-0.38268343236508973f, 0.92387953251128674f);
+    case 11: return make_float2(-0.55557023301960196f, 0.83146961230254546f);
+    case 12: return make_float2(-0.70710678118654746f, 0.70710678118654757f);
+    case 13: return make_float2(-0.83146961230254535f, 0.55557023301960218f);
+    case 14: return make_float2(-0.92387953251128674f, 0.38268343236508989f);
+    default: return make_float2(-0.98078528040323043f, 0.19509032201612861f);
+  }
 }
 
 int ofdm_position_of_bin(int m, int log2_m)
@@ -768,97 +780,129 @@ int ofdm_position_of_bin(int m, int log2_m)
   return p;
 }
 
-constexpr int OFDM_FILL_UNROLL = 8;
-
-template <int LOG2M>
-__global__ void __launch_bounds__(1024) k_ofdm(const OfdmArgs a)
+// Kernel schedule per (symbol, phase), M = 2^LOG2M points, first radix R0 = 2^(LOG2M mod 4):
+//   1. fill fused with the first pass: a thread gathers the R0 consecutive positions of a first-pass
+//      butterfly (code table read as one vector), does the R0-point DFT in registers, stores to smem;
+//   2. the middle radix-16 passes in shared memory;
+//   3. the last radix-16 pass fused with the output: butterfly i produces samples i + k M/16, which go
+//      (scaled) straight to global memory -- coalesced over i -- including the cyclic prefix and, for
+//      the odd-bin half of a 32K symbol, the in-place recombination with the even-bin half.
+template <int LOG2M, int T>
+__global__ void __launch_bounds__(T, 1024 / T) k_ofdm(const OfdmArgs a)
 {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   float2 *x = reinterpret_cast<float2 *>(smem_raw);
   constexpr int M = 1 << LOG2M;
+  constexpr int F = LOG2M & 3;
+  constexpr int R0 = 1 << F;                 // first radix (1 = no first pass)
+  constexpr int GROUPS = M / R0;             // first-pass butterflies
+  constexpr int GPB = R0 >= 8 ? 1 : 8 / R0;  // groups gathered per batch (8 positions in flight)
+  constexpr int NLAST = M / 16;              // NPREV of the last radix-16 pass
   const int N = a.fft_n;
   const int units = a.frames * a.num_symbols;
+  const int cp_from = N - a.gi;
 
   for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
     const int f = unit / a.num_symbols, l = unit - f * a.num_symbols;
     const int variant = (int)((a.frame_idx0 + (f % a.frames_per_channel)) % a.l1post_variants);
     const float2 *cells = a.cells + (long long)f * a.cells_stride;
-    const int l1_lo = a.l1post_base, l1_n = a.l1post_cells, l1_add = variant * a.l1post_cells;
+    const float2 *pool = a.pool + (long long)variant * a.pool_stride;
     float2 *out = a.out + (long long)f * a.out_stride;
     float2 *sym = out + 2048 + (long long)l * (N + a.gi);
 
     if (l == 0)
-      for (int i = threadIdx.x; i < 2048; i += blockDim.x) out[i] = __ldg(a.p1 + i);
+      for (int i = threadIdx.x; i < 2048; i += T) out[i] = __ldg(a.p1 + i);
 
     for (int phase = 0; phase < a.split; phase++) {
       const int32_t *code = a.code_pos + ((long long)l * a.split + phase) * M;
       const float *sinc = a.sinc_pos ? a.sinc_pos + (long long)phase * M : nullptr;
       __syncthreads();
-      // ---- carrier fill: position q of the sub-transform (table is in position order)
-      for (int q0 = threadIdx.x; q0 < M; q0 += blockDim.x * OFDM_FILL_UNROLL) {
-        int c[OFDM_FILL_UNROLL];
-        const float2 *src[OFDM_FILL_UNROLL];
-        float2 v[OFDM_FILL_UNROLL];
+      // ---- 1. carrier fill (+ first pass)
+#pragma unroll 1
+      for (int g0 = threadIdx.x; g0 < GROUPS; g0 += T * GPB) {
+        int c[GPB][R0];
+        float2 v[GPB][R0];
 #pragma unroll
-        for (int u = 0; u < OFDM_FILL_UNROLL; u++) {
-          const int q = q0 + u * blockDim.x;
-          c[u] = q < M ? __ldg(code + q) : -1;
+        for (int b = 0; b < GPB; b++) {
+          const int g = g0 + b * T;
+#pragma unroll
+          for (int r = 0; r < R0; r++) c[b][r] = g < GROUPS ? __ldg(code + g * R0 + r) : -1;
         }
 #pragma unroll
-        for (int u = 0; u < OFDM_FILL_UNROLL; u++) {
-          int idx = -(c[u] + 1);
-          if ((unsigned)(idx - l1_lo) < (unsigned)l1_n) idx += l1_add;
-          src[u] = c[u] >= 0 ? cells + c[u] : a.pool + idx;
-        }
+        for (int b = 0; b < GPB; b++)
 #pragma unroll
-        for (int u = 0; u < OFDM_FILL_UNROLL; u++) v[u] = __ldg(src[u]);
+          for (int r = 0; r < R0; r++) {
+            const int cc = c[b][r];
+            const float2 *base = cc >= 0 ? cells : pool;
+            v[b][r] = __ldg(base + (cc >= 0 ? cc : ~cc));
+          }
 #pragma unroll
-        for (int u = 0; u < OFDM_FILL_UNROLL; u++) {
-          const int q = q0 + u * blockDim.x;
-          if (q < M) {
-            if (sinc) { const float g = __ldg(sinc + q); v[u].x *= g; v[u].y *= g; }
-            x[swz(q)] = v[u];
+        for (int b = 0; b < GPB; b++) {
+          const int g = g0 + b * T;
+          if (g < GROUPS) {
+            if (sinc) {
+#pragma unroll
+              for (int r = 0; r < R0; r++) { const float s = __ldg(sinc + g * R0 + r); v[b][r].x *= s; v[b][r].y *= s; }
+            }
+            if (R0 > 1) dft_reg<R0>(v[b]);
+            const int sb = swz(g * R0);
+#pragma unroll
+            for (int k = 0; k < R0; k++) x[sb ^ swz(k)] = v[b][bitrev_c(k, R0)];
           }
         }
       }
       __syncthreads();
-      fft_inplace<LOG2M>(x, a.tw);
-      // ---- scale, store symbol and cyclic prefix
-      const int cp_from = N - a.gi;
-      if (a.split == 1) {
-        for (int t = threadIdx.x; t < M; t += blockDim.x) {
-          float2 v = x[swz(t)];
-          v.x *= a.norm; v.y *= a.norm;
-          sym[a.gi + t] = v;
-          if (t >= cp_from) sym[t - cp_from] = v;
-        }
-      }
-      else if (phase == 0) {
-        for (int t = threadIdx.x; t < M; t += blockDim.x) {
-          float2 v = x[swz(t)];
-          v.x *= a.norm; v.y *= a.norm;
-          sym[a.gi + t] = v;
-          sym[a.gi + t + M] = v;
-          if (t + M >= cp_from) sym[t + M - cp_from] = v;
-        }
-      }
-      else {
-        // odd-bin half: out[n] = E[n] + W_N^n O[n], out[n + N/2] = E[n] - W_N^n O[n]; loads batched 4 deep
-        for (int t0 = threadIdx.x; t0 < M; t0 += 4 * blockDim.x) {
-          float2 e[4], w[4];
+      // ---- 2. middle radix-16 passes
+      if (R0 * 16 < NLAST * 16 && R0 < NLAST) { fft_pass16<M, R0, T>(x, a.tw); __syncthreads(); }
+      if (R0 * 16 < NLAST) { fft_pass16<M, (R0 * 16 < NLAST ? R0 * 16 : 1), T>(x, a.tw); __syncthreads(); }
+      // ---- 3. last radix-16 pass fused with scale + store (+ cyclic prefix, + 32K recombination)
+#pragma unroll 1
+      for (int i = threadIdx.x; i < NLAST; i += T) {
+        const int sb = swz(i);
+        const float2 w1 = __ldg(a.tw + i);      // TW_STEP = M / (NLAST * 16) = 1
+        float2 v[16];
 #pragma unroll
-          for (int u = 0; u < 4; u++) {
-            const int t = t0 + u * blockDim.x;
-            if (t < M) { e[u] = sym[a.gi + t]; w[u] = __ldg(a.tw_split + t); }
+        for (int qd = 0; qd < 16; qd++) v[qd] = x[sb ^ swz(qd * NLAST)];
+        apply_twiddles<16>(v, w1);
+        dft_reg<16>(v);
+        if (a.split == 1) {
+#pragma unroll
+          for (int k = 0; k < 16; k++) {
+            float2 o = v[bitrev_c(k, 16)];
+            o.x *= a.norm; o.y *= a.norm;
+            const int t = i + k * NLAST;
+            sym[a.gi + t] = o;
+            if (t >= cp_from) sym[t - cp_from] = o;
           }
+        }
+        else if (phase == 0) {
 #pragma unroll
-          for (int u = 0; u < 4; u++) {
-            const int t = t0 + u * blockDim.x;
-            if (t < M) {
-              float2 v = cmul(x[swz(t)], w[u]);
-              v.x *= a.norm; v.y *= a.norm;
-              sym[a.gi + t] = cadd(e[u], v);
-              const float2 hi = csub(e[u], v);
+          for (int k = 0; k < 16; k++) {
+            float2 o = v[bitrev_c(k, 16)];
+            o.x *= a.norm; o.y *= a.norm;
+            const int t = i + k * NLAST;
+            sym[a.gi + t] = o;
+            sym[a.gi + t + M] = o;
+            if (t + M >= cp_from) sym[t + M - cp_from] = o;
+          }
+        }
+        else {
+          // odd-bin half: out[n] = E[n] + W_N^n O[n], out[n + N/2] = E[n] - W_N^n O[n], n = i + k M/16,
+          // W_N^n = W_N^i * exp(j 2 pi k / 32); E is re-read in two batches of 8
+          float2 wi = __ldg(a.tw_split + i);
+          wi.x *= a.norm; wi.y *= a.norm;
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            float2 e[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) e[k] = sym[a.gi + i + (8 * h + k) * NLAST];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+              const int kk = 8 * h + k;
+              const int t = i + kk * NLAST;
+              const float2 o = cmul(cmul(v[bitrev_c(kk, 16)], w32(kk)), wi);
+              sym[a.gi + t] = cadd(e[k], o);
+              const float2 hi = csub(e[k], o);
               sym[a.gi + t + M] = hi;
               if (t + M >= cp_from) sym[t + M - cp_from] = hi;
             }
@@ -869,35 +913,37 @@ __global__ void __launch_bounds__(1024) k_ofdm(const OfdmArgs a)
   }
 }
 
-void launch_ofdm(const OfdmArgs &a, cudaStream_t s)
+template <int LOG2M, int T>
+static void launch_ofdm_t(const OfdmArgs &a, cudaStream_t s)
 {
-  const int M = 1 << a.log2_m;
+  constexpr int M = 1 << LOG2M;
   const size_t smem = (size_t)M * sizeof(float2);
   const int units = a.frames * a.num_symbols;
-  if (units < 1) return;
-  void (*kern)(const OfdmArgs) = nullptr;
-  switch (a.log2_m) {
-    case 10: kern = k_ofdm<10>; break;
-    case 11: kern = k_ofdm<11>; break;
-    case 12: kern = k_ofdm<12>; break;
-    case 13: kern = k_ofdm<13>; break;
-    case 14: kern = k_ofdm<14>; break;
-    default: return;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(k_ofdm<LOG2M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr = true;
   }
-  static bool attr[16] = { false };
-  if (!attr[a.log2_m]) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr[a.log2_m] = true;
-  }
-  int threads = M >= 16384 ? 1024 : M >= 8192 ? 512 : 256;
-  // resident CTAs per SM limited by shared memory (227 KB usable)
-  int per_sm = (int)((227 * 1024) / (smem + 1024));
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ofdm<LOG2M, T>, T, smem);
   if (per_sm < 1) per_sm = 1;
-  if (per_sm > 2048 / threads) per_sm = 2048 / threads;
   int blocks = sm_count() * per_sm;
   if (blocks > units) blocks = units;
-  kern<<<blocks, threads, smem, s>>>(a);
+  k_ofdm<LOG2M, T><<<blocks, T, smem, s>>>(a);
   count_launch();
+}
+
+void launch_ofdm(const OfdmArgs &a, cudaStream_t s)
+{
+  if (a.frames * a.num_symbols < 1) return;
+  switch (a.log2_m) {
+    case 10: launch_ofdm_t<10, 256>(a, s); break;
+    case 11: launch_ofdm_t<11, 256>(a, s); break;
+    case 12: launch_ofdm_t<12, 256>(a, s); break;
+    case 13: launch_ofdm_t<13, 512>(a, s); break;
+    case 14: launch_ofdm_t<14, 1024>(a, s); break;
+    default: break;
+  }
 }
 
 } // namespace t2k

@@ -87,7 +87,8 @@ struct OfdmArgs {
   const float2 *cells; long long cells_stride;   // per T2 frame
   float2 *out;         long long out_stride;     // samples per T2 frame
   const int32_t *code_pos;   // [num_symbols][split][M] carrier codes in shared-memory POSITION order
-  const float2 *pool;
+  const float2 *pool;        // special cells, one copy per L1-post variant (copy v holds the L1-post cells of frame index v)
+  long long pool_stride;     // cells per copy
   int l1post_base, l1post_cells, l1post_variants;
   const float2 *p1;          // 2048
   const float *sinc_pos;     // [split][M] inverse-sinc factors in position order, or NULL
