@@ -284,7 +284,7 @@ struct MapHandle : dvbt2ll_handle {
     a.in = in; a.in_pitch = in_pitch; a.out = out; a.frames = frames;
     a.nldpc = plan.fec.nldpc; a.mod = plan.mod; a.cell_size = plan.cell_size; a.cyclic_delay = plan.cyclic_delay;
     a.bit_src = d_bitsrc.as<uint16_t>(); a.lut = d_lut.as<float2>();
-    a.ci_inv = 0; a.fec_shift = 0; a.fecblocks = 1;
+    a.ci_inv = 0; a.fec_shift = 0; a.fecblocks = 1; a.out16 = 0;
     a.ncol = plan.ncol;
     std::memcpy(a.col_of_bit, plan.col_of_bit, 16);
     std::memcpy(a.twist_of_col, plan.twist_of_col, 16);
@@ -429,6 +429,7 @@ struct OfdmDevice {
     a.fft_n = op.dims.fft_n; a.log2_m = log2_m; a.split = split;
     a.c_ps = op.dims.c_ps; a.left_nulls = op.left_nulls; a.gi = op.dims.gi; a.num_symbols = op.dims.num_symbols;
     a.norm = op.normalization;
+    a.cells16 = 0; a.runs = 0; a.run_ptr = 0; a.stage_cap = 0; a.lut = 0; a.lut_n = 0;
   }
 };
 
@@ -484,9 +485,10 @@ struct ChainHandle : dvbt2ll_handle {
   MapHandle map;
   t2::FramePlan fplan;
   t2::OfdmPlan oplan;
-  t2::ChainTables tables;
+  t2::Chain16Tables tables;
   OfdmDevice odev;
-  DevBuf d_bch, d_fec, d_cells, d_ts_stage, d_out_stage, d_ci_inv, d_fec_shift;
+  DevBuf d_bch, d_fec, d_cells, d_ts_stage, d_out_stage, d_ci_inv, d_fec_shift, d_runs, d_run_ptr;
+  int stage_cap;
   int max_frames, device;
   int last_frames;
   bool timing;
@@ -513,10 +515,13 @@ struct ChainHandle : dvbt2ll_handle {
     if ((r = odev.init(tables.code, tables.pool, oplan))) return r;
     CK(upload(d_ci_inv, fplan.cell_perm_inv));
     CK(upload(d_fec_shift, fplan.fec_shift));
+    CK(upload(d_runs, tables.runs));
+    CK(upload(d_run_ptr, tables.run_ptr));
+    stage_cap = (tables.max_slots + 7) & ~7;
     const size_t nfec = (size_t)max_frames * F();
     CK(d_bch.ensure(nfec * align16(bb.plan.fec.nbch / 8) + 64));
     CK(d_fec.ensure(nfec * align16(bb.plan.fec.nldpc / 8) + 64));
-    CK(d_cells.ensure(nfec * map.plan.cell_size * sizeof(float2)));
+    CK(d_cells.ensure(nfec * map.plan.cell_size * sizeof(uint16_t) + 64));   // 16-bit cell codes
     for (int i = 0; i < 5; i++) CK(cudaEventCreate(&ev[i]));
     return 0;
   }
@@ -546,13 +551,16 @@ struct ChainHandle : dvbt2ll_handle {
     t2k::launch_ldpc(la, s);
     if (timing) cudaEventRecord(ev[2], s);
     t2k::MapArgs ma;
-    map.fill_args(ma, d_fec.as<uint8_t>(), fp, d_cells.as<float2>(), nfec);
-    ma.ci_inv = d_ci_inv.as<uint16_t>(); ma.fec_shift = d_fec_shift.as<int32_t>(); ma.fecblocks = F();   // fused cell interleaver
+    map.fill_args(ma, d_fec.as<uint8_t>(), fp, 0, nfec);
+    ma.out16 = d_cells.as<uint16_t>();                                                                    // 16-bit cell codes,
+    ma.ci_inv = d_ci_inv.as<uint16_t>(); ma.fec_shift = d_fec_shift.as<int32_t>(); ma.fecblocks = F();   // cell-interleaved
     t2k::launch_map(ma, s);
     if (timing) cudaEventRecord(ev[3], s);
     t2k::OfdmArgs oa;
     odev.fill(oa, oplan, tables.pool);
-    oa.cells = d_cells.as<float2>(); oa.cells_stride = (long long)F() * map.plan.cell_size;
+    oa.cells = 0; oa.cells_stride = (long long)F() * map.plan.cell_size;
+    oa.cells16 = d_cells.as<uint16_t>(); oa.runs = d_runs.p; oa.run_ptr = d_run_ptr.as<int32_t>(); oa.stage_cap = stage_cap;
+    oa.lut = map.d_lut.as<float2>(); oa.lut_n = 1 << map.plan.mod;
     oa.out = (float2 *)d_out; oa.out_stride = oplan.samples_per_frame;
     oa.frames = frames; oa.frame_idx0 = first_frame; oa.frames_per_channel = n_frames;
     t2k::launch_ofdm(oa, s);
@@ -577,6 +585,11 @@ struct ChainHandle : dvbt2ll_handle {
     std::string n(name);
     if (n == "chain.code") return copy_vec(tables.code, out, cap);
     if (n == "chain.pool") return copy_vec(tables.pool.cells, out, cap);
+    if (n == "chain.runs") return copy_vec(tables.runs, out, cap);
+    if (n == "chain.run_ptr") return copy_vec(tables.run_ptr, out, cap);
+    if (n == "ofdm.sym_data_start") return copy_vec(oplan.sym_data_start, out, cap);
+    if (n == "frame.framed") return copy_vec(fplan.framed, out, cap);
+    if (n == "frame.fi_src") return copy_vec(fplan.fi_src, out, cap);
     long long r;
     if ((r = bb.plan_get(name, out, cap)) >= 0) return r;
     if ((r = ldpc.plan_get(name, out, cap)) >= 0) return r;
@@ -751,7 +764,7 @@ dvbt2ll_handle *dvbt2ll_chain_create(const dvbt2ll_chain_params *c, int max_fram
   ok = ok && t2::build_map_plan(c->framesize, c->rate, c->constellation, c->rotation, &h->map.plan, &err);
   ok = ok && t2::build_frame_plan(fp, &h->fplan, &err);
   ok = ok && t2::build_ofdm_plan(op, &h->oplan, &err);
-  ok = ok && t2::compose_chain(h->fplan, h->oplan, true, &h->tables, &err);
+  ok = ok && t2::compose_chain16(h->fplan, h->oplan, &h->tables, &err);
   if (!ok) { delete h; fail(DVBT2LL_ERR_INVALID, err); return 0; }
   return h;
 }
@@ -812,7 +825,7 @@ long long dvbt2ll_chain_tap(dvbt2ll_handle *h, const char *stage, void *out, lon
   std::string n(stage);
   if (n == "bch") { src = c->d_bch.p; bytes = nfec * align16(c->bb.plan.fec.nbch / 8); }
   else if (n == "fec") { src = c->d_fec.p; bytes = nfec * align16(c->bb.plan.fec.nldpc / 8); }
-  else if (n == "cells") { src = c->d_cells.p; bytes = nfec * c->map.plan.cell_size * sizeof(float2); }
+  else if (n == "cells") { src = c->d_cells.p; bytes = nfec * c->map.plan.cell_size * sizeof(uint16_t); }
   else return fail(DVBT2LL_ERR_INVALID, "chain: unknown tap");
   CK(cudaStreamSynchronize(c->stream));
   CK(cudaDeviceSynchronize());

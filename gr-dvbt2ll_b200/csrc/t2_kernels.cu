@@ -489,8 +489,21 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map(const MapArgs a)
     __syncthreads();
     auto cell = [&](int c) -> int { return cw[c + ((c >> 6) << 2)]; };     // padded layout, see above
     float2 *out = a.out + (long long)f * Nc;
-    if (a.ci_inv) {
-      // fused cell interleaver (chain mode): output position x holds cell ci_inv[(x - shift) mod Nc]
+    if (a.out16) {
+      // chain mode: 16-bit cell codes (own cell word | word supplying the imaginary part << 8), stored in
+      // cell-interleaved order: output position x holds cell ci_inv[(x - shift) mod Nc]
+      uint16_t *o16 = a.out16 + (long long)f * Nc;
+      const int shift = a.fec_shift[f % a.fecblocks];
+      for (int xo = threadIdx.x; xo < Nc; xo += blockDim.x) {
+        int y = xo - shift;
+        if (y < 0) y += Nc;
+        const int c = __ldg(a.ci_inv + y);
+        const int pc = c == 0 ? Nc - 1 : c - 1;
+        o16[xo] = (uint16_t)(cell(c) | (cell(a.cyclic_delay ? pc : c) << 8));
+      }
+    }
+    else if (a.ci_inv) {
+      // fused cell interleaver with complex output
       const int shift = a.fec_shift[f % a.fecblocks];
       for (int xo = threadIdx.x; xo < Nc; xo += blockDim.x) {
         int y = xo - shift;
@@ -787,12 +800,24 @@ int ofdm_position_of_bin(int m, int log2_m)
 //   3. the last radix-16 pass fused with the output: butterfly i produces samples i + k M/16, which go
 //      (scaled) straight to global memory -- coalesced over i -- including the cyclic prefix and, for
 //      the odd-bin half of a 32K symbol, the in-place recombination with the even-bin half.
-template <int LOG2M, int T>
+//
+// C16 (chain mode): data cells arrive as 16-bit codes in cell-interleaved order.  Per symbol the CTA first
+// copies the symbol's cells into a shared-memory staging area (slot = position in the pre-frequency-
+// interleaver frame order) run by run -- each run is a stretch of consecutive source cells -- so global
+// memory is read in contiguous pieces; the carrier fill then gathers from shared memory and decodes
+// through the constellation LUT (real part from the low byte's entry, imaginary from the high byte's).
+template <int LOG2M, int T, bool C16>
 __global__ void __launch_bounds__(T, 1024 / T) k_ofdm(const OfdmArgs a)
 {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   float2 *x = reinterpret_cast<float2 *>(smem_raw);
   constexpr int M = 1 << LOG2M;
+  uint16_t *stage = reinterpret_cast<uint16_t *>(x + M);
+  float *lut_re = reinterpret_cast<float *>(stage + a.stage_cap);
+  float *lut_im = lut_re + 256;
+  if (C16) {
+    for (int i = threadIdx.x; i < a.lut_n; i += T) { const float2 v = __ldg(a.lut + i); lut_re[i] = v.x; lut_im[i] = v.y; }
+  }
   constexpr int F = LOG2M & 3;
   constexpr int R0 = 1 << F;                 // first radix (1 = no first pass)
   constexpr int GROUPS = M / R0;             // first-pass butterflies
@@ -812,6 +837,17 @@ __global__ void __launch_bounds__(T, 1024 / T) k_ofdm(const OfdmArgs a)
 
     if (l == 0)
       for (int i = threadIdx.x; i < 2048; i += T) out[i] = __ldg(a.p1 + i);
+
+    if (C16) {
+      __syncthreads();      // the previous symbol's fill has finished reading the staging area
+      const uint16_t *src = a.cells16 + (long long)f * a.cells_stride;
+      const int r0 = __ldg(a.run_ptr + l), r1 = __ldg(a.run_ptr + l + 1);
+      const int4 *runs = reinterpret_cast<const int4 *>(a.runs);
+      for (int r = r0 + (threadIdx.x >> 5); r < r1; r += T / 32) {
+        const int4 run = __ldg(runs + r);       // src, slot, len, stride
+        for (int i = threadIdx.x & 31; i < run.z; i += 32) stage[run.y + i * run.w] = __ldg(src + run.x + i);
+      }
+    }
 
     for (int phase = 0; phase < a.split; phase++) {
       const int32_t *code = a.code_pos + ((long long)l * a.split + phase) * M;
@@ -833,8 +869,17 @@ __global__ void __launch_bounds__(T, 1024 / T) k_ofdm(const OfdmArgs a)
 #pragma unroll
           for (int r = 0; r < R0; r++) {
             const int cc = c[b][r];
-            const float2 *base = cc >= 0 ? cells : pool;
-            v[b][r] = __ldg(base + (cc >= 0 ? cc : ~cc));
+            if (C16) {
+              if (cc >= 0) {
+                const unsigned sc = stage[cc];
+                v[b][r] = make_float2(lut_re[sc & 255u], lut_im[sc >> 8]);
+              }
+              else v[b][r] = __ldg(pool + ~cc);
+            }
+            else {
+              const float2 *base = cc >= 0 ? cells : pool;
+              v[b][r] = __ldg(base + (cc >= 0 ? cc : ~cc));
+            }
           }
 #pragma unroll
         for (int b = 0; b < GPB; b++) {
@@ -913,37 +958,44 @@ __global__ void __launch_bounds__(T, 1024 / T) k_ofdm(const OfdmArgs a)
   }
 }
 
-template <int LOG2M, int T>
+template <int LOG2M, int T, bool C16>
 static void launch_ofdm_t(const OfdmArgs &a, cudaStream_t s)
 {
   constexpr int M = 1 << LOG2M;
-  const size_t smem = (size_t)M * sizeof(float2);
+  const size_t smem = (size_t)M * sizeof(float2) + (C16 ? (size_t)a.stage_cap * 2 + 2048 : 0);
   const int units = a.frames * a.num_symbols;
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(k_ofdm<LOG2M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_ofdm<LOG2M, T, C16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr = true;
   }
   int per_sm = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ofdm<LOG2M, T>, T, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ofdm<LOG2M, T, C16>, T, smem);
   if (per_sm < 1) per_sm = 1;
   int blocks = sm_count() * per_sm;
   if (blocks > units) blocks = units;
-  k_ofdm<LOG2M, T><<<blocks, T, smem, s>>>(a);
+  k_ofdm<LOG2M, T, C16><<<blocks, T, smem, s>>>(a);
   count_launch();
+}
+
+template <bool C16>
+static void launch_ofdm_c(const OfdmArgs &a, cudaStream_t s)
+{
+  switch (a.log2_m) {
+    case 10: launch_ofdm_t<10, 256, C16>(a, s); break;
+    case 11: launch_ofdm_t<11, 256, C16>(a, s); break;
+    case 12: launch_ofdm_t<12, 256, C16>(a, s); break;
+    case 13: launch_ofdm_t<13, 512, C16>(a, s); break;
+    case 14: launch_ofdm_t<14, 1024, C16>(a, s); break;
+    default: break;
+  }
 }
 
 void launch_ofdm(const OfdmArgs &a, cudaStream_t s)
 {
   if (a.frames * a.num_symbols < 1) return;
-  switch (a.log2_m) {
-    case 10: launch_ofdm_t<10, 256>(a, s); break;
-    case 11: launch_ofdm_t<11, 256>(a, s); break;
-    case 12: launch_ofdm_t<12, 256>(a, s); break;
-    case 13: launch_ofdm_t<13, 512>(a, s); break;
-    case 14: launch_ofdm_t<14, 1024>(a, s); break;
-    default: break;
-  }
+  if (a.cells16) launch_ofdm_c<true>(a, s);
+  else launch_ofdm_c<false>(a, s);
 }
 
 } // namespace t2k

@@ -53,6 +53,7 @@ struct MapArgs {
   uint8_t col_of_bit[16];
   uint8_t twist_of_col[16];
   // optional fused cell interleaver (chain mode): out[(perm[c] + shift_r) % cell_size] = cell c of FEC block r
+  uint16_t *out16;           // chain mode: 16-bit cell codes (own word | imaginary-part word << 8) instead of `out`
   const uint16_t *ci_inv;    // inverse of the cell permutation, or NULL for natural order
   const int32_t *fec_shift;  // [fecblocks] cyclic shift per FEC block of the T2 frame
   int fecblocks;
@@ -84,7 +85,13 @@ void launch_gather(const GatherArgs &a, cudaStream_t s);
 
 // ---- K5: carrier fill + IFFT + normalisation + guard interval + P1 --------------------------------
 struct OfdmArgs {
-  const float2 *cells; long long cells_stride;   // per T2 frame
+  const float2 *cells; long long cells_stride;   // per T2 frame (stride in cells for both cell formats)
+  // chain mode with 16-bit cells: cells16 != NULL selects it; then `code_pos` holds staging slots
+  const uint16_t *cells16;   // [frame][fecblocks * cell_size] cell-interleaved 16-bit codes
+  const void *runs;          // StageRun {src, slot, len, stride} as int4, grouped per symbol
+  const int32_t *run_ptr;    // [num_symbols + 1]
+  int stage_cap;             // staging slots reserved in shared memory (multiple of 8)
+  const float2 *lut; int lut_n;   // constellation LUT
   float2 *out;         long long out_stride;     // samples per T2 frame
   const int32_t *code_pos;   // [num_symbols][split][M] carrier codes in shared-memory POSITION order
   const float2 *pool;        // special cells, one copy per L1-post variant (copy v holds the L1-post cells of frame index v)

@@ -153,7 +153,9 @@ struct FramePlan {
   std::vector<int32_t> ti_src;         // time-interleaver read-out position -> input cell index (cell int. composed)
   std::vector<int32_t> ci_dst;         // input cell index -> index in cell-interleaved memory
   std::vector<uint16_t> cell_perm_inv; // inverse of cell_perm
-  std::vector<int32_t> code;           // [mapped_items]
+  std::vector<int32_t> code;           // [mapped_items]  == framed[fi_src[j]]
+  std::vector<int32_t> framed;         // [mapped_items] codes in frame order, BEFORE the frequency interleaver
+  std::vector<int32_t> fi_src;         // [mapped_items] frequency interleaver: out[j] = framed[fi_src[j]]
   CellPool pool;                       // [L1-pre 1840][L1-post x t2frames][dummy][zero]
   int pool_l1pre, pool_dummy, pool_zero;
 };
@@ -192,6 +194,21 @@ struct ChainTables {
 // data codes index that memory instead of the natural-order cells.
 bool compose_chain(const FramePlan &fp, const OfdmPlan &op, bool cells_cell_interleaved, ChainTables *out,
                    std::string *err);
+
+// Chain mode with 16-bit cells: the mapper kernel stores every data cell as (own cell word | previous cell
+// word << 8) in cell-interleaved order; the OFDM kernel first copies the cells of one symbol into a shared-
+// memory staging area indexed by the cell's position in the (pre frequency interleaver) frame order, using
+// RUNS -- maximal sequences of consecutive source cells that land at a constant slot stride (for a time-
+// interleaved PLP: one run per TI column) -- and then fills carriers from that staging area.
+struct StageRun { int32_t src; int32_t slot; int32_t len; int32_t stride; };
+struct Chain16Tables {
+  std::vector<int32_t> code;        // [num_symbols * c_ps]: >= 0 staging slot of the symbol, < 0 pool cell
+  std::vector<StageRun> runs;       // all symbols, grouped
+  std::vector<int32_t> run_ptr;     // [num_symbols + 1]
+  int max_slots;                    // largest number of staging slots of any symbol
+  CellPool pool;
+};
+bool compose_chain16(const FramePlan &fp, const OfdmPlan &op, Chain16Tables *out, std::string *err);
 
 // small utilities
 void bb_prbs_bits(int n, uint8_t *out);          // 1 bit per byte; reference :357-369

@@ -350,7 +350,8 @@ bool build_frame_plan(const FrameParams &prm, FramePlan *p, std::string *err)
   p->cell_size = cells_per_fecframe(prm.framesize, prm.constellation);
   if (!p->cell_size) { if (err) *err = "framemapperfint_cc: unknown constellation"; return false; }
   if (prm.fecblocks < 1 || prm.tiblocks < 0 || prm.t2frames < 1 || prm.t2frames > 255) {
-    if (err) *err = "framemapperfint_cc: fecblocks/tiblocks/t2frames out of range"; return false;
+    if (err) *err = "framemapperfint_cc: fecblocks/tiblocks/t2frames out of range";
+    return false;
   }
   if (prm.l1constellation < L1_MOD_BPSK || prm.l1constellation > L1_MOD_64QAM) { if (err) *err = "framemapperfint_cc: unknown L1 constellation"; return false; }
   if (!ofdm_dims(prm.carriermode, prm.fftsize, prm.pilotpattern, prm.guardinterval, prm.numdatasyms,
@@ -531,11 +532,15 @@ bool build_frame_plan(const FrameParams &prm, FramePlan *p, std::string *err)
     invert(Ho, He); invert(HoP2, HeP2); invert(HoFC, HeFC);
   }
   p->code.assign((size_t)p->mapped_items, 0);
+  p->fi_src.assign((size_t)p->mapped_items, 0);
   {
     size_t off = 0;
     int sym = 0;
     auto emit = [&](const std::vector<int32_t> &H, int n) {
-      for (int j = 0; j < n; j++) p->code[off + j] = framed[off + H[j]];
+      for (int j = 0; j < n; j++) {
+        p->fi_src[off + j] = (int32_t)(off + H[j]);
+        p->code[off + j] = framed[off + H[j]];
+      }
       off += n; sym++;
     };
     for (int j = 0; j < d.n_p2; j++) emit((sym & 1) ? HoP2 : HeP2, d.c_p2);
@@ -543,6 +548,7 @@ bool build_frame_plan(const FrameParams &prm, FramePlan *p, std::string *err)
     if (d.n_fc) emit((sym & 1) ? HoFC : HeFC, d.n_fc);
     if (off != (size_t)p->mapped_items) { if (err) *err = "internal: frame size"; return false; }
   }
+  p->framed.swap(framed);
   return true;
 }
 

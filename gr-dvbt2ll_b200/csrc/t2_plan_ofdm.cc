@@ -3,6 +3,7 @@
 // Block 5 of the reference (lib/pilotgenp1insert_cc_impl.cc).  Host only, runs once per make().
 #include "t2_plan.h"
 
+#include <algorithm>
 #include <cmath>
 #include <complex>
 #include <cstring>
@@ -308,6 +309,65 @@ bool compose_chain(const FramePlan &fp, const OfdmPlan &op, bool cells_cell_inte
     const int32_t f = fp.code[c];
     out->code[i] = f >= 0 ? (cells_cell_interleaved ? fp.ci_dst[f] : f) : -(1 + base + (-(f + 1)));
   }
+  return true;
+}
+
+bool compose_chain16(const FramePlan &fp, const OfdmPlan &op, Chain16Tables *out, std::string *err)
+{
+  if (fp.mapped_items != op.dims.active_items || fp.dims.c_ps != op.dims.c_ps) {
+    if (err) *err = "chain: frame mapper and pilot generator parameters do not describe the same frame";
+    return false;
+  }
+  const int base = (int)op.pool.cells.size();
+  out->pool = op.pool;
+  out->pool.cells.insert(out->pool.cells.end(), fp.pool.cells.begin(), fp.pool.cells.end());
+  out->pool.l1post_base = base + fp.pool.l1post_base;
+  out->pool.l1post_cells = fp.pool.l1post_cells;
+  out->pool.l1post_variants = fp.pool.l1post_variants;
+  const int L = op.dims.num_symbols, cps = op.dims.c_ps;
+  out->code.assign(op.code.size(), 0);
+  out->runs.clear();
+  out->run_ptr.assign(L + 1, 0);
+  out->max_slots = 0;
+  for (int l = 0; l < L; l++) {
+    const int s0 = op.sym_data_start[l], s1 = op.sym_data_start[l + 1];     // frame positions of this symbol
+    if (s1 - s0 > out->max_slots) out->max_slots = s1 - s0;
+    // carrier codes: data carrier -> slot = (pre frequency interleaver frame position) - s0
+    for (int k = 0; k < cps; k++) {
+      const int32_t c = op.code[(size_t)l * cps + k];
+      int32_t v;
+      if (c < 0) v = c;
+      else {
+        const int32_t pos = fp.fi_src[c];
+        const int32_t f = fp.framed[pos];
+        v = f >= 0 ? pos - s0 : -(1 + base + (-(f + 1)));
+      }
+      out->code[(size_t)l * cps + k] = v;
+    }
+    // runs: sort the symbol's (source, slot) pairs by source and merge constant-stride sequences
+    std::vector<std::pair<int32_t, int32_t> > ps;
+    for (int pos = s0; pos < s1; pos++) {
+      const int32_t f = fp.framed[pos];
+      if (f >= 0) ps.push_back(std::make_pair(fp.ci_dst[f], pos - s0));
+    }
+    std::sort(ps.begin(), ps.end());
+    out->run_ptr[l] = (int32_t)out->runs.size();
+    size_t i = 0;
+    while (i < ps.size()) {
+      StageRun r;
+      r.src = ps[i].first; r.slot = ps[i].second; r.len = 1; r.stride = 0;
+      size_t j = i + 1;
+      if (j < ps.size() && ps[j].first == ps[i].first + 1) {
+        r.stride = ps[j].second - ps[i].second;
+        // (runs are capped at 128 cells so that one warp never serialises a very long copy)
+        while (j < ps.size() && j - i < 128 && ps[j].first == ps[j - 1].first + 1 && ps[j].second - ps[j - 1].second == r.stride) j++;
+        r.len = (int32_t)(j - i);
+      }
+      out->runs.push_back(r);
+      i += r.len;
+    }
+  }
+  out->run_ptr[L] = (int32_t)out->runs.size();
   return true;
 }
 

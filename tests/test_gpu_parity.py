@@ -98,14 +98,17 @@ def test_chain_matches_reference(reflib, name):
     nbch = refs[0]["bch"].size // F
     nldpc = refs[0]["fec"].size // F
     bch = ch.tap("bch").reshape(nframes * F, -1)
-    cells = ch.tap("cells", np.complex64)
-    ci_dst = ch.plan("frame.ci_dst", np.int32)     # the chain's mapper stores cells already cell-interleaved
+    codes = ch.tap("cells", np.uint16)             # chain mode keeps cells as 16-bit codes, cell-interleaved
+    ci_dst = ch.plan("frame.ci_dst", np.int32)
+    lut = ch.plan("map.lut", np.complex64)
     for fr in range(nframes):
         r = refs[fr]
         got = np.unpackbits(bch[fr * F:(fr + 1) * F, :nbch // 8], axis=1).reshape(-1)
         assert bits_equal(got, r["bch"])
-        frame_cells = cells[fr * r["cells"].size:(fr + 1) * r["cells"].size]
-        assert cells_equal(frame_cells[ci_dst], r["cells"])
+        n = r["cells"].size
+        fc = codes[fr * n:(fr + 1) * n][ci_dst]
+        cells = (lut[fc & 255].real + 1j * lut[fc >> 8].imag).astype(np.complex64)
+        assert cells_equal(cells, r["cells"])
         s = out[fr * S:(fr + 1) * S]
         assert mer_db(s, r["samples"]) >= MER_MIN_DB
         assert max_err_over_rms(s, r["samples"]) <= MAX_ERR_OVER_RMS

@@ -105,15 +105,37 @@ def test_frame_and_ofdm_plans(name, cfg):
     assert max_err_over_rms(E.ofdm_emu(pg, y), want) < 1e-6
 
 
-def test_chain_table_is_composition():
-    """chain.code == ofdm.code composed with frame.code (what the fused kernel gathers through)."""
-    cfg = K.resolve("c1")
+@pytest.mark.parametrize("name", ["c1", "c2", "c3"])
+def test_chain16_tables(name):
+    """Chain mode: staging runs + per-carrier slots reproduce exactly the composition
+    frequency interleaver o frame o time interleaver o cell interleaver of the drop-in tables."""
+    cfg = K.resolve(name)
     ch = T.Chain(cfg, max_frames=1)
-    oc, fc, cc = ch.plan("ofdm.code", np.int32), ch.plan("frame.code", np.int32), ch.plan("chain.code", np.int32)
-    data = oc >= 0
-    assert np.array_equal(cc[~data], oc[~data])
-    f = fc[oc[data]]
-    ci_dst = ch.plan("frame.ci_dst", np.int32)     # fused chain: data codes index the cell-interleaved memory
-    assert np.array_equal(cc[data][f >= 0], ci_dst[f[f >= 0]])
+    oc, fc = ch.plan("ofdm.code", np.int32), ch.plan("frame.code", np.int32)
+    cc = ch.plan("chain.code", np.int32)
+    ci_dst = ch.plan("frame.ci_dst", np.int32)
+    runs = ch.plan("chain.runs", np.int32).reshape(-1, 4)
+    run_ptr = ch.plan("chain.run_ptr", np.int32)
+    starts = ch.plan("ofdm.sym_data_start", np.int32)
+    dims = ch.plan("ofdm.dims", np.int32)
+    cps, L = int(dims[8]), int(dims[14])
     assert np.array_equal(np.sort(ci_dst), np.arange(ci_dst.size))
-    assert ch.ts_bytes_per_frame == 12352 and ch.samples_per_frame == 31616 and ch.fecframes_per_frame == 8
+    rng = np.random.default_rng(3)
+    cells16 = rng.integers(0, 65536, ci_dst.size).astype(np.int64)       # cell-interleaved memory of one T2 frame
+    oc, cc = oc.reshape(L, cps), cc.reshape(L, cps)
+    assert runs[:, 2].max() <= 128
+    for l in range(L):
+        nslots = int(starts[l + 1] - starts[l])
+        stage = np.full(nslots, -1, dtype=np.int64)
+        for src, slot, ln, stride in runs[run_ptr[l]:run_ptr[l + 1]]:
+            idx = slot + np.arange(ln) * stride
+            assert idx.min() >= 0 and idx.max() < nslots
+            stage[idx] = cells16[src:src + ln]
+        data = oc[l] >= 0
+        assert np.array_equal(cc[l][~data], oc[l][~data])                  # pilots / nulls untouched
+        f = fc[oc[l][data]]                                                # drop-in frame mapper code of each data carrier
+        got = cc[l][data]
+        from_cells = f >= 0
+        assert np.all(got[from_cells] >= 0) and np.all(got[~from_cells] < 0)
+        assert np.array_equal(stage[got[from_cells]], cells16[ci_dst[f[from_cells]]])
+    assert ch.ts_bytes_per_frame == {"c1": 12352, "c2": 76304, "c3": 1084740}[name]
