@@ -284,7 +284,7 @@ struct MapHandle : dvbt2ll_handle {
     a.in = in; a.in_pitch = in_pitch; a.out = out; a.frames = frames;
     a.nldpc = plan.fec.nldpc; a.mod = plan.mod; a.cell_size = plan.cell_size; a.cyclic_delay = plan.cyclic_delay;
     a.bit_src = d_bitsrc.as<uint16_t>(); a.lut = d_lut.as<float2>();
-    a.ci_inv = 0; a.fec_shift = 0; a.fecblocks = 1; a.out16 = 0;
+    a.ci_inv = 0; a.fec_shift = 0; a.fecblocks = 1; a.out16 = 0; a.out16_frame_stride = 0;
     a.ncol = plan.ncol;
     std::memcpy(a.col_of_bit, plan.col_of_bit, 16);
     std::memcpy(a.twist_of_col, plan.twist_of_col, 16);
@@ -500,6 +500,8 @@ struct ChainHandle : dvbt2ll_handle {
   }
   ~ChainHandle() { for (int i = 0; i < 5; i++) if (ev[i]) cudaEventDestroy(ev[i]); }
   int F() const { return fplan.prm.fecblocks; }
+  // cells per T2 frame in the 16-bit cell memory, padded so every frame starts on an 8-byte boundary
+  long long cells16_stride() const { return ((long long)F() * map.plan.cell_size + 3) & ~3LL; }
   long long ts_per_frame() const { return bb.payload_bytes(F(), 0); }
   int output_multiple() const { return oplan.samples_per_frame; }
   int in_item() const { return 1; }
@@ -521,7 +523,7 @@ struct ChainHandle : dvbt2ll_handle {
     const size_t nfec = (size_t)max_frames * F();
     CK(d_bch.ensure(nfec * align16(bb.plan.fec.nbch / 8) + 64));
     CK(d_fec.ensure(nfec * align16(bb.plan.fec.nldpc / 8) + 64));
-    CK(d_cells.ensure(nfec * map.plan.cell_size * sizeof(uint16_t) + 64));   // 16-bit cell codes
+    CK(d_cells.ensure((size_t)max_frames * cells16_stride() * sizeof(uint16_t) + 64));   // 16-bit cell codes
     for (int i = 0; i < 5; i++) CK(cudaEventCreate(&ev[i]));
     return 0;
   }
@@ -552,13 +554,13 @@ struct ChainHandle : dvbt2ll_handle {
     if (timing) cudaEventRecord(ev[2], s);
     t2k::MapArgs ma;
     map.fill_args(ma, d_fec.as<uint8_t>(), fp, 0, nfec);
-    ma.out16 = d_cells.as<uint16_t>();                                                                    // 16-bit cell codes,
+    ma.out16 = d_cells.as<uint16_t>(); ma.out16_frame_stride = cells16_stride();                          // 16-bit cell codes,
     ma.ci_inv = d_ci_inv.as<uint16_t>(); ma.fec_shift = d_fec_shift.as<int32_t>(); ma.fecblocks = F();   // cell-interleaved
     t2k::launch_map(ma, s);
     if (timing) cudaEventRecord(ev[3], s);
     t2k::OfdmArgs oa;
     odev.fill(oa, oplan, tables.pool);
-    oa.cells = 0; oa.cells_stride = (long long)F() * map.plan.cell_size;
+    oa.cells = 0; oa.cells_stride = cells16_stride();
     oa.cells16 = d_cells.as<uint16_t>(); oa.runs = d_runs.p; oa.run_ptr = d_run_ptr.as<int32_t>(); oa.stage_cap = stage_cap;
     oa.lut = map.d_lut.as<float2>(); oa.lut_n = 1 << map.plan.mod;
     oa.out = (float2 *)d_out; oa.out_stride = oplan.samples_per_frame;
@@ -825,7 +827,7 @@ long long dvbt2ll_chain_tap(dvbt2ll_handle *h, const char *stage, void *out, lon
   std::string n(stage);
   if (n == "bch") { src = c->d_bch.p; bytes = nfec * align16(c->bb.plan.fec.nbch / 8); }
   else if (n == "fec") { src = c->d_fec.p; bytes = nfec * align16(c->bb.plan.fec.nldpc / 8); }
-  else if (n == "cells") { src = c->d_cells.p; bytes = nfec * c->map.plan.cell_size * sizeof(uint16_t); }
+  else if (n == "cells") { src = c->d_cells.p; bytes = (size_t)c->last_frames * c->cells16_stride() * sizeof(uint16_t); }
   else return fail(DVBT2LL_ERR_INVALID, "chain: unknown tap");
   CK(cudaStreamSynchronize(c->stream));
   CK(cudaDeviceSynchronize());

@@ -492,7 +492,7 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map(const MapArgs a)
     if (a.out16) {
       // chain mode: 16-bit cell codes (own cell word | word supplying the imaginary part << 8), stored in
       // cell-interleaved order: output position x holds cell ci_inv[(x - shift) mod Nc]
-      uint16_t *o16 = a.out16 + (long long)f * Nc;
+      uint16_t *o16 = a.out16 + (long long)(f / a.fecblocks) * a.out16_frame_stride + (long long)(f % a.fecblocks) * Nc;
       const int shift = a.fec_shift[f % a.fecblocks];
       for (int xo = threadIdx.x; xo < Nc; xo += blockDim.x) {
         int y = xo - shift;
@@ -815,8 +815,10 @@ __global__ void __launch_bounds__(T, 1024 / T) k_ofdm(const OfdmArgs a)
   uint16_t *stage = reinterpret_cast<uint16_t *>(x + M);
   float *lut_re = reinterpret_cast<float *>(stage + a.stage_cap);
   float *lut_im = lut_re + 256;
+  float2 *spool = reinterpret_cast<float2 *>(lut_im + 256);      // first 8 pool cells: zero and the pilot values
   if (C16) {
     for (int i = threadIdx.x; i < a.lut_n; i += T) { const float2 v = __ldg(a.lut + i); lut_re[i] = v.x; lut_im[i] = v.y; }
+    if (threadIdx.x < 8) spool[threadIdx.x] = __ldg(a.pool + threadIdx.x);
   }
   constexpr int F = LOG2M & 3;
   constexpr int R0 = 1 << F;                 // first radix (1 = no first pass)
@@ -840,12 +842,24 @@ __global__ void __launch_bounds__(T, 1024 / T) k_ofdm(const OfdmArgs a)
 
     if (C16) {
       __syncthreads();      // the previous symbol's fill has finished reading the staging area
-      const uint16_t *src = a.cells16 + (long long)f * a.cells_stride;
+      // copy the symbol's cells run by run in aligned 8-byte chunks (4 cells); four runs in flight per warp
+      const uint2 *src8 = reinterpret_cast<const uint2 *>(a.cells16 + (long long)f * a.cells_stride);
+      uint2 *stage8 = reinterpret_cast<uint2 *>(stage);
       const int r0 = __ldg(a.run_ptr + l), r1 = __ldg(a.run_ptr + l + 1);
       const int4 *runs = reinterpret_cast<const int4 *>(a.runs);
-      for (int r = r0 + (threadIdx.x >> 5); r < r1; r += T / 32) {
-        const int4 run = __ldg(runs + r);       // src, slot, len, stride
-        for (int i = threadIdx.x & 31; i < run.z; i += 32) stage[run.y + i * run.w] = __ldg(src + run.x + i);
+      const int lane = threadIdx.x & 31;
+      for (int rb = r0 + (threadIdx.x >> 5); rb < r1; rb += (T / 32) * 4) {
+        int4 run[4];
+        uint2 d[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int r = rb + u * (T / 32);
+          run[u] = r < r1 ? __ldg(runs + r) : make_int4(0, 0, 0, 0);       // src chunk, staging chunk, chunks
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (lane < run[u].z) d[u] = __ldg(src8 + run[u].x + lane);
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (lane < run[u].z) stage8[run[u].y + lane] = d[u];
       }
     }
 
@@ -874,7 +888,8 @@ __global__ void __launch_bounds__(T, 1024 / T) k_ofdm(const OfdmArgs a)
                 const unsigned sc = stage[cc];
                 v[b][r] = make_float2(lut_re[sc & 255u], lut_im[sc >> 8]);
               }
-              else v[b][r] = __ldg(pool + ~cc);
+              else if (cc >= -8) v[b][r] = spool[~cc];          // nulls and pilots
+              else v[b][r] = __ldg(pool + ~cc);                  // L1 signalling, dummy cells
             }
             else {
               const float2 *base = cc >= 0 ? cells : pool;
@@ -962,7 +977,7 @@ template <int LOG2M, int T, bool C16>
 static void launch_ofdm_t(const OfdmArgs &a, cudaStream_t s)
 {
   constexpr int M = 1 << LOG2M;
-  const size_t smem = (size_t)M * sizeof(float2) + (C16 ? (size_t)a.stage_cap * 2 + 2048 : 0);
+  const size_t smem = (size_t)M * sizeof(float2) + (C16 ? (size_t)a.stage_cap * 2 + 2048 + 64 : 0);
   const int units = a.frames * a.num_symbols;
   static bool attr = false;
   if (!attr) {

@@ -54,6 +54,7 @@ struct MapArgs {
   uint8_t twist_of_col[16];
   // optional fused cell interleaver (chain mode): out[(perm[c] + shift_r) % cell_size] = cell c of FEC block r
   uint16_t *out16;           // chain mode: 16-bit cell codes (own word | imaginary-part word << 8) instead of `out`
+  long long out16_frame_stride;   // cells between T2 frames in out16 (multiple of 4: frames stay 8-byte aligned)
   const uint16_t *ci_inv;    // inverse of the cell permutation, or NULL for natural order
   const int32_t *fec_shift;  // [fecblocks] cyclic shift per FEC block of the T2 frame
   int fecblocks;
@@ -88,7 +89,7 @@ struct OfdmArgs {
   const float2 *cells; long long cells_stride;   // per T2 frame (stride in cells for both cell formats)
   // chain mode with 16-bit cells: cells16 != NULL selects it; then `code_pos` holds staging slots
   const uint16_t *cells16;   // [frame][fecblocks * cell_size] cell-interleaved 16-bit codes
-  const void *runs;          // StageRun {src, slot, len, stride} as int4, grouped per symbol
+  const void *runs;          // StageRun {src chunk, staging chunk, chunks, -} as int4 (chunk = 4 cells), per symbol
   const int32_t *run_ptr;    // [num_symbols + 1]
   int stage_cap;             // staging slots reserved in shared memory (multiple of 8)
   const float2 *lut; int lut_n;   // constellation LUT

@@ -197,9 +197,9 @@ bool compose_chain(const FramePlan &fp, const OfdmPlan &op, bool cells_cell_inte
 
 // Chain mode with 16-bit cells: the mapper kernel stores every data cell as (own cell word | previous cell
 // word << 8) in cell-interleaved order; the OFDM kernel first copies the cells of one symbol into a shared-
-// memory staging area indexed by the cell's position in the (pre frequency interleaver) frame order, using
-// RUNS -- maximal sequences of consecutive source cells that land at a constant slot stride (for a time-
-// interleaved PLP: one run per TI column) -- and then fills carriers from that staging area.
+// memory staging area using RUNS -- maximal stretches of consecutive source cells (for a time-interleaved
+// PLP: one run per TI column), copied as aligned 8-byte chunks -- and then fills carriers from there.
+// src / slot / len are in units of 8-byte chunks (4 cells) of the frame's cell memory / the staging area
 struct StageRun { int32_t src; int32_t slot; int32_t len; int32_t stride; };
 struct Chain16Tables {
   std::vector<int32_t> code;        // [num_symbols * c_ps]: >= 0 staging slot of the symbol, < 0 pool cell

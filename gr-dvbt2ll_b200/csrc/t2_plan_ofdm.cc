@@ -331,8 +331,35 @@ bool compose_chain16(const FramePlan &fp, const OfdmPlan &op, Chain16Tables *out
   out->max_slots = 0;
   for (int l = 0; l < L; l++) {
     const int s0 = op.sym_data_start[l], s1 = op.sym_data_start[l + 1];     // frame positions of this symbol
-    if (s1 - s0 > out->max_slots) out->max_slots = s1 - s0;
-    // carrier codes: data carrier -> slot = (pre frequency interleaver frame position) - s0
+    // staging layout: the symbol's source cells sorted by source address, copied run by run in 8-byte
+    // chunks (4 cells).  A run is a maximal stretch of consecutive source cells (capped at 32 chunks); its
+    // first staging slot has the same position inside a chunk as its first source cell, so whole aligned
+    // chunks can be copied (up to 3 unused cells at either end).
+    std::vector<std::pair<int32_t, int32_t> > ps;      // (source cell, frame-order position - s0)
+    for (int pos = s0; pos < s1; pos++) {
+      const int32_t f = fp.framed[pos];
+      if (f >= 0) ps.push_back(std::make_pair(fp.ci_dst[f], pos - s0));
+    }
+    std::sort(ps.begin(), ps.end());
+    std::vector<int32_t> slot_of_pos(s1 - s0, -1);
+    out->run_ptr[l] = (int32_t)out->runs.size();
+    int32_t next_chunk = 0;                             // staging chunks used so far
+    size_t i = 0;
+    while (i < ps.size()) {
+      const int32_t src = ps[i].first;
+      const int32_t first_chunk = src >> 2;
+      size_t j = i + 1;
+      while (j < ps.size() && ps[j].first == ps[j - 1].first + 1 && (ps[j].first >> 2) - first_chunk < 32) j++;
+      const int32_t last_chunk = ps[j - 1].first >> 2;
+      StageRun r;
+      r.src = first_chunk; r.slot = next_chunk; r.len = last_chunk - first_chunk + 1; r.stride = 0;
+      for (size_t k = i; k < j; k++) slot_of_pos[ps[k].second] = 4 * next_chunk + (ps[k].first - 4 * first_chunk);
+      next_chunk += r.len;
+      out->runs.push_back(r);
+      i = j;
+    }
+    if (4 * next_chunk > out->max_slots) out->max_slots = 4 * next_chunk;
+    // carrier codes: data carrier -> staging slot of its cell
     for (int k = 0; k < cps; k++) {
       const int32_t c = op.code[(size_t)l * cps + k];
       int32_t v;
@@ -340,31 +367,9 @@ bool compose_chain16(const FramePlan &fp, const OfdmPlan &op, Chain16Tables *out
       else {
         const int32_t pos = fp.fi_src[c];
         const int32_t f = fp.framed[pos];
-        v = f >= 0 ? pos - s0 : -(1 + base + (-(f + 1)));
+        v = f >= 0 ? slot_of_pos[pos - s0] : -(1 + base + (-(f + 1)));
       }
       out->code[(size_t)l * cps + k] = v;
-    }
-    // runs: sort the symbol's (source, slot) pairs by source and merge constant-stride sequences
-    std::vector<std::pair<int32_t, int32_t> > ps;
-    for (int pos = s0; pos < s1; pos++) {
-      const int32_t f = fp.framed[pos];
-      if (f >= 0) ps.push_back(std::make_pair(fp.ci_dst[f], pos - s0));
-    }
-    std::sort(ps.begin(), ps.end());
-    out->run_ptr[l] = (int32_t)out->runs.size();
-    size_t i = 0;
-    while (i < ps.size()) {
-      StageRun r;
-      r.src = ps[i].first; r.slot = ps[i].second; r.len = 1; r.stride = 0;
-      size_t j = i + 1;
-      if (j < ps.size() && ps[j].first == ps[i].first + 1) {
-        r.stride = ps[j].second - ps[i].second;
-        // (runs are capped at 128 cells so that one warp never serialises a very long copy)
-        while (j < ps.size() && j - i < 128 && ps[j].first == ps[j - 1].first + 1 && ps[j].second - ps[j - 1].second == r.stride) j++;
-        r.len = (int32_t)(j - i);
-      }
-      out->runs.push_back(r);
-      i += r.len;
     }
   }
   out->run_ptr[L] = (int32_t)out->runs.size();

@@ -106,7 +106,8 @@ def test_chain_matches_reference(reflib, name):
         got = np.unpackbits(bch[fr * F:(fr + 1) * F, :nbch // 8], axis=1).reshape(-1)
         assert bits_equal(got, r["bch"])
         n = r["cells"].size
-        fc = codes[fr * n:(fr + 1) * n][ci_dst]
+        stride = (n + 3) & ~3                          # frames are padded to a multiple of 4 cells
+        fc = codes[fr * stride:fr * stride + n][ci_dst]
         cells = (lut[fc & 255].real + 1j * lut[fc >> 8].imag).astype(np.complex64)
         assert cells_equal(cells, r["cells"])
         s = out[fr * S:(fr + 1) * S]
