@@ -490,15 +490,16 @@ struct ChainHandle : dvbt2ll_handle {
   DevBuf d_bch, d_fec, d_cells, d_ts_stage, d_out_stage, d_ci_inv, d_fec_shift, d_runs, d_run_ptr;
   int stage_cap;
   int max_frames, device;
+  cudaStream_t stream2;
   int last_frames;
   bool timing;
   cudaEvent_t ev[5];
   float stage_ms[5];
-  ChainHandle() : dvbt2ll_handle(CHAIN), max_frames(0), device(0), last_frames(0), timing(false)
+  ChainHandle() : dvbt2ll_handle(CHAIN), max_frames(0), device(0), stream2(0), last_frames(0), timing(false)
   {
     for (int i = 0; i < 5; i++) { ev[i] = 0; stage_ms[i] = 0.f; }
   }
-  ~ChainHandle() { for (int i = 0; i < 5; i++) if (ev[i]) cudaEventDestroy(ev[i]); }
+  ~ChainHandle() { for (int i = 0; i < 5; i++) if (ev[i]) cudaEventDestroy(ev[i]); if (stream2) cudaStreamDestroy(stream2); }
   int F() const { return fplan.prm.fecblocks; }
   // cells per T2 frame in the 16-bit cell memory, padded so every frame starts on an 8-byte boundary
   long long cells16_stride() const { return ((long long)F() * map.plan.cell_size + 3) & ~3LL; }
@@ -527,11 +528,13 @@ struct ChainHandle : dvbt2ll_handle {
     for (int i = 0; i < 5; i++) CK(cudaEventCreate(&ev[i]));
     return 0;
   }
-  int run(const void *d_ts, long long ts_pitch, int n_channels, int n_frames, long long first_frame, void *d_out, cudaStream_t s)
+  // buf_frame: first T2-frame slot of the intermediate buffers to use (lets two batches be in flight on two streams)
+  int run(const void *d_ts, long long ts_pitch, int n_channels, int n_frames, long long first_frame, void *d_out, cudaStream_t s,
+          int buf_frame = 0)
   {
     const int frames = n_channels * n_frames;
     if (frames < 1) return 0;
-    if (frames > max_frames) return fail(DVBT2LL_ERR_INVALID, "chain: batch larger than max_frames given at create");
+    if (buf_frame + frames > max_frames) return fail(DVBT2LL_ERR_INVALID, "chain: batch larger than max_frames given at create");
     const int nfec = frames * F();
     const int bp = align16(bb.plan.fec.nbch / 8), fp = align16(bb.plan.fec.nldpc / 8);
     // stream position of the batch start (streams begin on a packet boundary at frame 0)
@@ -544,31 +547,34 @@ struct ChainHandle : dvbt2ll_handle {
 
     if (timing) cudaEventRecord(ev[0], s);
     t2k::BbArgs ba;
+    uint8_t *bch_buf = d_bch.as<uint8_t>() + (size_t)buf_frame * F() * bp;
+    uint8_t *fec_buf = d_fec.as<uint8_t>() + (size_t)buf_frame * F() * fp;
+    uint16_t *cell_buf = d_cells.as<uint16_t>() + (size_t)buf_frame * cells16_stride();
     bb.fill_args(ba, (const uint8_t *)d_ts, ts_pitch, n_channels, n_frames * F(), count0, fb0, first_frame > 0 ? 1 : 0,
-                 d_bch.as<uint8_t>(), bp);
+                 bch_buf, bp);
     t2k::launch_bb_bch(ba, s);
     if (timing) cudaEventRecord(ev[1], s);
     t2k::LdpcArgs la;
-    ldpc.fill_args(la, d_bch.as<uint8_t>(), bp, d_fec.as<uint8_t>(), fp, nfec);
+    ldpc.fill_args(la, bch_buf, bp, fec_buf, fp, nfec);
     t2k::launch_ldpc(la, s);
     if (timing) cudaEventRecord(ev[2], s);
     t2k::MapArgs ma;
-    map.fill_args(ma, d_fec.as<uint8_t>(), fp, 0, nfec);
-    ma.out16 = d_cells.as<uint16_t>(); ma.out16_frame_stride = cells16_stride();                          // 16-bit cell codes,
+    map.fill_args(ma, fec_buf, fp, 0, nfec);
+    ma.out16 = cell_buf; ma.out16_frame_stride = cells16_stride();                                        // 16-bit cell codes,
     ma.ci_inv = d_ci_inv.as<uint16_t>(); ma.fec_shift = d_fec_shift.as<int32_t>(); ma.fecblocks = F();   // cell-interleaved
     t2k::launch_map(ma, s);
     if (timing) cudaEventRecord(ev[3], s);
     t2k::OfdmArgs oa;
     odev.fill(oa, oplan, tables.pool);
     oa.cells = 0; oa.cells_stride = cells16_stride();
-    oa.cells16 = d_cells.as<uint16_t>(); oa.runs = d_runs.p; oa.run_ptr = d_run_ptr.as<int32_t>(); oa.stage_cap = stage_cap;
+    oa.cells16 = cell_buf; oa.runs = d_runs.p; oa.run_ptr = d_run_ptr.as<int32_t>(); oa.stage_cap = stage_cap;
     oa.lut = map.d_lut.as<float2>(); oa.lut_n = 1 << map.plan.mod;
     oa.out = (float2 *)d_out; oa.out_stride = oplan.samples_per_frame;
     oa.frames = frames; oa.frame_idx0 = first_frame; oa.frames_per_channel = n_frames;
     t2k::launch_ofdm(oa, s);
     if (timing) cudaEventRecord(ev[4], s);
     CK(cudaGetLastError());
-    last_frames = frames;
+    if (buf_frame == 0) last_frames = frames;
     return frames;
   }
   int work_device(const void *d_in, int ninput, void *d_out, int noutput, int *consumed, cudaStream_t s)
@@ -799,22 +805,38 @@ int dvbt2ll_chain_run_host(dvbt2ll_handle *h, const void *ts, long long ts_pitch
   if (c->device >= 0 && !c->dev_ready) CK(cudaSetDevice(c->device));
   int r = c->ensure_device();
   if (r) return r;
-  const long long per = c->ts_per_frame() * n_frames;
+  const long long per_ch = c->ts_per_frame() * n_frames;
   const long long hist = first_frame > 0 ? 187 : 0;
-  const long long dpitch = (per + hist + 255) & ~255LL;
+  const long long dpitch = (per_ch + hist + 255) & ~255LL;
   const size_t out_bytes = (size_t)n_channels * n_frames * c->oplan.samples_per_frame * sizeof(float2);
   CK(c->d_ts_stage.ensure((size_t)n_channels * dpitch + 512));
   CK(c->d_out_stage.ensure(out_bytes));
-  cudaStream_t s = c->stream;
   uint8_t *base = c->d_ts_stage.as<uint8_t>() + 256;
-  // host layout: channel-major with pitch ts_pitch; when first_frame > 0 each channel pointer must be preceded by 187 history bytes
-  CK(cudaMemcpy2DAsync(base - hist, (size_t)dpitch, (const uint8_t *)ts - hist, (size_t)ts_pitch, (size_t)(per + hist),
-                       (size_t)n_channels, cudaMemcpyHostToDevice, s));
-  r = c->run(base, dpitch, n_channels, n_frames, first_frame, c->d_out_stage.p, s);
-  if (r < 0) return r;
-  CK(cudaMemcpyAsync(out, c->d_out_stage.p, out_bytes, cudaMemcpyDeviceToHost, s));
-  CK(cudaStreamSynchronize(s));
-  return r;
+  float2 *dout = c->d_out_stage.as<float2>();
+  const size_t ch_out = (size_t)n_frames * c->oplan.samples_per_frame;          // samples per channel
+  // host layout: channel-major with pitch ts_pitch; when first_frame > 0 each channel pointer must be preceded
+  // by 187 history bytes.  Channels are processed in groups on two streams so that the H2D copy and the
+  // kernels of one group overlap the D2H copy of the previous one (the D2H copy dominates).
+  if (!c->stream2) CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+  int groups = n_channels >= 8 ? 8 : n_channels;
+  while (groups > 1 && 2 * ((n_channels + groups - 1) / groups) * n_frames > c->max_frames) groups--;
+  const int per = (n_channels + groups - 1) / groups;
+  if (2 * per * n_frames > c->max_frames) groups = 1;
+  int gi = 0;
+  for (int c0 = 0; c0 < n_channels; c0 += (groups == 1 ? n_channels : per), gi++) {
+    const int nc = groups == 1 ? n_channels : (c0 + per <= n_channels ? per : n_channels - c0);
+    cudaStream_t s = (gi & 1) ? c->stream2 : c->stream;
+    CK(cudaMemcpy2DAsync(base + (size_t)c0 * dpitch - hist, (size_t)dpitch, (const uint8_t *)ts + (size_t)c0 * ts_pitch - hist,
+                         (size_t)ts_pitch, (size_t)(per_ch + hist), (size_t)nc, cudaMemcpyHostToDevice, s));
+    r = c->run(base + (size_t)c0 * dpitch, dpitch, nc, n_frames, first_frame, dout + (size_t)c0 * ch_out, s,
+               groups == 1 ? 0 : (gi & 1) * per * n_frames);
+    if (r < 0) return r;
+    CK(cudaMemcpyAsync((float2 *)out + (size_t)c0 * ch_out, dout + (size_t)c0 * ch_out, (size_t)nc * ch_out * sizeof(float2),
+                       cudaMemcpyDeviceToHost, s));
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaStreamSynchronize(c->stream2));
+  return n_channels * n_frames;
 }
 
 long long dvbt2ll_chain_tap(dvbt2ll_handle *h, const char *stage, void *out, long long cap)
