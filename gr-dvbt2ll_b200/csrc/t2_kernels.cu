@@ -677,8 +677,9 @@ void launch_gather(const GatherArgs &a, cudaStream_t s)
 __host__ __device__ constexpr int swz(int p) { return p ^ (((p >> 4) ^ (p >> 8) ^ (p >> 12)) & 15); }
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// complex add / subtract as ONE packed FP32x2 instruction each (sm_100 FADD2 / FFMA2); a - b = fma(b, -1, a) is exact
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }
 
 // multiply by exp(+j 2 pi k / 16); k is a compile-time constant after unrolling
 __device__ __forceinline__ float2 tw16(float2 d, int k)
@@ -875,8 +876,25 @@ __global__ void __launch_bounds__(T, 1024 / T) k_ofdm(const OfdmArgs a)
 #pragma unroll
         for (int b = 0; b < GPB; b++) {
           const int g = g0 + b * T;
+          // the R0 codes of a group are contiguous and R0*4-byte aligned: one vector load
+          if (g >= GROUPS) {
 #pragma unroll
-          for (int r = 0; r < R0; r++) c[b][r] = g < GROUPS ? __ldg(code + g * R0 + r) : -1;
+            for (int r = 0; r < R0; r++) c[b][r] = -1;
+          }
+          else if (R0 == 4) {
+            const int4 q4 = __ldg(reinterpret_cast<const int4 *>(code) + g);
+            c[b][0] = q4.x; c[b][1] = q4.y; c[b][2 % R0] = q4.z; c[b][3 % R0] = q4.w;
+          }
+          else if (R0 == 8) {
+            const int4 q4 = __ldg(reinterpret_cast<const int4 *>(code) + 2 * g), q5 = __ldg(reinterpret_cast<const int4 *>(code) + 2 * g + 1);
+            c[b][0] = q4.x; c[b][1 % R0] = q4.y; c[b][2 % R0] = q4.z; c[b][3 % R0] = q4.w;
+            c[b][4 % R0] = q5.x; c[b][5 % R0] = q5.y; c[b][6 % R0] = q5.z; c[b][7 % R0] = q5.w;
+          }
+          else if (R0 == 2) {
+            const int2 q2 = __ldg(reinterpret_cast<const int2 *>(code) + g);
+            c[b][0] = q2.x; c[b][1 % R0] = q2.y;
+          }
+          else c[b][0] = __ldg(code + g);
         }
 #pragma unroll
         for (int b = 0; b < GPB; b++)
@@ -884,12 +902,12 @@ __global__ void __launch_bounds__(T, 1024 / T) k_ofdm(const OfdmArgs a)
           for (int r = 0; r < R0; r++) {
             const int cc = c[b][r];
             if (C16) {
-              if (cc >= 0) {
-                const unsigned sc = stage[cc];
-                v[b][r] = make_float2(lut_re[sc & 255u], lut_im[sc >> 8]);
-              }
-              else if (cc >= -8) v[b][r] = spool[~cc];          // nulls and pilots
-              else v[b][r] = __ldg(pool + ~cc);                  // L1 signalling, dummy cells
+              // branch-free for the common cases: data cell through the LUT, nulls / pilots from the small pool
+              const unsigned sc = stage[cc < 0 ? 0 : cc];
+              float2 val = make_float2(lut_re[sc & 255u], lut_im[sc >> 8]);
+              if (cc < 0) val = spool[(~cc) & 7];
+              if (cc < -8) val = __ldg(pool + ~cc);              // L1 signalling, dummy cells (P2 symbols only)
+              v[b][r] = val;
             }
             else {
               const float2 *base = cc >= 0 ? cells : pool;
@@ -902,7 +920,7 @@ __global__ void __launch_bounds__(T, 1024 / T) k_ofdm(const OfdmArgs a)
           if (g < GROUPS) {
             if (sinc) {
 #pragma unroll
-              for (int r = 0; r < R0; r++) { const float s = __ldg(sinc + g * R0 + r); v[b][r].x *= s; v[b][r].y *= s; }
+              for (int r = 0; r < R0; r++) { const float s = __ldg(sinc + g * R0 + r); v[b][r] = __fmul2_rn(v[b][r], make_float2(s, s)); }
             }
             if (R0 > 1) dft_reg<R0>(v[b]);
             const int sb = swz(g * R0);
@@ -929,7 +947,7 @@ __global__ void __launch_bounds__(T, 1024 / T) k_ofdm(const OfdmArgs a)
 #pragma unroll
           for (int k = 0; k < 16; k++) {
             float2 o = v[bitrev_c(k, 16)];
-            o.x *= a.norm; o.y *= a.norm;
+            o = __fmul2_rn(o, make_float2(a.norm, a.norm));
             const int t = i + k * NLAST;
             sym[a.gi + t] = o;
             if (t >= cp_from) sym[t - cp_from] = o;
@@ -939,18 +957,17 @@ __global__ void __launch_bounds__(T, 1024 / T) k_ofdm(const OfdmArgs a)
 #pragma unroll
           for (int k = 0; k < 16; k++) {
             float2 o = v[bitrev_c(k, 16)];
-            o.x *= a.norm; o.y *= a.norm;
-            const int t = i + k * NLAST;
-            sym[a.gi + t] = o;
-            sym[a.gi + t + M] = o;
-            if (t + M >= cp_from) sym[t + M - cp_from] = o;
+            o = __fmul2_rn(o, make_float2(a.norm, a.norm));
+            // even-bin half E[n]: parked in the first half of the symbol; the odd-bin phase reads it back and
+            // writes both halves and the cyclic prefix
+            sym[a.gi + i + k * NLAST] = o;
           }
         }
         else {
           // odd-bin half: out[n] = E[n] + W_N^n O[n], out[n + N/2] = E[n] - W_N^n O[n], n = i + k M/16,
           // W_N^n = W_N^i * exp(j 2 pi k / 32); E is re-read in two batches of 8
           float2 wi = __ldg(a.tw_split + i);
-          wi.x *= a.norm; wi.y *= a.norm;
+          wi = __fmul2_rn(wi, make_float2(a.norm, a.norm));
 #pragma unroll
           for (int h = 0; h < 2; h++) {
             float2 e[8];
