@@ -142,7 +142,12 @@ struct BbHandle : dvbt2ll_handle {
     std::vector<uint8_t> scr(plan.scramble);
     scr.resize((scr.size() + 7) & ~(size_t)3, 0);      // kernel XORs the scrambler word-wise
     CK(upload(d_scr, scr));
-    std::vector<uint8_t> crc(plan.crc8_tab, plan.crc8_tab + 256);
+    // CRC-8 slicing-by-4 tables: S1 = byte table, S(k+1)[x] = S1[Sk[x]] (a byte followed by k zero bytes)
+    std::vector<uint8_t> crc(1024);
+    for (int x = 0; x < 256; x++) {
+      uint8_t v = plan.crc8_tab[x];
+      for (int k = 0; k < 4; k++) { crc[k * 256 + x] = v; v = plan.crc8_tab[v]; }
+    }
     CK(upload(d_crc, crc));
     CK(upload(d_tab, plan.bch_byte_tab));
     CK(upload(d_cols, plan.bch_shift_cols));

@@ -76,20 +76,23 @@ __device__ __forceinline__ uint32_t load_u32_unaligned(const uint8_t *p)
 __global__ void __launch_bounds__(BB_WARPS * 32) k_bb_bch(const BbArgs a)
 {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  uint32_t *s_tab = reinterpret_cast<uint32_t *>(smem_raw);   // 256 * 6
-  uint32_t *s_cols = s_tab + 256 * 6;                         // 6 * 32 * 6
-  uint8_t *s_crc8 = reinterpret_cast<uint8_t *>(s_cols + 6 * 32 * 6);
-  uint8_t *s_buf = s_crc8 + 256;
+  uint32_t *s_tab = reinterpret_cast<uint32_t *>(smem_raw);   // 2 * 256 * 6: T0 = b x^r mod g, T1 = b x^(r+8) mod g
+  uint32_t *s_cols = s_tab + 2 * 256 * 6;                     // 6 * 32 * 6
+  uint8_t *s_crc8 = reinterpret_cast<uint8_t *>(s_cols + 6 * 32 * 6);   // 4 * 256: CRC-8 slicing-by-4 tables
+  uint8_t *s_buf = s_crc8 + 1024;
   const int nbytes = a.nbch / 8, msg_bytes = a.kbch / 8;
-  const int buf_pitch = (nbytes + 15) & ~15;
+  constexpr int HIST = 192;                                   // stream history kept in front of each frame buffer
+  const int buf_pitch = ((nbytes + 15) & ~15) + HIST;
 
-  for (int i = threadIdx.x; i < 256 * 6; i += blockDim.x) s_tab[i] = a.bch_tab[i];
+  for (int i = threadIdx.x; i < 2 * 256 * 6; i += blockDim.x) s_tab[i] = a.bch_tab[i];
   for (int i = threadIdx.x; i < 6 * 32 * 6; i += blockDim.x) s_cols[i] = a.bch_cols[i];
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_crc8[i] = a.crc8_tab[i];
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_crc8[i] = a.crc8_tab[i];
   __syncthreads();
+  const uint8_t *S1 = s_crc8, *S2 = s_crc8 + 256, *S3 = s_crc8 + 512, *S4 = s_crc8 + 768;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint8_t *buf = s_buf + warp * buf_pitch;
+  uint8_t *hist = s_buf + warp * buf_pitch;                   // hist[HIST - k] = TS byte k positions before the frame
+  uint8_t *buf = hist + HIST;
   uint32_t *bufw = reinterpret_cast<uint32_t *>(buf);
   const int total = a.n_channels * a.frames;
   const int D = a.payload_bytes;
@@ -114,8 +117,17 @@ __global__ void __launch_bounds__(BB_WARPS * 32) k_bb_bch(const BbArgs a)
       const uint8_t *src = ts + P0;
       if (lane < 2) buf[10 + lane] = src[lane];
       const int w_end = (10 + Dj) >> 2;                    // words [3, w_end) lie completely inside the payload
-      for (int w = 3 + lane; w < w_end; w += 32) bufw[w] = load_u32_unaligned(src + 4 * w - 10);
+      for (int w0 = 3 + lane; w0 < w_end; w0 += 128) {     // four loads in flight per lane
+        uint32_t d[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (w0 + 32 * u < w_end) d[u] = load_u32_unaligned(src + 4 * (w0 + 32 * u) - 10);
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (w0 + 32 * u < w_end) bufw[w0 + 32 * u] = d[u];
+      }
       for (int i = 4 * w_end - 10 + lane; i < Dj; i += 32) buf[10 + i] = src[i];
+      // the 187 bytes before the frame (previous packet's tail) for the first CRC-8; missing history reads as 0,
+      // which leaves a zero CRC state unchanged
+      for (int k = 1 + lane; k <= 187; k += 32) hist[HIST - k] = (P0 - k >= 0 || a.hist_valid) ? src[-k] : (uint8_t)0;
     }
     else {
       for (int i = lane; i < Dj; i += 32) buf[10 + i] = ts[hem_ts_index(P0 + i, a.count0)];
@@ -136,16 +148,16 @@ __global__ void __launch_bounds__(BB_WARPS * 32) k_bb_bch(const BbArgs a)
         const int si = i0 + 188 * (lane + 32 * rnd);
         if (si < Dj) {
           if (buf[10 + si] != 0x47) atomicAdd(a.sync_errors, 1);
-          uint8_t crc = 0;
+          // CRC-8 of the 187 bytes before the sync byte, four bytes per step (slicing by 4)
+          uint32_t crc = 0;
           int u = si - 187;
-          if (u < 0) {
-            long long g = P0 + u;
-            if (g < 0 && !a.hist_valid) g = 0;
-            for (; g < P0; g++) crc = s_crc8[ts[g] ^ crc];
-            u = 0;
+          for (; u < 0 && u < si; u++) crc = S1[hist[HIST + u] ^ crc];
+          for (; u + 4 <= si; u += 4) {
+            const uint8_t *p = buf + 10 + u;
+            crc = S4[p[0] ^ crc] ^ S3[p[1]] ^ S2[p[2]] ^ S1[p[3]];
           }
-          for (; u < si; u++) crc = s_crc8[buf[10 + u] ^ crc];
-          my_crc[rnd] = crc;
+          for (; u < si; u++) crc = S1[buf[10 + u] ^ crc];
+          my_crc[rnd] = (uint8_t)crc;
         }
       }
     }
@@ -169,7 +181,7 @@ __global__ void __launch_bounds__(BB_WARPS * 32) k_bb_bch(const BbArgs a)
       h[6] = hem ? 0x00 : 0x47;
       h[7] = (uint8_t)(syncd >> 8); h[8] = (uint8_t)syncd;
       uint8_t crc = 0;
-      for (int i = 0; i < 9; i++) crc = s_crc8[crc ^ h[i]];
+      for (int i = 0; i < 9; i++) crc = S1[crc ^ h[i]];
       h[9] = hem ? (crc ^ 1) : crc;
       for (int i = 0; i < 10; i++) buf[i] = h[i];
     }
@@ -186,7 +198,19 @@ __global__ void __launch_bounds__(BB_WARPS * 32) k_bb_bch(const BbArgs a)
       int s = lane * a.chunk_bytes - a.lead_zero_bytes;
       const int e = s + a.chunk_bytes;
       if (s < 0) s = 0;
-      for (int i = s; i < e; i++) {
+      int i = s;
+      // two message bytes per step: the two table rows are independent of each other (slicing by 2)
+      for (; i + 2 <= e; i += 2) {
+        const uint32_t *A = s_tab + 256 * 6 + 6 * ((r0 >> 24) ^ buf[i]);
+        const uint32_t *B = s_tab + 6 * (((r0 >> 16) & 0xFFu) ^ buf[i + 1]);
+        r0 = ((r0 << 16) | (r1 >> 16)) ^ A[0] ^ B[0];
+        r1 = ((r1 << 16) | (r2 >> 16)) ^ A[1] ^ B[1];
+        r2 = ((r2 << 16) | (r3 >> 16)) ^ A[2] ^ B[2];
+        r3 = ((r3 << 16) | (r4 >> 16)) ^ A[3] ^ B[3];
+        r4 = ((r4 << 16) | (r5 >> 16)) ^ A[4] ^ B[4];
+        r5 = (r5 << 16) ^ A[5] ^ B[5];
+      }
+      for (; i < e; i++) {
         const uint32_t *T = s_tab + 6 * ((r0 >> 24) ^ buf[i]);
         r0 = ((r0 << 8) | (r1 >> 24)) ^ T[0];
         r1 = ((r1 << 8) | (r2 >> 24)) ^ T[1];
@@ -243,8 +267,8 @@ __global__ void __launch_bounds__(BB_WARPS * 32) k_bb_bch(const BbArgs a)
 void launch_bb_bch(const BbArgs &a, cudaStream_t s)
 {
   const int nbytes = a.nbch / 8;
-  const int buf_pitch = (nbytes + 15) & ~15;
-  const size_t smem = 256 * 6 * 4 + 6 * 32 * 6 * 4 + 256 + (size_t)BB_WARPS * buf_pitch;
+  const int buf_pitch = ((nbytes + 15) & ~15) + 192;
+  const size_t smem = 2 * 256 * 6 * 4 + 6 * 32 * 6 * 4 + 1024 + (size_t)BB_WARPS * buf_pitch;
   const int total = a.n_channels * a.frames;
   if (total < 1) return;
   static bool attr = false;

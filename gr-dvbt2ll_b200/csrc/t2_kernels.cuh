@@ -18,8 +18,8 @@ struct BbArgs {
   int kbch, nbch, bch_r, payload_bytes, mode, inband, fecblocks;
   int chunk_bytes, lead_zero_bytes;
   const uint8_t *scramble;    // kbch / 8
-  const uint8_t *crc8_tab;    // 256
-  const uint32_t *bch_tab;    // 256 * 6
+  const uint8_t *crc8_tab;    // 4 * 256: slicing-by-4 tables S1..S4 (S1 = the plain byte table)
+  const uint32_t *bch_tab;    // 2 * 256 * 6: T0 then T1
   const uint32_t *bch_cols;   // 6 * 32 * 6
   const uint8_t *inband_bytes;// 13
   uint8_t *out;               // packed codewords, pitch out_pitch bytes per FECFRAME

@@ -65,7 +65,7 @@ struct BbPlan {
   std::vector<uint8_t> scramble;      // kbch/8 bytes of the BB PRBS (x^14 + x^15, init 0x4A80 form)
   uint8_t crc8_tab[256];              // CRC-8 poly 0xD5, MSB first (reference :222-240)
   // 192-bit left-aligned remainder registers as 6 big-endian words.
-  std::vector<uint32_t> bch_byte_tab; // [256][6]  (b(x) * x^r) mod g
+  std::vector<uint32_t> bch_byte_tab; // [2][256][6]: (b(x) x^r) mod g, then (b(x) x^(r+8)) mod g
   int chunk_bytes;                    // message bytes per lane (32 lanes per FECFRAME)
   int lead_zero_bytes;                // zero bytes virtually prepended so 32 * chunk_bytes covers kbch/8
   std::vector<uint32_t> bch_shift_cols; // [6][32][6] column form of "multiply by x^(8*chunk_bytes) mod g"

@@ -164,11 +164,15 @@ bool build_bb_plan(int framesize, int rate, int mode, int inband, int fecblocks,
 
   const std::vector<uint8_t> g = bch_generator(f.bch_r);
   const Reg192 taps = generator_taps(g);
-  p->bch_byte_tab.assign(256 * 6, 0);
+  // T0[b] = (b(x) x^r) mod g and T1[b] = (b(x) x^(r+8)) mod g: two message bytes are folded per step with two
+  // independent look-ups (slicing by 2)
+  p->bch_byte_tab.assign(2 * 256 * 6, 0);
   for (int b = 0; b < 256; b++) {
     Reg192 R;
     for (int i = 7; i >= 0; i--) lfsr_step(R, taps, (b >> i) & 1);
     std::memcpy(&p->bch_byte_tab[b * 6], R.w, sizeof(R.w));
+    for (int i = 0; i < 8; i++) lfsr_step(R, taps, 0);
+    std::memcpy(&p->bch_byte_tab[(256 + b) * 6], R.w, sizeof(R.w));
   }
 
   const int msg_bytes = f.kbch / 8;
