@@ -313,12 +313,19 @@ __global__ void __launch_bounds__(LDPC_WARPS * 32) k_ldpc(const LdpcArgs a, int 
     {
       uint32_t *ow = reinterpret_cast<uint32_t *>(out);
       const int nw = info_bytes >> 2;
-      for (int i = lane; i < nw; i += 32) ow[i] = __ldg(iw + i);
+      for (int i0 = lane; i0 < nw; i0 += 128) {
+        uint32_t d[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) if (i0 + 32 * k < nw) d[k] = __ldg(iw + i0 + 32 * k);
+#pragma unroll
+        for (int k = 0; k < 4; k++) if (i0 + 32 * k < nw) ow[i0 + 32 * k] = d[k];
+      }
       for (int b = (nw << 2) + lane; b < info_bytes; b += 32) out[b] = in[b];
     }
     // ---- wrap-extended groups: 13 words = circular bits [0, 416) of each 360-bit group
     // (windows are cut straight out of the packed codeword in global memory; bits past nbch never enter:
     //  the last window of a group is masked / taken from the group's own start)
+#pragma unroll 4
     for (int idx = lane; idx < G * 13; idx += 32) {
       const int g = idx / 13, w = idx - g * 13;
       const int base = 360 * g;
@@ -366,14 +373,35 @@ __global__ void __launch_bounds__(LDPC_WARPS * 32) k_ldpc(const LdpcArgs a, int 
       E = (x >> 1) ^ (carry ? 0xFFFFFFFFu : 0u);
       if (lane == 11) E &= 0xFF000000u;
     }
-    // ---- store parity rows (row t occupies bytes [nbch/8 + 45 t, +45)), applying E on the fly
-    for (int i0 = 0; i0 < q * 45; i0 += 32) {          // warp-uniform trip count (shuffle inside)
+    // ---- apply E, then store the parity rows: rows are 360-bit strings laid end to end after the info bits
+    for (int i0 = 0; i0 < q * 12; i0 += 32) {          // warp-uniform trip count (shuffle inside)
       const int idx = i0 + lane;
-      const bool on = idx < q * 45;
-      const int t = on ? idx / 45 : 0, b = on ? idx - t * 45 : 0;
-      const int w = b >> 2;
-      const uint32_t ew = __shfl_sync(0xffffffffu, E, w);
-      if (on) out[info_bytes + idx] = (uint8_t)((rows[t * 12 + w] ^ ew) >> (24 - 8 * (b & 3)));
+      const uint32_t ew = __shfl_sync(0xffffffffu, E, idx % 12);
+      if (idx < q * 12) rows[idx] ^= ew;
+    }
+    __syncwarp();
+    if ((info_bytes & 3) == 0) {
+      // word-wise: output word j holds parity bits [32 j, 32 j + 32) = a window of row t (+ the head of row t + 1)
+      uint32_t *pw = reinterpret_cast<uint32_t *>(out + info_bytes);
+      const int nwp = (q * 360) >> 5;                  // q * 45 bytes is a multiple of 4 only if q is; tail below
+      for (int j = lane; j < nwp; j += 32) {
+        const int P = j << 5;
+        const int t = P / 360, o = P - t * 360;
+        uint32_t v = window32(rows + t * 12, o);
+        const int n1 = 360 - o;                        // bits left in row t
+        if (n1 < 32) v = (v & ~(0xFFFFFFFFu >> n1)) | (rows[(t + 1) * 12] >> n1);
+        pw[j] = bswap32(v);
+      }
+      for (int b = (nwp << 2) + lane; b < q * 45; b += 32) {
+        const int t = b / 45, bb = b - t * 45;
+        out[info_bytes + b] = (uint8_t)(rows[t * 12 + (bb >> 2)] >> (24 - 8 * (bb & 3)));
+      }
+    }
+    else {
+      for (int b = lane; b < q * 45; b += 32) {
+        const int t = b / 45, bb = b - t * 45;
+        out[info_bytes + b] = (uint8_t)(rows[t * 12 + (bb >> 2)] >> (24 - 8 * (bb & 3)));
+      }
     }
     __syncwarp();
   }
@@ -455,7 +483,13 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map(const MapArgs a)
   for (int f = blockIdx.x; f < a.frames; f += gridDim.x) {
     const uint32_t *in = reinterpret_cast<const uint32_t *>(a.in + (long long)f * a.in_pitch);
     __syncthreads();
-    for (int i = threadIdx.x; i < nwords + 2; i += blockDim.x) u[i] = i < nwords ? bswap32(in[i]) : 0u;
+    for (int i0 = threadIdx.x; i0 < nwords + 2; i0 += 4 * MAP_THREADS) {      // four loads in flight per thread
+      uint32_t d[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) { const int i = i0 + k * MAP_THREADS; d[k] = i < nwords ? __ldg(in + i) : 0u; }
+#pragma unroll
+      for (int k = 0; k < 4; k++) { const int i = i0 + k * MAP_THREADS; if (i < nwords + 2) u[i] = bswap32(d[k]); }
+    }
     __syncthreads();
     if (a.ncol) {
       const int rows = a.nldpc / a.ncol;
@@ -518,12 +552,22 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map(const MapArgs a)
       // cell-interleaved order: output position x holds cell ci_inv[(x - shift) mod Nc]
       uint16_t *o16 = a.out16 + (long long)(f / a.fecblocks) * a.out16_frame_stride + (long long)(f % a.fecblocks) * Nc;
       const int shift = a.fec_shift[f % a.fecblocks];
-      for (int xo = threadIdx.x; xo < Nc; xo += blockDim.x) {
-        int y = xo - shift;
-        if (y < 0) y += Nc;
-        const int c = __ldg(a.ci_inv + y);
-        const int pc = c == 0 ? Nc - 1 : c - 1;
-        o16[xo] = (uint16_t)(cell(c) | (cell(a.cyclic_delay ? pc : c) << 8));
+      // eight permutation look-ups in flight per thread
+      for (int x0 = threadIdx.x; x0 < Nc; x0 += 8 * MAP_THREADS) {
+        int c[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          const int xo = x0 + k * MAP_THREADS;
+          int y = xo - shift;
+          if (y < 0) y += Nc;
+          c[k] = xo < Nc ? __ldg(a.ci_inv + y) : 0;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          const int xo = x0 + k * MAP_THREADS;
+          const int pc = c[k] == 0 ? Nc - 1 : c[k] - 1;
+          if (xo < Nc) o16[xo] = (uint16_t)(cell(c[k]) | (cell(a.cyclic_delay ? pc : c[k]) << 8));
+        }
       }
     }
     else if (a.ci_inv) {

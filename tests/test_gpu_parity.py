@@ -82,16 +82,30 @@ def test_blocks_match_golden(name):
         assert abs(np.sqrt(np.mean(np.abs(samples.astype(np.complex128)) ** 2)) - rms) <= 1e-5 * rms
 
 
-@pytest.mark.parametrize("name", ["c1", "c2", "c3", "c4"])
+CHAIN_VARIANTS = {
+    # in-band type B signalling + L1 scrambling + reserved-bias bits (v1.3.1), 16QAM L1, no time interleaver
+    "c1-inband-v131": dict(K.CONFIGS["c1"], inband=1, version=2, l1scrambled=1, reservedbiasbits=1, l1constellation=2,
+                           tiblocks=0, fecblocks=7),
+    # MISO group 2, reserved tones, inverse-sinc equalisation, 8K
+    "c2-miso-tr-eq": dict(K.CONFIGS["c2"], preamble=K.PREAMBLE_T2_MISO, misogroup=1, paprmode=2, equalization=1,
+                          fecblocks=17, tiblocks=5),
+    # 2K with 8 P2 symbols (zig-zag L1 mapping), QPSK L1, 64QAM data
+    "2k-zigzag": dict(K.CONFIGS["c1"], fftsize=K.FFTSIZE_2K, pilotpattern=K.PILOT_PP2, guardinterval=K.GI_1_8, numdatasyms=30,
+                      constellation=K.MOD_64QAM, rate=K.C3_5, fecblocks=14, l1constellation=1),
+}
+
+
+@pytest.mark.parametrize("name", ["c1", "c2", "c3", "c4"] + sorted(CHAIN_VARIANTS))
 def test_chain_matches_reference(reflib, name):
     """Fused device-resident chain (what bench.py times) against the reference flowgraph."""
-    cfg = K.resolve(name)
+    cfg = K.resolve(CHAIN_VARIANTS.get(name, name))
     nframes = 2
     ch = T.Chain(cfg, max_frames=nframes)
     n_ts = ch.ts_bytes_per_frame
     ts = K.make_ts(nframes * n_ts + 1000)
     refs = _ref_frames(reflib, cfg, ts, nframes)
     assert refs[0]["ts_used"] == n_ts
+    assert reflib.Chain(cfg).fm.warnings == 0
     out = ch.run_host(ts[:nframes * n_ts], 1, nframes)[0]
     S = ch.samples_per_frame
     F = cfg["fecblocks"]
