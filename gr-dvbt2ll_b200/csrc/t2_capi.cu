@@ -249,7 +249,7 @@ struct LdpcHandle : dvbt2ll_handle {
     if (frames < 1) return 0;
     if (ninput < frames * plan.fec.nbch) return fail(DVBT2LL_ERR_SHORT, "ldpc: not enough input items");
     const int ip = align16(plan.fec.nbch / 8), op = align16(plan.fec.nldpc / 8);
-    CK(d_in_packed.ensure((size_t)frames * ip + 16));
+    CK(d_in_packed.ensure((size_t)frames * ip + 64));
     CK(d_out_packed.ensure((size_t)frames * op + 16));
     t2k::launch_pack_bits((const uint8_t *)d_in, plan.fec.nbch, d_in_packed.as<uint8_t>(), ip, frames, s);
     t2k::LdpcArgs a;

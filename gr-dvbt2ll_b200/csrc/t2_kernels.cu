@@ -288,51 +288,54 @@ void launch_bb_bch(const BbArgs &a, cudaStream_t s)
 // ================================================================================================
 constexpr int LDPC_WARPS = 4;
 
-// 32 stream bits starting at bit position p of a packed (byte stream) global buffer that is 4-byte aligned
-__device__ __forceinline__ uint32_t window32_global(const uint32_t *__restrict__ w, int p)
+// 32 stream bits starting at bit position p of a packed byte stream held as raw (little-endian loaded) words
+__device__ __forceinline__ uint32_t window32_be(const uint32_t *w, int p)
 {
   const int k = p >> 5;
-  return __funnelshift_l(bswap32(__ldg(w + k + 1)), bswap32(__ldg(w + k)), p & 31);
+  return __funnelshift_l(bswap32(w[k + 1]), bswap32(w[k]), p & 31);
 }
 
-__global__ void __launch_bounds__(LDPC_WARPS * 32) k_ldpc(const LdpcArgs a, int warp_words)
+__global__ void __launch_bounds__(LDPC_WARPS * 32, 4) k_ldpc(const LdpcArgs a, int warp_words, int cw_words)
 {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint32_t *s_all = reinterpret_cast<uint32_t *>(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint32_t *ext = s_all + warp * warp_words;      // [groups][13]
-  uint32_t *rows = ext + a.groups * 13;           // [q][12]
+  uint32_t *cw = s_all + warp * warp_words;       // [cw_words] packed codeword as loaded (16-byte aligned), later reused:
+  uint32_t *rows = cw;                            // [q][12] parity rows
+  uint32_t *ext = cw + cw_words;                  // [groups][13]
   const int q = a.q, G = a.groups;
   const int info_bytes = a.nbch / 8;
 
   for (int job = blockIdx.x * LDPC_WARPS + warp; job < a.frames; job += gridDim.x * LDPC_WARPS) {
     const uint8_t *in = a.in + (long long)job * a.in_pitch;
     uint8_t *out = a.out + (long long)job * a.out_pitch;
-    const uint32_t *iw = reinterpret_cast<const uint32_t *>(in);
+    // ---- whole BCH codeword into shared memory with 16-byte asynchronous copies (all in flight at once)
+    {
+      const int n16 = (info_bytes + 8 + 15) >> 4;                    // a little beyond the end for the last windows
+      const unsigned dst0 = (unsigned)__cvta_generic_to_shared(cw);
+      for (int i = lane; i < n16; i += 32)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst0 + 16u * i), "l"(in + 16 * i));
+      asm volatile("cp.async.commit_group;\n" ::);
+      asm volatile("cp.async.wait_group 0;\n" ::);
+    }
+    __syncwarp();
     // ---- info bits pass through to the output
     {
       uint32_t *ow = reinterpret_cast<uint32_t *>(out);
       const int nw = info_bytes >> 2;
-      for (int i0 = lane; i0 < nw; i0 += 128) {
-        uint32_t d[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) if (i0 + 32 * k < nw) d[k] = __ldg(iw + i0 + 32 * k);
-#pragma unroll
-        for (int k = 0; k < 4; k++) if (i0 + 32 * k < nw) ow[i0 + 32 * k] = d[k];
-      }
-      for (int b = (nw << 2) + lane; b < info_bytes; b += 32) out[b] = in[b];
+      for (int i = lane; i < nw; i += 32) ow[i] = cw[i];
+      const uint8_t *cb = reinterpret_cast<const uint8_t *>(cw);
+      for (int b = (nw << 2) + lane; b < info_bytes; b += 32) out[b] = cb[b];
     }
     // ---- wrap-extended groups: 13 words = circular bits [0, 416) of each 360-bit group
-    // (windows are cut straight out of the packed codeword in global memory; bits past nbch never enter:
-    //  the last window of a group is masked / taken from the group's own start)
-#pragma unroll 4
+    // (bits past nbch never enter: the last window of a group is masked / taken from the group's own start)
     for (int idx = lane; idx < G * 13; idx += 32) {
       const int g = idx / 13, w = idx - g * 13;
       const int base = 360 * g;
       uint32_t v;
-      if (w < 11) v = window32_global(iw, base + 32 * w);
-      else if (w == 11) v = (window32_global(iw, base + 352) & 0xFF000000u) | (window32_global(iw, base) >> 8);
-      else v = window32_global(iw, base + 24);
+      if (w < 11) v = window32_be(cw, base + 32 * w);
+      else if (w == 11) v = (window32_be(cw, base + 352) & 0xFF000000u) | (window32_be(cw, base) >> 8);
+      else v = window32_be(cw, base + 24);
       ext[idx] = v;
     }
     __syncwarp();
@@ -409,7 +412,10 @@ __global__ void __launch_bounds__(LDPC_WARPS * 32) k_ldpc(const LdpcArgs a, int 
 
 void launch_ldpc(const LdpcArgs &a, cudaStream_t s)
 {
-  const int warp_words = a.groups * 13 + a.q * 12 + 4;
+  // per warp: extended groups + max(raw codeword, parity rows)
+  int cw_words = ((a.nbch / 8 + 8 + 15) >> 4) * 4 + 4;
+  if (cw_words < a.q * 12 + 4) cw_words = a.q * 12 + 4;
+  const int warp_words = (a.groups * 13 + cw_words + 3) & ~3;
   const size_t smem = (size_t)LDPC_WARPS * warp_words * 4;
   if (a.frames < 1) return;
   static bool attr = false;
@@ -420,7 +426,7 @@ void launch_ldpc(const LdpcArgs &a, cudaStream_t s)
   int blocks = (a.frames + LDPC_WARPS - 1) / LDPC_WARPS;
   const int cap = sm_count() * per_sm;
   if (blocks > cap) blocks = cap;
-  k_ldpc<<<blocks, LDPC_WARPS * 32, smem, s>>>(a, warp_words);
+  k_ldpc<<<blocks, LDPC_WARPS * 32, smem, s>>>(a, warp_words, cw_words);
   count_launch();
 }
 
@@ -462,8 +468,8 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map(const MapArgs a)
 {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int nwords = (a.nldpc + 31) / 32;
-  uint32_t *u = reinterpret_cast<uint32_t *>(smem_raw);                   // [nwords + 2]
-  float2 *lut = reinterpret_cast<float2 *>(u + ((nwords + 3) & ~1));      // [1 << mod]
+  uint32_t *u = reinterpret_cast<uint32_t *>(smem_raw);                   // packed codeword, raw byte order, + slack
+  float2 *lut = reinterpret_cast<float2 *>(u + ((nwords + 11) & ~3));     // [1 << mod]
   uint8_t *cw = reinterpret_cast<uint8_t *>(lut + (1 << a.mod));          // [cell_size rounded up to 64]
   for (int i = threadIdx.x; i < (1 << a.mod); i += blockDim.x) lut[i] = a.lut[i];
   const int mod = a.mod, Nc = a.cell_size;
@@ -483,12 +489,15 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map(const MapArgs a)
   for (int f = blockIdx.x; f < a.frames; f += gridDim.x) {
     const uint32_t *in = reinterpret_cast<const uint32_t *>(a.in + (long long)f * a.in_pitch);
     __syncthreads();
-    for (int i0 = threadIdx.x; i0 < nwords + 2; i0 += 4 * MAP_THREADS) {      // four loads in flight per thread
-      uint32_t d[4];
-#pragma unroll
-      for (int k = 0; k < 4; k++) { const int i = i0 + k * MAP_THREADS; d[k] = i < nwords ? __ldg(in + i) : 0u; }
-#pragma unroll
-      for (int k = 0; k < 4; k++) { const int i = i0 + k * MAP_THREADS; if (i < nwords + 2) u[i] = bswap32(d[k]); }
+    {
+      // packed codeword into shared memory as raw bytes with 16-byte asynchronous copies (frames are 16-byte pitched)
+      const int n16 = (nwords + 3) >> 2;
+      const unsigned dst0 = (unsigned)__cvta_generic_to_shared(u);
+      for (int i = threadIdx.x; i < n16; i += MAP_THREADS)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst0 + 16u * i), "l"(reinterpret_cast<const uint8_t *>(in) + 16 * i));
+      asm volatile("cp.async.commit_group;\n" ::);
+      asm volatile("cp.async.wait_group 0;\n" ::);
+      if (threadIdx.x < 4) u[4 * n16 + threadIdx.x] = 0u;
     }
     __syncthreads();
     if (a.ncol) {
@@ -507,8 +516,8 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map(const MapArgs a)
             if (s0 < 0) s0 += rows;
             const int base = s_base[rho];
             const int n1 = rows - s0;
-            uint32_t w = window32(u, base + s0);
-            if (n1 < 32) w = (w & ~(0xFFFFFFFFu >> n1)) | (window32(u, base) >> n1);
+            uint32_t w = window32_be(u, base + s0);
+            if (n1 < 32) w = (w & ~(0xFFFFFFFFu >> n1)) | (window32_be(u, base) >> n1);
             A[y] = w;
           }
         }
@@ -539,7 +548,7 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map(const MapArgs a)
         uint32_t v = 0;
         for (int b = 0; b < mod; b++) {
           const int p = __ldg(src + b);
-          v = (v << 1) | ((u[p >> 5] >> (31 - (p & 31))) & 1u);
+          v = (v << 1) | ((reinterpret_cast<const uint8_t *>(u)[p >> 3] >> (7 - (p & 7))) & 1u);
         }
         cw[c + ((c >> 6) << 2)] = (uint8_t)v;
       }
@@ -596,7 +605,7 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map(const MapArgs a)
 void launch_map(const MapArgs &a, cudaStream_t s)
 {
   const int nwords = (a.nldpc + 31) / 32;
-  const size_t smem = (size_t)((nwords + 3) & ~1) * 4 + (size_t)(1 << a.mod) * 8 + ((a.cell_size + 127) & ~63) + 4 * (a.cell_size / 64 + 2);
+  const size_t smem = (size_t)((nwords + 11) & ~3) * 4 + (size_t)(1 << a.mod) * 8 + ((a.cell_size + 127) & ~63) + 4 * (a.cell_size / 64 + 2);
   int blocks = a.frames;
   const int cap = sm_count() * 16;
   if (blocks > cap) blocks = cap;
