@@ -376,7 +376,7 @@ struct FrameHandle : dvbt2ll_handle {
 
 // ================================================================================================
 struct OfdmDevice {
-  DevBuf d_code, d_pool, d_p1, d_sinc, d_tw, d_tw_split;
+  DevBuf d_code, d_pool, d_p1, d_sinc, d_tw, d_tw_split, d_scratch;
   int log2_m, split;
   long long pool_stride;
   int init(const std::vector<int32_t> &code, const t2::CellPool &pool, const t2::OfdmPlan &op)
@@ -422,7 +422,13 @@ struct OfdmDevice {
       CK(upload(d_sinc, sinc_pos));
     }
     CK(upload(d_tw, make_twiddles(M, M)));
-    if (split == 2) CK(upload(d_tw_split, make_twiddles(N, M)));
+    if (split == 2) {
+      CK(upload(d_tw_split, make_twiddles(N, M)));
+      int dev = 0, sms = 148;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      CK(d_scratch.ensure((size_t)(sms + 8) * 2 * M * sizeof(float2)));     // one slot per resident CTA
+    }
     return 0;
   }
   void fill(t2k::OfdmArgs &a, const t2::OfdmPlan &op, const t2::CellPool &pool) const
@@ -435,6 +441,7 @@ struct OfdmDevice {
     a.c_ps = op.dims.c_ps; a.left_nulls = op.left_nulls; a.gi = op.dims.gi; a.num_symbols = op.dims.num_symbols;
     a.norm = op.normalization;
     a.cells16 = 0; a.runs = 0; a.run_ptr = 0; a.stage_cap = 0; a.lut = 0; a.lut_n = 0;
+    a.out_fmt = 0; a.sink_gain = 1.0f; a.scratch = d_scratch.as<float2>();
   }
 };
 
@@ -457,7 +464,7 @@ struct OfdmHandle : dvbt2ll_handle {
     t2k::OfdmArgs a;
     dev.fill(a, plan, plan.pool);
     a.cells = (const float2 *)d_in; a.cells_stride = plan.dims.active_items;
-    a.out = (float2 *)d_out; a.out_stride = plan.samples_per_frame;
+    a.out = d_out; a.out_stride = plan.samples_per_frame;
     a.frames = frames; a.frame_idx0 = 0; a.frames_per_channel = frames;
     t2k::launch_ofdm(a, s);
     CK(cudaGetLastError());
@@ -495,12 +502,14 @@ struct ChainHandle : dvbt2ll_handle {
   DevBuf d_bch, d_fec, d_cells, d_ts_stage, d_out_stage, d_ci_inv, d_fec_shift, d_runs, d_run_ptr;
   int stage_cap;
   int max_frames, device;
+  int sink_fmt;          // 0 complex64 (what pilotgenp1insert_cc emits), 1 interleaved int16 I/Q
+  float sink_gain;       // the flowgraph's multiply_const stage folded into the last kernel
   cudaStream_t stream2;
   int last_frames;
   bool timing;
   cudaEvent_t ev[5];
   float stage_ms[5];
-  ChainHandle() : dvbt2ll_handle(CHAIN), max_frames(0), device(0), stream2(0), last_frames(0), timing(false)
+  ChainHandle() : dvbt2ll_handle(CHAIN), max_frames(0), device(0), sink_fmt(0), sink_gain(1.0f), stream2(0), last_frames(0), timing(false)
   {
     for (int i = 0; i < 5; i++) { ev[i] = 0; stage_ms[i] = 0.f; }
   }
@@ -511,7 +520,7 @@ struct ChainHandle : dvbt2ll_handle {
   long long ts_per_frame() const { return bb.payload_bytes(F(), 0); }
   int output_multiple() const { return oplan.samples_per_frame; }
   int in_item() const { return 1; }
-  int out_item() const { return 8; }
+  int out_item() const { return sink_fmt ? 4 : 8; }
   int forecast(int noutput) const { return (int)(ts_per_frame() * (noutput / oplan.samples_per_frame)); }
   int dev_init()
   {
@@ -574,7 +583,8 @@ struct ChainHandle : dvbt2ll_handle {
     oa.cells = 0; oa.cells_stride = cells16_stride();
     oa.cells16 = cell_buf; oa.runs = d_runs.p; oa.run_ptr = d_run_ptr.as<int32_t>(); oa.stage_cap = stage_cap;
     oa.lut = map.d_lut.as<float2>(); oa.lut_n = 1 << map.plan.mod;
-    oa.out = (float2 *)d_out; oa.out_stride = oplan.samples_per_frame;
+    oa.out = d_out; oa.out_stride = oplan.samples_per_frame;
+    oa.out_fmt = sink_fmt; oa.sink_gain = sink_gain; oa.norm = oplan.normalization * sink_gain;
     oa.frames = frames; oa.frame_idx0 = first_frame; oa.frames_per_channel = n_frames;
     t2k::launch_ofdm(oa, s);
     if (timing) cudaEventRecord(ev[4], s);
@@ -813,11 +823,12 @@ int dvbt2ll_chain_run_host(dvbt2ll_handle *h, const void *ts, long long ts_pitch
   const long long per_ch = c->ts_per_frame() * n_frames;
   const long long hist = first_frame > 0 ? 187 : 0;
   const long long dpitch = (per_ch + hist + 255) & ~255LL;
-  const size_t out_bytes = (size_t)n_channels * n_frames * c->oplan.samples_per_frame * sizeof(float2);
+  const size_t ssz = c->sink_fmt ? 4 : 8;                                        // bytes per output sample
+  const size_t out_bytes = (size_t)n_channels * n_frames * c->oplan.samples_per_frame * ssz;
   CK(c->d_ts_stage.ensure((size_t)n_channels * dpitch + 512));
   CK(c->d_out_stage.ensure(out_bytes));
   uint8_t *base = c->d_ts_stage.as<uint8_t>() + 256;
-  float2 *dout = c->d_out_stage.as<float2>();
+  uint8_t *dout = c->d_out_stage.as<uint8_t>();
   const size_t ch_out = (size_t)n_frames * c->oplan.samples_per_frame;          // samples per channel
   // host layout: channel-major with pitch ts_pitch; when first_frame > 0 each channel pointer must be preceded
   // by 187 history bytes.  Channels are processed in groups on two streams so that the H2D copy and the
@@ -833,10 +844,10 @@ int dvbt2ll_chain_run_host(dvbt2ll_handle *h, const void *ts, long long ts_pitch
     cudaStream_t s = (gi & 1) ? c->stream2 : c->stream;
     CK(cudaMemcpy2DAsync(base + (size_t)c0 * dpitch - hist, (size_t)dpitch, (const uint8_t *)ts + (size_t)c0 * ts_pitch - hist,
                          (size_t)ts_pitch, (size_t)(per_ch + hist), (size_t)nc, cudaMemcpyHostToDevice, s));
-    r = c->run(base + (size_t)c0 * dpitch, dpitch, nc, n_frames, first_frame, dout + (size_t)c0 * ch_out, s,
+    r = c->run(base + (size_t)c0 * dpitch, dpitch, nc, n_frames, first_frame, dout + (size_t)c0 * ch_out * ssz, s,
                groups == 1 ? 0 : (gi & 1) * per * n_frames);
     if (r < 0) return r;
-    CK(cudaMemcpyAsync((float2 *)out + (size_t)c0 * ch_out, dout + (size_t)c0 * ch_out, (size_t)nc * ch_out * sizeof(float2),
+    CK(cudaMemcpyAsync((uint8_t *)out + (size_t)c0 * ch_out * ssz, dout + (size_t)c0 * ch_out * ssz, (size_t)nc * ch_out * ssz,
                        cudaMemcpyDeviceToHost, s));
   }
   CK(cudaStreamSynchronize(c->stream));
@@ -860,6 +871,16 @@ long long dvbt2ll_chain_tap(dvbt2ll_handle *h, const char *stage, void *out, lon
   CK(cudaDeviceSynchronize());
   if (out && cap > 0) CK(cudaMemcpy(out, src, (size_t)cap < bytes ? (size_t)cap : bytes, cudaMemcpyDeviceToHost));
   return (long long)bytes;
+}
+
+int dvbt2ll_chain_set_sink(dvbt2ll_handle *h, int format, float gain)
+{
+  ChainHandle *c = as_chain(h);
+  if (!c) return fail(DVBT2LL_ERR_INVALID, "not a chain handle");
+  if (format != 0 && format != 1) return fail(DVBT2LL_ERR_INVALID, "chain: sink format must be 0 (complex64) or 1 (int16 I/Q)");
+  c->sink_fmt = format;
+  c->sink_gain = gain;
+  return 0;
 }
 
 void dvbt2ll_chain_enable_timing(dvbt2ll_handle *h, int on) { ChainHandle *c = as_chain(h); if (c) c->timing = on != 0; }

@@ -871,6 +871,17 @@ int ofdm_position_of_bin(int m, int log2_m)
   return p;
 }
 
+// one output sample: complex64, or (sink format 1) interleaved 16-bit I/Q = round(x * 32767), saturated
+__device__ __forceinline__ void store_sample(void *base, long long idx, float2 v, int fmt)
+{
+  if (fmt == 0) reinterpret_cast<float2 *>(base)[idx] = v;
+  else {
+    int xi = __float2int_rn(v.x * 32767.f), yi = __float2int_rn(v.y * 32767.f);
+    xi = max(-32768, min(32767, xi)); yi = max(-32768, min(32767, yi));
+    reinterpret_cast<short2 *>(base)[idx] = make_short2((short)xi, (short)yi);
+  }
+}
+
 // Kernel schedule per (symbol, phase), M = 2^LOG2M points, first radix R0 = 2^(LOG2M mod 4):
 //   1. fill fused with the first pass: a thread gathers the R0 consecutive positions of a first-pass
 //      butterfly (code table read as one vector), does the R0-point DFT in registers, stores to smem;
@@ -912,11 +923,18 @@ __global__ void __launch_bounds__(T, 1024 / T) k_ofdm(const OfdmArgs a)
     const int variant = (int)((a.frame_idx0 + (f % a.frames_per_channel)) % a.l1post_variants);
     const float2 *cells = a.cells + (long long)f * a.cells_stride;
     const float2 *pool = a.pool + (long long)variant * a.pool_stride;
-    float2 *out = a.out + (long long)f * a.out_stride;
-    float2 *sym = out + 2048 + (long long)l * (N + a.gi);
+    // output addressing in samples relative to a.out (element size depends on the sink format)
+    const long long out0 = (long long)f * a.out_stride;
+    const long long sym0 = out0 + 2048 + (long long)l * (N + a.gi);
+    const int fmt = a.out_fmt;
+    float2 *park = a.scratch + (long long)blockIdx.x * M;     // even-bin half of a 32K symbol, per CTA, L2 resident
 
     if (l == 0)
-      for (int i = threadIdx.x; i < 2048; i += T) out[i] = __ldg(a.p1 + i);
+      for (int i = threadIdx.x; i < 2048; i += T) {
+        float2 p = __ldg(a.p1 + i);
+        p.x *= a.sink_gain; p.y *= a.sink_gain;
+        store_sample(a.out, out0 + i, p, fmt);
+      }
 
     if (C16) {
       __syncthreads();      // the previous symbol's fill has finished reading the staging area
@@ -1026,8 +1044,8 @@ __global__ void __launch_bounds__(T, 1024 / T) k_ofdm(const OfdmArgs a)
             float2 o = v[bitrev_c(k, 16)];
             o = __fmul2_rn(o, make_float2(a.norm, a.norm));
             const int t = i + k * NLAST;
-            sym[a.gi + t] = o;
-            if (t >= cp_from) sym[t - cp_from] = o;
+            store_sample(a.out, sym0 + a.gi + t, o, fmt);
+            if (t >= cp_from) store_sample(a.out, sym0 + t - cp_from, o, fmt);
           }
         }
         else if (phase == 0) {
@@ -1035,9 +1053,9 @@ __global__ void __launch_bounds__(T, 1024 / T) k_ofdm(const OfdmArgs a)
           for (int k = 0; k < 16; k++) {
             float2 o = v[bitrev_c(k, 16)];
             o = __fmul2_rn(o, make_float2(a.norm, a.norm));
-            // even-bin half E[n]: parked in the first half of the symbol; the odd-bin phase reads it back and
-            // writes both halves and the cyclic prefix
-            sym[a.gi + i + k * NLAST] = o;
+            // even-bin half E[n]: parked in this CTA's scratch slot (stays in L2); the odd-bin phase reads it
+            // back (same thread, same address) and writes both halves and the cyclic prefix exactly once
+            park[i + k * NLAST] = o;
           }
         }
         else {
@@ -1049,16 +1067,16 @@ __global__ void __launch_bounds__(T, 1024 / T) k_ofdm(const OfdmArgs a)
           for (int h = 0; h < 2; h++) {
             float2 e[8];
 #pragma unroll
-            for (int k = 0; k < 8; k++) e[k] = sym[a.gi + i + (8 * h + k) * NLAST];
+            for (int k = 0; k < 8; k++) e[k] = __ldcg(park + i + (8 * h + k) * NLAST);
 #pragma unroll
             for (int k = 0; k < 8; k++) {
               const int kk = 8 * h + k;
               const int t = i + kk * NLAST;
               const float2 o = cmul(cmul(v[bitrev_c(kk, 16)], w32(kk)), wi);
-              sym[a.gi + t] = cadd(e[k], o);
+              store_sample(a.out, sym0 + a.gi + t, cadd(e[k], o), fmt);
               const float2 hi = csub(e[k], o);
-              sym[a.gi + t + M] = hi;
-              if (t + M >= cp_from) sym[t + M - cp_from] = hi;
+              store_sample(a.out, sym0 + a.gi + t + M, hi, fmt);
+              if (t + M >= cp_from) store_sample(a.out, sym0 + t + M - cp_from, hi, fmt);
             }
           }
         }

@@ -28,7 +28,7 @@ EXPORTED_SYMBOLS = [
     "dvbt2ll_interleavermod_create", "dvbt2ll_framemapperfint_create", "dvbt2ll_pilotgenp1insert_create",
     "dvbt2ll_chain_create", "dvbt2ll_chain_ts_bytes_per_frame", "dvbt2ll_chain_samples_per_frame",
     "dvbt2ll_chain_fecframes_per_frame", "dvbt2ll_chain_run_device", "dvbt2ll_chain_run_host",
-    "dvbt2ll_chain_tap", "dvbt2ll_chain_stage_ms", "dvbt2ll_chain_enable_timing",
+    "dvbt2ll_chain_tap", "dvbt2ll_chain_stage_ms", "dvbt2ll_chain_enable_timing", "dvbt2ll_chain_set_sink",
 ]
 
 
@@ -79,6 +79,7 @@ def lib():
         L.dvbt2ll_chain_tap.argtypes = [vp, C.c_char_p, vp, cll]
         L.dvbt2ll_chain_stage_ms.argtypes = [vp, C.POINTER(C.c_float)]
         L.dvbt2ll_chain_enable_timing.argtypes = [vp, ci]
+        L.dvbt2ll_chain_set_sink.argtypes = [vp, ci, C.c_float]
         _lib = L
     return _lib
 
@@ -231,11 +232,24 @@ class Chain(_Block):
     def fecframes_per_frame(self):
         return int(lib().dvbt2ll_chain_fecframes_per_frame(self._h))
 
+    sink_format = 0
+
+    def set_sink(self, fmt, gain=1.0):
+        """fmt 0: complex64 (default); fmt 1: interleaved int16 I/Q = round(gain * x * 32767). gain = the flowgraph's multiply_const."""
+        r = lib().dvbt2ll_chain_set_sink(self._h, int(fmt), float(gain))
+        if r < 0:
+            raise ValueError(last_error())
+        self.sink_format = int(fmt)
+
     def run_host(self, ts, n_channels, n_frames, first_frame=0, out=None):
-        """ts: uint8 array [n_channels, >= n_frames*ts_bytes_per_frame] (host). Returns complex64 [n_channels, n_frames*samples]."""
+        """ts: uint8 array [n_channels, >= n_frames*ts_bytes_per_frame] (host). Returns complex64 [n_channels, n_frames*samples]
+        (int16 [n_channels, n_frames*samples, 2] with sink format 1)."""
         ts = np.ascontiguousarray(ts, dtype=np.uint8).reshape(n_channels, -1)
         if out is None:
-            out = np.empty((n_channels, n_frames * self.samples_per_frame), dtype=np.complex64)
+            if self.sink_format:
+                out = np.empty((n_channels, n_frames * self.samples_per_frame, 2), dtype=np.int16)
+            else:
+                out = np.empty((n_channels, n_frames * self.samples_per_frame), dtype=np.complex64)
         r = lib().dvbt2ll_chain_run_host(self._h, ts.ctypes.data, ts.shape[1], n_channels, n_frames, first_frame,
                                          out.ctypes.data)
         if r < 0:

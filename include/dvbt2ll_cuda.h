@@ -117,6 +117,11 @@ DVBT2LL_API_EXPORT int dvbt2ll_chain_run_device(dvbt2ll_handle *h, const void *d
 /* Same with HOST buffers: H2D copy, run, D2H copy, synchronize. */
 DVBT2LL_API_EXPORT int dvbt2ll_chain_run_host(dvbt2ll_handle *h, const void *ts, long long ts_pitch, int n_channels,
                                               int n_frames, long long first_frame, void *out);
+/* Optional sink stage of the flowgraph folded into the last kernel (apps/vv009-4kshort.grc: multiply_const 0.2 ->
+ * USRP sink, which converts to 16-bit I/Q): gain scales the baseband; format 0 = complex64 (default, identical to
+ * pilotgenp1insert_cc's output when gain = 1), format 1 = interleaved int16 I/Q = round(gain * x * 32767), saturated.
+ * With format 1 the output buffers of dvbt2ll_chain_run_* hold 4 bytes per sample. */
+DVBT2LL_API_EXPORT int dvbt2ll_chain_set_sink(dvbt2ll_handle *h, int format, float gain);
 /* Stage taps of the most recent chain run, for parity tests: "bch" (packed bits), "fec" (packed, parity
  * in interleaved-row order), "cells" (complex64).  Copies to HOST; returns bytes or negative error. */
 DVBT2LL_API_EXPORT long long dvbt2ll_chain_tap(dvbt2ll_handle *h, const char *stage, void *out, long long cap);

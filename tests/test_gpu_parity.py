@@ -302,3 +302,28 @@ def test_full_size_batch_invariance():
     e = (np.abs(sym[:, :, gi:].astype(np.complex128)) ** 2).sum(axis=2)          # [channel, symbol]
     rel = np.abs(e / e.mean(axis=0, keepdims=True) - 1.0)
     assert rel[:, 1:].max() < 0.05        # data symbols: unit-power random cells, same pilots
+
+
+def test_chain_sink_gain_and_int16(reflib):
+    """The flowgraph's sink side folded into the last kernel: multiply_const(0.2) and 16-bit I/Q conversion."""
+    cfg = K.resolve("c4")
+    ch = T.Chain(cfg, max_frames=2)
+    n_ts = ch.ts_bytes_per_frame
+    ts = K.make_ts(2 * n_ts)
+    ref_out = ch.run_host(ts, 1, 2)[0]
+    ch.set_sink(0, 0.2)
+    scaled = ch.run_host(ts, 1, 2)[0]
+    assert max_err_over_rms(scaled, (ref_out * np.float32(0.2)).astype(np.complex64)) <= 1e-6
+    ch.set_sink(1, 0.2)
+    q = ch.run_host(ts, 1, 2)[0]
+    want = np.clip(np.rint(ref_out.view(np.float32).astype(np.float64) * 0.2 * 32767.0), -32768, 32767).reshape(-1, 2)
+    assert q.shape == want.shape and q.dtype == np.int16
+    assert np.abs(q.astype(np.int64) - want.astype(np.int64)).max() <= 1
+    cfg3 = K.resolve("c3")                                   # 32K path (even/odd halves) with the int16 sink
+    ch3 = T.Chain(cfg3, max_frames=1)
+    ts3 = K.make_ts(ch3.ts_bytes_per_frame)
+    f32 = ch3.run_host(ts3, 1, 1)[0]
+    ch3.set_sink(1, 0.2)
+    q3 = ch3.run_host(ts3, 1, 1)[0]
+    want3 = np.clip(np.rint(f32.view(np.float32).astype(np.float64) * 0.2 * 32767.0), -32768, 32767).reshape(-1, 2)
+    assert np.abs(q3.astype(np.int64) - want3.astype(np.int64)).max() <= 1
