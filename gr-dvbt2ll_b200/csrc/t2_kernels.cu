@@ -872,14 +872,14 @@ int ofdm_position_of_bin(int m, int log2_m)
 }
 
 // one output sample: complex64, or (sink format 1) interleaved 16-bit I/Q = round(x * 32767), saturated
-__device__ __forceinline__ void store_sample(void *base, long long idx, float2 v, int fmt)
+template <int FMT> struct SinkT { typedef float2 type; };
+template <> struct SinkT<1> { typedef short2 type; };
+__device__ __forceinline__ void store_sample(float2 *p, int idx, float2 v) { p[idx] = v; }
+__device__ __forceinline__ void store_sample(short2 *p, int idx, float2 v)
 {
-  if (fmt == 0) reinterpret_cast<float2 *>(base)[idx] = v;
-  else {
-    int xi = __float2int_rn(v.x * 32767.f), yi = __float2int_rn(v.y * 32767.f);
-    xi = max(-32768, min(32767, xi)); yi = max(-32768, min(32767, yi));
-    reinterpret_cast<short2 *>(base)[idx] = make_short2((short)xi, (short)yi);
-  }
+  int xi = __float2int_rn(v.x * 32767.f), yi = __float2int_rn(v.y * 32767.f);
+  xi = max(-32768, min(32767, xi)); yi = max(-32768, min(32767, yi));
+  p[idx] = make_short2((short)xi, (short)yi);
 }
 
 // Kernel schedule per (symbol, phase), M = 2^LOG2M points, first radix R0 = 2^(LOG2M mod 4):
@@ -895,7 +895,7 @@ __device__ __forceinline__ void store_sample(void *base, long long idx, float2 v
 // interleaver frame order) run by run -- each run is a stretch of consecutive source cells -- so global
 // memory is read in contiguous pieces; the carrier fill then gathers from shared memory and decodes
 // through the constellation LUT (real part from the low byte's entry, imaginary from the high byte's).
-template <int LOG2M, int T, bool C16>
+template <int LOG2M, int T, bool C16, int FMT>
 __global__ void __launch_bounds__(T, 1024 / T) k_ofdm(const OfdmArgs a)
 {
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -924,16 +924,18 @@ __global__ void __launch_bounds__(T, 1024 / T) k_ofdm(const OfdmArgs a)
     const float2 *cells = a.cells + (long long)f * a.cells_stride;
     const float2 *pool = a.pool + (long long)variant * a.pool_stride;
     // output addressing in samples relative to a.out (element size depends on the sink format)
-    const long long out0 = (long long)f * a.out_stride;
-    const long long sym0 = out0 + 2048 + (long long)l * (N + a.gi);
-    const int fmt = a.out_fmt;
-    float2 *park = a.scratch + (long long)blockIdx.x * M;     // even-bin half of a 32K symbol, per CTA, L2 resident
+    typedef typename SinkT<FMT>::type sample_t;
+    sample_t *out = reinterpret_cast<sample_t *>(a.out) + (long long)f * a.out_stride;
+    sample_t *sym = out + 2048 + (long long)l * (N + a.gi);
+    // parking space for the even-bin half of a 32K symbol: the first half of the symbol itself when the output is
+    // complex64 (the odd-bin phase overwrites it in place, the lines are still in L2), a per-CTA scratch slot otherwise
+    float2 *park = FMT == 0 ? reinterpret_cast<float2 *>(sym) + a.gi : a.scratch + (long long)blockIdx.x * M;
 
     if (l == 0)
       for (int i = threadIdx.x; i < 2048; i += T) {
         float2 p = __ldg(a.p1 + i);
         p.x *= a.sink_gain; p.y *= a.sink_gain;
-        store_sample(a.out, out0 + i, p, fmt);
+        store_sample(out, i, p);
       }
 
     if (C16) {
@@ -1044,8 +1046,8 @@ __global__ void __launch_bounds__(T, 1024 / T) k_ofdm(const OfdmArgs a)
             float2 o = v[bitrev_c(k, 16)];
             o = __fmul2_rn(o, make_float2(a.norm, a.norm));
             const int t = i + k * NLAST;
-            store_sample(a.out, sym0 + a.gi + t, o, fmt);
-            if (t >= cp_from) store_sample(a.out, sym0 + t - cp_from, o, fmt);
+            store_sample(sym, a.gi + t, o);
+            if (t >= cp_from) store_sample(sym, t - cp_from, o);
           }
         }
         else if (phase == 0) {
@@ -1067,16 +1069,16 @@ __global__ void __launch_bounds__(T, 1024 / T) k_ofdm(const OfdmArgs a)
           for (int h = 0; h < 2; h++) {
             float2 e[8];
 #pragma unroll
-            for (int k = 0; k < 8; k++) e[k] = __ldcg(park + i + (8 * h + k) * NLAST);
+            for (int k = 0; k < 8; k++) e[k] = park[i + (8 * h + k) * NLAST];
 #pragma unroll
             for (int k = 0; k < 8; k++) {
               const int kk = 8 * h + k;
               const int t = i + kk * NLAST;
               const float2 o = cmul(cmul(v[bitrev_c(kk, 16)], w32(kk)), wi);
-              store_sample(a.out, sym0 + a.gi + t, cadd(e[k], o), fmt);
+              store_sample(sym, a.gi + t, cadd(e[k], o));
               const float2 hi = csub(e[k], o);
-              store_sample(a.out, sym0 + a.gi + t + M, hi, fmt);
-              if (t + M >= cp_from) store_sample(a.out, sym0 + t + M - cp_from, hi, fmt);
+              store_sample(sym, a.gi + t + M, hi);
+              if (t + M >= cp_from) store_sample(sym, t + M - cp_from, hi);
             }
           }
         }
@@ -1085,7 +1087,7 @@ __global__ void __launch_bounds__(T, 1024 / T) k_ofdm(const OfdmArgs a)
   }
 }
 
-template <int LOG2M, int T, bool C16>
+template <int LOG2M, int T, bool C16, int FMT>
 static void launch_ofdm_t(const OfdmArgs &a, cudaStream_t s)
 {
   constexpr int M = 1 << LOG2M;
@@ -1093,27 +1095,27 @@ static void launch_ofdm_t(const OfdmArgs &a, cudaStream_t s)
   const int units = a.frames * a.num_symbols;
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(k_ofdm<LOG2M, T, C16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(k_ofdm<LOG2M, T, C16, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr = true;
   }
   int per_sm = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ofdm<LOG2M, T, C16>, T, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ofdm<LOG2M, T, C16, FMT>, T, smem);
   if (per_sm < 1) per_sm = 1;
   int blocks = sm_count() * per_sm;
   if (blocks > units) blocks = units;
-  k_ofdm<LOG2M, T, C16><<<blocks, T, smem, s>>>(a);
+  k_ofdm<LOG2M, T, C16, FMT><<<blocks, T, smem, s>>>(a);
   count_launch();
 }
 
-template <bool C16>
+template <bool C16, int FMT>
 static void launch_ofdm_c(const OfdmArgs &a, cudaStream_t s)
 {
   switch (a.log2_m) {
-    case 10: launch_ofdm_t<10, 256, C16>(a, s); break;
-    case 11: launch_ofdm_t<11, 256, C16>(a, s); break;
-    case 12: launch_ofdm_t<12, 256, C16>(a, s); break;
-    case 13: launch_ofdm_t<13, 512, C16>(a, s); break;
-    case 14: launch_ofdm_t<14, 1024, C16>(a, s); break;
+    case 10: launch_ofdm_t<10, 256, C16, FMT>(a, s); break;
+    case 11: launch_ofdm_t<11, 256, C16, FMT>(a, s); break;
+    case 12: launch_ofdm_t<12, 256, C16, FMT>(a, s); break;
+    case 13: launch_ofdm_t<13, 512, C16, FMT>(a, s); break;
+    case 14: launch_ofdm_t<14, 1024, C16, FMT>(a, s); break;
     default: break;
   }
 }
@@ -1121,8 +1123,11 @@ static void launch_ofdm_c(const OfdmArgs &a, cudaStream_t s)
 void launch_ofdm(const OfdmArgs &a, cudaStream_t s)
 {
   if (a.frames * a.num_symbols < 1) return;
-  if (a.cells16) launch_ofdm_c<true>(a, s);
-  else launch_ofdm_c<false>(a, s);
+  if (a.cells16) {
+    if (a.out_fmt) launch_ofdm_c<true, 1>(a, s);
+    else launch_ofdm_c<true, 0>(a, s);
+  }
+  else launch_ofdm_c<false, 0>(a, s);      // the drop-in block always emits complex64
 }
 
 } // namespace t2k
