@@ -327,3 +327,47 @@ def test_chain_sink_gain_and_int16(reflib):
     q3 = ch3.run_host(ts3, 1, 1)[0]
     want3 = np.clip(np.rint(f32.view(np.float32).astype(np.float64) * 0.2 * 32767.0), -32768, 32767).reshape(-1, 2)
     assert np.abs(q3.astype(np.int64) - want3.astype(np.int64)).max() <= 1
+
+
+@pytest.mark.parametrize("fs,rate", [(1, r) for r in (K.C1_2, K.C3_5, K.C2_3, K.C3_4, K.C4_5, K.C5_6)] +
+                         [(0, r) for r in (K.C1_3, K.C2_5, K.C1_2, K.C3_5, K.C2_3, K.C3_4, K.C4_5, K.C5_6)])
+def test_bch_and_ldpc_all_codes(fs, rate):
+    """All 14 T2 code configurations through BB framing + BCH + LDPC on the GPU against the oracle
+    (BCH codewords divisible by g(x) and H.c = 0 are checked for the oracle itself in tests/test_oracle.py)."""
+    from oracle import t2oracle as O
+    p = O.fec_params(fs, rate)
+    bb = T.bbheaderbch_bb(fs, rate, 0, 0, 1, 0)
+    ob = O.BbHeaderBch(fs, rate, 0, 0, 1, 0)
+    ld = T.ldpc_bb(fs, rate)
+    nfr = 5
+    ts = K.make_ts(nfr * bb.forecast(p["nbch"]) + 400, seed=fs * 100 + rate + 1)
+    bch, used = bb.work(ts, nfr)
+    want, used2 = ob.work(ts, nfr)
+    assert used == used2 and bits_equal(bch, want)
+    fec, _ = ld.work(bch, nfr)
+    assert bits_equal(fec, O.ldpc_encode(want.reshape(nfr, p["nbch"]), fs, rate).reshape(-1))
+
+
+def test_pilotgen_mode_sweep():
+    """Block 5 over FFT sizes x pilot patterns x carrier modes x SISO/MISO x reserved tones against the oracle."""
+    from oracle import t2oracle as O
+    from common import pg_args
+    rng = np.random.default_rng(9)
+    base = dict(K.resolve("c1"))
+    cases = []
+    for fft, pps in ((K.FFTSIZE_1K, (0, 4)), (K.FFTSIZE_2K, (2, 6)), (K.FFTSIZE_4K, (1, 3)), (K.FFTSIZE_8K, (0, 7)),
+                     (K.FFTSIZE_16K_T2GI, (5, 7)), (K.FFTSIZE_32K_T2GI, (3, 5))):
+        for pp in pps:
+            for ext, pre, mg, papr in ((0, 0, 0, 0), (1, 1, 1, 2), (1, 0, 0, 3)):
+                cases.append(dict(base, fftsize=fft, pilotpattern=pp, carriermode=ext, preamble=pre, misogroup=mg, paprmode=papr,
+                                  guardinterval=K.GI_1_16, numdatasyms=4, vlength=K.VLENGTH[fft], equalization=pp & 1))
+    assert len(cases) == 36
+    for cfg in cases:
+        pg = T.pilotgenp1insert_cc(*pg_args(cfg))
+        opg = O.PilotGen(cfg)
+        n_in = pg.forecast(pg.output_multiple)
+        assert n_in == opg.d["active"]
+        x = (rng.standard_normal(n_in) + 1j * rng.standard_normal(n_in)).astype(np.complex64)
+        y, _ = pg.work(x, 1)
+        want = opg.work(x)
+        assert max_err_over_rms(y, want) <= MAX_ERR_OVER_RMS, {k: cfg[k] for k in ("fftsize", "pilotpattern", "carriermode", "preamble", "paprmode")}
