@@ -73,6 +73,8 @@ __device__ __forceinline__ uint32_t load_u32_unaligned(const uint8_t *p)
   return __funnelshift_r(lo, __ldg(w + 1), sh);
 }
 
+// W6 = false: remainder register of at most 160 bits (5 words): the sixth word is identically zero and skipped
+template <bool W6>
 __global__ void __launch_bounds__(BB_WARPS * 32) k_bb_bch(const BbArgs a)
 {
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -207,8 +209,8 @@ __global__ void __launch_bounds__(BB_WARPS * 32) k_bb_bch(const BbArgs a)
         r1 = ((r1 << 16) | (r2 >> 16)) ^ A[1] ^ B[1];
         r2 = ((r2 << 16) | (r3 >> 16)) ^ A[2] ^ B[2];
         r3 = ((r3 << 16) | (r4 >> 16)) ^ A[3] ^ B[3];
-        r4 = ((r4 << 16) | (r5 >> 16)) ^ A[4] ^ B[4];
-        r5 = (r5 << 16) ^ A[5] ^ B[5];
+        r4 = ((r4 << 16) | (W6 ? r5 >> 16 : 0u)) ^ A[4] ^ B[4];
+        if (W6) r5 = (r5 << 16) ^ A[5] ^ B[5];
       }
       for (; i < e; i++) {
         const uint32_t *T = s_tab + 6 * ((r0 >> 24) ^ buf[i]);
@@ -216,8 +218,8 @@ __global__ void __launch_bounds__(BB_WARPS * 32) k_bb_bch(const BbArgs a)
         r1 = ((r1 << 8) | (r2 >> 24)) ^ T[1];
         r2 = ((r2 << 8) | (r3 >> 24)) ^ T[2];
         r3 = ((r3 << 8) | (r4 >> 24)) ^ T[3];
-        r4 = ((r4 << 8) | (r5 >> 24)) ^ T[4];
-        r5 = (r5 << 8) ^ T[5];
+        r4 = ((r4 << 8) | (W6 ? r5 >> 24 : 0u)) ^ T[4];
+        if (W6) r5 = (r5 << 8) ^ T[5];
       }
     }
     // ---- Horner combine: acc = acc * x^(8*chunk) + R_i, the multiply evaluated column-wise:
@@ -228,16 +230,19 @@ __global__ void __launch_bounds__(BB_WARPS * 32) k_bb_bch(const BbArgs a)
              c4 = __shfl_sync(0xffffffffu, r4, 0), c5 = __shfl_sync(0xffffffffu, r5, 0);
     {
       // this lane's six column masks stay in registers for the whole combine
-      uint32_t col[6][6];
+      constexpr int NW = W6 ? 6 : 5;
+      uint32_t col[NW][NW];
 #pragma unroll
-      for (int w = 0; w < 6; w++)
+      for (int w = 0; w < NW; w++)
 #pragma unroll
-        for (int k = 0; k < 6; k++) col[w][k] = s_cols[(w * 32 + lane) * 6 + k];
+        for (int k = 0; k < NW; k++) col[w][k] = s_cols[(w * 32 + lane) * 6 + k];
       for (int i = 1; i < 32; i++) {
         uint32_t n[6];
+        n[5] = 0;
 #pragma unroll
-        for (int w = 0; w < 6; w++) {
-          const uint32_t x = (c0 & col[w][0]) ^ (c1 & col[w][1]) ^ (c2 & col[w][2]) ^ (c3 & col[w][3]) ^ (c4 & col[w][4]) ^ (c5 & col[w][5]);
+        for (int w = 0; w < NW; w++) {
+          uint32_t x = (c0 & col[w][0]) ^ (c1 & col[w][1]) ^ (c2 & col[w][2]) ^ (c3 & col[w][3]) ^ (c4 & col[w][4]);
+          if (W6) x ^= c5 & col[w][NW - 1];
           n[w] = __ballot_sync(0xffffffffu, __popc(x) & 1);
         }
         c0 = n[0] ^ __shfl_sync(0xffffffffu, r0, i);
@@ -272,14 +277,21 @@ void launch_bb_bch(const BbArgs &a, cudaStream_t s)
   const int total = a.n_channels * a.frames;
   if (total < 1) return;
   static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(k_bb_bch, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr = true; }
+  if (!attr) {
+    cudaFuncSetAttribute(k_bb_bch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(k_bb_bch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    attr = true;
+  }
+  const bool w6 = a.bch_r > 160;
   int per_sm = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bb_bch, BB_WARPS * 32, smem);
+  if (w6) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bb_bch<true>, BB_WARPS * 32, smem);
+  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bb_bch<false>, BB_WARPS * 32, smem);
   if (per_sm < 1) per_sm = 1;
   int blocks = (total + BB_WARPS - 1) / BB_WARPS;
   const int cap = sm_count() * per_sm;        // one resident wave; warps loop over the remaining FECFRAMEs
   if (blocks > cap) blocks = cap;
-  k_bb_bch<<<blocks, BB_WARPS * 32, smem, s>>>(a);
+  if (w6) k_bb_bch<true><<<blocks, BB_WARPS * 32, smem, s>>>(a);
+  else k_bb_bch<false><<<blocks, BB_WARPS * 32, smem, s>>>(a);
   count_launch();
 }
 
