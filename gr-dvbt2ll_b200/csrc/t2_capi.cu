@@ -507,13 +507,19 @@ struct ChainHandle : dvbt2ll_handle {
   cudaStream_t stream2;
   int last_frames;
   bool timing;
-  cudaEvent_t ev[5];
-  float stage_ms[5];
+  enum { TIMING_SLOTS = 64 };
+  cudaEvent_t ev[TIMING_SLOTS][5];     // per-run event sets so the timed loop never has to synchronise
+  long long n_timed;
   ChainHandle() : dvbt2ll_handle(CHAIN), max_frames(0), device(0), sink_fmt(0), sink_gain(1.0f), stream2(0), last_frames(0), timing(false)
   {
-    for (int i = 0; i < 5; i++) { ev[i] = 0; stage_ms[i] = 0.f; }
+    n_timed = 0;
+    for (int s = 0; s < TIMING_SLOTS; s++) for (int i = 0; i < 5; i++) ev[s][i] = 0;
   }
-  ~ChainHandle() { for (int i = 0; i < 5; i++) if (ev[i]) cudaEventDestroy(ev[i]); if (stream2) cudaStreamDestroy(stream2); }
+  ~ChainHandle()
+  {
+    for (int s = 0; s < TIMING_SLOTS; s++) for (int i = 0; i < 5; i++) if (ev[s][i]) cudaEventDestroy(ev[s][i]);
+    if (stream2) cudaStreamDestroy(stream2);
+  }
   int F() const { return fplan.prm.fecblocks; }
   // cells per T2 frame in the 16-bit cell memory, padded so every frame starts on an 8-byte boundary
   long long cells16_stride() const { return ((long long)F() * map.plan.cell_size + 3) & ~3LL; }
@@ -539,7 +545,7 @@ struct ChainHandle : dvbt2ll_handle {
     CK(d_bch.ensure(nfec * align16(bb.plan.fec.nbch / 8) + 64));
     CK(d_fec.ensure(nfec * align16(bb.plan.fec.nldpc / 8) + 64));
     CK(d_cells.ensure((size_t)max_frames * cells16_stride() * sizeof(uint16_t) + 64));   // 16-bit cell codes
-    for (int i = 0; i < 5; i++) CK(cudaEventCreate(&ev[i]));
+    for (int s = 0; s < TIMING_SLOTS; s++) for (int i = 0; i < 5; i++) CK(cudaEventCreate(&ev[s][i]));
     return 0;
   }
   // buf_frame: first T2-frame slot of the intermediate buffers to use (lets two batches be in flight on two streams)
@@ -559,7 +565,8 @@ struct ChainHandle : dvbt2ll_handle {
     const long long p_before = j0 * bb.plan.payload_bytes - 13 * nb0;
     const int count0 = (int)(p_before % 188);
 
-    if (timing) cudaEventRecord(ev[0], s);
+    cudaEvent_t *tev = ev[n_timed % TIMING_SLOTS];
+    if (timing) cudaEventRecord(tev[0], s);
     t2k::BbArgs ba;
     uint8_t *bch_buf = d_bch.as<uint8_t>() + (size_t)buf_frame * F() * bp;
     uint8_t *fec_buf = d_fec.as<uint8_t>() + (size_t)buf_frame * F() * fp;
@@ -567,17 +574,17 @@ struct ChainHandle : dvbt2ll_handle {
     bb.fill_args(ba, (const uint8_t *)d_ts, ts_pitch, n_channels, n_frames * F(), count0, fb0, first_frame > 0 ? 1 : 0,
                  bch_buf, bp);
     t2k::launch_bb_bch(ba, s);
-    if (timing) cudaEventRecord(ev[1], s);
+    if (timing) cudaEventRecord(tev[1], s);
     t2k::LdpcArgs la;
     ldpc.fill_args(la, bch_buf, bp, fec_buf, fp, nfec);
     t2k::launch_ldpc(la, s);
-    if (timing) cudaEventRecord(ev[2], s);
+    if (timing) cudaEventRecord(tev[2], s);
     t2k::MapArgs ma;
     map.fill_args(ma, fec_buf, fp, 0, nfec);
     ma.out16 = cell_buf; ma.out16_frame_stride = cells16_stride();                                        // 16-bit cell codes,
     ma.ci_inv = d_ci_inv.as<uint16_t>(); ma.fec_shift = d_fec_shift.as<int32_t>(); ma.fecblocks = F();   // cell-interleaved
     t2k::launch_map(ma, s);
-    if (timing) cudaEventRecord(ev[3], s);
+    if (timing) cudaEventRecord(tev[3], s);
     t2k::OfdmArgs oa;
     odev.fill(oa, oplan, tables.pool);
     oa.cells = 0; oa.cells_stride = cells16_stride();
@@ -587,7 +594,7 @@ struct ChainHandle : dvbt2ll_handle {
     oa.out_fmt = sink_fmt; oa.sink_gain = sink_gain; oa.norm = oplan.normalization * sink_gain;
     oa.frames = frames; oa.frame_idx0 = first_frame; oa.frames_per_channel = n_frames;
     t2k::launch_ofdm(oa, s);
-    if (timing) cudaEventRecord(ev[4], s);
+    if (timing) { cudaEventRecord(tev[4], s); n_timed++; }
     CK(cudaGetLastError());
     if (buf_frame == 0) last_frames = frames;
     return frames;
@@ -883,16 +890,29 @@ int dvbt2ll_chain_set_sink(dvbt2ll_handle *h, int format, float gain)
   return 0;
 }
 
-void dvbt2ll_chain_enable_timing(dvbt2ll_handle *h, int on) { ChainHandle *c = as_chain(h); if (c) c->timing = on != 0; }
+void dvbt2ll_chain_enable_timing(dvbt2ll_handle *h, int on)
+{
+  ChainHandle *c = as_chain(h);
+  if (c) { c->timing = on != 0; c->n_timed = 0; }
+}
 
 int dvbt2ll_chain_stage_ms(dvbt2ll_handle *h, float *ms5)
 {
   ChainHandle *c = as_chain(h);
   if (!c || !ms5) return fail(DVBT2LL_ERR_INVALID, "not a chain handle");
-  if (!c->timing || !c->dev_ready) return fail(DVBT2LL_ERR_INVALID, "chain: timing not enabled");
-  CK(cudaEventSynchronize(c->ev[4]));
-  for (int i = 0; i < 4; i++) CK(cudaEventElapsedTime(&ms5[i], c->ev[i], c->ev[i + 1]));
-  CK(cudaEventElapsedTime(&ms5[4], c->ev[0], c->ev[4]));
+  if (!c->timing || !c->dev_ready || c->n_timed < 1) return fail(DVBT2LL_ERR_INVALID, "chain: timing not enabled or nothing run");
+  // average over the runs recorded since timing was enabled (at most the last TIMING_SLOTS)
+  const long long n = c->n_timed < ChainHandle::TIMING_SLOTS ? c->n_timed : ChainHandle::TIMING_SLOTS;
+  for (int i = 0; i < 5; i++) ms5[i] = 0.f;
+  for (long long k = 0; k < n; k++) {
+    cudaEvent_t *e = c->ev[(c->n_timed - 1 - k) % ChainHandle::TIMING_SLOTS];
+    CK(cudaEventSynchronize(e[4]));
+    float t;
+    for (int i = 0; i < 4; i++) { CK(cudaEventElapsedTime(&t, e[i], e[i + 1])); ms5[i] += t; }
+    CK(cudaEventElapsedTime(&t, e[0], e[4]));
+    ms5[4] += t;
+  }
+  for (int i = 0; i < 5; i++) ms5[i] /= (float)n;
   return 0;
 }
 

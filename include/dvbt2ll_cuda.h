@@ -125,7 +125,8 @@ DVBT2LL_API_EXPORT int dvbt2ll_chain_set_sink(dvbt2ll_handle *h, int format, flo
 /* Stage taps of the most recent chain run, for parity tests: "bch" (packed bits), "fec" (packed, parity
  * in interleaved-row order), "cells" (complex64).  Copies to HOST; returns bytes or negative error. */
 DVBT2LL_API_EXPORT long long dvbt2ll_chain_tap(dvbt2ll_handle *h, const char *stage, void *out, long long cap);
-/* Device time in ms of each stage kernel of the most recent chain run (bb_bch, ldpc, map, ofdm, total). */
+/* Device time in ms of each stage kernel (bb_bch, ldpc, map, ofdm, total), averaged over the chain runs issued since
+ * timing was enabled (at most the last 64); events are recorded per run, so the caller's timed loop needs no sync. */
 DVBT2LL_API_EXPORT int dvbt2ll_chain_stage_ms(dvbt2ll_handle *h, float *ms5);
 DVBT2LL_API_EXPORT void dvbt2ll_chain_enable_timing(dvbt2ll_handle *h, int on);
 
