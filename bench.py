@@ -226,8 +226,11 @@ def run_ours(args):
         ts_np[c, :nfr * n_ts] = K.make_ts(nfr * n_ts, seed=K.TS_SEED + rank * nch + c)
     d_ts = ts_host.to(dev)
     d_out = torch.empty((nch, nfr * S), dtype=torch.complex64, device=dev)
-    stream = torch.cuda.current_stream()
+    # a dedicated (non-default) stream: its handle is what the C ABI launches on and what the CUDA events time
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     sp = stream.cuda_stream
+    assert sp != 0
 
     def step():
         chain.run_device(d_ts.data_ptr(), pitch, nch, nfr, 0, d_out.data_ptr(), sp)
