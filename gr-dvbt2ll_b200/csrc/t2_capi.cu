@@ -523,7 +523,19 @@ struct ChainHandle : dvbt2ll_handle {
   int F() const { return fplan.prm.fecblocks; }
   // cells per T2 frame in the 16-bit cell memory, padded so every frame starts on an 8-byte boundary
   long long cells16_stride() const { return ((long long)F() * map.plan.cell_size + 3) & ~3LL; }
-  long long ts_per_frame() const { return bb.payload_bytes(F(), 0); }
+  // TS byte index (per channel, stream starts on a packet boundary) at which T2 frame `frame` begins
+  long long stream_pos(long long frame) const
+  {
+    const long long j0 = frame * F();
+    long long nb0 = 0;
+    if (bb.plan.inband) nb0 = (j0 + bb.plan.fecblocks - 1) / bb.plan.fecblocks;
+    const long long P = j0 * bb.plan.payload_bytes - 13 * nb0;          // payload bytes before the frame
+    if (bb.plan.mode == t2::INPUTMODE_NORMAL || P == 0) return P;
+    const long long last = P - 1;                                       // high efficiency mode: sync bytes are skipped,
+    return 1 + last + last / 187 + 1;                                   // packets = 1 sync + 187 payload bytes
+  }
+  long long ts_bytes(long long first_frame, int n_frames) const { return stream_pos(first_frame + n_frames) - stream_pos(first_frame); }
+  long long ts_per_frame() const { return ts_bytes(0, 1); }
   int output_multiple() const { return oplan.samples_per_frame; }
   int in_item() const { return 1; }
   int out_item() const { return sink_fmt ? 4 : 8; }
@@ -560,10 +572,7 @@ struct ChainHandle : dvbt2ll_handle {
     // stream position of the batch start (streams begin on a packet boundary at frame 0)
     const long long j0 = first_frame * F();
     const int fb0 = bb.plan.inband ? (int)(j0 % bb.plan.fecblocks) : 0;
-    long long nb0 = 0;
-    if (bb.plan.inband) nb0 = (j0 + bb.plan.fecblocks - 1) / bb.plan.fecblocks;
-    const long long p_before = j0 * bb.plan.payload_bytes - 13 * nb0;
-    const int count0 = (int)(p_before % 188);
+    const int count0 = (int)(stream_pos(first_frame) % 188);
 
     cudaEvent_t *tev = ev[n_timed % TIMING_SLOTS];
     if (timing) cudaEventRecord(tev[0], s);
@@ -604,10 +613,10 @@ struct ChainHandle : dvbt2ll_handle {
     const int frames = noutput / oplan.samples_per_frame;
     if (consumed) *consumed = 0;
     if (frames < 1) return 0;
-    if ((long long)ninput < ts_per_frame() * frames) return fail(DVBT2LL_ERR_SHORT, "chain: not enough input items");
+    if ((long long)ninput < ts_bytes(0, frames)) return fail(DVBT2LL_ERR_SHORT, "chain: not enough input items");
     int r = run(d_in, 0, 1, frames, 0, d_out, s);
     if (r < 0) return r;
-    if (consumed) *consumed = (int)(ts_per_frame() * frames);
+    if (consumed) *consumed = (int)ts_bytes(0, frames);
     return frames * oplan.samples_per_frame;
   }
   long long plan_get(const char *name, void *out, long long cap) const
@@ -687,7 +696,7 @@ int dvbt2ll_work(dvbt2ll_handle *h, const void *in, int ninput, void *out, int n
   // items to stage in
   long long need;
   if (h->kind == dvbt2ll_handle::BB) need = static_cast<BbHandle *>(h)->ts_needed(frames);
-  else if (h->kind == dvbt2ll_handle::CHAIN) need = static_cast<ChainHandle *>(h)->ts_per_frame() * frames;
+  else if (h->kind == dvbt2ll_handle::CHAIN) need = static_cast<ChainHandle *>(h)->ts_bytes(0, frames);
   else need = (long long)h->forecast(nout);
   if (ninput < need) return fail(DVBT2LL_ERR_SHORT, "not enough input items for the requested output");
   DevBuf &d_in = h->stage_in, &d_out = h->stage_out;
@@ -788,7 +797,6 @@ dvbt2ll_handle *dvbt2ll_chain_create(const dvbt2ll_chain_params *c, int max_fram
   t2::OfdmParams op = { c->carriermode, c->fftsize, c->pilotpattern, c->guardinterval, c->numdatasyms, c->paprmode,
                         c->version, c->preamble, c->misogroup, c->equalization, c->bandwidth, c->vlength };
   bool ok = true;
-  if (c->inputmode != t2::INPUTMODE_NORMAL) { ok = false; err = "chain: only INPUTMODE_NORMAL is supported in chain mode (TS bytes per frame must be constant)"; }
   ok = ok && t2::build_bb_plan(c->framesize, c->rate, c->inputmode, c->inband, c->fecblocks, c->tsrate, &h->bb.plan, &err);
   ok = ok && t2::build_ldpc_plan(c->framesize, c->rate, &h->ldpc.plan, &err);
   ok = ok && t2::build_map_plan(c->framesize, c->rate, c->constellation, c->rotation, &h->map.plan, &err);
@@ -805,6 +813,11 @@ static ChainHandle *as_chain(const dvbt2ll_handle *h)
 }
 
 long long dvbt2ll_chain_ts_bytes_per_frame(const dvbt2ll_handle *h) { ChainHandle *c = as_chain(h); return c ? c->ts_per_frame() : -1; }
+long long dvbt2ll_chain_ts_bytes(const dvbt2ll_handle *h, long long first_frame, int n_frames)
+{
+  ChainHandle *c = as_chain(h);
+  return c ? c->ts_bytes(first_frame, n_frames) : -1;
+}
 long long dvbt2ll_chain_samples_per_frame(const dvbt2ll_handle *h) { ChainHandle *c = as_chain(h); return c ? c->oplan.samples_per_frame : -1; }
 int dvbt2ll_chain_fecframes_per_frame(const dvbt2ll_handle *h) { ChainHandle *c = as_chain(h); return c ? c->F() : -1; }
 
@@ -827,7 +840,7 @@ int dvbt2ll_chain_run_host(dvbt2ll_handle *h, const void *ts, long long ts_pitch
   if (c->device >= 0 && !c->dev_ready) CK(cudaSetDevice(c->device));
   int r = c->ensure_device();
   if (r) return r;
-  const long long per_ch = c->ts_per_frame() * n_frames;
+  const long long per_ch = c->ts_bytes(first_frame, n_frames);
   const long long hist = first_frame > 0 ? 187 : 0;
   const long long dpitch = (per_ch + hist + 255) & ~255LL;
   const size_t ssz = c->sink_fmt ? 4 : 8;                                        // bytes per output sample

@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = [
     "dvbt2ll_output_multiple", "dvbt2ll_forecast", "dvbt2ll_work", "dvbt2ll_work_device", "dvbt2ll_warnings",
     "dvbt2ll_destroy", "dvbt2ll_plan_get", "dvbt2ll_bbheaderbch_create", "dvbt2ll_ldpc_create",
     "dvbt2ll_interleavermod_create", "dvbt2ll_framemapperfint_create", "dvbt2ll_pilotgenp1insert_create",
-    "dvbt2ll_chain_create", "dvbt2ll_chain_ts_bytes_per_frame", "dvbt2ll_chain_samples_per_frame",
+    "dvbt2ll_chain_create", "dvbt2ll_chain_ts_bytes_per_frame", "dvbt2ll_chain_ts_bytes", "dvbt2ll_chain_samples_per_frame",
     "dvbt2ll_chain_fecframes_per_frame", "dvbt2ll_chain_run_device", "dvbt2ll_chain_run_host",
     "dvbt2ll_chain_tap", "dvbt2ll_chain_stage_ms", "dvbt2ll_chain_enable_timing", "dvbt2ll_chain_set_sink",
 ]
@@ -70,6 +70,8 @@ def lib():
         L.dvbt2ll_chain_create.argtypes = [C.POINTER(ChainParams), ci, ci]
         L.dvbt2ll_chain_ts_bytes_per_frame.restype = cll
         L.dvbt2ll_chain_ts_bytes_per_frame.argtypes = [vp]
+        L.dvbt2ll_chain_ts_bytes.restype = cll
+        L.dvbt2ll_chain_ts_bytes.argtypes = [vp, cll, ci]
         L.dvbt2ll_chain_samples_per_frame.restype = cll
         L.dvbt2ll_chain_samples_per_frame.argtypes = [vp]
         L.dvbt2ll_chain_fecframes_per_frame.argtypes = [vp]
@@ -223,6 +225,10 @@ class Chain(_Block):
     @property
     def ts_bytes_per_frame(self):
         return int(lib().dvbt2ll_chain_ts_bytes_per_frame(self._h))
+
+    def ts_bytes(self, first_frame, n_frames):
+        """TS bytes per channel consumed by T2 frames [first_frame, first_frame + n_frames)."""
+        return int(lib().dvbt2ll_chain_ts_bytes(self._h, int(first_frame), int(n_frames)))
 
     @property
     def samples_per_frame(self):

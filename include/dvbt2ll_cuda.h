@@ -105,11 +105,14 @@ typedef struct dvbt2ll_chain_params {
 /* device < 0: current device.  max_frames = largest channels*frames batch a single run will be given. */
 DVBT2LL_API_EXPORT dvbt2ll_handle *dvbt2ll_chain_create(const dvbt2ll_chain_params *p, int max_frames, int device);
 DVBT2LL_API_EXPORT long long dvbt2ll_chain_ts_bytes_per_frame(const dvbt2ll_handle *h);
+/* TS bytes (per channel) consumed by T2 frames [first_frame, first_frame + n_frames): constant per frame in normal
+ * input mode; in high-efficiency mode the dropped sync bytes make it depend on the stream position. */
+DVBT2LL_API_EXPORT long long dvbt2ll_chain_ts_bytes(const dvbt2ll_handle *h, long long first_frame, int n_frames);
 DVBT2LL_API_EXPORT long long dvbt2ll_chain_samples_per_frame(const dvbt2ll_handle *h);
 DVBT2LL_API_EXPORT int dvbt2ll_chain_fecframes_per_frame(const dvbt2ll_handle *h);
 /* n_channels independent transport streams, each contributing n_frames consecutive T2 frames starting at
  * its stream frame number first_frame (streams start on a packet boundary at frame 0).  d_ts: channel-major,
- * n_frames*ts_bytes_per_frame (+ 0..187 trailing bytes ignored) bytes per channel with pitch ts_pitch.
+ * dvbt2ll_chain_ts_bytes(h, first_frame, n_frames) bytes per channel with pitch ts_pitch.
  * d_out: complex64, channel-major, n_frames*samples_per_frame per channel.  Asynchronous on `stream`. */
 DVBT2LL_API_EXPORT int dvbt2ll_chain_run_device(dvbt2ll_handle *h, const void *d_ts, long long ts_pitch,
                                                 int n_channels, int n_frames, long long first_frame,

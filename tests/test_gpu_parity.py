@@ -89,6 +89,8 @@ CHAIN_VARIANTS = {
     # MISO group 2, reserved tones, inverse-sinc equalisation, 8K
     "c2-miso-tr-eq": dict(K.CONFIGS["c2"], preamble=K.PREAMBLE_T2_MISO, misogroup=1, paprmode=2, equalization=1,
                           fecblocks=17, tiblocks=5),
+    # high-efficiency input mode (sync bytes dropped, variable TS consumption per T2 frame) + in-band signalling
+    "c1-hiefficiency": dict(K.CONFIGS["c1"], inputmode=1, inband=1, version=2, fecblocks=7),
     # 2K with 8 P2 symbols (zig-zag L1 mapping), QPSK L1, 64QAM data
     "2k-zigzag": dict(K.CONFIGS["c1"], fftsize=K.FFTSIZE_2K, pilotpattern=K.PILOT_PP2, guardinterval=K.GI_1_8, numdatasyms=30,
                       constellation=K.MOD_64QAM, rate=K.C3_5, fecblocks=14, l1constellation=1),
@@ -99,14 +101,15 @@ CHAIN_VARIANTS = {
 def test_chain_matches_reference(reflib, name):
     """Fused device-resident chain (what bench.py times) against the reference flowgraph."""
     cfg = K.resolve(CHAIN_VARIANTS.get(name, name))
-    nframes = 2
+    nframes = 4 if name == "c1-hiefficiency" else 2      # frame 3 of the HEM stream consumes one byte less
     ch = T.Chain(cfg, max_frames=nframes)
     n_ts = ch.ts_bytes_per_frame
-    ts = K.make_ts(nframes * n_ts + 1000)
+    n_all = ch.ts_bytes(0, nframes)
+    ts = K.make_ts(n_all + 1000)
     refs = _ref_frames(reflib, cfg, ts, nframes)
-    assert refs[0]["ts_used"] == n_ts
+    assert refs[0]["ts_used"] == n_ts and sum(r["ts_used"] for r in refs) == n_all
     assert reflib.Chain(cfg).fm.warnings == 0
-    out = ch.run_host(ts[:nframes * n_ts], 1, nframes)[0]
+    out = ch.run_host(ts[:n_all], 1, nframes)[0]
     S = ch.samples_per_frame
     F = cfg["fecblocks"]
     nbch = refs[0]["bch"].size // F
