@@ -376,10 +376,14 @@ struct FrameHandle : dvbt2ll_handle {
 
 // ================================================================================================
 struct OfdmDevice {
-  DevBuf d_code, d_pool, d_p1, d_sinc, d_tw, d_tw_split, d_scratch;
+  DevBuf d_code, d_pool, d_p1, d_sinc, d_tw, d_tw_split, d_scratch, d_sym_flags;
   int log2_m, split;
   long long pool_stride;
-  int init(const std::vector<int32_t> &code, const t2::CellPool &pool, const t2::OfdmPlan &op)
+  // c16: `code` holds staging slots (chain mode, 16-bit cells) and is re-encoded for the kernel's branch-free fill:
+  //   data carrier         -> 2 * slot            (byte offset into the staging area, < 65536)
+  //   small pool cell p<8  -> (p + 1) << 16       (zero / pilot amplitudes, kept in shared memory)
+  //   other pool cell      -> 0x80000000 | index  (L1 signalling, dummy cells; symbols holding any are flagged)
+  int init(const std::vector<int32_t> &code, const t2::CellPool &pool, const t2::OfdmPlan &op, bool c16 = false)
   {
     // one copy of the pool per L1-post variant: in copy v the L1-post slot holds variant v, so the kernel
     // selects a pool base per frame instead of patching indices per cell
@@ -407,14 +411,25 @@ struct OfdmDevice {
     std::vector<int> pos(M);
     for (int m = 0; m < M; m++) pos[m] = t2k::ofdm_position_of_bin(m, log2_m);
     std::vector<int32_t> code_pos((size_t)L * N, -1);
+    std::vector<int32_t> sym_flags(L, 0);
     for (int l = 0; l < L; l++)
       for (int p = 0; p < split; p++)
         for (int m = 0; m < M; m++) {
           const int c = (split * m + p + N / 2) & (N - 1);
           const int k = c - op.left_nulls;
-          code_pos[((size_t)l * split + p) * M + pos[m]] = (k >= 0 && k < cps) ? code[(size_t)l * cps + k] : -1;
+          int32_t v = (k >= 0 && k < cps) ? code[(size_t)l * cps + k] : -1;
+          if (c16) {
+            if (v >= 0) {
+              if (v >= 32768) return fail(DVBT2LL_ERR_INVALID, "chain: staging slot out of range");
+              v = 2 * v;
+            }
+            else if (~v < 8) v = (~v + 1) << 16;
+            else { v = (int32_t)(0x80000000u | (uint32_t)(~v)); sym_flags[l] = 1; }
+          }
+          code_pos[((size_t)l * split + p) * M + pos[m]] = v;
         }
     CK(upload(d_code, code_pos));
+    CK(upload(d_sym_flags, sym_flags));
     if (!op.inv_sinc.empty()) {
       std::vector<float> sinc_pos((size_t)N);
       for (int p = 0; p < split; p++)
@@ -440,7 +455,8 @@ struct OfdmDevice {
     a.fft_n = op.dims.fft_n; a.log2_m = log2_m; a.split = split;
     a.c_ps = op.dims.c_ps; a.left_nulls = op.left_nulls; a.gi = op.dims.gi; a.num_symbols = op.dims.num_symbols;
     a.norm = op.normalization;
-    a.cells16 = 0; a.runs = 0; a.run_ptr = 0; a.stage_cap = 0; a.lut = 0; a.lut_n = 0;
+    a.cells16 = 0; a.chunk_src = 0; a.chunk_ptr = 0; a.stage_cap = 0; a.lut = 0; a.lut_n = 0;
+    a.sym_flags = d_sym_flags.as<int32_t>();
     a.out_fmt = 0; a.sink_gain = 1.0f; a.scratch = d_scratch.as<float2>();
   }
 };
@@ -499,7 +515,7 @@ struct ChainHandle : dvbt2ll_handle {
   t2::OfdmPlan oplan;
   t2::Chain16Tables tables;
   OfdmDevice odev;
-  DevBuf d_bch, d_fec, d_cells, d_ts_stage, d_out_stage, d_ci_inv, d_fec_shift, d_runs, d_run_ptr;
+  DevBuf d_bch, d_fec, d_cells, d_ts_stage, d_out_stage, d_ci_inv, d_fec_shift, d_chunk_src, d_chunk_ptr;
   int stage_cap;
   int max_frames, device;
   int sink_fmt;          // 0 complex64 (what pilotgenp1insert_cc emits), 1 interleaved int16 I/Q
@@ -547,11 +563,11 @@ struct ChainHandle : dvbt2ll_handle {
     if ((r = bb.dev_init())) return r;
     if ((r = ldpc.dev_init())) return r;
     if ((r = map.dev_init())) return r;
-    if ((r = odev.init(tables.code, tables.pool, oplan))) return r;
+    if ((r = odev.init(tables.code, tables.pool, oplan, true))) return r;
     CK(upload(d_ci_inv, fplan.cell_perm_inv));
     CK(upload(d_fec_shift, fplan.fec_shift));
-    CK(upload(d_runs, tables.runs));
-    CK(upload(d_run_ptr, tables.run_ptr));
+    CK(upload(d_chunk_src, tables.chunk_src));
+    CK(upload(d_chunk_ptr, tables.chunk_ptr));
     stage_cap = (tables.max_slots + 7) & ~7;
     const size_t nfec = (size_t)max_frames * F();
     CK(d_bch.ensure(nfec * align16(bb.plan.fec.nbch / 8) + 64));
@@ -597,7 +613,7 @@ struct ChainHandle : dvbt2ll_handle {
     t2k::OfdmArgs oa;
     odev.fill(oa, oplan, tables.pool);
     oa.cells = 0; oa.cells_stride = cells16_stride();
-    oa.cells16 = cell_buf; oa.runs = d_runs.p; oa.run_ptr = d_run_ptr.as<int32_t>(); oa.stage_cap = stage_cap;
+    oa.cells16 = cell_buf; oa.chunk_src = d_chunk_src.as<int32_t>(); oa.chunk_ptr = d_chunk_ptr.as<int32_t>(); oa.stage_cap = stage_cap;
     oa.lut = map.d_lut.as<float2>(); oa.lut_n = 1 << map.plan.mod;
     oa.out = d_out; oa.out_stride = oplan.samples_per_frame;
     oa.out_fmt = sink_fmt; oa.sink_gain = sink_gain; oa.norm = oplan.normalization * sink_gain;
@@ -624,8 +640,8 @@ struct ChainHandle : dvbt2ll_handle {
     std::string n(name);
     if (n == "chain.code") return copy_vec(tables.code, out, cap);
     if (n == "chain.pool") return copy_vec(tables.pool.cells, out, cap);
-    if (n == "chain.runs") return copy_vec(tables.runs, out, cap);
-    if (n == "chain.run_ptr") return copy_vec(tables.run_ptr, out, cap);
+    if (n == "chain.chunk_src") return copy_vec(tables.chunk_src, out, cap);
+    if (n == "chain.chunk_ptr") return copy_vec(tables.chunk_ptr, out, cap);
     if (n == "ofdm.sym_data_start") return copy_vec(oplan.sym_data_start, out, cap);
     if (n == "frame.framed") return copy_vec(fplan.framed, out, cap);
     if (n == "frame.fi_src") return copy_vec(fplan.fi_src, out, cap);

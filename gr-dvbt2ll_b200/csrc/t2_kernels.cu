@@ -753,17 +753,20 @@ void launch_gather(const GatherArgs &a, cudaStream_t s)
 // digit-reversed positions so the result comes out in natural order.  The host lays the per-symbol
 // carrier code table out in POSITION order (t2k::ofdm_position_of_bin), so the fill stage reads the
 // table coalesced, writes shared memory linearly and never computes a digit reversal.
-// Shared-memory index swizzle: the low nibble is XORed with the fold of the upper nibbles, which
-// makes every access pattern used below (unit stride and the power-of-two strides of the butterflies)
-// conflict-free per half-warp for 8-byte elements.  swz() is XOR-linear, so inside a butterfly the
-// element addresses are swz(base) ^ constant.
+// Shared-memory layout: one spare slot per 16 points (padx below), conflict-free per half-warp for 8-byte
+// elements for every access pattern used, with compile-time address offsets inside a butterfly.
 //
 // N = 32K does not fit (256 KB): it is split by bin parity (decimation in time at the top level):
 // phase 0 transforms the even bins and stores E[n] to out[n] and out[n + N/2]; phase 1 transforms the
 // odd bins and adds / subtracts W_N^n O[n] in place (the same thread re-reads what it wrote, from L2).
 // Each carrier is gathered exactly once and every global store is a full, contiguous line.
 
-__host__ __device__ constexpr int swz(int p) { return p ^ (((p >> 4) ^ (p >> 8) ^ (p >> 12)) & 15); }
+// Shared-memory layout of the transform: point p lives at float2 index padx(p) = p + p / 16 (one spare slot per 16).
+// Every access pattern of the pass schedule -- 16 consecutive points, stride-4/8/16 groups of a first pass, and the
+// stride-NPREV butterflies -- then hits 16 distinct 8-byte bank pairs per half-warp, and because padx(a + b) =
+// padx(a) + padx(b) whenever b is a multiple of 16 (or a, b are the block / digit parts of a small-stride butterfly),
+// the 16 addresses of a butterfly are ONE base register plus compile-time offsets.
+__host__ __device__ constexpr int padx(int p) { return p + (p >> 4); }
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 // complex add / subtract as ONE packed FP32x2 instruction each (sm_100 FADD2 / FFMA2); a - b = fma(b, -1, a) is exact
@@ -832,15 +835,15 @@ __device__ __forceinline__ void fft_pass16(float2 *x, const float2 *__restrict__
 #pragma unroll 1
   for (int u = threadIdx.x; u < NB; u += T) {
     const int i = u & (NPREV - 1);
-    const int sb = swz((u - i) * 16 + i);
+    float2 *xb = x + padx((u - i) * 16 + i);
     const float2 w1 = __ldg(tw + i * TW_STEP);
     float2 v[16];
 #pragma unroll
-    for (int qd = 0; qd < 16; qd++) v[qd] = x[sb ^ swz(qd * NPREV)];
+    for (int qd = 0; qd < 16; qd++) v[qd] = xb[padx(qd * NPREV)];
     apply_twiddles<16>(v, w1);
     dft_reg<16>(v);
 #pragma unroll
-    for (int k = 0; k < 16; k++) x[sb ^ swz(k * NPREV)] = v[bitrev_c(k, 16)];
+    for (int k = 0; k < 16; k++) xb[padx(k * NPREV)] = v[bitrev_c(k, 16)];
   }
 }
 
@@ -903,28 +906,98 @@ __device__ __forceinline__ void store_sample(short2 *p, int idx, float2 v)
 //      the odd-bin half of a 32K symbol, the in-place recombination with the even-bin half.
 //
 // C16 (chain mode): data cells arrive as 16-bit codes in cell-interleaved order.  Per symbol the CTA first
-// copies the symbol's cells into a shared-memory staging area (slot = position in the pre-frequency-
-// interleaver frame order) run by run -- each run is a stretch of consecutive source cells -- so global
-// memory is read in contiguous pieces; the carrier fill then gathers from shared memory and decodes
-// through the constellation LUT (real part from the low byte's entry, imaginary from the high byte's).
+// copies the symbol's cells into a shared-memory staging area in aligned 8-byte chunks (chunk_src names the
+// source chunk of every staging chunk; runs of consecutive source cells stay contiguous, so global memory is
+// read in contiguous pieces); the carrier fill then gathers from shared memory and decodes through the
+// constellation LUT (real part from the low byte's entry, imaginary from the high byte's).
+
+// carrier fill of one (symbol, phase), fused with the first pass of radix R0.  POOL: the symbol has carriers taken
+// from the big pool (L1 signalling / dummy cells); SINC: inverse-sinc equalisation factors are applied.
+template <int LOG2M, int T, bool C16, bool POOL, bool SINC>
+__device__ __forceinline__ void ofdm_fill(float2 *x, const int32_t *__restrict__ code, const float *__restrict__ sinc,
+                                          const uint8_t *stage, const float *lut_re, const float *lut_im,
+                                          const uint8_t *spool_m8, const float2 *__restrict__ cells,
+                                          const float2 *__restrict__ pool)
+{
+  constexpr int M = 1 << LOG2M;
+  constexpr int R0 = 1 << (LOG2M & 3);       // first radix (1 = no first pass)
+  constexpr int GROUPS = M / R0;             // first-pass butterflies
+  constexpr int GPB0 = R0 >= 8 ? 1 : 8 / R0; // groups gathered per batch (8 positions in flight)
+  constexpr int GPB = GPB0 * T > GROUPS ? GROUPS / T : GPB0;
+  static_assert(GROUPS % (T * GPB) == 0, "fill batches must tile the transform");
+#pragma unroll 1
+  for (int g0 = threadIdx.x; g0 < GROUPS; g0 += T * GPB) {
+    int c[GPB][R0];
+    float2 v[GPB][R0];
+#pragma unroll
+    for (int b = 0; b < GPB; b++) {
+      const int g = g0 + b * T;
+      // the R0 codes of a group are contiguous and R0*4-byte aligned: one vector load
+      if (R0 == 4) {
+        const int4 q4 = __ldg(reinterpret_cast<const int4 *>(code) + g);
+        c[b][0] = q4.x; c[b][1 % R0] = q4.y; c[b][2 % R0] = q4.z; c[b][3 % R0] = q4.w;
+      }
+      else if (R0 == 8) {
+        const int4 q4 = __ldg(reinterpret_cast<const int4 *>(code) + 2 * g), q5 = __ldg(reinterpret_cast<const int4 *>(code) + 2 * g + 1);
+        c[b][0] = q4.x; c[b][1 % R0] = q4.y; c[b][2 % R0] = q4.z; c[b][3 % R0] = q4.w;
+        c[b][4 % R0] = q5.x; c[b][5 % R0] = q5.y; c[b][6 % R0] = q5.z; c[b][7 % R0] = q5.w;
+      }
+      else if (R0 == 2) {
+        const int2 q2 = __ldg(reinterpret_cast<const int2 *>(code) + g);
+        c[b][0] = q2.x; c[b][1 % R0] = q2.y;
+      }
+      else c[b][0] = __ldg(code + g);
+    }
+#pragma unroll
+    for (int b = 0; b < GPB; b++)
+#pragma unroll
+      for (int r = 0; r < R0; r++) {
+        const int cc = c[b][r];
+        if (C16) {
+          // data cell: 16-bit code from the staging area through the LUT (a dummy read of offset 0 for the others);
+          // small pool cell (null, pilots): (p + 1) << 16 -> spool[p]; big pool cell: sign bit set (POOL symbols only)
+          const unsigned off = POOL && cc < 0 ? 0u : (unsigned)cc & 0xFFFFu;
+          const unsigned sc = *reinterpret_cast<const uint16_t *>(stage + off);
+          float2 val = make_float2(lut_re[sc & 255u], lut_im[sc >> 8]);
+          if (cc >= 0x10000) val = *reinterpret_cast<const float2 *>(spool_m8 + ((unsigned)cc >> 13));
+          if (POOL && cc < 0) val = __ldg(pool + (cc & 0x7FFFFFFF));
+          v[b][r] = val;
+        }
+        else {
+          const float2 *base = cc >= 0 ? cells : pool;
+          v[b][r] = __ldg(base + (cc >= 0 ? cc : ~cc));
+        }
+      }
+#pragma unroll
+    for (int b = 0; b < GPB; b++) {
+      const int g = g0 + b * T;
+      if (SINC) {
+#pragma unroll
+        for (int r = 0; r < R0; r++) { const float sf = __ldg(sinc + g * R0 + r); v[b][r] = __fmul2_rn(v[b][r], make_float2(sf, sf)); }
+      }
+      if (R0 > 1) dft_reg<R0>(v[b]);
+      float2 *xb = x + padx(g * R0);
+#pragma unroll
+      for (int k = 0; k < R0; k++) xb[k] = v[b][bitrev_c(k, R0)];
+    }
+  }
+}
+
 template <int LOG2M, int T, bool C16, int FMT>
 __global__ void __launch_bounds__(T, 1024 / T) k_ofdm(const OfdmArgs a)
 {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   float2 *x = reinterpret_cast<float2 *>(smem_raw);
   constexpr int M = 1 << LOG2M;
-  uint16_t *stage = reinterpret_cast<uint16_t *>(x + M);
-  float *lut_re = reinterpret_cast<float *>(stage + a.stage_cap);
+  uint8_t *stage = reinterpret_cast<uint8_t *>(x + padx(M));
+  float *lut_re = reinterpret_cast<float *>(stage + 2 * a.stage_cap);
   float *lut_im = lut_re + 256;
   float2 *spool = reinterpret_cast<float2 *>(lut_im + 256);      // first 8 pool cells: zero and the pilot values
   if (C16) {
     for (int i = threadIdx.x; i < a.lut_n; i += T) { const float2 v = __ldg(a.lut + i); lut_re[i] = v.x; lut_im[i] = v.y; }
     if (threadIdx.x < 8) spool[threadIdx.x] = __ldg(a.pool + threadIdx.x);
   }
-  constexpr int F = LOG2M & 3;
-  constexpr int R0 = 1 << F;                 // first radix (1 = no first pass)
-  constexpr int GROUPS = M / R0;             // first-pass butterflies
-  constexpr int GPB = R0 >= 8 ? 1 : 8 / R0;  // groups gathered per batch (8 positions in flight)
+  constexpr int R0 = 1 << (LOG2M & 3);       // first radix (1 = no first pass)
   constexpr int NLAST = M / 16;              // NPREV of the last radix-16 pass
   const int N = a.fft_n;
   const int units = a.frames * a.num_symbols;
@@ -950,93 +1023,41 @@ __global__ void __launch_bounds__(T, 1024 / T) k_ofdm(const OfdmArgs a)
         store_sample(out, i, p);
       }
 
+    bool pool_sym = false;
     if (C16) {
       __syncthreads();      // the previous symbol's fill has finished reading the staging area
-      // copy the symbol's cells run by run in aligned 8-byte chunks (4 cells); four runs in flight per warp
+      // copy the symbol's cells in aligned 8-byte chunks (4 cells), four chunks in flight per thread
       const uint2 *src8 = reinterpret_cast<const uint2 *>(a.cells16 + (long long)f * a.cells_stride);
       uint2 *stage8 = reinterpret_cast<uint2 *>(stage);
-      const int r0 = __ldg(a.run_ptr + l), r1 = __ldg(a.run_ptr + l + 1);
-      const int4 *runs = reinterpret_cast<const int4 *>(a.runs);
-      const int lane = threadIdx.x & 31;
-      for (int rb = r0 + (threadIdx.x >> 5); rb < r1; rb += (T / 32) * 4) {
-        int4 run[4];
+      const int c0 = __ldg(a.chunk_ptr + l), n_chunks = __ldg(a.chunk_ptr + l + 1) - c0;
+      const int32_t *csrc = a.chunk_src + c0;
+      pool_sym = __ldg(a.sym_flags + l) != 0;
+#pragma unroll 1
+      for (int i0 = threadIdx.x; i0 < n_chunks; i0 += 4 * T) {
+        int sidx[4];
         uint2 d[4];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-          const int r = rb + u * (T / 32);
-          run[u] = r < r1 ? __ldg(runs + r) : make_int4(0, 0, 0, 0);       // src chunk, staging chunk, chunks
-        }
+        for (int u = 0; u < 4; u++) sidx[u] = i0 + u * T < n_chunks ? __ldg(csrc + i0 + u * T) : -1;
 #pragma unroll
-        for (int u = 0; u < 4; u++) if (lane < run[u].z) d[u] = __ldg(src8 + run[u].x + lane);
+        for (int u = 0; u < 4; u++) d[u] = sidx[u] >= 0 ? __ldg(src8 + sidx[u]) : make_uint2(0u, 0u);
 #pragma unroll
-        for (int u = 0; u < 4; u++) if (lane < run[u].z) stage8[run[u].y + lane] = d[u];
+        for (int u = 0; u < 4; u++) if (sidx[u] >= 0) stage8[i0 + u * T] = d[u];
       }
     }
 
     for (int phase = 0; phase < a.split; phase++) {
       const int32_t *code = a.code_pos + ((long long)l * a.split + phase) * M;
       const float *sinc = a.sinc_pos ? a.sinc_pos + (long long)phase * M : nullptr;
+      const uint8_t *spool_m8 = reinterpret_cast<const uint8_t *>(spool) - 8;
       __syncthreads();
       // ---- 1. carrier fill (+ first pass)
-#pragma unroll 1
-      for (int g0 = threadIdx.x; g0 < GROUPS; g0 += T * GPB) {
-        int c[GPB][R0];
-        float2 v[GPB][R0];
-#pragma unroll
-        for (int b = 0; b < GPB; b++) {
-          const int g = g0 + b * T;
-          // the R0 codes of a group are contiguous and R0*4-byte aligned: one vector load
-          if (g >= GROUPS) {
-#pragma unroll
-            for (int r = 0; r < R0; r++) c[b][r] = -1;
-          }
-          else if (R0 == 4) {
-            const int4 q4 = __ldg(reinterpret_cast<const int4 *>(code) + g);
-            c[b][0] = q4.x; c[b][1] = q4.y; c[b][2 % R0] = q4.z; c[b][3 % R0] = q4.w;
-          }
-          else if (R0 == 8) {
-            const int4 q4 = __ldg(reinterpret_cast<const int4 *>(code) + 2 * g), q5 = __ldg(reinterpret_cast<const int4 *>(code) + 2 * g + 1);
-            c[b][0] = q4.x; c[b][1 % R0] = q4.y; c[b][2 % R0] = q4.z; c[b][3 % R0] = q4.w;
-            c[b][4 % R0] = q5.x; c[b][5 % R0] = q5.y; c[b][6 % R0] = q5.z; c[b][7 % R0] = q5.w;
-          }
-          else if (R0 == 2) {
-            const int2 q2 = __ldg(reinterpret_cast<const int2 *>(code) + g);
-            c[b][0] = q2.x; c[b][1 % R0] = q2.y;
-          }
-          else c[b][0] = __ldg(code + g);
-        }
-#pragma unroll
-        for (int b = 0; b < GPB; b++)
-#pragma unroll
-          for (int r = 0; r < R0; r++) {
-            const int cc = c[b][r];
-            if (C16) {
-              // branch-free for the common cases: data cell through the LUT, nulls / pilots from the small pool
-              const unsigned sc = stage[cc < 0 ? 0 : cc];
-              float2 val = make_float2(lut_re[sc & 255u], lut_im[sc >> 8]);
-              if (cc < 0) val = spool[(~cc) & 7];
-              if (cc < -8) val = __ldg(pool + ~cc);              // L1 signalling, dummy cells (P2 symbols only)
-              v[b][r] = val;
-            }
-            else {
-              const float2 *base = cc >= 0 ? cells : pool;
-              v[b][r] = __ldg(base + (cc >= 0 ? cc : ~cc));
-            }
-          }
-#pragma unroll
-        for (int b = 0; b < GPB; b++) {
-          const int g = g0 + b * T;
-          if (g < GROUPS) {
-            if (sinc) {
-#pragma unroll
-              for (int r = 0; r < R0; r++) { const float s = __ldg(sinc + g * R0 + r); v[b][r] = __fmul2_rn(v[b][r], make_float2(s, s)); }
-            }
-            if (R0 > 1) dft_reg<R0>(v[b]);
-            const int sb = swz(g * R0);
-#pragma unroll
-            for (int k = 0; k < R0; k++) x[sb ^ swz(k)] = v[b][bitrev_c(k, R0)];
-          }
-        }
+      if (sinc) {
+        if (pool_sym) ofdm_fill<LOG2M, T, C16, true, true>(x, code, sinc, stage, lut_re, lut_im, spool_m8, cells, pool);
+        else ofdm_fill<LOG2M, T, C16, false, true>(x, code, sinc, stage, lut_re, lut_im, spool_m8, cells, pool);
+      }
+      else {
+        if (pool_sym) ofdm_fill<LOG2M, T, C16, true, false>(x, code, sinc, stage, lut_re, lut_im, spool_m8, cells, pool);
+        else ofdm_fill<LOG2M, T, C16, false, false>(x, code, sinc, stage, lut_re, lut_im, spool_m8, cells, pool);
       }
       __syncthreads();
       // ---- 2. middle radix-16 passes
@@ -1045,52 +1066,56 @@ __global__ void __launch_bounds__(T, 1024 / T) k_ofdm(const OfdmArgs a)
       // ---- 3. last radix-16 pass fused with scale + store (+ cyclic prefix, + 32K recombination)
 #pragma unroll 1
       for (int i = threadIdx.x; i < NLAST; i += T) {
-        const int sb = swz(i);
+        const float2 *xb = x + padx(i);
         const float2 w1 = __ldg(a.tw + i);      // TW_STEP = M / (NLAST * 16) = 1
         float2 v[16];
 #pragma unroll
-        for (int qd = 0; qd < 16; qd++) v[qd] = x[sb ^ swz(qd * NLAST)];
+        for (int qd = 0; qd < 16; qd++) v[qd] = xb[padx(qd * NLAST)];
         apply_twiddles<16>(v, w1);
         dft_reg<16>(v);
+        // sample t = i + k NLAST: one 64-bit base per destination, compile-time offsets k NLAST
+        sample_t *o = sym + a.gi + i;
         if (a.split == 1) {
+          sample_t *ocp = sym + ((long long)i - cp_from);       // cyclic prefix: sample t >= N - gi also goes to t - (N - gi)
 #pragma unroll
           for (int k = 0; k < 16; k++) {
-            float2 o = v[bitrev_c(k, 16)];
-            o = __fmul2_rn(o, make_float2(a.norm, a.norm));
-            const int t = i + k * NLAST;
-            store_sample(sym, a.gi + t, o);
-            if (t >= cp_from) store_sample(sym, t - cp_from, o);
+            float2 r = v[bitrev_c(k, 16)];
+            r = __fmul2_rn(r, make_float2(a.norm, a.norm));
+            store_sample(o, k * NLAST, r);
+            if (i + k * NLAST >= cp_from) store_sample(ocp, k * NLAST, r);
           }
         }
         else if (phase == 0) {
+          float2 *pk = park + i;
 #pragma unroll
           for (int k = 0; k < 16; k++) {
-            float2 o = v[bitrev_c(k, 16)];
-            o = __fmul2_rn(o, make_float2(a.norm, a.norm));
-            // even-bin half E[n]: parked in this CTA's scratch slot (stays in L2); the odd-bin phase reads it
-            // back (same thread, same address) and writes both halves and the cyclic prefix exactly once
-            park[i + k * NLAST] = o;
+            float2 r = v[bitrev_c(k, 16)];
+            r = __fmul2_rn(r, make_float2(a.norm, a.norm));
+            // even-bin half E[n]: parked (stays in L2); the odd-bin phase reads it back (same thread, same
+            // address) and writes both halves and the cyclic prefix exactly once
+            pk[k * NLAST] = r;
           }
         }
         else {
           // odd-bin half: out[n] = E[n] + W_N^n O[n], out[n + N/2] = E[n] - W_N^n O[n], n = i + k M/16,
           // W_N^n = W_N^i * exp(j 2 pi k / 32); E is re-read in two batches of 8
+          const float2 *pk = park + i;
+          sample_t *ocp = sym + ((long long)i + M - cp_from);
           float2 wi = __ldg(a.tw_split + i);
           wi = __fmul2_rn(wi, make_float2(a.norm, a.norm));
 #pragma unroll
           for (int h = 0; h < 2; h++) {
             float2 e[8];
 #pragma unroll
-            for (int k = 0; k < 8; k++) e[k] = park[i + (8 * h + k) * NLAST];
+            for (int k = 0; k < 8; k++) e[k] = pk[(8 * h + k) * NLAST];
 #pragma unroll
             for (int k = 0; k < 8; k++) {
               const int kk = 8 * h + k;
-              const int t = i + kk * NLAST;
-              const float2 o = cmul(cmul(v[bitrev_c(kk, 16)], w32(kk)), wi);
-              store_sample(sym, a.gi + t, cadd(e[k], o));
-              const float2 hi = csub(e[k], o);
-              store_sample(sym, a.gi + t + M, hi);
-              if (t + M >= cp_from) store_sample(sym, t + M - cp_from, hi);
+              const float2 r = cmul(cmul(v[bitrev_c(kk, 16)], w32(kk)), wi);
+              store_sample(o, kk * NLAST, cadd(e[k], r));
+              const float2 hi = csub(e[k], r);
+              store_sample(o, kk * NLAST + M, hi);
+              if (i + kk * NLAST + M >= cp_from) store_sample(ocp, kk * NLAST, hi);
             }
           }
         }
@@ -1103,7 +1128,7 @@ template <int LOG2M, int T, bool C16, int FMT>
 static void launch_ofdm_t(const OfdmArgs &a, cudaStream_t s)
 {
   constexpr int M = 1 << LOG2M;
-  const size_t smem = (size_t)M * sizeof(float2) + (C16 ? (size_t)a.stage_cap * 2 + 2048 + 64 : 0);
+  const size_t smem = (size_t)padx(M) * sizeof(float2) + (C16 ? (size_t)a.stage_cap * 2 + 2048 + 64 : 0);
   const int units = a.frames * a.num_symbols;
   static bool attr = false;
   if (!attr) {

@@ -87,10 +87,12 @@ void launch_gather(const GatherArgs &a, cudaStream_t s);
 // ---- K5: carrier fill + IFFT + normalisation + guard interval + P1 --------------------------------
 struct OfdmArgs {
   const float2 *cells; long long cells_stride;   // per T2 frame (stride in cells for both cell formats)
-  // chain mode with 16-bit cells: cells16 != NULL selects it; then `code_pos` holds staging slots
+  // chain mode with 16-bit cells: cells16 != NULL selects it; then `code_pos` holds the encoding described at
+  // OfdmDevice::init (2 * staging slot | (small pool cell + 1) << 16 | 0x80000000 + pool cell)
   const uint16_t *cells16;   // [frame][fecblocks * cell_size] cell-interleaved 16-bit codes
-  const void *runs;          // StageRun {src chunk, staging chunk, chunks, -} as int4 (chunk = 4 cells), per symbol
-  const int32_t *run_ptr;    // [num_symbols + 1]
+  const int32_t *chunk_src;  // source chunk (8 bytes = 4 cells) of every staging chunk, symbols back to back
+  const int32_t *chunk_ptr;  // [num_symbols + 1]
+  const int32_t *sym_flags;  // [num_symbols] bit 0: the symbol has carriers coded 0x80000000 + pool cell
   int stage_cap;             // staging slots reserved in shared memory (multiple of 8)
   const float2 *lut; int lut_n;   // constellation LUT
   void *out;           long long out_stride;     // samples per T2 frame (complex64, or short2 when out_fmt = 1)

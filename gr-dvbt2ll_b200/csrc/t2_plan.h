@@ -197,14 +197,14 @@ bool compose_chain(const FramePlan &fp, const OfdmPlan &op, bool cells_cell_inte
 
 // Chain mode with 16-bit cells: the mapper kernel stores every data cell as (own cell word | previous cell
 // word << 8) in cell-interleaved order; the OFDM kernel first copies the cells of one symbol into a shared-
-// memory staging area using RUNS -- maximal stretches of consecutive source cells (for a time-interleaved
-// PLP: one run per TI column), copied as aligned 8-byte chunks -- and then fills carriers from there.
-// src / slot / len are in units of 8-byte chunks (4 cells) of the frame's cell memory / the staging area
-struct StageRun { int32_t src; int32_t slot; int32_t len; int32_t stride; };
+// memory staging area in aligned 8-byte CHUNKS (4 cells): the symbol's source cells are sorted by address and
+// grouped into runs of consecutive cells (for a time-interleaved PLP: one run per TI column); staging chunk i of
+// symbol l is a copy of source chunk chunk_src[chunk_ptr[l] + i] of the frame's cell memory (up to 3 unused cells
+// at either end of a run).  The carriers are then filled from the staging area.
 struct Chain16Tables {
   std::vector<int32_t> code;        // [num_symbols * c_ps]: >= 0 staging slot of the symbol, < 0 pool cell
-  std::vector<StageRun> runs;       // all symbols, grouped
-  std::vector<int32_t> run_ptr;     // [num_symbols + 1]
+  std::vector<int32_t> chunk_src;   // all symbols, grouped: source chunk of each staging chunk
+  std::vector<int32_t> chunk_ptr;   // [num_symbols + 1]
   int max_slots;                    // largest number of staging slots of any symbol
   CellPool pool;
 };

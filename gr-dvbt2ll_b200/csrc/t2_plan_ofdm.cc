@@ -326,15 +326,15 @@ bool compose_chain16(const FramePlan &fp, const OfdmPlan &op, Chain16Tables *out
   out->pool.l1post_variants = fp.pool.l1post_variants;
   const int L = op.dims.num_symbols, cps = op.dims.c_ps;
   out->code.assign(op.code.size(), 0);
-  out->runs.clear();
-  out->run_ptr.assign(L + 1, 0);
+  out->chunk_src.clear();
+  out->chunk_ptr.assign(L + 1, 0);
   out->max_slots = 0;
   for (int l = 0; l < L; l++) {
     const int s0 = op.sym_data_start[l], s1 = op.sym_data_start[l + 1];     // frame positions of this symbol
     // staging layout: the symbol's source cells sorted by source address, copied run by run in 8-byte
-    // chunks (4 cells).  A run is a maximal stretch of consecutive source cells (capped at 32 chunks); its
-    // first staging slot has the same position inside a chunk as its first source cell, so whole aligned
-    // chunks can be copied (up to 3 unused cells at either end).
+    // chunks (4 cells).  A run is a maximal stretch of consecutive source cells; its first staging slot
+    // has the same position inside a chunk as its first source cell, so whole aligned chunks can be
+    // copied (up to 3 unused cells at either end).
     std::vector<std::pair<int32_t, int32_t> > ps;      // (source cell, frame-order position - s0)
     for (int pos = s0; pos < s1; pos++) {
       const int32_t f = fp.framed[pos];
@@ -342,20 +342,18 @@ bool compose_chain16(const FramePlan &fp, const OfdmPlan &op, Chain16Tables *out
     }
     std::sort(ps.begin(), ps.end());
     std::vector<int32_t> slot_of_pos(s1 - s0, -1);
-    out->run_ptr[l] = (int32_t)out->runs.size();
+    out->chunk_ptr[l] = (int32_t)out->chunk_src.size();
     int32_t next_chunk = 0;                             // staging chunks used so far
     size_t i = 0;
     while (i < ps.size()) {
       const int32_t src = ps[i].first;
       const int32_t first_chunk = src >> 2;
       size_t j = i + 1;
-      while (j < ps.size() && ps[j].first == ps[j - 1].first + 1 && (ps[j].first >> 2) - first_chunk < 32) j++;
+      while (j < ps.size() && ps[j].first == ps[j - 1].first + 1) j++;
       const int32_t last_chunk = ps[j - 1].first >> 2;
-      StageRun r;
-      r.src = first_chunk; r.slot = next_chunk; r.len = last_chunk - first_chunk + 1; r.stride = 0;
       for (size_t k = i; k < j; k++) slot_of_pos[ps[k].second] = 4 * next_chunk + (ps[k].first - 4 * first_chunk);
-      next_chunk += r.len;
-      out->runs.push_back(r);
+      for (int32_t c = first_chunk; c <= last_chunk; c++) out->chunk_src.push_back(c);
+      next_chunk += last_chunk - first_chunk + 1;
       i = j;
     }
     if (4 * next_chunk > out->max_slots) out->max_slots = 4 * next_chunk;
@@ -372,7 +370,7 @@ bool compose_chain16(const FramePlan &fp, const OfdmPlan &op, Chain16Tables *out
       out->code[(size_t)l * cps + k] = v;
     }
   }
-  out->run_ptr[L] = (int32_t)out->runs.size();
+  out->chunk_ptr[L] = (int32_t)out->chunk_src.size();
   return true;
 }
 

@@ -107,15 +107,15 @@ def test_frame_and_ofdm_plans(name, cfg):
 
 @pytest.mark.parametrize("name", ["c1", "c2", "c3"])
 def test_chain16_tables(name):
-    """Chain mode: staging runs + per-carrier slots reproduce exactly the composition
+    """Chain mode: staging chunks + per-carrier slots reproduce exactly the composition
     frequency interleaver o frame o time interleaver o cell interleaver of the drop-in tables."""
     cfg = K.resolve(name)
     ch = T.Chain(cfg, max_frames=1)
     oc, fc = ch.plan("ofdm.code", np.int32), ch.plan("frame.code", np.int32)
     cc = ch.plan("chain.code", np.int32)
     ci_dst = ch.plan("frame.ci_dst", np.int32)
-    runs = ch.plan("chain.runs", np.int32).reshape(-1, 4)
-    run_ptr = ch.plan("chain.run_ptr", np.int32)
+    chunk_src = ch.plan("chain.chunk_src", np.int32)
+    chunk_ptr = ch.plan("chain.chunk_ptr", np.int32)
     starts = ch.plan("ofdm.sym_data_start", np.int32)
     dims = ch.plan("ofdm.dims", np.int32)
     cps, L = int(dims[8]), int(dims[14])
@@ -123,15 +123,11 @@ def test_chain16_tables(name):
     rng = np.random.default_rng(3)
     cells16 = rng.integers(0, 65536, ci_dst.size).astype(np.int64)       # cell-interleaved memory of one T2 frame
     oc, cc = oc.reshape(L, cps), cc.reshape(L, cps)
-    assert runs[:, 2].max() <= 32                      # chunks per run: one warp iteration
     pad = (-ci_dst.size) % 4
     mem = np.concatenate([cells16, np.zeros(pad + 4, dtype=np.int64)])
     for l in range(L):
-        rr = runs[run_ptr[l]:run_ptr[l + 1]]
-        nslots = int(4 * (rr[:, 1] + rr[:, 2]).max()) if len(rr) else 0
-        stage = np.full(nslots, -1, dtype=np.int64)
-        for src, slot, ln, _ in rr:                   # aligned 8-byte chunks = 4 cells
-            stage[4 * slot:4 * (slot + ln)] = mem[4 * src:4 * (src + ln)]
+        src = chunk_src[chunk_ptr[l]:chunk_ptr[l + 1]].astype(np.int64)     # aligned 8-byte chunks = 4 cells
+        stage = mem[(4 * src[:, None] + np.arange(4)[None, :]).reshape(-1)]
         data = oc[l] >= 0
         assert np.array_equal(cc[l][~data], oc[l][~data])                  # pilots / nulls untouched
         f = fc[oc[l][data]]                                                # drop-in frame mapper code of each data carrier
