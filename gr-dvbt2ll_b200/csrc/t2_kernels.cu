@@ -911,43 +911,61 @@ __device__ __forceinline__ void store_sample(short2 *p, int idx, float2 v)
 // read in contiguous pieces); the carrier fill then gathers from shared memory and decodes through the
 // constellation LUT (real part from the low byte's entry, imaginary from the high byte's).
 
+// geometry of the carrier fill: a thread handles GPB first-pass butterflies (groups of R0 consecutive positions) per batch
+template <int LOG2M, int T>
+struct FillGeom {
+  static constexpr int M = 1 << LOG2M;
+  static constexpr int R0 = 1 << (LOG2M & 3);       // first radix (1 = no first pass)
+  static constexpr int GROUPS = M / R0;             // first-pass butterflies
+  static constexpr int GPB0 = R0 >= 8 ? 1 : 8 / R0; // groups gathered per batch (8 positions in flight)
+  static constexpr int GPB = GPB0 * T > GROUPS ? GROUPS / T : GPB0;
+  static constexpr int STEP = T * GPB;
+  static_assert(GROUPS % STEP == 0, "fill batches must tile the transform");
+};
+
+// the carrier codes of one fill batch: the R0 codes of a group are contiguous and R0*4-byte aligned (one vector load)
+template <int LOG2M, int T>
+__device__ __forceinline__ void fill_load_codes(const int32_t *__restrict__ code, int g0,
+                                                int (&c)[FillGeom<LOG2M, T>::GPB][FillGeom<LOG2M, T>::R0])
+{
+  typedef FillGeom<LOG2M, T> G;
+  constexpr int R0 = G::R0;
+#pragma unroll
+  for (int b = 0; b < G::GPB; b++) {
+    const int g = g0 + b * T;
+    if (R0 == 4) {
+      const int4 q4 = __ldg(reinterpret_cast<const int4 *>(code) + g);
+      c[b][0] = q4.x; c[b][1 % R0] = q4.y; c[b][2 % R0] = q4.z; c[b][3 % R0] = q4.w;
+    }
+    else if (R0 == 8) {
+      const int4 q4 = __ldg(reinterpret_cast<const int4 *>(code) + 2 * g), q5 = __ldg(reinterpret_cast<const int4 *>(code) + 2 * g + 1);
+      c[b][0] = q4.x; c[b][1 % R0] = q4.y; c[b][2 % R0] = q4.z; c[b][3 % R0] = q4.w;
+      c[b][4 % R0] = q5.x; c[b][5 % R0] = q5.y; c[b][6 % R0] = q5.z; c[b][7 % R0] = q5.w;
+    }
+    else if (R0 == 2) {
+      const int2 q2 = __ldg(reinterpret_cast<const int2 *>(code) + g);
+      c[b][0] = q2.x; c[b][1 % R0] = q2.y;
+    }
+    else c[b][0] = __ldg(code + g);
+  }
+}
+
 // carrier fill of one (symbol, phase), fused with the first pass of radix R0.  POOL: the symbol has carriers taken
 // from the big pool (L1 signalling / dummy cells); SINC: inverse-sinc equalisation factors are applied.
+// `c` holds the codes of the thread's first batch (loaded by the caller ahead of the barrier that precedes the fill);
+// the codes of batch n + 1 are fetched while batch n is processed.
 template <int LOG2M, int T, bool C16, bool POOL, bool SINC>
 __device__ __forceinline__ void ofdm_fill(float2 *x, const int32_t *__restrict__ code, const float *__restrict__ sinc,
+                                          int (&c)[FillGeom<LOG2M, T>::GPB][FillGeom<LOG2M, T>::R0],
                                           const uint8_t *stage, const float *lut_re, const float *lut_im,
                                           const uint8_t *spool_m8, const float2 *__restrict__ cells,
                                           const float2 *__restrict__ pool)
 {
-  constexpr int M = 1 << LOG2M;
-  constexpr int R0 = 1 << (LOG2M & 3);       // first radix (1 = no first pass)
-  constexpr int GROUPS = M / R0;             // first-pass butterflies
-  constexpr int GPB0 = R0 >= 8 ? 1 : 8 / R0; // groups gathered per batch (8 positions in flight)
-  constexpr int GPB = GPB0 * T > GROUPS ? GROUPS / T : GPB0;
-  static_assert(GROUPS % (T * GPB) == 0, "fill batches must tile the transform");
+  typedef FillGeom<LOG2M, T> G;
+  constexpr int R0 = G::R0, GPB = G::GPB;
 #pragma unroll 1
-  for (int g0 = threadIdx.x; g0 < GROUPS; g0 += T * GPB) {
-    int c[GPB][R0];
+  for (int g0 = threadIdx.x; g0 < G::GROUPS; g0 += G::STEP) {
     float2 v[GPB][R0];
-#pragma unroll
-    for (int b = 0; b < GPB; b++) {
-      const int g = g0 + b * T;
-      // the R0 codes of a group are contiguous and R0*4-byte aligned: one vector load
-      if (R0 == 4) {
-        const int4 q4 = __ldg(reinterpret_cast<const int4 *>(code) + g);
-        c[b][0] = q4.x; c[b][1 % R0] = q4.y; c[b][2 % R0] = q4.z; c[b][3 % R0] = q4.w;
-      }
-      else if (R0 == 8) {
-        const int4 q4 = __ldg(reinterpret_cast<const int4 *>(code) + 2 * g), q5 = __ldg(reinterpret_cast<const int4 *>(code) + 2 * g + 1);
-        c[b][0] = q4.x; c[b][1 % R0] = q4.y; c[b][2 % R0] = q4.z; c[b][3 % R0] = q4.w;
-        c[b][4 % R0] = q5.x; c[b][5 % R0] = q5.y; c[b][6 % R0] = q5.z; c[b][7 % R0] = q5.w;
-      }
-      else if (R0 == 2) {
-        const int2 q2 = __ldg(reinterpret_cast<const int2 *>(code) + g);
-        c[b][0] = q2.x; c[b][1 % R0] = q2.y;
-      }
-      else c[b][0] = __ldg(code + g);
-    }
 #pragma unroll
     for (int b = 0; b < GPB; b++)
 #pragma unroll
@@ -968,6 +986,7 @@ __device__ __forceinline__ void ofdm_fill(float2 *x, const int32_t *__restrict__
           v[b][r] = __ldg(base + (cc >= 0 ? cc : ~cc));
         }
       }
+    if (g0 + G::STEP < G::GROUPS) fill_load_codes<LOG2M, T>(code, g0 + G::STEP, c);
 #pragma unroll
     for (int b = 0; b < GPB; b++) {
       const int g = g0 + b * T;
@@ -983,7 +1002,7 @@ __device__ __forceinline__ void ofdm_fill(float2 *x, const int32_t *__restrict__
   }
 }
 
-template <int LOG2M, int T, bool C16, int FMT>
+template <int LOG2M, int T, bool C16, int FMT, int SPLIT>
 __global__ void __launch_bounds__(T, 1024 / T) k_ofdm(const OfdmArgs a)
 {
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -1002,6 +1021,27 @@ __global__ void __launch_bounds__(T, 1024 / T) k_ofdm(const OfdmArgs a)
   const int N = a.fft_n;
   const int units = a.frames * a.num_symbols;
   const int cp_from = N - a.gi;
+  const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
+
+  // C16: copy the cells of symbol `u` into the staging area in aligned 8-byte chunks (4 cells), asynchronously
+  // (cp.async; the caller waits before the fill).  Issued for symbol u + gridDim.x as soon as symbol u's last fill
+  // has finished reading the staging area, so the copy runs under the FFT passes.
+  auto stage_issue = [&](int u) {
+    const int uf = u / a.num_symbols, ul = u - uf * a.num_symbols;
+    const uint8_t *src = reinterpret_cast<const uint8_t *>(a.cells16 + (long long)uf * a.cells_stride);
+    const int c0 = __ldg(a.chunk_ptr + ul), n_chunks = __ldg(a.chunk_ptr + ul + 1) - c0;
+    const int32_t *csrc = a.chunk_src + c0;
+#pragma unroll 1
+    for (int i0 = threadIdx.x; i0 < n_chunks; i0 += 4 * T) {
+      int sidx[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) sidx[q] = i0 + q * T < n_chunks ? __ldg(csrc + i0 + q * T) : -1;
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+        if (sidx[q] >= 0)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(stage_s + 8u * (uint32_t)(i0 + q * T)), "l"(src + 8ll * sidx[q]) : "memory");
+    }
+  };
 
   for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
     const int f = unit / a.num_symbols, l = unit - f * a.num_symbols;
@@ -1024,42 +1064,31 @@ __global__ void __launch_bounds__(T, 1024 / T) k_ofdm(const OfdmArgs a)
       }
 
     bool pool_sym = false;
+    if (C16) pool_sym = __ldg(a.sym_flags + l) != 0;
+    int c[FillGeom<LOG2M, T>::GPB][FillGeom<LOG2M, T>::R0];
+    fill_load_codes<LOG2M, T>(a.code_pos + (long long)l * SPLIT * M, threadIdx.x, c);
     if (C16) {
-      __syncthreads();      // the previous symbol's fill has finished reading the staging area
-      // copy the symbol's cells in aligned 8-byte chunks (4 cells), four chunks in flight per thread
-      const uint2 *src8 = reinterpret_cast<const uint2 *>(a.cells16 + (long long)f * a.cells_stride);
-      uint2 *stage8 = reinterpret_cast<uint2 *>(stage);
-      const int c0 = __ldg(a.chunk_ptr + l), n_chunks = __ldg(a.chunk_ptr + l + 1) - c0;
-      const int32_t *csrc = a.chunk_src + c0;
-      pool_sym = __ldg(a.sym_flags + l) != 0;
-#pragma unroll 1
-      for (int i0 = threadIdx.x; i0 < n_chunks; i0 += 4 * T) {
-        int sidx[4];
-        uint2 d[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) sidx[u] = i0 + u * T < n_chunks ? __ldg(csrc + i0 + u * T) : -1;
-#pragma unroll
-        for (int u = 0; u < 4; u++) d[u] = sidx[u] >= 0 ? __ldg(src8 + sidx[u]) : make_uint2(0u, 0u);
-#pragma unroll
-        for (int u = 0; u < 4; u++) if (sidx[u] >= 0) stage8[i0 + u * T] = d[u];
-      }
+      if (unit == (int)blockIdx.x) stage_issue(unit);      // later symbols are prefetched during the previous one
+      asm volatile("cp.async.wait_all;\n" ::: "memory");
     }
 
-    for (int phase = 0; phase < a.split; phase++) {
-      const int32_t *code = a.code_pos + ((long long)l * a.split + phase) * M;
+    for (int phase = 0; phase < SPLIT; phase++) {
+      const int32_t *code = a.code_pos + ((long long)l * SPLIT + phase) * M;
       const float *sinc = a.sinc_pos ? a.sinc_pos + (long long)phase * M : nullptr;
       const uint8_t *spool_m8 = reinterpret_cast<const uint8_t *>(spool) - 8;
-      __syncthreads();
+      if (phase) fill_load_codes<LOG2M, T>(code, threadIdx.x, c);
+      __syncthreads();      // staging area landed (phase 0) / previous phase has finished reading x
       // ---- 1. carrier fill (+ first pass)
       if (sinc) {
-        if (pool_sym) ofdm_fill<LOG2M, T, C16, true, true>(x, code, sinc, stage, lut_re, lut_im, spool_m8, cells, pool);
-        else ofdm_fill<LOG2M, T, C16, false, true>(x, code, sinc, stage, lut_re, lut_im, spool_m8, cells, pool);
+        if (pool_sym) ofdm_fill<LOG2M, T, C16, true, true>(x, code, sinc, c, stage, lut_re, lut_im, spool_m8, cells, pool);
+        else ofdm_fill<LOG2M, T, C16, false, true>(x, code, sinc, c, stage, lut_re, lut_im, spool_m8, cells, pool);
       }
       else {
-        if (pool_sym) ofdm_fill<LOG2M, T, C16, true, false>(x, code, sinc, stage, lut_re, lut_im, spool_m8, cells, pool);
-        else ofdm_fill<LOG2M, T, C16, false, false>(x, code, sinc, stage, lut_re, lut_im, spool_m8, cells, pool);
+        if (pool_sym) ofdm_fill<LOG2M, T, C16, true, false>(x, code, sinc, c, stage, lut_re, lut_im, spool_m8, cells, pool);
+        else ofdm_fill<LOG2M, T, C16, false, false>(x, code, sinc, c, stage, lut_re, lut_im, spool_m8, cells, pool);
       }
       __syncthreads();
+      if (C16 && phase == SPLIT - 1 && unit + (int)gridDim.x < units) stage_issue(unit + gridDim.x);
       // ---- 2. middle radix-16 passes
       if (R0 * 16 < NLAST * 16 && R0 < NLAST) { fft_pass16<M, R0, T>(x, a.tw); __syncthreads(); }
       if (R0 * 16 < NLAST) { fft_pass16<M, (R0 * 16 < NLAST ? R0 * 16 : 1), T>(x, a.tw); __syncthreads(); }
@@ -1075,7 +1104,7 @@ __global__ void __launch_bounds__(T, 1024 / T) k_ofdm(const OfdmArgs a)
         dft_reg<16>(v);
         // sample t = i + k NLAST: one 64-bit base per destination, compile-time offsets k NLAST
         sample_t *o = sym + a.gi + i;
-        if (a.split == 1) {
+        if (SPLIT == 1) {
           sample_t *ocp = sym + ((long long)i - cp_from);       // cyclic prefix: sample t >= N - gi also goes to t - (N - gi)
 #pragma unroll
           for (int k = 0; k < 16; k++) {
@@ -1124,7 +1153,7 @@ __global__ void __launch_bounds__(T, 1024 / T) k_ofdm(const OfdmArgs a)
   }
 }
 
-template <int LOG2M, int T, bool C16, int FMT>
+template <int LOG2M, int T, bool C16, int FMT, int SPLIT>
 static void launch_ofdm_t(const OfdmArgs &a, cudaStream_t s)
 {
   constexpr int M = 1 << LOG2M;
@@ -1132,15 +1161,15 @@ static void launch_ofdm_t(const OfdmArgs &a, cudaStream_t s)
   const int units = a.frames * a.num_symbols;
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(k_ofdm<LOG2M, T, C16, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(k_ofdm<LOG2M, T, C16, FMT, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr = true;
   }
   int per_sm = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ofdm<LOG2M, T, C16, FMT>, T, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ofdm<LOG2M, T, C16, FMT, SPLIT>, T, smem);
   if (per_sm < 1) per_sm = 1;
   int blocks = sm_count() * per_sm;
   if (blocks > units) blocks = units;
-  k_ofdm<LOG2M, T, C16, FMT><<<blocks, T, smem, s>>>(a);
+  k_ofdm<LOG2M, T, C16, FMT, SPLIT><<<blocks, T, smem, s>>>(a);
   count_launch();
 }
 
@@ -1148,11 +1177,14 @@ template <bool C16, int FMT>
 static void launch_ofdm_c(const OfdmArgs &a, cudaStream_t s)
 {
   switch (a.log2_m) {
-    case 10: launch_ofdm_t<10, 256, C16, FMT>(a, s); break;
-    case 11: launch_ofdm_t<11, 256, C16, FMT>(a, s); break;
-    case 12: launch_ofdm_t<12, 256, C16, FMT>(a, s); break;
-    case 13: launch_ofdm_t<13, 512, C16, FMT>(a, s); break;
-    case 14: launch_ofdm_t<14, 1024, C16, FMT>(a, s); break;
+    case 10: launch_ofdm_t<10, 256, C16, FMT, 1>(a, s); break;
+    case 11: launch_ofdm_t<11, 256, C16, FMT, 1>(a, s); break;
+    case 12: launch_ofdm_t<12, 256, C16, FMT, 1>(a, s); break;
+    case 13: launch_ofdm_t<13, 512, C16, FMT, 1>(a, s); break;
+    case 14:
+      if (a.split == 2) launch_ofdm_t<14, 1024, C16, FMT, 2>(a, s);
+      else launch_ofdm_t<14, 1024, C16, FMT, 1>(a, s);
+      break;
     default: break;
   }
 }
