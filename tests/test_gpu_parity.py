@@ -94,6 +94,21 @@ CHAIN_VARIANTS = {
     # 2K with 8 P2 symbols (zig-zag L1 mapping), QPSK L1, 64QAM data
     "2k-zigzag": dict(K.CONFIGS["c1"], fftsize=K.FFTSIZE_2K, pilotpattern=K.PILOT_PP2, guardinterval=K.GI_1_8, numdatasyms=30,
                       constellation=K.MOD_64QAM, rate=K.C3_5, fecblocks=14, l1constellation=1),
+    # 1K (16 P2 symbols), BPSK L1, 16QAM rotated, one TI block
+    "1k-bpsk-l1": dict(K.CONFIGS["c1"], fftsize=K.FFTSIZE_1K, pilotpattern=K.PILOT_PP4, guardinterval=K.GI_1_16, numdatasyms=40,
+                       constellation=K.MOD_16QAM, rate=K.C2_3, l1constellation=K.L1_MOD_BPSK, tiblocks=1, fecblocks=9),
+    # T2-Lite preamble (v1.3.1), 16K, rotated QPSK with the short 1/3 code, QPSK L1
+    "16k-lite": dict(K.CONFIGS["c1"], fftsize=K.FFTSIZE_16K, pilotpattern=K.PILOT_PP3, guardinterval=K.GI_1_8, numdatasyms=12,
+                     constellation=K.MOD_QPSK, rate=K.C1_3, preamble=K.PREAMBLE_T2_LITE_SISO, version=K.VERSION_131,
+                     l1constellation=K.L1_MOD_QPSK, tiblocks=2, fecblocks=19),
+    # 8K extended carriers, PP8, reserved tones, rotated 64QAM 3/4
+    "8k-ext-pp8-tr": dict(K.CONFIGS["c2"], carriermode=K.CARRIERS_EXTENDED, pilotpattern=K.PILOT_PP8, guardinterval=K.GI_1_16,
+                          numdatasyms=20, constellation=K.MOD_64QAM, rate=K.C3_4, rotation=1, paprmode=K.PAPR_TR, tiblocks=1,
+                          fecblocks=13),
+    # 32K with the T2-only guard interval 19/256, normal carriers, rotated 16QAM 5/6, frame-closing symbol
+    "32k-t2gi": dict(K.CONFIGS["c3"], fftsize=K.FFTSIZE_32K_T2GI, guardinterval=K.GI_19_256, pilotpattern=K.PILOT_PP4,
+                     numdatasyms=7, constellation=K.MOD_16QAM, rate=K.C5_6, tiblocks=1, carriermode=K.CARRIERS_NORMAL,
+                     fecblocks=12),
 }
 
 
