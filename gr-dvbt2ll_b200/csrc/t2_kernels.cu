@@ -832,7 +832,7 @@ __device__ __forceinline__ void fft_pass16(float2 *x, const float2 *__restrict__
 {
   constexpr int NB = M / 16;
   constexpr int TW_STEP = M / (NPREV * 16);
-#pragma unroll 1
+#pragma unroll (NB / T == 2 ? 2 : 1)
   for (int u = threadIdx.x; u < NB; u += T) {
     const int i = u & (NPREV - 1);
     float2 *xb = x + padx((u - i) * 16 + i);
@@ -1003,7 +1003,7 @@ __device__ __forceinline__ void ofdm_fill(float2 *x, const int32_t *__restrict__
 }
 
 template <int LOG2M, int T, bool C16, int FMT, int SPLIT>
-__global__ void __launch_bounds__(T, 1024 / T) k_ofdm(const OfdmArgs a)
+__global__ void __launch_bounds__(T, (LOG2M == 14 ? 1 : 1024 / T)) k_ofdm(const OfdmArgs a)
 {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   float2 *x = reinterpret_cast<float2 *>(smem_raw);
@@ -1182,8 +1182,9 @@ static void launch_ofdm_c(const OfdmArgs &a, cudaStream_t s)
     case 12: launch_ofdm_t<12, 256, C16, FMT, 1>(a, s); break;
     case 13: launch_ofdm_t<13, 512, C16, FMT, 1>(a, s); break;
     case 14:
-      if (a.split == 2) launch_ofdm_t<14, 1024, C16, FMT, 2>(a, s);
-      else launch_ofdm_t<14, 1024, C16, FMT, 1>(a, s);
+      // 512 threads with up to 128 registers each: two butterflies per thread and pass, interleaved by the compiler
+      if (a.split == 2) launch_ofdm_t<14, 512, C16, FMT, 2>(a, s);
+      else launch_ofdm_t<14, 512, C16, FMT, 1>(a, s);
       break;
     default: break;
   }
