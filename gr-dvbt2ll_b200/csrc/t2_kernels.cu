@@ -482,7 +482,9 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map(const MapArgs a)
   const int nwords = (a.nldpc + 31) / 32;
   uint32_t *u = reinterpret_cast<uint32_t *>(smem_raw);                   // packed codeword, raw byte order, + slack
   float2 *lut = reinterpret_cast<float2 *>(u + ((nwords + 11) & ~3));     // [1 << mod]
-  uint8_t *cw = reinterpret_cast<uint8_t *>(lut + (1 << a.mod));          // [cell_size rounded up to 64]
+  // cell codes of the FECFRAME: own cell word | (word supplying the imaginary part << 8), i.e. the previous cell's
+  // word under the cyclic Q delay, the cell's own otherwise.  Padded: cell c at index c + 2 (c / 64).
+  uint16_t *cw = reinterpret_cast<uint16_t *>(lut + (1 << a.mod));
   for (int i = threadIdx.x; i < (1 << a.mod); i += blockDim.x) lut[i] = a.lut[i];
   const int mod = a.mod, Nc = a.cell_size;
   __shared__ int s_base[16], s_twist[16];      // per output bit: first codeword bit of its column, twist
@@ -537,20 +539,41 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map(const MapArgs a)
         // transpose32 uses (row, MSB-first column) coordinates: window bit i (from the MSB) of row y moves to
         // bit y (from the MSB) of A[i], so A[i] is the ncol-bit word of row d0 + i of the twist matrix.
         // Emit cells (two per word when ncol = 2 mod, else one) as packed bytes.
+        // Four consecutive cells as bytes w = [c0 c1 c2 c3] (c0 lowest), then their codes by byte permutes: with
+        // the Q delay [c0 | prev << 8, c1 | c0 << 8], [c2 | c1 << 8, c3 | c2 << 8] (prev = c3 of the previous
+        // four; the first cell of the thread is patched below), without it [c0 | c0 << 8, ...].
         const uint32_t mask = (1u << mod) - 1u;
+        const uint32_t sel0 = a.cyclic_delay ? 0x0170u : 0x1100u, sel1 = a.cyclic_delay ? 0x2312u : 0x3322u;
+        uint32_t wprev = 0;
         if (a.ncol == 2 * mod) {
-          uint32_t *dst = reinterpret_cast<uint32_t *>(cw + 2 * d0 + 4 * g);      // 64 cells + 1 pad word per thread
+          uint32_t *dst = reinterpret_cast<uint32_t *>(cw + 2 * d0 + 2 * g);      // 64 cells + 1 pad word per thread
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
             const uint32_t p0 = A[i], p1 = A[i + 1];
-            dst[i >> 1] = (p0 >> mod) | ((p0 & mask) << 8) | ((p1 >> mod) << 16) | ((p1 & mask) << 24);
+            const uint32_t w = (p0 >> mod) | ((p0 & mask) << 8) | ((p1 >> mod) << 16) | ((p1 & mask) << 24);
+            dst[i] = __byte_perm(w, wprev, sel0);
+            dst[i + 1] = __byte_perm(w, wprev, sel1);
+            wprev = w;
           }
         }
         else {
-          uint32_t *dst = reinterpret_cast<uint32_t *>(cw + d0 + 4 * (g >> 1));   // 32 cells per thread, pad per 64
+          uint32_t *dst = reinterpret_cast<uint32_t *>(cw + d0 + 2 * (g >> 1));   // 32 cells per thread, pad per 64
 #pragma unroll
-          for (int i = 0; i < 32; i += 4)
-            dst[i >> 2] = (A[i] & mask) | ((A[i + 1] & mask) << 8) | ((A[i + 2] & mask) << 16) | ((A[i + 3] & mask) << 24);
+          for (int i = 0; i < 32; i += 4) {
+            const uint32_t w = (A[i] & mask) | ((A[i + 1] & mask) << 8) | ((A[i + 2] & mask) << 16) | ((A[i + 3] & mask) << 24);
+            dst[i >> 1] = __byte_perm(w, wprev, sel0);
+            dst[(i >> 1) + 1] = __byte_perm(w, wprev, sel1);
+            wprev = w;
+          }
+        }
+      }
+      if (a.cyclic_delay) {
+        // first cell of every thread's run: the imaginary part comes from the last cell of the previous run
+        __syncthreads();
+        const int run = a.ncol == 2 * mod ? 64 : 32;
+        for (int c = threadIdx.x * run; c < Nc; c += blockDim.x * run) {
+          const int pc = c == 0 ? Nc - 1 : c - 1;
+          reinterpret_cast<uint8_t *>(cw)[2 * (c + 2 * (c >> 6)) + 1] = (uint8_t)cw[pc + 2 * (pc >> 6)];
         }
       }
     }
@@ -562,32 +585,41 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map(const MapArgs a)
           const int p = __ldg(src + b);
           v = (v << 1) | ((reinterpret_cast<const uint8_t *>(u)[p >> 3] >> (7 - (p & 7))) & 1u);
         }
-        cw[c + ((c >> 6) << 2)] = (uint8_t)v;
+        cw[c + 2 * (c >> 6)] = (uint16_t)(v | (v << 8));
+      }
+      if (a.cyclic_delay) {
+        __syncthreads();
+        // only high bytes are written and only low bytes read: no ordering needed between the threads
+        for (int c = threadIdx.x; c < Nc; c += blockDim.x) {
+          const int pc = c == 0 ? Nc - 1 : c - 1;
+          reinterpret_cast<uint8_t *>(cw)[2 * (c + 2 * (c >> 6)) + 1] = (uint8_t)cw[pc + 2 * (pc >> 6)];
+        }
       }
     }
     __syncthreads();
-    auto cell = [&](int c) -> int { return cw[c + ((c >> 6) << 2)]; };     // padded layout, see above
+    auto code = [&](int c) -> unsigned { return cw[c + 2 * (c >> 6)]; };     // padded layout, see above
     float2 *out = a.out + (long long)f * Nc;
     if (a.out16) {
-      // chain mode: 16-bit cell codes (own cell word | word supplying the imaginary part << 8), stored in
-      // cell-interleaved order: output position x holds cell ci_inv[(x - shift) mod Nc]
+      // chain mode: the 16-bit codes in cell-interleaved order: cell ci_inv[y] goes to position (y + shift) mod Nc.
+      // Two segments with a constant position - y, so table reads and stores are a base pointer + constant offsets.
       uint16_t *o16 = a.out16 + (long long)(f / a.fecblocks) * a.out16_frame_stride + (long long)(f % a.fecblocks) * Nc;
       const int shift = a.fec_shift[f % a.fecblocks];
-      // eight permutation look-ups in flight per thread
-      for (int x0 = threadIdx.x; x0 < Nc; x0 += 8 * MAP_THREADS) {
-        int c[8];
+#pragma unroll 1
+      for (int seg = 0; seg < 2; seg++) {
+        const int y_end = seg ? Nc : Nc - shift;
+        uint16_t *o = o16 + (seg ? shift - Nc : shift);
+        // eight permutation look-ups in flight per thread
+#pragma unroll 1
+        for (int y0 = (seg ? Nc - shift : 0) + threadIdx.x; y0 < y_end; y0 += 8 * MAP_THREADS) {
+          const uint16_t *ci = a.ci_inv + y0;
+          uint16_t *oy = o + y0;
+          const int left = y_end - y0;
+          int c[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-          const int xo = x0 + k * MAP_THREADS;
-          int y = xo - shift;
-          if (y < 0) y += Nc;
-          c[k] = xo < Nc ? __ldg(a.ci_inv + y) : 0;
-        }
+          for (int k = 0; k < 8; k++) c[k] = k * MAP_THREADS < left ? __ldg(ci + k * MAP_THREADS) : 0;
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-          const int xo = x0 + k * MAP_THREADS;
-          const int pc = c[k] == 0 ? Nc - 1 : c[k] - 1;
-          if (xo < Nc) o16[xo] = (uint16_t)(cell(c[k]) | (cell(a.cyclic_delay ? pc : c[k]) << 8));
+          for (int k = 0; k < 8; k++)
+            if (k * MAP_THREADS < left) oy[k * MAP_THREADS] = (uint16_t)code(c[k]);
         }
       }
     }
@@ -597,19 +629,15 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map(const MapArgs a)
       for (int xo = threadIdx.x; xo < Nc; xo += blockDim.x) {
         int y = xo - shift;
         if (y < 0) y += Nc;
-        const int c = __ldg(a.ci_inv + y);
-        const int pc = c == 0 ? Nc - 1 : c - 1;
-        out[xo] = make_float2(lut[cell(c)].x, lut[cell(a.cyclic_delay ? pc : c)].y);
-      }
-    }
-    else if (a.cyclic_delay) {
-      for (int c = threadIdx.x; c < Nc; c += blockDim.x) {
-        const int pc = c == 0 ? Nc - 1 : c - 1;
-        out[c] = make_float2(lut[cell(c)].x, lut[cell(pc)].y);
+        const unsigned cd = code(__ldg(a.ci_inv + y));
+        out[xo] = make_float2(lut[cd & 255u].x, lut[cd >> 8].y);
       }
     }
     else {
-      for (int c = threadIdx.x; c < Nc; c += blockDim.x) out[c] = lut[cell(c)];
+      for (int c = threadIdx.x; c < Nc; c += blockDim.x) {
+        const unsigned cd = code(c);
+        out[c] = make_float2(lut[cd & 255u].x, lut[cd >> 8].y);
+      }
     }
   }
 }
@@ -617,11 +645,16 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map(const MapArgs a)
 void launch_map(const MapArgs &a, cudaStream_t s)
 {
   const int nwords = (a.nldpc + 31) / 32;
-  const size_t smem = (size_t)((nwords + 11) & ~3) * 4 + (size_t)(1 << a.mod) * 8 + ((a.cell_size + 127) & ~63) + 4 * (a.cell_size / 64 + 2);
+  const size_t smem = (size_t)((nwords + 11) & ~3) * 4 + (size_t)(1 << a.mod) * 8 + 2 * (((a.cell_size + 127) & ~63) + 2 * (a.cell_size / 64 + 2));
   int blocks = a.frames;
   const int cap = sm_count() * 16;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) return;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(k_map, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);   // QPSK normal: 32400 cell codes
+    attr = true;
+  }
   k_map<<<blocks, MAP_THREADS, smem, s>>>(a);
   count_launch();
 }
