@@ -307,6 +307,13 @@ __device__ __forceinline__ uint32_t window32_be(const uint32_t *w, int p)
   return __funnelshift_l(bswap32(w[k + 1]), bswap32(w[k]), p & 31);
 }
 
+// big-endian 32-bit value at byte offset `off` of a byte stream held as raw (little-endian loaded) words
+__device__ __forceinline__ uint32_t be32_at(const uint32_t *w, int off)
+{
+  const int k = off >> 2;
+  return __byte_perm(w[k], w[k + 1], 0x0123u + 0x1111u * (unsigned)(off & 3));
+}
+
 __global__ void __launch_bounds__(LDPC_WARPS * 32, 4) k_ldpc(const LdpcArgs a, int warp_words, int cw_words)
 {
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -339,15 +346,13 @@ __global__ void __launch_bounds__(LDPC_WARPS * 32, 4) k_ldpc(const LdpcArgs a, i
       const uint8_t *cb = reinterpret_cast<const uint8_t *>(cw);
       for (int b = (nw << 2) + lane; b < info_bytes; b += 32) out[b] = cb[b];
     }
-    // ---- wrap-extended groups: 13 words = circular bits [0, 416) of each 360-bit group
-    // (bits past nbch never enter: the last window of a group is masked / taken from the group's own start)
+    // ---- wrap-extended groups: 13 words = circular bits [0, 416) of each 360-bit group.  A group is 45 bytes, so
+    // word w is the big-endian 32-bit value at byte 45 g + 4 w (w <= 10), bytes {44, 0, 1, 2} (w = 11) or bytes 3..6
+    // (w = 12): unaligned loads by byte permute (bytes past the group only land in positions that are masked off)
     for (int idx = lane; idx < G * 13; idx += 32) {
       const int g = idx / 13, w = idx - g * 13;
-      const int base = 360 * g;
-      uint32_t v;
-      if (w < 11) v = window32_be(cw, base + 32 * w);
-      else if (w == 11) v = (window32_be(cw, base + 352) & 0xFF000000u) | (window32_be(cw, base) >> 8);
-      else v = window32_be(cw, base + 24);
+      uint32_t v = be32_at(cw, 45 * g + (w == 12 ? 3 : 4 * w));
+      if (w == 11) v = (v & 0xFF000000u) | (be32_at(cw, 45 * g) >> 8);
       ext[idx] = v;
     }
     __syncwarp();
