@@ -137,6 +137,7 @@ struct BbHandle : dvbt2ll_handle {
     const int base = (noutput - 80 - (plan.fec.nbch - plan.fec.kbch)) / 8;
     return plan.mode == t2::INPUTMODE_NORMAL ? base : base + ((plan.fec.kbch - 80) / 8) / 187 + 1;
   }
+  uint32_t crc_mask[8];
   int dev_init()
   {
     std::vector<uint8_t> scr(plan.scramble);
@@ -149,6 +150,13 @@ struct BbHandle : dvbt2ll_handle {
       for (int k = 0; k < 4; k++) { crc[k * 256 + x] = v; v = plan.crc8_tab[v]; }
     }
     CK(upload(d_crc, crc));
+    // the same four-byte step as parity masks (GF(2)-linear in the 32 bits): byte i of the word is followed by 3 - i more
+    for (int k = 0; k < 8; k++) {
+      crc_mask[k] = 0;
+      for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 8; j++)
+          if ((crc[(3 - i) * 256 + (1 << j)] >> k) & 1) crc_mask[k] |= 1u << (8 * i + j);
+    }
     CK(upload(d_tab, plan.bch_byte_tab));
     CK(upload(d_cols, plan.bch_shift_cols));
     CK(upload(d_ib, plan.inband_bytes));
@@ -180,6 +188,7 @@ struct BbHandle : dvbt2ll_handle {
     a.mode = plan.mode; a.inband = plan.inband ? 1 : 0; a.fecblocks = plan.fecblocks;
     a.chunk_bytes = plan.chunk_bytes; a.lead_zero_bytes = plan.lead_zero_bytes;
     a.scramble = d_scr.as<uint8_t>(); a.crc8_tab = d_crc.as<uint8_t>(); a.bch_tab = d_tab.as<uint32_t>();
+    for (int k = 0; k < 8; k++) a.crc8_mask[k] = crc_mask[k];
     a.bch_cols = d_cols.as<uint32_t>(); a.inband_bytes = d_ib.as<uint8_t>();
     a.out = d_out; a.out_pitch = out_pitch; a.sync_errors = d_err.as<int>();
   }

@@ -93,8 +93,7 @@ __global__ void __launch_bounds__(BB_WARPS * 32) k_bb_bch(const BbArgs a)
   const uint8_t *S1 = s_crc8, *S2 = s_crc8 + 256, *S3 = s_crc8 + 512, *S4 = s_crc8 + 768;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint8_t *hist = s_buf + warp * buf_pitch;                   // hist[HIST - k] = TS byte k positions before the frame
-  uint8_t *buf = hist + HIST;
+  uint8_t *buf = s_buf + warp * buf_pitch + HIST;             // buf[10 - k] = TS byte k positions before the frame's payload
   uint32_t *bufw = reinterpret_cast<uint32_t *>(buf);
   const int total = a.n_channels * a.frames;
   const int D = a.payload_bytes;
@@ -129,7 +128,8 @@ __global__ void __launch_bounds__(BB_WARPS * 32) k_bb_bch(const BbArgs a)
       for (int i = 4 * w_end - 10 + lane; i < Dj; i += 32) buf[10 + i] = src[i];
       // the 187 bytes before the frame (previous packet's tail) for the first CRC-8; missing history reads as 0,
       // which leaves a zero CRC state unchanged
-      for (int k = 1 + lane; k <= 187; k += 32) hist[HIST - k] = (P0 - k >= 0 || a.hist_valid) ? src[-k] : (uint8_t)0;
+      // (kept contiguous with the payload, under the place the BB header is written to afterwards)
+      for (int k = 1 + lane; k <= 187; k += 32) buf[10 - k] = (P0 - k >= 0 || a.hist_valid) ? src[-k] : (uint8_t)0;
     }
     else {
       for (int i = lane; i < Dj; i += 32) buf[10 + i] = ts[hem_ts_index(P0 + i, a.count0)];
@@ -150,15 +150,24 @@ __global__ void __launch_bounds__(BB_WARPS * 32) k_bb_bch(const BbArgs a)
         const int si = i0 + 188 * (lane + 32 * rnd);
         if (si < Dj) {
           if (buf[10 + si] != 0x47) atomicAdd(a.sync_errors, 1);
-          // CRC-8 of the 187 bytes before the sync byte, four bytes per step (slicing by 4)
-          uint32_t crc = 0;
-          int u = si - 187;
-          for (; u < 0 && u < si; u++) crc = S1[hist[HIST + u] ^ crc];
-          for (; u + 4 <= si; u += 4) {
-            const uint8_t *p = buf + 10 + u;
-            crc = S4[p[0] ^ crc] ^ S3[p[1]] ^ S2[p[2]] ^ S1[p[3]];
+          // CRC-8 of the 187 bytes before the sync byte, four bytes per step: 47 unaligned little-endian words
+          // starting one byte early (that byte zeroed: leading zeros leave a zero state alone); the step is
+          // GF(2)-linear in (word ^ state), evaluated as eight parities -- no table look-ups
+          const uint8_t *p = buf + 10 + si - 188;
+          const uint32_t *pw = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
+          const int sh = (int)(reinterpret_cast<uintptr_t>(p) & 3) * 8;
+          uint32_t crc = 0, lo = pw[0];
+#pragma unroll 1
+          for (int st = 0; st < 47; st++) {
+            const uint32_t hi = pw[st + 1];
+            uint32_t t = __funnelshift_r(lo, hi, sh);
+            lo = hi;
+            if (st == 0) t &= 0xFFFFFF00u;
+            t ^= crc;
+            crc = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) crc |= (__popc(t & a.crc8_mask[k]) & 1u) << k;
           }
-          for (; u < si; u++) crc = S1[buf[10 + u] ^ crc];
           my_crc[rnd] = (uint8_t)crc;
         }
       }

@@ -19,6 +19,8 @@ struct BbArgs {
   int chunk_bytes, lead_zero_bytes;
   const uint8_t *scramble;    // kbch / 8
   const uint8_t *crc8_tab;    // 4 * 256: slicing-by-4 tables S1..S4 (S1 = the plain byte table)
+  uint32_t crc8_mask[8];      // bit k of the CRC-8 after the four bytes of little-endian word t (state XORed into the
+                              // first byte) = parity(t & crc8_mask[k])
   const uint32_t *bch_tab;    // 2 * 256 * 6: T0 then T1
   const uint32_t *bch_cols;   // 6 * 32 * 6
   const uint8_t *inband_bytes;// 13
