@@ -46,7 +46,7 @@ __device__ __forceinline__ uint32_t window32(const uint32_t *w, int p)
 // ================================================================================================
 // K1  BB framing + scrambler + BCH
 // ================================================================================================
-constexpr int BB_WARPS = 8;
+constexpr int BB_MAX_WARPS = 32;      // warps (= FECFRAMEs in flight) per CTA; fewer when the frame buffers do not fit
 
 __device__ __forceinline__ int multiples_in(int a, int b, int m)   // multiples of m in [a, b), a,b >= 0
 {
@@ -75,22 +75,31 @@ __device__ __forceinline__ uint32_t load_u32_unaligned(const uint8_t *p)
 
 // W6 = false: remainder register of at most 160 bits (5 words): the sixth word is identically zero and skipped
 template <bool W6>
-__global__ void __launch_bounds__(BB_WARPS * 32) k_bb_bch(const BbArgs a)
+__global__ void __launch_bounds__(BB_MAX_WARPS * 32) k_bb_bch(const BbArgs a)
 {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  uint32_t *s_tab = reinterpret_cast<uint32_t *>(smem_raw);   // 2 * 256 * 6: T0 = b x^r mod g, T1 = b x^(r+8) mod g
-  uint32_t *s_cols = s_tab + 2 * 256 * 6;                     // 6 * 32 * 6
-  uint8_t *s_crc8 = reinterpret_cast<uint8_t *>(s_cols + 6 * 32 * 6);   // 4 * 256: CRC-8 slicing-by-4 tables
-  uint8_t *s_buf = s_crc8 + 1024;
+  // BCH remainder tables, one row per message NIBBLE and one private copy per lane: word w of row n of table k
+  // (k = nibble position inside a 16-bit step: n x^(r + 4k) mod g) for lane l sits at ((k*16 + n)*NW + w)*32 + l,
+  // i.e. always in bank l -- 32 lanes looking up 32 different rows never conflict (a byte-indexed table shared by
+  // the warp costs ~3.3 wavefronts per access instead)
+  constexpr int NW = W6 ? 6 : 5;
+  uint32_t *s_ntab = reinterpret_cast<uint32_t *>(smem_raw);  // 4 * 16 * NW * 32
+  uint32_t *s_cols = s_ntab + 4 * 16 * NW * 32;               // 6 * 32 * 6
+  uint8_t *s_crc8 = reinterpret_cast<uint8_t *>(s_cols + 6 * 32 * 6);   // 256: CRC-8 byte table (BB header)
+  uint8_t *s_buf = s_crc8 + 256;
   const int nbytes = a.nbch / 8, msg_bytes = a.kbch / 8;
   constexpr int HIST = 192;                                   // stream history kept in front of each frame buffer
   const int buf_pitch = ((nbytes + 15) & ~15) + HIST;
 
-  for (int i = threadIdx.x; i < 2 * 256 * 6; i += blockDim.x) s_tab[i] = a.bch_tab[i];
+  for (int i = threadIdx.x; i < 4 * 16 * NW * 32; i += blockDim.x) {
+    const int w = (i >> 5) % NW, kn = (i >> 5) / NW, k = kn >> 4, n = kn & 15;
+    // from the byte tables T0 = b x^r, T1 = b x^(r+8): nibble n at position k is byte (n << 4*(k&1)) of table k>>1
+    s_ntab[i] = a.bch_tab[((k >> 1) * 256 + (n << (4 * (k & 1)))) * 6 + w];
+  }
   for (int i = threadIdx.x; i < 6 * 32 * 6; i += blockDim.x) s_cols[i] = a.bch_cols[i];
-  for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_crc8[i] = a.crc8_tab[i];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_crc8[i] = a.crc8_tab[i];
   __syncthreads();
-  const uint8_t *S1 = s_crc8, *S2 = s_crc8 + 256, *S3 = s_crc8 + 512, *S4 = s_crc8 + 768;
+  const uint8_t *S1 = s_crc8;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t *buf = s_buf + warp * buf_pitch + HIST;             // buf[10 - k] = TS byte k positions before the frame's payload
@@ -100,7 +109,8 @@ __global__ void __launch_bounds__(BB_WARPS * 32) k_bb_bch(const BbArgs a)
   const bool hem = a.mode != 0;
   const uint32_t *scr32 = reinterpret_cast<const uint32_t *>(a.scramble);   // zero padded to a word multiple
 
-  for (int job = blockIdx.x * BB_WARPS + warp; job < total; job += gridDim.x * BB_WARPS) {
+  const int nwarps = blockDim.x >> 5;
+  for (int job = blockIdx.x * nwarps + warp; job < total; job += gridDim.x * nwarps) {
     const int c = job / a.frames, j = job - c * a.frames;
     const uint8_t *ts = a.ts + (long long)c * a.ts_pitch;
     const int nb = a.inband ? multiples_in(a.fec_block0, a.fec_block0 + j, a.fecblocks) : 0;
@@ -210,25 +220,29 @@ __global__ void __launch_bounds__(BB_WARPS * 32) k_bb_bch(const BbArgs a)
       const int e = s + a.chunk_bytes;
       if (s < 0) s = 0;
       int i = s;
-      // two message bytes per step: the two table rows are independent of each other (slicing by 2)
+      // two message bytes per step: four nibble rows, all independent of each other
+      const uint32_t *nt = s_ntab + lane;
+      constexpr int ROW = NW * 32;              // words between rows of a table
       for (; i + 2 <= e; i += 2) {
-        const uint32_t *A = s_tab + 256 * 6 + 6 * ((r0 >> 24) ^ buf[i]);
-        const uint32_t *B = s_tab + 6 * (((r0 >> 16) & 0xFFu) ^ buf[i + 1]);
-        r0 = ((r0 << 16) | (r1 >> 16)) ^ A[0] ^ B[0];
-        r1 = ((r1 << 16) | (r2 >> 16)) ^ A[1] ^ B[1];
-        r2 = ((r2 << 16) | (r3 >> 16)) ^ A[2] ^ B[2];
-        r3 = ((r3 << 16) | (r4 >> 16)) ^ A[3] ^ B[3];
-        r4 = ((r4 << 16) | (W6 ? r5 >> 16 : 0u)) ^ A[4] ^ B[4];
-        if (W6) r5 = (r5 << 16) ^ A[5] ^ B[5];
+        const uint32_t x = (r0 >> 16) ^ ((uint32_t)buf[i] << 8) ^ buf[i + 1];
+        const uint32_t *t3 = nt + (48 + (x >> 12)) * ROW, *t2 = nt + (32 + ((x >> 8) & 15u)) * ROW,
+                       *t1 = nt + (16 + ((x >> 4) & 15u)) * ROW, *t0 = nt + (x & 15u) * ROW;
+        r0 = ((r0 << 16) | (r1 >> 16)) ^ t3[0] ^ t2[0] ^ t1[0] ^ t0[0];
+        r1 = ((r1 << 16) | (r2 >> 16)) ^ t3[32] ^ t2[32] ^ t1[32] ^ t0[32];
+        r2 = ((r2 << 16) | (r3 >> 16)) ^ t3[64] ^ t2[64] ^ t1[64] ^ t0[64];
+        r3 = ((r3 << 16) | (r4 >> 16)) ^ t3[96] ^ t2[96] ^ t1[96] ^ t0[96];
+        r4 = ((r4 << 16) | (W6 ? r5 >> 16 : 0u)) ^ t3[128] ^ t2[128] ^ t1[128] ^ t0[128];
+        if (W6) r5 = (r5 << 16) ^ t3[NW * 32 - 32] ^ t2[NW * 32 - 32] ^ t1[NW * 32 - 32] ^ t0[NW * 32 - 32];
       }
       for (; i < e; i++) {
-        const uint32_t *T = s_tab + 6 * ((r0 >> 24) ^ buf[i]);
-        r0 = ((r0 << 8) | (r1 >> 24)) ^ T[0];
-        r1 = ((r1 << 8) | (r2 >> 24)) ^ T[1];
-        r2 = ((r2 << 8) | (r3 >> 24)) ^ T[2];
-        r3 = ((r3 << 8) | (r4 >> 24)) ^ T[3];
-        r4 = ((r4 << 8) | (W6 ? r5 >> 24 : 0u)) ^ T[4];
-        if (W6) r5 = (r5 << 8) ^ T[5];
+        const uint32_t x = (r0 >> 24) ^ buf[i];
+        const uint32_t *t1 = nt + (16 + (x >> 4)) * ROW, *t0 = nt + (x & 15u) * ROW;
+        r0 = ((r0 << 8) | (r1 >> 24)) ^ t1[0] ^ t0[0];
+        r1 = ((r1 << 8) | (r2 >> 24)) ^ t1[32] ^ t0[32];
+        r2 = ((r2 << 8) | (r3 >> 24)) ^ t1[64] ^ t0[64];
+        r3 = ((r3 << 8) | (r4 >> 24)) ^ t1[96] ^ t0[96];
+        r4 = ((r4 << 8) | (W6 ? r5 >> 24 : 0u)) ^ t1[128] ^ t0[128];
+        if (W6) r5 = (r5 << 8) ^ t1[NW * 32 - 32] ^ t0[NW * 32 - 32];
       }
     }
     // ---- Horner combine: acc = acc * x^(8*chunk) + R_i, the multiply evaluated column-wise:
@@ -282,25 +296,25 @@ void launch_bb_bch(const BbArgs &a, cudaStream_t s)
 {
   const int nbytes = a.nbch / 8;
   const int buf_pitch = ((nbytes + 15) & ~15) + 192;
-  const size_t smem = 2 * 256 * 6 * 4 + 6 * 32 * 6 * 4 + 1024 + (size_t)BB_WARPS * buf_pitch;
+  const bool w6 = a.bch_r > 160;
+  const size_t fixed = (size_t)4 * 16 * (w6 ? 6 : 5) * 32 * 4 + 6 * 32 * 6 * 4 + 256;
   const int total = a.n_channels * a.frames;
   if (total < 1) return;
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(k_bb_bch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    cudaFuncSetAttribute(k_bb_bch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(k_bb_bch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(k_bb_bch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr = true;
   }
-  const bool w6 = a.bch_r > 160;
-  int per_sm = 1;
-  if (w6) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bb_bch<true>, BB_WARPS * 32, smem);
-  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bb_bch<false>, BB_WARPS * 32, smem);
-  if (per_sm < 1) per_sm = 1;
-  int blocks = (total + BB_WARPS - 1) / BB_WARPS;
-  const int cap = sm_count() * per_sm;        // one resident wave; warps loop over the remaining FECFRAMEs
+  // one CTA per SM (the lane-private tables take 40-48 KB), as many warps as frame buffers fit
+  int warps = BB_MAX_WARPS;
+  while (warps > 4 && fixed + (size_t)warps * buf_pitch > 227 * 1024) warps -= 4;
+  const size_t smem = fixed + (size_t)warps * buf_pitch;
+  int blocks = (total + warps - 1) / warps;
+  const int cap = sm_count();                 // one resident wave; warps loop over the remaining FECFRAMEs
   if (blocks > cap) blocks = cap;
-  if (w6) k_bb_bch<true><<<blocks, BB_WARPS * 32, smem, s>>>(a);
-  else k_bb_bch<false><<<blocks, BB_WARPS * 32, smem, s>>>(a);
+  if (w6) k_bb_bch<true><<<blocks, warps * 32, smem, s>>>(a);
+  else k_bb_bch<false><<<blocks, warps * 32, smem, s>>>(a);
   count_launch();
 }
 
