@@ -626,7 +626,8 @@ struct ChainHandle : dvbt2ll_handle {
     oa.lut = map.d_lut.as<float2>(); oa.lut_n = 1 << map.plan.mod;
     oa.out = d_out; oa.out_stride = oplan.samples_per_frame;
     oa.out_fmt = sink_fmt; oa.sink_gain = sink_gain; oa.norm = oplan.normalization * sink_gain;
-    oa.frames = frames; oa.frame_idx0 = first_frame; oa.frames_per_channel = n_frames;
+    oa.frames = frames; oa.frames_per_channel = n_frames;
+    oa.frame_idx0 = (int)(first_frame % (tables.pool.l1post_variants > 0 ? tables.pool.l1post_variants : 1));
     t2k::launch_ofdm(oa, s);
     if (timing) { cudaEventRecord(tev[4], s); n_timed++; }
     CK(cudaGetLastError());

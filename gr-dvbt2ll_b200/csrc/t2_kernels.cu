@@ -1106,7 +1106,7 @@ __global__ void __launch_bounds__(T, (LOG2M == 14 ? 1 : 1024 / T)) k_ofdm(const 
 
   for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
     const int f = unit / a.num_symbols, l = unit - f * a.num_symbols;
-    const int variant = (int)((a.frame_idx0 + (f % a.frames_per_channel)) % a.l1post_variants);
+    const int variant = (a.frame_idx0 + (f % a.frames_per_channel)) % a.l1post_variants;
     const float2 *cells = a.cells + (long long)f * a.cells_stride;
     const float2 *pool = a.pool + (long long)variant * a.pool_stride;
     // output addressing in samples relative to a.out (element size depends on the sink format)

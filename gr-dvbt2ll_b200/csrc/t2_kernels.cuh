@@ -112,7 +112,7 @@ struct OfdmArgs {
   int fft_n, log2_m, split;  // M = 1 << log2_m, split = N / M (1 or 2)
   int c_ps, left_nulls, gi, num_symbols;
   float norm;
-  int frames; long long frame_idx0;   // t2 frame numbers: frame_idx0 + f (per channel layout below)
+  int frames; int frame_idx0;         // t2 frame number of the first frame, reduced mod l1post_variants by the host
   int frames_per_channel;    // frame f -> t2 frame number frame_idx0 + (f % frames_per_channel)
 };
 void launch_ofdm(const OfdmArgs &a, cudaStream_t s);
