@@ -978,7 +978,8 @@ struct FillGeom {
   static constexpr int M = 1 << LOG2M;
   static constexpr int R0 = 1 << (LOG2M & 3);       // first radix (1 = no first pass)
   static constexpr int GROUPS = M / R0;             // first-pass butterflies
-  static constexpr int GPB0 = R0 >= 8 ? 1 : 8 / R0; // groups gathered per batch (8 positions in flight)
+  static constexpr int INFL = LOG2M == 14 ? 16 : 8; // positions in flight per thread (16 where 128 registers are available)
+  static constexpr int GPB0 = R0 >= INFL ? 1 : INFL / R0; // groups gathered per batch
   static constexpr int GPB = GPB0 * T > GROUPS ? GROUPS / T : GPB0;
   static constexpr int STEP = T * GPB;
   static_assert(GROUPS % STEP == 0, "fill batches must tile the transform");
