@@ -1019,7 +1019,7 @@ __device__ __forceinline__ void fill_load_codes(const int32_t *__restrict__ code
 template <int LOG2M, int T, bool C16, bool POOL, bool SINC>
 __device__ __forceinline__ void ofdm_fill(float2 *x, const int32_t *__restrict__ code, const float *__restrict__ sinc,
                                           int (&c)[FillGeom<LOG2M, T>::GPB][FillGeom<LOG2M, T>::R0],
-                                          const uint8_t *stage, const float *lut_re, const float *lut_im,
+                                          const uint8_t *stage, const float *lut_re, const float *lut_im, int lut_rep_shift,
                                           const uint8_t *spool_m8, const float2 *__restrict__ cells,
                                           const float2 *__restrict__ pool)
 {
@@ -1038,7 +1038,11 @@ __device__ __forceinline__ void ofdm_fill(float2 *x, const int32_t *__restrict__
           // small pool cell (null, pilots): (p + 1) << 16 -> spool[p]; big pool cell: sign bit set (POOL symbols only)
           const unsigned off = POOL && cc < 0 ? 0u : (unsigned)cc & 0xFFFFu;
           const unsigned sc = *reinterpret_cast<const uint16_t *>(stage + off);
-          float2 val = make_float2(lut_re[sc & 255u], lut_im[sc >> 8]);
+          // the LUTs are replicated 2^lut_rep_shift times (entry e, copy c at e * copies + c) and a lane reads copy
+          // lane mod copies: with 16 copies only lanes l and l + 16 can collide (2 wavefronts instead of ~3.4)
+          const unsigned esh = 2 + lut_rep_shift, emask = 255u << esh, lane_off = (threadIdx.x & ((1u << lut_rep_shift) - 1u)) << 2;
+          float2 val = make_float2(*reinterpret_cast<const float *>(reinterpret_cast<const uint8_t *>(lut_re) + (((sc << esh) & emask) | lane_off)),
+                                   *reinterpret_cast<const float *>(reinterpret_cast<const uint8_t *>(lut_im) + ((((sc >> 8) << esh) & emask) | lane_off)));
           if (cc >= 0x10000) val = *reinterpret_cast<const float2 *>(spool_m8 + ((unsigned)cc >> 13));
           if (POOL && cc < 0) val = __ldg(pool + (cc & 0x7FFFFFFF));
           v[b][r] = val;
@@ -1072,10 +1076,11 @@ __global__ void __launch_bounds__(T, (LOG2M == 14 ? 1 : 1024 / T)) k_ofdm(const 
   constexpr int M = 1 << LOG2M;
   uint8_t *stage = reinterpret_cast<uint8_t *>(x + padx(M));
   float *lut_re = reinterpret_cast<float *>(stage + 2 * a.stage_cap);
-  float *lut_im = lut_re + 256;
-  float2 *spool = reinterpret_cast<float2 *>(lut_im + 256);      // first 8 pool cells: zero and the pilot values
+  const int lut_rep_shift = a.lut_rep_shift, lut_rep = 1 << lut_rep_shift;
+  float *lut_im = lut_re + 256 * lut_rep;
+  float2 *spool = reinterpret_cast<float2 *>(lut_im + 256 * lut_rep);      // first 8 pool cells: zero and the pilot values
   if (C16) {
-    for (int i = threadIdx.x; i < a.lut_n; i += T) { const float2 v = __ldg(a.lut + i); lut_re[i] = v.x; lut_im[i] = v.y; }
+    for (int i = threadIdx.x; i < a.lut_n * lut_rep; i += T) { const float2 v = __ldg(a.lut + (i >> lut_rep_shift)); lut_re[i] = v.x; lut_im[i] = v.y; }
     if (threadIdx.x < 8) spool[threadIdx.x] = __ldg(a.pool + threadIdx.x);
   }
   constexpr int R0 = 1 << (LOG2M & 3);       // first radix (1 = no first pass)
@@ -1142,12 +1147,12 @@ __global__ void __launch_bounds__(T, (LOG2M == 14 ? 1 : 1024 / T)) k_ofdm(const 
       __syncthreads();      // staging area landed (phase 0) / previous phase has finished reading x
       // ---- 1. carrier fill (+ first pass)
       if (sinc) {
-        if (pool_sym) ofdm_fill<LOG2M, T, C16, true, true>(x, code, sinc, c, stage, lut_re, lut_im, spool_m8, cells, pool);
-        else ofdm_fill<LOG2M, T, C16, false, true>(x, code, sinc, c, stage, lut_re, lut_im, spool_m8, cells, pool);
+        if (pool_sym) ofdm_fill<LOG2M, T, C16, true, true>(x, code, sinc, c, stage, lut_re, lut_im, lut_rep_shift, spool_m8, cells, pool);
+        else ofdm_fill<LOG2M, T, C16, false, true>(x, code, sinc, c, stage, lut_re, lut_im, lut_rep_shift, spool_m8, cells, pool);
       }
       else {
-        if (pool_sym) ofdm_fill<LOG2M, T, C16, true, false>(x, code, sinc, c, stage, lut_re, lut_im, spool_m8, cells, pool);
-        else ofdm_fill<LOG2M, T, C16, false, false>(x, code, sinc, c, stage, lut_re, lut_im, spool_m8, cells, pool);
+        if (pool_sym) ofdm_fill<LOG2M, T, C16, true, false>(x, code, sinc, c, stage, lut_re, lut_im, lut_rep_shift, spool_m8, cells, pool);
+        else ofdm_fill<LOG2M, T, C16, false, false>(x, code, sinc, c, stage, lut_re, lut_im, lut_rep_shift, spool_m8, cells, pool);
       }
       __syncthreads();
       if (C16 && phase == SPLIT - 1 && unit + (int)gridDim.x < units) stage_issue(unit + gridDim.x);
@@ -1219,7 +1224,7 @@ template <int LOG2M, int T, bool C16, int FMT, int SPLIT>
 static void launch_ofdm_t(const OfdmArgs &a, cudaStream_t s)
 {
   constexpr int M = 1 << LOG2M;
-  const size_t smem = (size_t)padx(M) * sizeof(float2) + (C16 ? (size_t)a.stage_cap * 2 + 2048 + 64 : 0);
+  const size_t smem = (size_t)padx(M) * sizeof(float2) + (C16 ? (size_t)a.stage_cap * 2 + ((size_t)2048 << a.lut_rep_shift) + 64 : 0);
   const int units = a.frames * a.num_symbols;
   static bool attr = false;
   if (!attr) {
@@ -1252,9 +1257,13 @@ static void launch_ofdm_c(const OfdmArgs &a, cudaStream_t s)
   }
 }
 
-void launch_ofdm(const OfdmArgs &a, cudaStream_t s)
+void launch_ofdm(const OfdmArgs &a0, cudaStream_t s)
 {
-  if (a.frames * a.num_symbols < 1) return;
+  if (a0.frames * a0.num_symbols < 1) return;
+  OfdmArgs a = a0;
+  // 16 copies of the constellation LUTs when shared memory allows (chain mode)
+  a.lut_rep_shift = 0;
+  if (a.cells16 && (size_t)padx(1 << a.log2_m) * sizeof(float2) + (size_t)a.stage_cap * 2 + (2048 << 4) + 64 <= 227 * 1024) a.lut_rep_shift = 4;
   if (a.cells16) {
     if (a.out_fmt) launch_ofdm_c<true, 1>(a, s);
     else launch_ofdm_c<true, 0>(a, s);

@@ -97,6 +97,7 @@ struct OfdmArgs {
   const int32_t *sym_flags;  // [num_symbols] bit 0: the symbol has carriers coded 0x80000000 + pool cell
   int stage_cap;             // staging slots reserved in shared memory (multiple of 8)
   const float2 *lut; int lut_n;   // constellation LUT
+  int lut_rep_shift;         // set by launch_ofdm: log2 of the number of LUT copies kept in shared memory
   void *out;           long long out_stride;     // samples per T2 frame (complex64, or short2 when out_fmt = 1)
   int out_fmt;               // 0 = complex64, 1 = interleaved 16-bit I/Q (x * 32767, saturated)
   float sink_gain;           // extra gain folded into `norm` and the P1 samples (1 = the reference block's output)
