@@ -867,7 +867,10 @@ int dvbt2ll_chain_run_host(dvbt2ll_handle *h, const void *ts, long long ts_pitch
   int r = c->ensure_device();
   if (r) return r;
   const long long per_ch = c->ts_bytes(first_frame, n_frames);
-  const long long hist = first_frame > 0 ? 187 : 0;
+  // normal input mode: the CRC-8 that replaces the first sync byte covers the 187 bytes before the pointer
+  const long long hist = (first_frame > 0 && c->bb.plan.mode == t2::INPUTMODE_NORMAL) ? 187 : 0;
+  if (n_channels < 0 || n_frames < 0 || (n_channels > 1 && ts_pitch < per_ch + hist))
+    return fail(DVBT2LL_ERR_INVALID, "chain: ts_pitch smaller than the TS bytes (+ 187 history bytes) of one channel");
   const long long dpitch = (per_ch + hist + 255) & ~255LL;
   const size_t ssz = c->sink_fmt ? 4 : 8;                                        // bytes per output sample
   const size_t out_bytes = (size_t)n_channels * n_frames * c->oplan.samples_per_frame * ssz;

@@ -112,7 +112,9 @@ DVBT2LL_API_EXPORT long long dvbt2ll_chain_samples_per_frame(const dvbt2ll_handl
 DVBT2LL_API_EXPORT int dvbt2ll_chain_fecframes_per_frame(const dvbt2ll_handle *h);
 /* n_channels independent transport streams, each contributing n_frames consecutive T2 frames starting at
  * its stream frame number first_frame (streams start on a packet boundary at frame 0).  d_ts: channel-major,
- * dvbt2ll_chain_ts_bytes(h, first_frame, n_frames) bytes per channel with pitch ts_pitch.
+ * dvbt2ll_chain_ts_bytes(h, first_frame, n_frames) bytes per channel with pitch ts_pitch.  In normal input mode with
+ * first_frame > 0 each channel pointer must be preceded by the 187 stream bytes before it (CRC-8 of the packet in
+ * flight), so ts_pitch >= bytes + 187; high-efficiency mode needs no history.
  * d_out: complex64, channel-major, n_frames*samples_per_frame per channel.  Asynchronous on `stream`. */
 DVBT2LL_API_EXPORT int dvbt2ll_chain_run_device(dvbt2ll_handle *h, const void *d_ts, long long ts_pitch,
                                                 int n_channels, int n_frames, long long first_frame,

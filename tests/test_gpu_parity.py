@@ -172,6 +172,27 @@ def test_chain_multichannel_and_offset(reflib):
     assert max_err_over_rms(out2[0], out[0, S:3 * S]) <= 1e-6
 
 
+def test_chain_hiefficiency_offset_batches():
+    """High-efficiency input mode: the TS bytes a T2 frame consumes depend on the stream position; batches that start
+    at frames 1 and 3 (pointer advanced by dvbt2ll_chain_ts_bytes) reproduce the frames of one batch from frame 0,
+    for two channels at once."""
+    cfg = K.resolve(CHAIN_VARIANTS["c1-hiefficiency"])
+    nch, nframes = 2, 5
+    ch = T.Chain(cfg, max_frames=nch * nframes)
+    S = ch.samples_per_frame
+    n_all = ch.ts_bytes(0, nframes)
+    assert len({ch.ts_bytes(f, 1) for f in range(nframes)}) > 1          # really position dependent
+    ts = np.stack([K.make_ts(n_all, seed=K.TS_SEED + c) for c in range(nch)])
+    full = ch.run_host(ts, nch, nframes)
+    for first, n in ((1, 2), (3, 2), (4, 1)):
+        off = ch.ts_bytes(0, first)
+        sub = np.ascontiguousarray(ts[:, off:off + ch.ts_bytes(first, n)])
+        out = np.empty((nch, n * S), dtype=np.complex64)
+        r = T.lib().dvbt2ll_chain_run_host(ch._h, sub.ctypes.data, sub.shape[1], nch, n, first, out.ctypes.data)
+        assert r == nch * n, T.last_error()
+        assert np.array_equal(out, full[:, first * S:(first + n) * S])
+
+
 def test_ragged_and_empty_calls():
     """noutput that is not a multiple of one frame produces floor() frames; zero output is a no-op;
     too little input is an error, not a partial frame."""
