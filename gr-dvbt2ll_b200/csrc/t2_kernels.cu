@@ -463,9 +463,7 @@ void launch_ldpc(const LdpcArgs &a, cudaStream_t s)
   int per_sm = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ldpc, LDPC_WARPS * 32, smem);
   if (per_sm < 1) per_sm = 1;
-  int blocks = (a.frames + LDPC_WARPS - 1) / LDPC_WARPS;
-  const int cap = sm_count() * per_sm;
-  if (blocks > cap) blocks = cap;
+  const int blocks = (a.frames + LDPC_WARPS - 1) / LDPC_WARPS;      // one FECFRAME per warp, no loop: finest tail
   k_ldpc<<<blocks, LDPC_WARPS * 32, smem, s>>>(a, warp_words, cw_words);
   count_launch();
 }
@@ -674,9 +672,8 @@ void launch_map(const MapArgs &a, cudaStream_t s)
 {
   const int nwords = (a.nldpc + 31) / 32;
   const size_t smem = (size_t)((nwords + 11) & ~3) * 4 + (size_t)(1 << a.mod) * 8 + 2 * (((a.cell_size + 127) & ~63) + 2 * (a.cell_size / 64 + 2));
-  int blocks = a.frames;
-  const int cap = sm_count() * 16;
-  if (blocks > cap) blocks = cap;
+  // one FECFRAME per CTA: the hardware scheduler balances the tail at frame granularity
+  const int blocks = a.frames;
   if (blocks < 1) return;
   static bool attr = false;
   if (!attr) {
