@@ -321,7 +321,7 @@ void launch_bb_bch(const BbArgs &a, cudaStream_t s)
 // ================================================================================================
 // K2  LDPC
 // ================================================================================================
-constexpr int LDPC_WARPS = 4;
+constexpr int LDPC_WARPS = 3;
 
 // 32 stream bits starting at bit position p of a packed byte stream held as raw (little-endian loaded) words
 __device__ __forceinline__ uint32_t window32_be(const uint32_t *w, int p)
@@ -337,7 +337,7 @@ __device__ __forceinline__ uint32_t be32_at(const uint32_t *w, int off)
   return __byte_perm(w[k], w[k + 1], 0x0123u + 0x1111u * (unsigned)(off & 3));
 }
 
-__global__ void __launch_bounds__(LDPC_WARPS * 32, 4) k_ldpc(const LdpcArgs a, int warp_words, int cw_words)
+__global__ void __launch_bounds__(LDPC_WARPS * 32, 6) k_ldpc(const LdpcArgs a, int warp_words, int cw_words)
 {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint32_t *s_all = reinterpret_cast<uint32_t *>(smem_raw);
