@@ -334,40 +334,29 @@ __device__ __forceinline__ uint32_t window32_be(const uint32_t *w, int p)
 __device__ __forceinline__ uint32_t be32_at(const uint32_t *w, int off)
 {
   const int k = off >> 2;
-  return __byte_perm(w[k], w[k + 1], 0x0123u + 0x1111u * (unsigned)(off & 3));
+  return __byte_perm(__ldg(w + k), __ldg(w + k + 1), 0x0123u + 0x1111u * (unsigned)(off & 3));
 }
 
-__global__ void __launch_bounds__(LDPC_WARPS * 32, 6) k_ldpc(const LdpcArgs a, int warp_words, int cw_words)
+__global__ void __launch_bounds__(LDPC_WARPS * 32, 8) k_ldpc(const LdpcArgs a, int warp_words, int cw_words)
 {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint32_t *s_all = reinterpret_cast<uint32_t *>(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint32_t *cw = s_all + warp * warp_words;       // [cw_words] packed codeword as loaded (16-byte aligned), later reused:
-  uint32_t *rows = cw;                            // [q][12] parity rows
-  uint32_t *ext = cw + cw_words;                  // [groups][13]
+  uint32_t *rows = s_all + warp * warp_words;     // [q][12] parity rows
+  uint32_t *ext = rows + cw_words;                // [groups][13]
   const int q = a.q, G = a.groups;
   const int info_bytes = a.nbch / 8;
 
   for (int job = blockIdx.x * LDPC_WARPS + warp; job < a.frames; job += gridDim.x * LDPC_WARPS) {
     const uint8_t *in = a.in + (long long)job * a.in_pitch;
     uint8_t *out = a.out + (long long)job * a.out_pitch;
-    // ---- whole BCH codeword into shared memory with 16-byte asynchronous copies (all in flight at once)
-    {
-      const int n16 = (info_bytes + 8 + 15) >> 4;                    // a little beyond the end for the last windows
-      const unsigned dst0 = (unsigned)__cvta_generic_to_shared(cw);
-      for (int i = lane; i < n16; i += 32)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst0 + 16u * i), "l"(in + 16 * i));
-      asm volatile("cp.async.commit_group;\n" ::);
-      asm volatile("cp.async.wait_group 0;\n" ::);
-    }
-    __syncwarp();
+    const uint32_t *cw = reinterpret_cast<const uint32_t *>(in);      // packed BCH codeword, read through L1
     // ---- info bits pass through to the output
     {
       uint32_t *ow = reinterpret_cast<uint32_t *>(out);
       const int nw = info_bytes >> 2;
-      for (int i = lane; i < nw; i += 32) ow[i] = cw[i];
-      const uint8_t *cb = reinterpret_cast<const uint8_t *>(cw);
-      for (int b = (nw << 2) + lane; b < info_bytes; b += 32) out[b] = cb[b];
+      for (int i = lane; i < nw; i += 32) ow[i] = __ldg(cw + i);
+      for (int b = (nw << 2) + lane; b < info_bytes; b += 32) out[b] = __ldg(in + b);
     }
     // ---- wrap-extended groups: 13 words = circular bits [0, 416) of each 360-bit group.  A group is 45 bytes, so
     // word w is the big-endian 32-bit value at byte 45 g + 4 w (w <= 10), bytes {44, 0, 1, 2} (w = 11) or bytes 3..6
@@ -452,9 +441,8 @@ __global__ void __launch_bounds__(LDPC_WARPS * 32, 6) k_ldpc(const LdpcArgs a, i
 
 void launch_ldpc(const LdpcArgs &a, cudaStream_t s)
 {
-  // per warp: extended groups + max(raw codeword, parity rows)
-  int cw_words = ((a.nbch / 8 + 8 + 15) >> 4) * 4 + 4;
-  if (cw_words < a.q * 12 + 4) cw_words = a.q * 12 + 4;
+  // per warp: extended groups + parity rows (the codeword itself is read from global memory / L1)
+  const int cw_words = a.q * 12 + 4;
   const int warp_words = (a.groups * 13 + cw_words + 3) & ~3;
   const size_t smem = (size_t)LDPC_WARPS * warp_words * 4;
   if (a.frames < 1) return;
