@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(BB_MAX_WARPS * 32) k_bb_bch(const BbArgs a)
           const uint32_t *pw = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
           const int sh = (int)(reinterpret_cast<uintptr_t>(p) & 3) * 8;
           uint32_t crc = 0, lo = pw[0];
-#pragma unroll 1
+#pragma unroll 4
           for (int st = 0; st < 47; st++) {
             const uint32_t hi = pw[st + 1];
             uint32_t t = __funnelshift_r(lo, hi, sh);
