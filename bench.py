@@ -194,6 +194,28 @@ def run_reference_arm(args):
 
 
 # --------------------------------------------------------------------------------------------------
+def bind_to_gpu_cpus(torch, local):
+    """Run this rank on the CPU cores NVML reports as local to its GPU, so the pinned host buffers of the e2e path
+    are first-touched on the GPU's NUMA node.  Returns (cores bound, original affinity) -- (0, None) if unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID("GPU-" + str(torch.cuda.get_device_properties(local).uuid))
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        orig = os.sched_getaffinity(0)
+        cpus = [i for i in range(words * 64) if (mask[i // 64] >> (i % 64)) & 1 and i in orig]
+        if cpus and len(cpus) < len(orig):
+            os.sched_setaffinity(0, cpus)
+            return len(cpus), orig
+    except Exception:
+        pass
+    return 0, None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -207,6 +229,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cores, orig_affinity = bind_to_gpu_cpus(torch, local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -365,6 +388,8 @@ def run_ours(args):
                 "map_kernel_gbs": map_bytes / (stage_ms["map"] * 1e-3) / 1e9}
 
     cpu = None
+    if orig_affinity is not None:
+        os.sched_setaffinity(0, orig_affinity)
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_run(cfg, args.cpu_frames, 1)
         if r is not None:
@@ -385,7 +410,8 @@ def run_ours(args):
         "x_realtime": value / K.REALTIME_MSPS, "x_realtime_per_gpu": value / K.REALTIME_MSPS / world,
         "fecframes_per_s": frames * F * world / (ms_per_step * 1e-3),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(nch * nfr * n_ts), "d2h_bytes_per_step": int(frames * S * 8),
-                "api": "dvbt2ll_chain_run_host (pinned host buffers)", "checksum": checksum},
+                "api": "dvbt2ll_chain_run_host (pinned host buffers)", "checksum": checksum,
+                "host_cores_local_to_gpu": numa_cores},
         "e2e_int16_sink": {"value": e2e16_value, "unit": UNIT, "d2h_bytes_per_step": int(frames * S * 4),
                            "note": "same call with dvbt2ll_chain_set_sink(format=int16 I/Q, gain=0.2): the flowgraph's multiply_const + sc16 conversion fused into the last kernel"},
         "gpu_launches": int(launches),
