@@ -220,11 +220,22 @@ __global__ void __launch_bounds__(BB_MAX_WARPS * 32) k_bb_bch(const BbArgs a)
       const int e = s + a.chunk_bytes;
       if (s < 0) s = 0;
       int i = s;
-      // two message bytes per step: four nibble rows, all independent of each other
       const uint32_t *nt = s_ntab + lane;
       constexpr int ROW = NW * 32;              // words between rows of a table
-      for (; i + 2 <= e; i += 2) {
-        const uint32_t x = (r0 >> 16) ^ ((uint32_t)buf[i] << 8) ^ buf[i + 1];
+      // one message byte: two nibble rows
+      auto step8 = [&](uint32_t byte) {
+        const uint32_t x = (r0 >> 24) ^ byte;
+        const uint32_t *t1 = nt + (16 + (x >> 4)) * ROW, *t0 = nt + (x & 15u) * ROW;
+        r0 = ((r0 << 8) | (r1 >> 24)) ^ t1[0] ^ t0[0];
+        r1 = ((r1 << 8) | (r2 >> 24)) ^ t1[32] ^ t0[32];
+        r2 = ((r2 << 8) | (r3 >> 24)) ^ t1[64] ^ t0[64];
+        r3 = ((r3 << 8) | (r4 >> 24)) ^ t1[96] ^ t0[96];
+        r4 = ((r4 << 8) | (W6 ? r5 >> 24 : 0u)) ^ t1[128] ^ t0[128];
+        if (W6) r5 = (r5 << 8) ^ t1[NW * 32 - 32] ^ t0[NW * 32 - 32];
+      };
+      // two message bytes (big-endian halfword): four nibble rows, all independent of each other
+      auto step16 = [&](uint32_t half) {
+        const uint32_t x = (r0 >> 16) ^ half;
         const uint32_t *t3 = nt + (48 + (x >> 12)) * ROW, *t2 = nt + (32 + ((x >> 8) & 15u)) * ROW,
                        *t1 = nt + (16 + ((x >> 4) & 15u)) * ROW, *t0 = nt + (x & 15u) * ROW;
         r0 = ((r0 << 16) | (r1 >> 16)) ^ t3[0] ^ t2[0] ^ t1[0] ^ t0[0];
@@ -233,17 +244,16 @@ __global__ void __launch_bounds__(BB_MAX_WARPS * 32) k_bb_bch(const BbArgs a)
         r3 = ((r3 << 16) | (r4 >> 16)) ^ t3[96] ^ t2[96] ^ t1[96] ^ t0[96];
         r4 = ((r4 << 16) | (W6 ? r5 >> 16 : 0u)) ^ t3[128] ^ t2[128] ^ t1[128] ^ t0[128];
         if (W6) r5 = (r5 << 16) ^ t3[NW * 32 - 32] ^ t2[NW * 32 - 32] ^ t1[NW * 32 - 32] ^ t0[NW * 32 - 32];
+      };
+      // head: single bytes up to a word boundary of the frame buffer (the same 0..3 bytes for every lane: the chunk
+      // length is a multiple of 4); body: one conflict-free 32-bit load per four message bytes; tail: single bytes
+      for (; (i & 3) && i < e; i++) step8(buf[i]);
+      for (; i + 4 <= e; i += 4) {
+        const uint32_t mw = bufw[i >> 2];
+        step16(__byte_perm(mw, 0u, 0x4401u));
+        step16(__byte_perm(mw, 0u, 0x4423u));
       }
-      for (; i < e; i++) {
-        const uint32_t x = (r0 >> 24) ^ buf[i];
-        const uint32_t *t1 = nt + (16 + (x >> 4)) * ROW, *t0 = nt + (x & 15u) * ROW;
-        r0 = ((r0 << 8) | (r1 >> 24)) ^ t1[0] ^ t0[0];
-        r1 = ((r1 << 8) | (r2 >> 24)) ^ t1[32] ^ t0[32];
-        r2 = ((r2 << 8) | (r3 >> 24)) ^ t1[64] ^ t0[64];
-        r3 = ((r3 << 8) | (r4 >> 24)) ^ t1[96] ^ t0[96];
-        r4 = ((r4 << 8) | (W6 ? r5 >> 24 : 0u)) ^ t1[128] ^ t0[128];
-        if (W6) r5 = (r5 << 8) ^ t1[NW * 32 - 32] ^ t0[NW * 32 - 32];
-      }
+      for (; i < e; i++) step8(buf[i]);
     }
     // ---- Horner combine: acc = acc * x^(8*chunk) + R_i, the multiply evaluated column-wise:
     // lane l computes output bit (31 - l) of every word as parity(acc & column) and a ballot

@@ -176,7 +176,10 @@ bool build_bb_plan(int framesize, int rate, int mode, int inband, int fecblocks,
   }
 
   const int msg_bytes = f.kbch / 8;
-  p->chunk_bytes = (msg_bytes + 31) / 32;
+  // bytes per lane: a multiple of 4 with an odd word count, so that the lanes' 32-bit message loads start on word
+  // boundaries (up to the common residue msg_bytes mod 4) and fall into 32 different shared-memory banks
+  p->chunk_bytes = ((msg_bytes + 31) / 32 + 3) & ~3;
+  if (((p->chunk_bytes >> 2) & 1) == 0) p->chunk_bytes += 4;
   p->lead_zero_bytes = 32 * p->chunk_bytes - msg_bytes;
 
   // rows of "multiply by x^(8 * chunk_bytes) mod g": image of each register position
