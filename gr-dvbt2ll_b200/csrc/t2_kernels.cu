@@ -883,16 +883,19 @@ __device__ __forceinline__ void apply_twiddles(float2 (&v)[R], float2 w1)
 }
 
 // one in-place DIT pass of radix 16 over M points; NPREV = length of the already transformed sub-blocks
-template <int M, int NPREV, int T>
-__device__ __forceinline__ void fft_pass16(float2 *x, const float2 *__restrict__ tw)
+// PRE: the twiddle base W^i of the thread's butterflies (i = threadIdx.x mod NPREV, the same for every u when T is a
+// multiple of NPREV) was loaded once by the caller and is passed in `wpre`
+template <int M, int NPREV, int T, bool PRE = false>
+__device__ __forceinline__ void fft_pass16(float2 *x, const float2 *__restrict__ tw, float2 wpre = make_float2(1.f, 0.f))
 {
   constexpr int NB = M / 16;
   constexpr int TW_STEP = M / (NPREV * 16);
+  static_assert(!PRE || T % NPREV == 0, "preloaded twiddle needs a thread-constant butterfly index");
 #pragma unroll (NB / T == 2 ? 2 : 1)
   for (int u = threadIdx.x; u < NB; u += T) {
     const int i = u & (NPREV - 1);
     float2 *xb = x + padx((u - i) * 16 + i);
-    const float2 w1 = __ldg(tw + i * TW_STEP);
+    const float2 w1 = PRE ? wpre : __ldg(tw + i * TW_STEP);
     float2 v[16];
 #pragma unroll
     for (int qd = 0; qd < 16; qd++) v[qd] = xb[padx(qd * NPREV)];
@@ -1084,6 +1087,19 @@ __global__ void __launch_bounds__(T, (LOG2M == 14 ? 1 : 1024 / T)) k_ofdm(const 
   const int units = a.frames * a.num_symbols;
   const int cp_from = N - a.gi;
   const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
+  // 16K sub-transform with 512 threads: every thread runs the same butterflies for every symbol, so their twiddle
+  // bases stay in registers for the whole kernel (no L2 round trip at the start of each pass: L1 is ~2 KB here)
+  constexpr bool REGTW = LOG2M == 14 && T == 512;
+  float2 tw_p1 = make_float2(1.f, 0.f), tw_p2 = tw_p1, tw_last[2] = { tw_p1, tw_p1 }, tw_rec[2] = { tw_p1, tw_p1 };
+  if (REGTW) {
+    tw_p1 = __ldg(a.tw + (threadIdx.x & 3) * (M / 64));
+    tw_p2 = __ldg(a.tw + (threadIdx.x & 63) * (M / 1024));
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      tw_last[j] = __ldg(a.tw + threadIdx.x + j * T);
+      if (SPLIT == 2) tw_rec[j] = __fmul2_rn(__ldg(a.tw_split + threadIdx.x + j * T), make_float2(a.norm, a.norm));
+    }
+  }
 
   // C16: copy the cells of symbol `u` into the staging area in aligned 8-byte chunks (4 cells), asynchronously
   // (cp.async; the caller waits before the fill).  Issued for symbol u + gridDim.x as soon as symbol u's last fill
@@ -1152,13 +1168,19 @@ __global__ void __launch_bounds__(T, (LOG2M == 14 ? 1 : 1024 / T)) k_ofdm(const 
       __syncthreads();
       if (C16 && phase == SPLIT - 1 && unit + (int)gridDim.x < units) stage_issue(unit + gridDim.x);
       // ---- 2. middle radix-16 passes
-      if (R0 * 16 < NLAST * 16 && R0 < NLAST) { fft_pass16<M, R0, T>(x, a.tw); __syncthreads(); }
-      if (R0 * 16 < NLAST) { fft_pass16<M, (R0 * 16 < NLAST ? R0 * 16 : 1), T>(x, a.tw); __syncthreads(); }
+      if (REGTW) {
+        fft_pass16<M, 4, T, REGTW>(x, a.tw, tw_p1); __syncthreads();
+        fft_pass16<M, 64, T, REGTW>(x, a.tw, tw_p2); __syncthreads();
+      }
+      else {
+        if (R0 * 16 < NLAST * 16 && R0 < NLAST) { fft_pass16<M, R0, T>(x, a.tw); __syncthreads(); }
+        if (R0 * 16 < NLAST) { fft_pass16<M, (R0 * 16 < NLAST ? R0 * 16 : 1), T>(x, a.tw); __syncthreads(); }
+      }
       // ---- 3. last radix-16 pass fused with scale + store (+ cyclic prefix, + 32K recombination)
 #pragma unroll 1
-      for (int i = threadIdx.x; i < NLAST; i += T) {
+      for (int i = threadIdx.x, it = 0; i < NLAST; i += T, it++) {
         const float2 *xb = x + padx(i);
-        const float2 w1 = __ldg(a.tw + i);      // TW_STEP = M / (NLAST * 16) = 1
+        const float2 w1 = REGTW ? (it ? tw_last[1] : tw_last[0]) : __ldg(a.tw + i);      // TW_STEP = M / (NLAST * 16) = 1
         float2 v[16];
 #pragma unroll
         for (int qd = 0; qd < 16; qd++) v[qd] = xb[padx(qd * NLAST)];
@@ -1192,8 +1214,7 @@ __global__ void __launch_bounds__(T, (LOG2M == 14 ? 1 : 1024 / T)) k_ofdm(const 
           // W_N^n = W_N^i * exp(j 2 pi k / 32); E is re-read in two batches of 8
           const float2 *pk = park + i;
           sample_t *ocp = sym + ((long long)i + M - cp_from);
-          float2 wi = __ldg(a.tw_split + i);
-          wi = __fmul2_rn(wi, make_float2(a.norm, a.norm));
+          const float2 wi = REGTW ? (it ? tw_rec[1] : tw_rec[0]) : __fmul2_rn(__ldg(a.tw_split + i), make_float2(a.norm, a.norm));
 #pragma unroll
           for (int h = 0; h < 2; h++) {
             float2 e[8];
