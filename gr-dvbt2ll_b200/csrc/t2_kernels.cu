@@ -1104,20 +1104,31 @@ __global__ void __launch_bounds__(T, (LOG2M == 14 ? 1 : 1024 / T)) k_ofdm(const 
   // C16: copy the cells of symbol `u` into the staging area in aligned 8-byte chunks (4 cells), asynchronously
   // (cp.async; the caller waits before the fill).  Issued for symbol u + gridDim.x as soon as symbol u's last fill
   // has finished reading the staging area, so the copy runs under the FFT passes.
-  auto stage_issue = [&](int u) {
+  // The source-chunk indices come from L2 (~700 cycles); stage_index requests the first SB per thread (all of them
+  // at 16K / 32K) -- it is called BEFORE the barrier that ends the last fill, so the wait is spent at the barrier --
+  // and stage_issue starts the copies.
+  constexpr int SB = 16;
+  struct StageJob { const uint8_t *src; const int32_t *csrc; int n_chunks; int sidx[SB]; };
+  auto stage_index = [&](int u, StageJob &j) {
     const int uf = u / a.num_symbols, ul = u - uf * a.num_symbols;
-    const uint8_t *src = reinterpret_cast<const uint8_t *>(a.cells16 + (long long)uf * a.cells_stride);
-    const int c0 = __ldg(a.chunk_ptr + ul), n_chunks = __ldg(a.chunk_ptr + ul + 1) - c0;
-    const int32_t *csrc = a.chunk_src + c0;
+    j.src = reinterpret_cast<const uint8_t *>(a.cells16 + (long long)uf * a.cells_stride);
+    const int c0 = __ldg(a.chunk_ptr + ul);
+    j.n_chunks = __ldg(a.chunk_ptr + ul + 1) - c0;
+    j.csrc = a.chunk_src + c0;
+#pragma unroll
+    for (int q = 0; q < SB; q++) j.sidx[q] = (int)threadIdx.x + q * T < j.n_chunks ? __ldg(j.csrc + threadIdx.x + q * T) : -1;
+  };
+  auto stage_issue = [&](StageJob &j) {
 #pragma unroll 1
-    for (int i0 = threadIdx.x; i0 < n_chunks; i0 += 4 * T) {
-      int sidx[4];
+    for (int i0 = threadIdx.x; i0 < j.n_chunks; i0 += SB * T) {
+      if (i0 != (int)threadIdx.x) {
 #pragma unroll
-      for (int q = 0; q < 4; q++) sidx[q] = i0 + q * T < n_chunks ? __ldg(csrc + i0 + q * T) : -1;
+        for (int q = 0; q < SB; q++) j.sidx[q] = i0 + q * T < j.n_chunks ? __ldg(j.csrc + i0 + q * T) : -1;
+      }
 #pragma unroll
-      for (int q = 0; q < 4; q++)
-        if (sidx[q] >= 0)
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(stage_s + 8u * (uint32_t)(i0 + q * T)), "l"(src + 8ll * sidx[q]) : "memory");
+      for (int q = 0; q < SB; q++)
+        if (j.sidx[q] >= 0)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(stage_s + 8u * (uint32_t)(i0 + q * T)), "l"(j.src + 8ll * j.sidx[q]) : "memory");
     }
   };
 
@@ -1146,7 +1157,7 @@ __global__ void __launch_bounds__(T, (LOG2M == 14 ? 1 : 1024 / T)) k_ofdm(const 
     int c[FillGeom<LOG2M, T>::GPB][FillGeom<LOG2M, T>::R0];
     fill_load_codes<LOG2M, T>(a.code_pos + (long long)l * SPLIT * M, threadIdx.x, c);
     if (C16) {
-      if (unit == (int)blockIdx.x) stage_issue(unit);      // later symbols are prefetched during the previous one
+      if (unit == (int)blockIdx.x) { StageJob j; stage_index(unit, j); stage_issue(j); }      // later symbols are prefetched during the previous one
       asm volatile("cp.async.wait_all;\n" ::: "memory");
     }
 
@@ -1165,8 +1176,11 @@ __global__ void __launch_bounds__(T, (LOG2M == 14 ? 1 : 1024 / T)) k_ofdm(const 
         if (pool_sym) ofdm_fill<LOG2M, T, C16, true, false>(x, code, sinc, c, stage, lut_re, lut_im, lut_rep_shift, spool_m8, cells, pool);
         else ofdm_fill<LOG2M, T, C16, false, false>(x, code, sinc, c, stage, lut_re, lut_im, lut_rep_shift, spool_m8, cells, pool);
       }
+      const bool stage_next = C16 && phase == SPLIT - 1 && unit + (int)gridDim.x < units;
+      StageJob sj;
+      if (stage_next) stage_index(unit + gridDim.x, sj);
       __syncthreads();
-      if (C16 && phase == SPLIT - 1 && unit + (int)gridDim.x < units) stage_issue(unit + gridDim.x);
+      if (stage_next) stage_issue(sj);
       // ---- 2. middle radix-16 passes
       if (REGTW) {
         fft_pass16<M, 4, T, REGTW>(x, a.tw, tw_p1); __syncthreads();
