@@ -193,6 +193,34 @@ def test_chain_hiefficiency_offset_batches():
         assert np.array_equal(out, full[:, first * S:(first + n) * S])
 
 
+def test_two_handles_on_two_threads():
+    """Handles are independent (SURVEY 8(b) threading contract): two chains driven from two host threads at the same
+    time give the same samples as when run one after the other."""
+    import threading
+    cfgs = [K.resolve("c1"), K.resolve(CHAIN_VARIANTS["2k-zigzag"])]
+    chains = [T.Chain(c, max_frames=8) for c in cfgs]
+    tss = [np.stack([K.make_ts(2 * ch.ts_bytes_per_frame, seed=K.TS_SEED + 7 * i + c) for c in range(4)]) for i, ch in enumerate(chains)]
+    want = [ch.run_host(ts, 4, 2).copy() for ch, ts in zip(chains, tss)]
+    got = [None, None]
+    errs = []
+
+    def work(i):
+        try:
+            for _ in range(5):
+                got[i] = chains[i].run_host(tss[i], 4, 2).copy()
+        except Exception as e:          # pragma: no cover
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs
+    for i in range(2):
+        assert np.array_equal(got[i], want[i])
+
+
 def test_ragged_and_empty_calls():
     """noutput that is not a multiple of one frame produces floor() frames; zero output is a no-op;
     too little input is an error, not a partial frame."""
