@@ -526,6 +526,7 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map(const MapArgs a)
 
   for (int f = blockIdx.x; f < a.frames; f += gridDim.x) {
     const uint32_t *in = reinterpret_cast<const uint32_t *>(a.in + (long long)f * a.in_pitch);
+    const int shift = a.fec_shift ? __ldg(a.fec_shift + f % a.fecblocks) : 0;     // requested early: used by the last stage
     __syncthreads();
     {
       // packed codeword into shared memory as raw bytes with 16-byte asynchronous copies (frames are 16-byte pitched)
@@ -627,7 +628,6 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map(const MapArgs a)
       // chain mode: the 16-bit codes in cell-interleaved order: cell ci_inv[y] goes to position (y + shift) mod Nc.
       // Two segments with a constant position - y, so table reads and stores are a base pointer + constant offsets.
       uint16_t *o16 = a.out16 + (long long)(f / a.fecblocks) * a.out16_frame_stride + (long long)(f % a.fecblocks) * Nc;
-      const int shift = a.fec_shift[f % a.fecblocks];
 #pragma unroll 1
       for (int seg = 0; seg < 2; seg++) {
         const int y_end = seg ? Nc : Nc - shift;
@@ -649,7 +649,6 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map(const MapArgs a)
     }
     else if (a.ci_inv) {
       // fused cell interleaver with complex output
-      const int shift = a.fec_shift[f % a.fecblocks];
       for (int xo = threadIdx.x; xo < Nc; xo += blockDim.x) {
         int y = xo - shift;
         if (y < 0) y += Nc;
