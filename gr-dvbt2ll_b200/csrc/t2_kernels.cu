@@ -319,6 +319,9 @@ void launch_bb_bch(const BbArgs &a, cudaStream_t s)
   // one CTA per SM (the lane-private tables take 40-48 KB), as many warps as frame buffers fit
   int warps = BB_MAX_WARPS;
   while (warps > 4 && fixed + (size_t)warps * buf_pitch > 227 * 1024) warps -= 4;
+  // small batches: spread the FECFRAMEs over all SMs instead of filling a few CTAs
+  const int spread = (total + sm_count() - 1) / sm_count();
+  if (spread < warps) warps = spread < 1 ? 1 : spread;
   const size_t smem = fixed + (size_t)warps * buf_pitch;
   int blocks = (total + warps - 1) / warps;
   const int cap = sm_count();                 // one resident wave; warps loop over the remaining FECFRAMEs
