@@ -950,7 +950,7 @@ int ofdm_position_of_bin(int m, int log2_m)
 // one output sample: complex64, or (sink format 1) interleaved 16-bit I/Q = round(x * 32767), saturated
 template <int FMT> struct SinkT { typedef float2 type; };
 template <> struct SinkT<1> { typedef short2 type; };
-__device__ __forceinline__ void store_sample(float2 *p, int idx, float2 v) { p[idx] = v; }
+__device__ __forceinline__ void store_sample(float2 *p, int idx, float2 v) { __stcs(p + idx, v); }
 __device__ __forceinline__ void store_sample(short2 *p, int idx, float2 v)
 {
   int xi = __float2int_rn(v.x * 32767.f), yi = __float2int_rn(v.y * 32767.f);
