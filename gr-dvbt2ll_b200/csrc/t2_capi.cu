@@ -418,7 +418,7 @@ struct OfdmDevice {
     // i.e. carrier k = that - left_nulls (null carriers outside [0, C_PS) take pool cell 0 = zero).
     const int L = op.dims.num_symbols, cps = op.dims.c_ps;
     std::vector<int> pos(M);
-    for (int m = 0; m < M; m++) pos[m] = t2k::ofdm_position_of_bin(m, log2_m);
+    for (int m = 0; m < M; m++) pos[m] = t2k::ofdm_table_index(t2k::ofdm_position_of_bin(m, log2_m), log2_m);
     std::vector<int32_t> code_pos((size_t)L * N, -1);
     std::vector<int32_t> sym_flags(L, 0);
     for (int l = 0; l < L; l++)

@@ -931,13 +931,41 @@ __device__ __forceinline__ float2 w32(int k)
   }
 }
 
+// exp(+j 2 pi k / 64), k < 8, compile-time after unrolling
+__device__ __forceinline__ float2 w64(int k)
+{
+  switch (k) {
+    case 0: return make_float2(1.f, 0.f);
+    case 1: return make_float2(0.99518472667219693f, 0.098017140329560604f);
+    case 2: return make_float2(0.98078528040323043f, 0.19509032201612825f);
+    case 3: return make_float2(0.95694033573220882f, 0.29028467725446233f);
+    case 4: return make_float2(0.92387953251128674f, 0.38268343236508978f);
+    case 5: return make_float2(0.88192126434835505f, 0.47139673682599764f);
+    case 6: return make_float2(0.83146961230254524f, 0.55557023301960218f);
+    default: return make_float2(0.77301045336273699f, 0.63439328416364549f);
+  }
+}
+
+// where the per-position tables (carrier codes, inverse-sinc factors) keep the entry of shared-memory position p:
+// p itself, except for the 16K sub-transform, whose fill reads 16 consecutive positions per thread as four vector
+// loads -- stored [quad][group][4] so that each load is contiguous across the warp
+int ofdm_table_index(int p, int log2_m)
+{
+  if (log2_m != 14) return p;
+  const int g = p >> 4, q = (p >> 2) & 3, r = p & 3;
+  return ((q << 10) + g) * 4 + r;
+}
+
 int ofdm_position_of_bin(int m, int log2_m)
 {
   // digits of m taken from the most significant end go to the least significant end of the position
+  // pass order: the short radix 2^(log2_m mod 4) first, then radix 16 -- except the 16K sub-transform, which runs
+  // 16, 16, 16, 4 (first pass fused with the carrier fill, the cheap radix-4 pass fused with the output)
   const int first = log2_m & 3;
   int lg[4], nr = 0;
-  if (first) lg[nr++] = first;
+  if (first && log2_m != 14) lg[nr++] = first;
   for (int i = 0; i < log2_m / 4; i++) lg[nr++] = 4;
+  if (first && log2_m == 14) lg[nr++] = first;
   int p = 0, out_shift = 0, rem = log2_m;
   for (int j = 0; j < nr; j++) {
     rem -= lg[j];
@@ -976,7 +1004,7 @@ __device__ __forceinline__ void store_sample(short2 *p, int idx, float2 v)
 template <int LOG2M, int T>
 struct FillGeom {
   static constexpr int M = 1 << LOG2M;
-  static constexpr int R0 = 1 << (LOG2M & 3);       // first radix (1 = no first pass)
+  static constexpr int R0 = LOG2M == 14 ? 16 : 1 << (LOG2M & 3);   // first radix (1 = no first pass)
   static constexpr int GROUPS = M / R0;             // first-pass butterflies
   static constexpr int INFL = LOG2M == 14 ? 16 : 8; // positions in flight per thread (16 where 128 registers are available)
   static constexpr int GPB0 = R0 >= INFL ? 1 : INFL / R0; // groups gathered per batch
@@ -1003,6 +1031,14 @@ __device__ __forceinline__ void fill_load_codes(const int32_t *__restrict__ code
       const int4 q4 = __ldg(reinterpret_cast<const int4 *>(code) + 2 * g), q5 = __ldg(reinterpret_cast<const int4 *>(code) + 2 * g + 1);
       c[b][0] = q4.x; c[b][1 % R0] = q4.y; c[b][2 % R0] = q4.z; c[b][3 % R0] = q4.w;
       c[b][4 % R0] = q5.x; c[b][5 % R0] = q5.y; c[b][6 % R0] = q5.z; c[b][7 % R0] = q5.w;
+    }
+    else if (R0 == 16) {
+      // table laid out [quad q][group g][4] (ofdm_table_index): a warp's load of quad q is one contiguous 512 bytes
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int4 q4 = __ldg(reinterpret_cast<const int4 *>(code) + q * G::GROUPS + g);
+        c[b][(4 * q) % R0] = q4.x; c[b][(4 * q + 1) % R0] = q4.y; c[b][(4 * q + 2) % R0] = q4.z; c[b][(4 * q + 3) % R0] = q4.w;
+      }
     }
     else if (R0 == 2) {
       const int2 q2 = __ldg(reinterpret_cast<const int2 *>(code) + g);
@@ -1058,7 +1094,10 @@ __device__ __forceinline__ void ofdm_fill(float2 *x, const int32_t *__restrict__
       const int g = g0 + b * T;
       if (SINC) {
 #pragma unroll
-        for (int r = 0; r < R0; r++) { const float sf = __ldg(sinc + g * R0 + r); v[b][r] = __fmul2_rn(v[b][r], make_float2(sf, sf)); }
+        for (int r = 0; r < R0; r++) {
+          const float sf = __ldg(sinc + (R0 == 16 ? (((r >> 2) * G::GROUPS + g) * 4 + (r & 3)) : g * R0 + r));
+          v[b][r] = __fmul2_rn(v[b][r], make_float2(sf, sf));
+        }
       }
       if (R0 > 1) dft_reg<R0>(v[b]);
       float2 *xb = x + padx(g * R0);
@@ -1091,16 +1130,15 @@ __global__ void __launch_bounds__(T, (LOG2M == 14 ? 1 : 1024 / T)) k_ofdm(const 
   const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
   // 16K sub-transform with 512 threads: every thread runs the same butterflies for every symbol, so their twiddle
   // bases stay in registers for the whole kernel (no L2 round trip at the start of each pass: L1 is ~2 KB here)
-  constexpr bool REGTW = LOG2M == 14 && T == 512;
-  float2 tw_p1 = make_float2(1.f, 0.f), tw_p2 = tw_p1, tw_last[2] = { tw_p1, tw_p1 }, tw_rec[2] = { tw_p1, tw_p1 };
+  // Pass schedule of the 16K sub-transform: radix 16 (in the fill, no twiddles), 16, 16, 4 (in the output).
+  constexpr bool REGTW = LOG2M == 14;
+  static_assert(!REGTW || T == 512, "the 16K schedule is written for 512 threads");
+  float2 tw_p1 = make_float2(1.f, 0.f), tw_p2 = tw_p1, tw_last = tw_p1, tw_rec = tw_p1;
   if (REGTW) {
-    tw_p1 = __ldg(a.tw + (threadIdx.x & 3) * (M / 64));
-    tw_p2 = __ldg(a.tw + (threadIdx.x & 63) * (M / 1024));
-#pragma unroll
-    for (int j = 0; j < 2; j++) {
-      tw_last[j] = __ldg(a.tw + threadIdx.x + j * T);
-      if (SPLIT == 2) tw_rec[j] = __fmul2_rn(__ldg(a.tw_split + threadIdx.x + j * T), make_float2(a.norm, a.norm));
-    }
+    tw_p1 = __ldg(a.tw + (threadIdx.x & 15) * (M / 256));       // pass with NPREV = 16:  W_M^{i M/256},  i = u mod 16
+    tw_p2 = __ldg(a.tw + (threadIdx.x & 255) * (M / 4096));     // pass with NPREV = 256: W_M^{i M/4096}, i = u mod 256
+    tw_last = __ldg(a.tw + threadIdx.x);                        // last pass: W_M^{tid}; butterfly tid + 512 j adds exp(j 2 pi j / 32)
+    if (SPLIT == 2) tw_rec = __fmul2_rn(__ldg(a.tw_split + threadIdx.x), make_float2(a.norm, a.norm));   // W_N^{tid} * norm
   }
 
   // C16: copy the cells of symbol `u` into the staging area in aligned 8-byte chunks (4 cells), asynchronously
@@ -1185,18 +1223,79 @@ __global__ void __launch_bounds__(T, (LOG2M == 14 ? 1 : 1024 / T)) k_ofdm(const 
       if (stage_next) stage_issue(sj);
       // ---- 2. middle radix-16 passes
       if (REGTW) {
-        fft_pass16<M, 4, T, REGTW>(x, a.tw, tw_p1); __syncthreads();
-        fft_pass16<M, 64, T, REGTW>(x, a.tw, tw_p2); __syncthreads();
+        fft_pass16<M, 16, T, REGTW>(x, a.tw, tw_p1); __syncthreads();
+        fft_pass16<M, 256, T, REGTW>(x, a.tw, tw_p2); __syncthreads();
       }
       else {
         if (R0 * 16 < NLAST * 16 && R0 < NLAST) { fft_pass16<M, R0, T>(x, a.tw); __syncthreads(); }
         if (R0 * 16 < NLAST) { fft_pass16<M, (R0 * 16 < NLAST ? R0 * 16 : 1), T>(x, a.tw); __syncthreads(); }
       }
-      // ---- 3. last radix-16 pass fused with scale + store (+ cyclic prefix, + 32K recombination)
+      // ---- 3. last pass fused with scale + store (+ cyclic prefix, + 32K recombination)
+      if constexpr (REGTW) {
+        // radix 4 over the whole sub-transform: butterfly i = tid + 512 j (j < 8) reads x[i + q M/4] and produces the
+        // samples i + k M/4.  W_M^i = W_M^tid * exp(j 2 pi j / 32); for the 32K recombination W_N^(i + k M/4) =
+        // W_N^tid * exp(j 2 pi j / 64) * exp(j 2 pi k / 8).  The parked even-bin values of butterfly j + 1 are requested
+        // from L2 while butterfly j is computed.
+        constexpr int NL = M / 4, NBT = NL / T;
+        constexpr int XS = NL + NL / 16;                      // padx(q * NL) = q * XS
+        sample_t *o = sym + a.gi + threadIdx.x;
+        const bool odd_phase = SPLIT == 2 && phase == 1;
+        const float2 *pk = park + threadIdx.x;
+        float2 e[4], en[4];
+        if (odd_phase) {
+#pragma unroll
+          for (int k = 0; k < 4; k++) e[k] = pk[k * NL];
+        }
+#pragma unroll
+        for (int j = 0; j < NBT; j++) {
+          const int i = threadIdx.x + j * T;
+          const float2 *xb = x + padx(i);
+          float2 v[4];
+#pragma unroll
+          for (int q = 0; q < 4; q++) v[q] = xb[q * XS];
+          if (odd_phase && j + 1 < NBT) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) en[k] = pk[(j + 1) * T + k * NL];
+          }
+          const float2 w1 = j ? cmul(tw_last, w32(j)) : tw_last;
+          const float2 w2 = cmul(w1, w1), w3 = cmul(w2, w1);
+          v[1] = cmul(v[1], w1); v[2] = cmul(v[2], w2); v[3] = cmul(v[3], w3);
+          dft_reg<4>(v);
+          if (SPLIT == 1) {
+            sample_t *ocp = sym + ((long long)threadIdx.x - cp_from);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              const float2 r = __fmul2_rn(v[bitrev_c(k, 4)], make_float2(a.norm, a.norm));
+              store_sample(o, j * T + k * NL, r);
+              if (i + k * NL >= cp_from) store_sample(ocp, j * T + k * NL, r);
+            }
+          }
+          else if (phase == 0) {
+            float2 *pw = park + threadIdx.x;
+#pragma unroll
+            for (int k = 0; k < 4; k++) pw[j * T + k * NL] = __fmul2_rn(v[bitrev_c(k, 4)], make_float2(a.norm, a.norm));
+          }
+          else {
+            sample_t *ocp = sym + ((long long)threadIdx.x + M - cp_from);
+            const float2 wi = j ? cmul(tw_rec, w64(j)) : tw_rec;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              const float2 r = cmul(tw16(v[bitrev_c(k, 4)], 2 * k), wi);
+              store_sample(o, j * T + k * NL, cadd(e[k], r));
+              const float2 hi = csub(e[k], r);
+              store_sample(o, j * T + k * NL + M, hi);
+              if (i + k * NL + M >= cp_from) store_sample(ocp, j * T + k * NL, hi);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) e[k] = en[k];
+          }
+        }
+      }
+      else
 #pragma unroll 1
-      for (int i = threadIdx.x, it = 0; i < NLAST; i += T, it++) {
+      for (int i = threadIdx.x; i < NLAST; i += T) {
         const float2 *xb = x + padx(i);
-        const float2 w1 = REGTW ? (it ? tw_last[1] : tw_last[0]) : __ldg(a.tw + i);      // TW_STEP = M / (NLAST * 16) = 1
+        const float2 w1 = __ldg(a.tw + i);      // TW_STEP = M / (NLAST * 16) = 1
         float2 v[16];
 #pragma unroll
         for (int qd = 0; qd < 16; qd++) v[qd] = xb[padx(qd * NLAST)];
@@ -1230,7 +1329,7 @@ __global__ void __launch_bounds__(T, (LOG2M == 14 ? 1 : 1024 / T)) k_ofdm(const 
           // W_N^n = W_N^i * exp(j 2 pi k / 32); E is re-read in two batches of 8
           const float2 *pk = park + i;
           sample_t *ocp = sym + ((long long)i + M - cp_from);
-          const float2 wi = REGTW ? (it ? tw_rec[1] : tw_rec[0]) : __fmul2_rn(__ldg(a.tw_split + i), make_float2(a.norm, a.norm));
+          const float2 wi = __fmul2_rn(__ldg(a.tw_split + i), make_float2(a.norm, a.norm));
 #pragma unroll
           for (int h = 0; h < 2; h++) {
             float2 e[8];

@@ -120,6 +120,8 @@ void launch_ofdm(const OfdmArgs &a, cudaStream_t s);
 // shared-memory position (before swizzle) at which the carrier-fill stage must store bin m of an
 // M = 2^log2_m point sub-transform (mixed-radix digit reversal matching the kernel's pass schedule)
 int ofdm_position_of_bin(int m, int log2_m);
+// index inside the per-(symbol, phase) tables at which the entry of position p is kept
+int ofdm_table_index(int p, int log2_m);
 
 long long kernel_launch_count();
 
