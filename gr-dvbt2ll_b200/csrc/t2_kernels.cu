@@ -1118,6 +1118,7 @@ __global__ void __launch_bounds__(T, (LOG2M == 14 ? 1 : 1024 / T)) k_ofdm(const 
   const int lut_rep_shift = a.lut_rep_shift, lut_rep = 1 << lut_rep_shift;
   float *lut_im = lut_re + 256 * lut_rep;
   float2 *spool = reinterpret_cast<float2 *>(lut_im + 256 * lut_rep);      // first 8 pool cells: zero and the pilot values
+  int *idxbuf = reinterpret_cast<int *>(spool + 8);                         // [stage_cap / 4] source chunk of every staging chunk
   if (C16) {
     for (int i = threadIdx.x; i < a.lut_n * lut_rep; i += T) { const float2 v = __ldg(a.lut + (i >> lut_rep_shift)); lut_re[i] = v.x; lut_im[i] = v.y; }
     if (threadIdx.x < 8) spool[threadIdx.x] = __ldg(a.pool + threadIdx.x);
@@ -1144,31 +1145,27 @@ __global__ void __launch_bounds__(T, (LOG2M == 14 ? 1 : 1024 / T)) k_ofdm(const 
   // C16: copy the cells of symbol `u` into the staging area in aligned 8-byte chunks (4 cells), asynchronously
   // (cp.async; the caller waits before the fill).  Issued for symbol u + gridDim.x as soon as symbol u's last fill
   // has finished reading the staging area, so the copy runs under the FFT passes.
-  // The source-chunk indices come from L2 (~700 cycles); stage_index requests the first SB per thread (all of them
-  // at 16K / 32K) -- it is called BEFORE the barrier that ends the last fill, so the wait is spent at the barrier --
-  // and stage_issue starts the copies.
-  constexpr int SB = 16;
-  struct StageJob { const uint8_t *src; const int32_t *csrc; int n_chunks; int sidx[SB]; };
-  auto stage_index = [&](int u, StageJob &j) {
-    const int uf = u / a.num_symbols, ul = u - uf * a.num_symbols;
-    j.src = reinterpret_cast<const uint8_t *>(a.cells16 + (long long)uf * a.cells_stride);
-    const int c0 = __ldg(a.chunk_ptr + ul);
-    j.n_chunks = __ldg(a.chunk_ptr + ul + 1) - c0;
-    j.csrc = a.chunk_src + c0;
-#pragma unroll
-    for (int q = 0; q < SB; q++) j.sidx[q] = (int)threadIdx.x + q * T < j.n_chunks ? __ldg(j.csrc + threadIdx.x + q * T) : -1;
+  // The source-chunk indices (chunk_src) come from L2 (~700 cycles) and every copy needs its own, so they are
+  // pipelined one symbol further ahead than the data: idx_prefetch copies the indices of a symbol into idxbuf
+  // asynchronously (4-byte cp.async, no registers), stage_copy later reads them from shared memory and starts the data
+  // copies.  Slot i of idxbuf / chunk i of the staging area always belong to thread i mod T.
+  const uint32_t idx_s = (uint32_t)__cvta_generic_to_shared(idxbuf);
+  auto idx_prefetch = [&](int u) {
+    const int ul = u % a.num_symbols;
+    const int c0 = __ldg(a.chunk_ptr + ul), n_chunks = __ldg(a.chunk_ptr + ul + 1) - c0;
+    const int32_t *csrc = a.chunk_src + c0;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < n_chunks; i += T)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(idx_s + 4u * (uint32_t)i), "l"(csrc + i) : "memory");
   };
-  auto stage_issue = [&](StageJob &j) {
-#pragma unroll 1
-    for (int i0 = threadIdx.x; i0 < j.n_chunks; i0 += SB * T) {
-      if (i0 != (int)threadIdx.x) {
-#pragma unroll
-        for (int q = 0; q < SB; q++) j.sidx[q] = i0 + q * T < j.n_chunks ? __ldg(j.csrc + i0 + q * T) : -1;
-      }
-#pragma unroll
-      for (int q = 0; q < SB; q++)
-        if (j.sidx[q] >= 0)
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(stage_s + 8u * (uint32_t)(i0 + q * T)), "l"(j.src + 8ll * j.sidx[q]) : "memory");
+  auto stage_copy = [&](int u, bool from_idxbuf) {
+    const int uf = u / a.num_symbols, ul = u - uf * a.num_symbols;
+    const uint8_t *src = reinterpret_cast<const uint8_t *>(a.cells16 + (long long)uf * a.cells_stride);
+    const int c0 = __ldg(a.chunk_ptr + ul), n_chunks = __ldg(a.chunk_ptr + ul + 1) - c0;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < n_chunks; i += T) {
+      const int sidx = from_idxbuf ? idxbuf[i] : __ldg(a.chunk_src + c0 + i);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(stage_s + 8u * (uint32_t)i), "l"(src + 8ll * sidx) : "memory");
     }
   };
 
@@ -1197,7 +1194,10 @@ __global__ void __launch_bounds__(T, (LOG2M == 14 ? 1 : 1024 / T)) k_ofdm(const 
     int c[FillGeom<LOG2M, T>::GPB][FillGeom<LOG2M, T>::R0];
     fill_load_codes<LOG2M, T>(a.code_pos + (long long)l * SPLIT * M, threadIdx.x, c);
     if (C16) {
-      if (unit == (int)blockIdx.x) { StageJob j; stage_index(unit, j); stage_issue(j); }      // later symbols are prefetched during the previous one
+      if (unit == (int)blockIdx.x) {      // first symbol of this CTA: indices straight from global memory
+        stage_copy(unit, false);
+        if (unit + (int)gridDim.x < units) idx_prefetch(unit + gridDim.x);
+      }
       asm volatile("cp.async.wait_all;\n" ::: "memory");
     }
 
@@ -1216,11 +1216,13 @@ __global__ void __launch_bounds__(T, (LOG2M == 14 ? 1 : 1024 / T)) k_ofdm(const 
         if (pool_sym) ofdm_fill<LOG2M, T, C16, true, false>(x, code, sinc, c, stage, lut_re, lut_im, lut_rep_shift, spool_m8, cells, pool);
         else ofdm_fill<LOG2M, T, C16, false, false>(x, code, sinc, c, stage, lut_re, lut_im, lut_rep_shift, spool_m8, cells, pool);
       }
-      const bool stage_next = C16 && phase == SPLIT - 1 && unit + (int)gridDim.x < units;
-      StageJob sj;
-      if (stage_next) stage_index(unit + gridDim.x, sj);
       __syncthreads();
-      if (stage_next) stage_issue(sj);
+      // every fill of the symbol has read its cells: the next symbol's cells may replace them (under the passes), and
+      // the indices of the symbol after that may replace the ones just used
+      if (C16 && phase == SPLIT - 1 && unit + (int)gridDim.x < units) {
+        stage_copy(unit + gridDim.x, true);
+        if (unit + 2 * (int)gridDim.x < units) idx_prefetch(unit + 2 * gridDim.x);
+      }
       // ---- 2. middle radix-16 passes
       if (REGTW) {
         fft_pass16<M, 16, T, REGTW>(x, a.tw, tw_p1); __syncthreads();
@@ -1355,7 +1357,7 @@ template <int LOG2M, int T, bool C16, int FMT, int SPLIT>
 static void launch_ofdm_t(const OfdmArgs &a, cudaStream_t s)
 {
   constexpr int M = 1 << LOG2M;
-  const size_t smem = (size_t)padx(M) * sizeof(float2) + (C16 ? (size_t)a.stage_cap * 2 + ((size_t)2048 << a.lut_rep_shift) + 64 : 0);
+  const size_t smem = (size_t)padx(M) * sizeof(float2) + (C16 ? (size_t)a.stage_cap * 3 + ((size_t)2048 << a.lut_rep_shift) + 64 : 0);
   const int units = a.frames * a.num_symbols;
   static bool attr = false;
   if (!attr) {
@@ -1392,9 +1394,11 @@ void launch_ofdm(const OfdmArgs &a0, cudaStream_t s)
 {
   if (a0.frames * a0.num_symbols < 1) return;
   OfdmArgs a = a0;
-  // 16 copies of the constellation LUTs when shared memory allows (chain mode)
+  // up to 16 copies of the constellation LUTs, as many as shared memory allows (chain mode)
   a.lut_rep_shift = 0;
-  if (a.cells16 && (size_t)padx(1 << a.log2_m) * sizeof(float2) + (size_t)a.stage_cap * 2 + (2048 << 4) + 64 <= 227 * 1024) a.lut_rep_shift = 4;
+  if (a.cells16)
+    for (int sh = 4; sh > 0; sh--)
+      if ((size_t)padx(1 << a.log2_m) * sizeof(float2) + (size_t)a.stage_cap * 3 + ((size_t)2048 << sh) + 64 <= 227 * 1024) { a.lut_rep_shift = sh; break; }
   if (a.cells16) {
     if (a.out_fmt) launch_ofdm_c<true, 1>(a, s);
     else launch_ofdm_c<true, 0>(a, s);
