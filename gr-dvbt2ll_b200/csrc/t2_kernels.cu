@@ -1150,18 +1150,23 @@ __global__ void __launch_bounds__(T, (LOG2M == 14 ? 1 : 1024 / T)) k_ofdm(const 
   // asynchronously (4-byte cp.async, no registers), stage_copy later reads them from shared memory and starts the data
   // copies.  Slot i of idxbuf / chunk i of the staging area always belong to thread i mod T.
   const uint32_t idx_s = (uint32_t)__cvta_generic_to_shared(idxbuf);
-  auto idx_prefetch = [&](int u) {
+  // (first chunk, chunk count) of a symbol's staging list; requested a symbol ahead of their use (cp1, cp2 below)
+  auto chunk_range = [&](int u) {
     const int ul = u % a.num_symbols;
-    const int c0 = __ldg(a.chunk_ptr + ul), n_chunks = __ldg(a.chunk_ptr + ul + 1) - c0;
-    const int32_t *csrc = a.chunk_src + c0;
+    const int c0 = __ldg(a.chunk_ptr + ul);
+    return make_int2(c0, __ldg(a.chunk_ptr + ul + 1) - c0);
+  };
+  auto idx_prefetch = [&](int2 cr) {
+    const int n_chunks = cr.y;
+    const int32_t *csrc = a.chunk_src + cr.x;
 #pragma unroll 4
     for (int i = threadIdx.x; i < n_chunks; i += T)
       asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(idx_s + 4u * (uint32_t)i), "l"(csrc + i) : "memory");
   };
-  auto stage_copy = [&](int u, bool from_idxbuf) {
-    const int uf = u / a.num_symbols, ul = u - uf * a.num_symbols;
+  auto stage_copy = [&](int u, int2 cr, bool from_idxbuf) {
+    const int uf = u / a.num_symbols;
     const uint8_t *src = reinterpret_cast<const uint8_t *>(a.cells16 + (long long)uf * a.cells_stride);
-    const int c0 = __ldg(a.chunk_ptr + ul), n_chunks = __ldg(a.chunk_ptr + ul + 1) - c0;
+    const int c0 = cr.x, n_chunks = cr.y;
 #pragma unroll 4
     for (int i = threadIdx.x; i < n_chunks; i += T) {
       const int sidx = from_idxbuf ? idxbuf[i] : __ldg(a.chunk_src + c0 + i);
@@ -1169,8 +1174,11 @@ __global__ void __launch_bounds__(T, (LOG2M == 14 ? 1 : 1024 / T)) k_ofdm(const 
     }
   };
 
+  int2 cp1 = make_int2(0, 0), cp2 = cp1;      // staging lists of the next symbol of this CTA and of the one after it
+  if (C16 && (int)(blockIdx.x + gridDim.x) < units) cp1 = chunk_range(blockIdx.x + gridDim.x);
   for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
     const int f = unit / a.num_symbols, l = unit - f * a.num_symbols;
+    if (C16 && unit + 2 * (int)gridDim.x < units) cp2 = chunk_range(unit + 2 * gridDim.x);
     const int variant = (a.frame_idx0 + (f % a.frames_per_channel)) % a.l1post_variants;
     const float2 *cells = a.cells + (long long)f * a.cells_stride;
     const float2 *pool = a.pool + (long long)variant * a.pool_stride;
@@ -1195,8 +1203,8 @@ __global__ void __launch_bounds__(T, (LOG2M == 14 ? 1 : 1024 / T)) k_ofdm(const 
     fill_load_codes<LOG2M, T>(a.code_pos + (long long)l * SPLIT * M, threadIdx.x, c);
     if (C16) {
       if (unit == (int)blockIdx.x) {      // first symbol of this CTA: indices straight from global memory
-        stage_copy(unit, false);
-        if (unit + (int)gridDim.x < units) idx_prefetch(unit + gridDim.x);
+        stage_copy(unit, chunk_range(unit), false);
+        if (unit + (int)gridDim.x < units) idx_prefetch(cp1);
       }
       asm volatile("cp.async.wait_all;\n" ::: "memory");
     }
@@ -1220,8 +1228,9 @@ __global__ void __launch_bounds__(T, (LOG2M == 14 ? 1 : 1024 / T)) k_ofdm(const 
       // every fill of the symbol has read its cells: the next symbol's cells may replace them (under the passes), and
       // the indices of the symbol after that may replace the ones just used
       if (C16 && phase == SPLIT - 1 && unit + (int)gridDim.x < units) {
-        stage_copy(unit + gridDim.x, true);
-        if (unit + 2 * (int)gridDim.x < units) idx_prefetch(unit + 2 * gridDim.x);
+        stage_copy(unit + gridDim.x, cp1, true);
+        if (unit + 2 * (int)gridDim.x < units) idx_prefetch(cp2);
+        cp1 = cp2;
       }
       // ---- 2. middle radix-16 passes
       if (REGTW) {
@@ -1395,10 +1404,16 @@ void launch_ofdm(const OfdmArgs &a0, cudaStream_t s)
   if (a0.frames * a0.num_symbols < 1) return;
   OfdmArgs a = a0;
   // up to 16 copies of the constellation LUTs, as many as shared memory allows (chain mode)
+  // (without lowering the number of CTAs per SM that fit without replication; 2 resident CTAs at most are useful below 16K)
   a.lut_rep_shift = 0;
-  if (a.cells16)
+  if (a.cells16) {
+    const size_t base = (size_t)padx(1 << a.log2_m) * sizeof(float2) + (size_t)a.stage_cap * 3 + 64, sm_bytes = 227 * 1024;
+    size_t ctas = sm_bytes / (base + 2048 + 1024);
+    if (ctas < 1) ctas = 1;
+    if (ctas > 2) ctas = 2;
     for (int sh = 4; sh > 0; sh--)
-      if ((size_t)padx(1 << a.log2_m) * sizeof(float2) + (size_t)a.stage_cap * 3 + ((size_t)2048 << sh) + 64 <= 227 * 1024) { a.lut_rep_shift = sh; break; }
+      if (base + ((size_t)2048 << sh) + 1024 <= sm_bytes / ctas) { a.lut_rep_shift = sh; break; }
+  }
   if (a.cells16) {
     if (a.out_fmt) launch_ofdm_c<true, 1>(a, s);
     else launch_ofdm_c<true, 0>(a, s);
