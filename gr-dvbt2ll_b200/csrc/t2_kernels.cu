@@ -605,6 +605,31 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map(const MapArgs a)
         }
       }
     }
+    else if (mod == 2 && (Nc & 3) == 0) {
+      // QPSK: four cells per step -- their eight source bit positions are one 16-byte load
+      const uint8_t *ub = reinterpret_cast<const uint8_t *>(u);
+      for (int c = 4 * threadIdx.x; c < Nc; c += 4 * blockDim.x) {
+        const uint4 pp = __ldg(reinterpret_cast<const uint4 *>(a.bit_src) + (c >> 2));
+        const uint32_t w[4] = { pp.x, pp.y, pp.z, pp.w };
+        uint32_t code[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const uint32_t p0 = w[k] & 0xFFFFu, p1 = w[k] >> 16;
+          const uint32_t v = (((ub[p0 >> 3] >> (7 - (p0 & 7))) & 1u) << 1) | ((ub[p1 >> 3] >> (7 - (p1 & 7))) & 1u);
+          code[k] = v | (v << 8);
+        }
+        uint32_t *dst = reinterpret_cast<uint32_t *>(cw + c + 2 * (c >> 6));
+        dst[0] = code[0] | (code[1] << 16);
+        dst[1] = code[2] | (code[3] << 16);
+      }
+      if (a.cyclic_delay) {
+        __syncthreads();
+        for (int c = threadIdx.x; c < Nc; c += blockDim.x) {
+          const int pc = c == 0 ? Nc - 1 : c - 1;
+          reinterpret_cast<uint8_t *>(cw)[2 * (c + 2 * (c >> 6)) + 1] = (uint8_t)cw[pc + 2 * (pc >> 6)];
+        }
+      }
+    }
     else {
       for (int c = threadIdx.x; c < Nc; c += blockDim.x) {
         const uint16_t *src = a.bit_src + c * mod;
