@@ -126,6 +126,16 @@ __global__ void __launch_bounds__(BB_MAX_WARPS * 32) k_bb_bch(const BbArgs a)
     // ---- stage the raw payload in shared memory (buf byte 10 + i = payload byte i)
     if (!hem) {
       const uint8_t *src = ts + P0;
+      {
+        // the TS is read once, from DRAM: ask L2 for the payload of this warp's NEXT FECFRAME now
+        const int nj = job + gridDim.x * nwarps;
+        if (nj < total) {
+          const int nc = nj / a.frames, njj = nj - nc * a.frames;
+          const int nnb = a.inband ? multiples_in(a.fec_block0, a.fec_block0 + njj, a.fecblocks) : 0;
+          const uint8_t *nsrc = a.ts + (long long)nc * a.ts_pitch + ((long long)njj * D - 13LL * nnb);
+          for (int o = lane * 128; o < D; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nsrc + o));
+        }
+      }
       if (lane < 2) buf[10 + lane] = src[lane];
       const int w_end = (10 + Dj) >> 2;                    // words [3, w_end) lie completely inside the payload
       for (int w0 = 3 + lane; w0 < w_end; w0 += 128) {     // four loads in flight per lane
