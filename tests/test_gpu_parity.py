@@ -147,6 +147,35 @@ def test_chain_matches_reference(reflib, name):
         assert max_err_over_rms(s, r["samples"]) <= MAX_ERR_OVER_RMS
 
 
+def _fuzz_configs():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "fuzz_configs.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("idx", range(16))
+def test_chain_random_configs(reflib, idx):
+    """16 random valid parameter sets (tools/make_fuzz_configs.py: FFT / guard interval / pilot pattern per EN 302 755,
+    all constellations, rotation, both frame sizes, L1 modulations, reserved tones, in-band, both input modes, inverse
+    sinc, extended carriers, v1.1.1 / v1.3.1) against the reference flowgraph, two channels x three T2 frames."""
+    cfg = K.resolve(_fuzz_configs()[idx])
+    nch, nframes = 2, 3
+    ch = T.Chain(cfg, max_frames=nch * nframes)
+    n_all = ch.ts_bytes(0, nframes)
+    S = ch.samples_per_frame
+    ts = np.stack([K.make_ts(n_all + 400, seed=K.TS_SEED + 31 * idx + c) for c in range(nch)])
+    out = ch.run_host(np.ascontiguousarray(ts[:, :n_all]), nch, nframes)
+    for c in range(nch):
+        refs = _ref_frames(reflib, cfg, ts[c], nframes)
+        assert sum(r["ts_used"] for r in refs) == n_all
+        for fr in range(nframes):
+            s = out[c, fr * S:(fr + 1) * S]
+            assert s.size == refs[fr]["samples"].size
+            assert mer_db(s, refs[fr]["samples"]) >= MER_MIN_DB
+            assert max_err_over_rms(s, refs[fr]["samples"]) <= MAX_ERR_OVER_RMS
+
+
 def test_chain_multichannel_and_offset(reflib):
     """c5-style batching: independent channels (seed + channel) in one launch, and a batch that starts at
     T2 frame 1 (stream history in front of the pointer) equals the tail of a batch that starts at frame 0."""

@@ -1,0 +1,87 @@
+#!/usr/bin/env python
+"""Draws random valid parameter sets for the chain parity sweep (tests/golden/fuzz_configs.json).
+
+FFT size / guard interval / pilot pattern follow the allowed combinations of EN 302 755 (SISO table); the number of FEC
+blocks is the largest the reference's own capacity check accepts without a warning (oracle/_ref, CPU).  Run here (needs
+/root/reference through oracle/_ref); the GPU test only reads the JSON."""
+import json
+import os
+import random
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "gr-dvbt2ll_b200", "python"))
+from oracle import ref as R                      # noqa: E402
+from dvbt2ll_b200 import configs as K            # noqa: E402
+
+ALLOWED = {   # fft -> gi -> pilot patterns (0-based PP1..PP8)
+    K.FFTSIZE_1K: {K.GI_1_16: (3, 4), K.GI_1_8: (1, 2), K.GI_1_4: (0,)},
+    K.FFTSIZE_2K: {K.GI_1_32: (6, 3), K.GI_1_16: (3, 4), K.GI_1_8: (1, 2), K.GI_1_4: (0,)},
+    K.FFTSIZE_4K: {K.GI_1_32: (6, 3), K.GI_1_16: (3, 4), K.GI_1_8: (1, 2), K.GI_1_4: (0,)},
+    K.FFTSIZE_8K: {K.GI_1_128: (6,), K.GI_1_32: (6, 3), K.GI_1_16: (7, 3, 4), K.GI_19_256: (7, 3, 4),
+                   K.GI_1_8: (1, 2, 7), K.GI_19_128: (1, 2, 7), K.GI_1_4: (0, 7)},
+    K.FFTSIZE_16K: {K.GI_1_128: (6,), K.GI_1_32: (6, 3, 5), K.GI_1_16: (1, 7, 3, 4), K.GI_19_256: (1, 7, 3, 4),
+                    K.GI_1_8: (1, 2, 7), K.GI_19_128: (1, 2, 7), K.GI_1_4: (0, 7)},
+    K.FFTSIZE_32K: {K.GI_1_128: (6,), K.GI_1_32: (3, 5), K.GI_1_16: (1, 7, 3), K.GI_19_256: (1, 7, 3),
+                    K.GI_1_8: (1, 7), K.GI_19_128: (1, 7)},
+}
+SHORT_RATES = (K.C1_3, K.C2_5, K.C3_5, K.C2_3, K.C4_5)          # short 1/2, 3/4, 5/6: the reference's dead-code LDPC overruns
+NORMAL_RATES = (K.C1_2, K.C3_5, K.C2_3, K.C3_4, K.C4_5, K.C5_6)
+
+
+def ok(cfg):
+    try:
+        return R.Chain(K.resolve(cfg)).fm.warnings == 0
+    except Exception:
+        return False
+
+
+def draw(rng):
+    fft = rng.choice(list(ALLOWED))
+    gi = rng.choice(list(ALLOWED[fft]))
+    pp = rng.choice(ALLOWED[fft][gi])
+    short = rng.random() < 0.7 or fft in (K.FFTSIZE_1K, K.FFTSIZE_2K)
+    cfg = dict(K.CONFIGS["c1"], fftsize=fft, guardinterval=gi, pilotpattern=pp,
+               framesize=K.FECFRAME_SHORT if short else K.FECFRAME_NORMAL,
+               rate=rng.choice(SHORT_RATES if short else NORMAL_RATES),
+               constellation=rng.choice((K.MOD_QPSK, K.MOD_16QAM, K.MOD_64QAM, K.MOD_256QAM)),
+               rotation=rng.choice((0, 1)), carriermode=rng.choice((0, 1)) if fft >= K.FFTSIZE_8K or fft in (K.FFTSIZE_16K, K.FFTSIZE_32K) else 0,
+               l1constellation=rng.choice((0, 1, 2, 3)), paprmode=rng.choice((K.PAPR_OFF, K.PAPR_TR)),
+               version=rng.choice((K.VERSION_111, K.VERSION_131)), inband=rng.choice((0, 1)), inputmode=rng.choice((0, 1)),
+               misogroup=0, preamble=K.PREAMBLE_T2_SISO, equalization=rng.choice((0, 1)), t2frames=rng.choice((2, 3, 4)),
+               numdatasyms=rng.choice((3, 5, 8, 12)) if fft in (K.FFTSIZE_16K, K.FFTSIZE_32K) else rng.choice((6, 10, 20, 40)))
+    if cfg["version"] == K.VERSION_111:
+        cfg["l1scrambled"] = 0
+    else:
+        cfg["l1scrambled"] = rng.choice((0, 1))
+    if fft in (K.FFTSIZE_1K, K.FFTSIZE_2K, K.FFTSIZE_4K):
+        cfg["carriermode"] = 0
+    best = None
+    for fb in range(1, 60):
+        c = dict(cfg, fecblocks=fb, tiblocks=0)
+        if ok(c):
+            best = fb
+        elif best is not None:
+            break
+    if best is None:
+        return None
+    cfg["fecblocks"] = best if rng.random() < 0.5 else rng.randint(1, best)
+    cfg["tiblocks"] = rng.choice([t for t in (0, 1, 2, 3) if t <= cfg["fecblocks"]])
+    return cfg if ok(cfg) else None
+
+
+def main():
+    rng = random.Random(20261018)
+    out = []
+    while len(out) < 16:
+        c = draw(rng)
+        if c is not None:
+            out.append(c)
+            print(len(out), {k: c[k] for k in ("fftsize", "guardinterval", "pilotpattern", "framesize", "rate", "constellation", "fecblocks", "tiblocks")}, flush=True)
+    with open(os.path.join(ROOT, "tests", "golden", "fuzz_configs.json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+
+
+if __name__ == "__main__":
+    main()
