@@ -5,6 +5,8 @@ Bars (BASELINE.json north_star): BBFRAME/FECFRAME bits bit-exact; cells bit-exac
 reference's float arithmetic, so better than the 1-ulp bar); frame-mapper output bit-exact; time-domain
 baseband MER >= 90 dB and max error <= 1e-5 of RMS against the oracle's double-precision IFFT.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -150,11 +152,11 @@ def test_chain_matches_reference(reflib, name):
 def _fuzz_configs():
     import json
     import os
-    with open(os.path.join(os.path.dirname(__file__), "golden", "fuzz_configs.json")) as f:
+    with open(os.environ.get("DVBT2LL_FUZZ", os.path.join(os.path.dirname(__file__), "golden", "fuzz_configs.json"))) as f:
         return json.load(f)
 
 
-@pytest.mark.parametrize("idx", range(16))
+@pytest.mark.parametrize("idx", range(int(os.environ.get("DVBT2LL_FUZZ_N", "16"))))
 def test_chain_random_configs(reflib, idx):
     """16 random valid parameter sets (tools/make_fuzz_configs.py: FFT / guard interval / pilot pattern per EN 302 755,
     all constellations, rotation, both frame sizes, L1 modulations, reserved tones, in-band, both input modes, inverse

@@ -72,14 +72,18 @@ def draw(rng):
 
 
 def main():
-    rng = random.Random(20261018)
+    # usage: make_fuzz_configs.py [seed [count [output.json]]]
+    seed = int(sys.argv[1]) if len(sys.argv) > 1 else 20261018
+    count = int(sys.argv[2]) if len(sys.argv) > 2 else 16
+    path = sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, "tests", "golden", "fuzz_configs.json")
+    rng = random.Random(seed)
     out = []
-    while len(out) < 16:
+    while len(out) < count:
         c = draw(rng)
         if c is not None:
             out.append(c)
             print(len(out), {k: c[k] for k in ("fftsize", "guardinterval", "pilotpattern", "framesize", "rate", "constellation", "fecblocks", "tiblocks")}, flush=True)
-    with open(os.path.join(ROOT, "tests", "golden", "fuzz_configs.json"), "w") as f:
+    with open(path, "w") as f:
         json.dump(out, f, indent=1, sort_keys=True)
 
 
