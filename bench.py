@@ -4,12 +4,16 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is one pass of the fused chain (TS bytes -> complex baseband) over one batch of synthetic
-transport streams: BASELINE.json config 5 = 64 independent 32K / 256QAM-rotated / CR 2/3 channels
-(config 3), one T2 frame per channel per step, per GPU (weak scaling: every rank processes its own 64
-channels, seeds 0x12345678 + global channel index; no data-path collective).
+A "step" is one pass of the fused chain (TS bytes -> complex baseband) over one batch of synthetic transport
+streams: BASELINE.json config 5 = 64 independent 32K / 256QAM-rotated / CR 2/3 channels (config 3), one T2
+frame per channel per step, the 64 channels sharded over the N GPUs of the job (64 / N channels each: STRONG
+scaling, "config 5 as stated") with seeds 0x12345678 + global channel index.  There is no data-path
+collective; at N > 1 every step ends with the ordered reassembly of all ranks' frames on GPU 0 through the
+library's own entry points (dvbt2ll_gather_*: one NVLink peer copy per rank on a side stream, double-buffered,
+overlapping the rank's next step) and that reassembly is INSIDE the timed value.
 
-value      = whole-job output Msamples/s with the TS already resident in HBM (CUDA events, max over ranks)
+value      = whole-job output Msamples/s, TS resident in HBM, at N > 1 including the ordered reassembly on GPU 0
+             (CUDA events on the launching streams, max over ranks)
 e2e        = same metric through dvbt2ll_chain_run_host(): pinned HOST TS in, HOST samples out, copies timed
 roofline   = the dominant kernel (k_ofdm: carrier fill + IFFT + GI) against the measured HBM copy peak
 cpu_baseline / --impl reference = the UNMODIFIED reference flowgraph (oracle/_ref, GNU Radio shim) on host cores
@@ -33,6 +37,7 @@ import numpy as np  # noqa: E402
 
 METRIC = "t2_baseband_msps"
 UNIT = "Msamples/s"
+NVLINK_PEER_GBS = 770.0     # measured peer copy per direction per GPU on this pool (B200_PROFILING.md); nominal 900
 
 
 def parse():
@@ -42,18 +47,29 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c3", help="per-channel configuration (c1..c4)")
-    ap.add_argument("--channels", type=int, default=64, help="independent channels per GPU per step")
+    ap.add_argument("--channels", type=int, default=64, help="independent channels of the whole job per step")
     ap.add_argument("--frames", type=int, default=1, help="T2 frames per channel per step")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-frames", type=int, default=24, help="T2 frames timed for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip per_config / dropin_e2e (N = 1 extras)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the untimed per-rank parity check")
     return ap.parse_args()
 
 
 def workload_name(args):
-    return "c5: %d x %s channels (32K ext, 256QAM rot, CR 2/3, GI 1/128, PP7, 202 FECFRAMEs/T2 frame), %d T2 frame/channel/step per GPU" % (
-        args.channels, args.config, args.frames) if args.config == "c3" else "%d x %s channels, %d T2 frame/channel/step per GPU" % (
-        args.channels, args.config, args.frames)
+    if args.config == "c3":
+        return ("c5: %d x c3 channels (32K ext, 256QAM rot, CR 2/3, GI 1/128, PP7, 202 FECFRAMEs/T2 frame), %d T2 frame/channel/step, "
+                "channels sharded over the GPUs" % (args.channels, args.frames))
+    return "%d x %s channels, %d T2 frame/channel/step, channels sharded over the GPUs" % (args.channels, args.config, args.frames)
+
+
+def config_dict(args, S, F):
+    """The `config` object: identical keys and values on the repo arm and the reference arm."""
+    frames = args.channels * args.frames
+    return {"workload": workload_name(args), "per_channel_config": args.config, "channels": args.channels,
+            "t2_frames_per_channel_per_step": args.frames, "t2_frames_per_step": frames,
+            "fecframes_per_step": frames * F, "samples_per_step": frames * S}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -113,29 +129,34 @@ class ClockSampler(object):
 # CPU reference arm: unmodified reference flowgraph (oracle/_ref) on host cores
 # --------------------------------------------------------------------------------------------------
 def _ref_worker(job):
-    cfg, seed, nframes = job
+    cfg, seeds, nframes = job
     from oracle import ref
     from dvbt2ll_b200 import configs as K
     ref.lib().ref_set_quiet(1)
     ref.lib().ref_set_fft_fast(1)      # float Stockham FFT stand-in for FFTW (oracle/shim/gnuradio/fft/fft.h)
-    ch = ref.Chain(cfg)
-    ts = K.make_ts((nframes + 1) * ch.ts_bytes_per_t2_frame() + 1000, seed=seed)
+    ref.lib().ref_fft_seconds(1)
     timers = {}
-    t0 = time.perf_counter()
-    n = 0
-    for _ in range(nframes):
-        n += ch.run_frame(ts, timers=timers)["samples"].size
-    return n, time.perf_counter() - t0, timers
+    n, busy = 0, 0.0
+    for seed in seeds:                 # one channel per seed, nframes consecutive T2 frames of it
+        ch = ref.Chain(cfg)
+        ts = K.make_ts((nframes + 1) * ch.ts_bytes_per_t2_frame() + 1000, seed=seed)
+        t0 = time.perf_counter()
+        for _ in range(nframes):
+            n += ch.run_frame(ts, timers=timers)["samples"].size
+        busy += time.perf_counter() - t0
+    timers["fft"] = ref.lib().ref_fft_seconds(1)
+    return n, busy, timers
 
 
-def cpu_reference_run(cfg, nframes_total, procs):
-    """Times the reference chain on `procs` host processes (independent channels). Returns dict."""
+def cpu_reference_run(cfg, channels, nframes, procs):
+    """Times `channels` independent channels x `nframes` T2 frames of the reference chain on `procs` host
+    processes (channels dealt round-robin). Returns dict or None."""
     from oracle import ref
     if not ref.available():
         return None
     from dvbt2ll_b200 import configs as K
-    per = max(1, nframes_total // procs)
-    jobs = [(cfg, K.TS_SEED + i, per) for i in range(procs)]
+    procs = max(1, min(procs, channels))
+    jobs = [(cfg, [K.TS_SEED + c for c in range(p, channels, procs)], nframes) for p in range(procs)]
     t0 = time.perf_counter()
     if procs == 1:
         res = [_ref_worker(jobs[0])]
@@ -150,8 +171,19 @@ def cpu_reference_run(cfg, nframes_total, procs):
     for r in res:
         for k, v in r[2].items():
             stage[k] = stage.get(k, 0.0) + v
-    return {"samples": samples, "seconds": busy, "wall": wall, "frames": per * procs,
+    return {"samples": samples, "seconds": busy, "wall": wall, "frames": channels * nframes, "procs": procs,
             "stage_seconds": {k: round(v, 4) for k, v in stage.items()}}
+
+
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.startswith("model name"):
+                    return ln.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown CPU"
 
 
 def run_reference_arm(args):
@@ -160,14 +192,15 @@ def run_reference_arm(args):
     if rank != 0:
         return
     cfg = K.resolve(args.config)
-    procs = max(1, min(os.cpu_count() or 1, 64))
-    frames_per_step = procs          # one T2 frame per process per step (bounded sample)
-    for _ in range(max(0, min(args.warmup, 1))):
-        cpu_reference_run(cfg, procs, procs)
+    procs = max(1, min(len(os.sched_getaffinity(0)), 64, args.channels))
+    warm = max(0, min(args.warmup, 1))
+    for _ in range(warm):
+        cpu_reference_run(cfg, min(procs, args.channels), 1, procs)
     tot_s, tot_t = 0, 0.0
     stage = {}
+    r = None
     for _ in range(args.steps):
-        r = cpu_reference_run(cfg, frames_per_step, procs)
+        r = cpu_reference_run(cfg, args.channels, args.frames, procs)     # the whole step: every channel, 64 / P per process
         if r is None:
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libdvbt2ll_ref.so not built"}))
             return
@@ -176,17 +209,22 @@ def run_reference_arm(args):
             stage[k] = stage.get(k, 0.0) + v
     value = tot_s / tot_t / 1e6
     F = cfg["fecblocks"]
-    ch_samples = r["samples"] / r["frames"]
+    S = r["samples"] // r["frames"]
+    stage_sum = sum(v for k, v in stage.items() if k != "fft")
+    fft_share = stage.get("fft", 0.0) / stage_sum if stage_sum > 0 else None
+    sample = ("%d channels x %d T2 frame(s) of %s per step (the whole step) x %d steps, %d worker processes (%d channel(s) each) on %s; "
+              "unmodified reference sources + GNU Radio shim, single-precision radix-4 FFT stand-in for FFTW; stage CPU-seconds %s" % (
+                  args.channels, args.frames, args.config, args.steps, r["procs"], (args.channels + r["procs"] - 1) // r["procs"], cpu_model(),
+                  json.dumps({k: round(v, 2) for k, v in stage.items()})))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, args.steps), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u8/f32", "data": "synthetic",
-        "config": {"workload": workload_name(args), "sample": "%d T2 frames of %s per step on %d processes" % (frames_per_step, args.config, procs)},
-        "x_realtime": value / K.REALTIME_MSPS, "fecframes_per_s": value * 1e6 / ch_samples * F,
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "reference",
-                         "sample": "%d T2 frames (%s) per step x %d steps, one chain per process, unmodified reference sources + GNU Radio shim, "
-                                   "single-precision Stockham FFT stand-in for FFTW; stage CPU-seconds %s" % (
-                                       frames_per_step, args.config, args.steps, json.dumps({k: round(v, 2) for k, v in stage.items()}))},
+        "warmup": warm, "ms_per_step": 1e3 * tot_t / max(1, args.steps), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u8/f32", "data": "synthetic",
+        "config": config_dict(args, S, F),
+        "x_realtime": value / K.REALTIME_MSPS, "fecframes_per_s": value * 1e6 / S * F,
+        "fft_share_of_cpu_time": fft_share,
+        "value_without_fft": (value / (1.0 - fft_share)) if fft_share is not None and fft_share < 1 else None,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["procs"], "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -194,26 +232,163 @@ def run_reference_arm(args):
 
 
 # --------------------------------------------------------------------------------------------------
-def bind_to_gpu_cpus(torch, local):
-    """Run this rank on the CPU cores NVML reports as local to its GPU, so the pinned host buffers of the e2e path
-    are first-touched on the GPU's NUMA node.  Returns (cores bound, original affinity) -- (0, None) if unavailable."""
-    try:
-        import pynvml
-        pynvml.nvmlInit()
+def mer_db(got, want):
+    err = np.sum(np.abs(got.astype(np.complex128) - want) ** 2)
+    sig = np.sum(np.abs(want.astype(np.complex128)) ** 2)
+    return float(10 * np.log10(sig / max(err, 1e-300)))
+
+
+def reference_frame(cfg, ts_row):
+    """First T2 frame of one channel through the checker (oracle/_ref when built, else the numpy oracle)."""
+    from oracle import ref
+    if ref.available():
+        ref.lib().ref_set_quiet(1)
+        ref.lib().ref_set_fft_fast(0)
+        return ref.Chain(cfg).run_frame(np.concatenate([ts_row, np.zeros(2048, np.uint8)]))["samples"], "oracle/_ref"
+    from oracle import t2oracle
+    return t2oracle.chain(cfg, ts_row, 1)["samples"], "oracle/t2oracle.py"
+
+
+def stage_roofline(chain, cfg, frames, stage_ms, peak, peak_src):
+    """Dominant-kernel roofline of a chain configuration from the per-stage CUDA-event times."""
+    S, F = chain.samples_per_frame, chain.fecframes_per_frame
+    nldpc = 64800 if cfg["framesize"] else 16200
+    cell_size = nldpc // (2 * (cfg["constellation"] + 1))
+    dims = chain.plan("ofdm.dims", np.int32)
+    active_items = int(dims[15])
+    ofdm_bytes = frames * 8 * (active_items + S)              # SURVEY 8(d): 8*mapped_items + 8*samples per T2 frame
+    map_bytes = frames * F * (nldpc // 8 + 2 * cell_size)     # chain mode: packed codewords in, 16-bit cell codes out
+    ach = ofdm_bytes / (stage_ms["ofdm"] * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "k_ofdm (cell staging + carrier fill + IFFT + scale + guard interval + P1)",
+            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": ofdm_bytes, "kernel_ms": stage_ms["ofdm"], "stage_ms": stage_ms,
+            "map_kernel_gbs": map_bytes / (stage_ms["map"] * 1e-3) / 1e9}
+
+
+def time_chain(torch, chain, stream, d_ts, pitch, nch, nfr, d_out, steps, min_warm_s=0.2):
+    """Warm up, then time `steps` device-resident runs with CUDA events on the launching stream. Returns (ms/step, stage_ms)."""
+    sp = stream.cuda_stream
+    chain.enable_timing(False)
+    t_w, n_w = time.perf_counter(), 0
+    while n_w < 3 or time.perf_counter() - t_w < min_warm_s:
+        chain.run_device(d_ts.data_ptr(), pitch, nch, nfr, 0, d_out.data_ptr(), sp)
+        n_w += 1
+        if n_w % 8 == 0:
+            torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    chain.enable_timing(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        chain.run_device(d_ts.data_ptr(), pitch, nch, nfr, 0, d_out.data_ptr(), sp)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    st = chain.stage_ms()
+    chain.enable_timing(False)
+    return e0.elapsed_time(e1) / steps, st, n_w
+
+
+def per_config_extras(torch, T, K, dev, stream, peak, peak_src, steps):
+    """c1, c2, c4 (BASELINE.json configs[0], [1], [3]) on one GPU, 64 channels each: device MS/s, x real time, FECFRAMEs/s,
+    per-stage ms, dominant-kernel roofline, and the unmodified reference on one host core beside it."""
+    out = {}
+    for name, nch, nfr in (("c1", 64, 8), ("c2", 64, 1), ("c4", 64, 1)):
+        cfg = K.resolve(name)
+        chain = T.Chain(cfg, max_frames=nch * nfr, device=dev.index)
+        n_ts, S, F = chain.ts_bytes_per_frame, chain.samples_per_frame, chain.fecframes_per_frame
+        pitch = (nfr * n_ts + 255) // 256 * 256
+        ts = np.zeros((nch, pitch), np.uint8)
+        for c in range(nch):
+            ts[c, :nfr * n_ts] = K.make_ts(nfr * n_ts, seed=K.TS_SEED + c)
+        d_ts = torch.from_numpy(ts).to(dev)
+        d_out = torch.empty((nch, nfr * S), dtype=torch.complex64, device=dev)
+        ms, st, _ = time_chain(torch, chain, stream, d_ts, pitch, nch, nfr, d_out, steps)
+        frames = nch * nfr
+        v = frames * S / (ms * 1e-3) / 1e6
+        ent = {"workload": "%d x %s channels x %d T2 frame(s) per step" % (nch, name, nfr), "value": v, "unit": UNIT,
+               "ms_per_step": ms, "x_realtime": v / K.REALTIME_MSPS, "fecframes_per_s": frames * F / (ms * 1e-3),
+               "launches_per_step": 4, "roofline": stage_roofline(chain, cfg, frames, st, peak, peak_src)}
+        # launch-bound small frames: the same step replayed from a CUDA graph (one graph launch instead of four kernel launches)
         try:
-            h = pynvml.nvmlDeviceGetHandleByUUID("GPU-" + str(torch.cuda.get_device_properties(local).uuid))
-        except Exception:
-            h = pynvml.nvmlDeviceGetHandleByIndex(local)
-        words = (os.cpu_count() + 63) // 64
-        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
-        orig = os.sched_getaffinity(0)
-        cpus = [i for i in range(words * 64) if (mask[i // 64] >> (i % 64)) & 1 and i in orig]
-        if cpus and len(cpus) < len(orig):
-            os.sched_setaffinity(0, cpus)
-            return len(cpus), orig
-    except Exception:
-        pass
-    return 0, None
+            sp = stream.cuda_stream
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                chain.run_device(d_ts.data_ptr(), pitch, nch, nfr, 0, d_out.data_ptr(), sp)
+            for _ in range(3):
+                g.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(steps):
+                g.replay()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            gms = e0.elapsed_time(e1) / steps
+            ent["cuda_graph"] = {"ms_per_step": gms, "value": frames * S / (gms * 1e-3) / 1e6, "speedup_vs_stream_launches": ms / gms}
+            del g
+        except Exception as e:      # pragma: no cover
+            ent["cuda_graph"] = {"error": str(e)[:200]}
+            torch.cuda.synchronize()
+        # the reference on ONE host core, bounded to a few seconds
+        nf_cpu = {"c1": 40, "c2": 6, "c4": 4}[name]
+        r = cpu_reference_run(cfg, 1, nf_cpu, 1)
+        if r is not None:
+            cv = r["samples"] / r["seconds"] / 1e6
+            ent["cpu_reference_1core"] = {"value": cv, "unit": UNIT, "sample": "%d consecutive T2 frames of one channel" % nf_cpu,
+                                          "stage_seconds": r["stage_seconds"]}
+            ent["gpu_over_1core"] = v / cv
+        out[name] = ent
+        del chain, d_ts, d_out
+    return out
+
+
+def dropin_extras(torch, T, K, cfg_name, frames_timed):
+    """The reference-facing per-block path: one T2 frame per round through the five dvbt2ll_work() handles
+    (bbheaderbch -> ldpc -> interleavermod -> framemapper -> pilotgen) on PAGEABLE host buffers -- what a GNU Radio
+    scheduler hands to general_work() -- then with the buffers registered on first sight, then with the device-resident
+    hand-off between adjacent handles."""
+    cfg = K.resolve(cfg_name)
+    res = {}
+    for mode in ("pageable", "host_register", "host_register+link"):
+        b = T.blocks_for(cfg)
+        order = [b["bb"], b["ldpc"], b["im"], b["fm"], b["pg"]]
+        F = cfg["fecblocks"]
+        if mode != "pageable":
+            for blk in order:
+                blk.set_host_register(True)
+        if mode.endswith("link"):
+            for i in range(4):
+                order[i].link_to(order[i + 1])
+        nframes = [F, F, F, 1, 1]
+        bufs = [np.empty(n * blk.output_multiple, dtype=blk.out_dtype) for blk, n in zip(order, nframes)]
+        need0 = b["bb"].forecast(F * b["bb"].output_multiple) + 1024
+        ts_all = K.make_ts((frames_timed + 2) * need0, seed=K.TS_SEED)
+        ts_buf = np.empty(need0, np.uint8)          # the scheduler's input buffer: fixed address, refilled every round
+        pos = 0
+
+        def one_frame():
+            nonlocal pos
+            ts_buf[:] = ts_all[pos:pos + need0]
+            _, used = order[0].work_into(ts_buf, bufs[0], nframes[0])
+            pos += used
+            for i in range(1, 5):
+                order[i].work_into(bufs[i - 1], bufs[i], nframes[i])
+
+        one_frame()
+        t0 = time.perf_counter()
+        for _ in range(frames_timed):
+            one_frame()
+        dt = (time.perf_counter() - t0) / frames_timed
+        S = bufs[4].size
+        res[mode] = {"value": S / dt / 1e6, "unit": UNIT, "ms_per_t2_frame": dt * 1e3,
+                     "link_hits": sum(blk.link_hits for blk in order[1:])}
+        nbytes = [ts_buf.nbytes] + [x.nbytes for x in bufs]
+        res["h2d_bytes_per_frame"] = int(sum(nbytes[:5]))
+        res["d2h_bytes_per_frame"] = int(sum(nbytes[1:]))
+        del order, b            # handles first (they unregister), buffers after
+        del bufs, ts_buf
+    res["api"] = "five dvbt2ll_work() handles, 1 T2 frame (%d FECFRAMEs) per round, %s" % (cfg["fecblocks"], cfg_name)
+    return res
 
 
 def run_ours(args):
@@ -221,6 +396,7 @@ def run_ours(args):
     import torch.distributed as dist
     import dvbt2ll_b200 as T
     from dvbt2ll_b200 import configs as K
+    from dvbt2ll_b200 import shard
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -229,81 +405,206 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    numa_cores, orig_affinity = bind_to_gpu_cpus(torch, local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
     cfg = K.resolve(args.config)
-    cell_size = (64800 if cfg["framesize"] else 16200) // (2 * (cfg["constellation"] + 1))
-    nch, nfr = args.channels, args.frames
+    nfr = args.frames
+    my_ch = shard.channels_for_rank(args.channels, world, rank)          # config 5 as stated: 64 / N channels per GPU
+    nch = len(my_ch)
+    counts = [len(shard.channels_for_rank(args.channels, world, r)) for r in range(world)]
     frames = nch * nfr
-    chain = T.Chain(cfg, max_frames=frames, device=local)
+    weak_nch = args.channels                                             # extra: the same 64 channels on EVERY GPU
+    chain = T.Chain(cfg, max_frames=max(frames, weak_nch * nfr if world > 1 else 0, 1), device=local)
     n_ts, S, F = chain.ts_bytes_per_frame, chain.samples_per_frame, chain.fecframes_per_frame
     pitch = (nfr * n_ts + 255) // 256 * 256
 
     # synthetic TS: one independent stream per channel (seed + global channel index), pinned on the host
-    ts_host = torch.empty((nch, pitch), dtype=torch.uint8).pin_memory()
+    ts_host = torch.empty((max(nch, 1), pitch), dtype=torch.uint8).pin_memory()
     ts_np = ts_host.numpy()
-    for c in range(nch):
-        ts_np[c, :nfr * n_ts] = K.make_ts(nfr * n_ts, seed=K.TS_SEED + rank * nch + c)
+    for i, c in enumerate(my_ch):
+        ts_np[i, :nfr * n_ts] = K.make_ts(nfr * n_ts, seed=K.TS_SEED + c)
     d_ts = ts_host.to(dev)
-    d_out = torch.empty((nch, nfr * S), dtype=torch.complex64, device=dev)
+    d_out = torch.empty((max(nch, 1), nfr * S), dtype=torch.complex64, device=dev)
     # a dedicated (non-default) stream: its handle is what the C ABI launches on and what the CUDA events time
     stream = torch.cuda.Stream(device=dev)
+    consumer = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     sp = stream.cuda_stream
     assert sp != 0
-
-    def step():
-        chain.run_device(d_ts.data_ptr(), pitch, nch, nfr, 0, d_out.data_ptr(), sp)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def allmax(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- untimed: every rank checks one of its OWN channels (its last) against the checker
+    parity = {"ok": None}
+    if not args.no_parity and nch > 0:
+        chain.run_device(d_ts.data_ptr(), pitch, nch, nfr, 0, d_out.data_ptr(), sp)
+        torch.cuda.synchronize()
+        got = d_out[nch - 1, :S].cpu().numpy()
+        want, src = reference_frame(cfg, ts_np[nch - 1, :nfr * n_ts])
+        m = mer_db(got, want)
+        parity = {"ok": bool(m >= 90.0), "mer_db": m, "channel": my_ch[-1], "checker": src}
+        if not parity["ok"]:
+            raise SystemExit("bench.py: rank %d channel %d differs from %s (MER %.1f dB)" % (rank, my_ch[-1], src, m))
+    parity_ok_ranks = 1 if parity["ok"] else 0
+    if world > 1:
+        t = torch.tensor([parity_ok_ranks], device=dev, dtype=torch.int64)
+        dist.all_reduce(t)
+        parity_ok_ranks = int(t.item())
+
+    # ---- ordered reassembly on GPU 0 (N > 1): the library's gather, connected once
+    G = None
+    part_bytes = nfr * S * 8
+    offs, sizes, slot_bytes = shard.slot_layout(counts, part_bytes)
+    if world > 1:
+        G = T.Gather(rank, world, 0, local, slot_bytes, sizes[rank], n_slots=2)
+        blobs = [None] * world
+        dist.all_gather_object(blobs, G.export())
+        G.connect(blobs)
+        barrier()
+
+    cp = consumer.cuda_stream
+    step_no = [0]
+
+    def gather_step(ssz=8):
+        """One step with the reassembly: produce in place (root) or locally, push, root waits and releases."""
+        k = step_no[0]
+        step_no[0] += 1
+        off, nb = offs[rank] * ssz // 8, sizes[rank] * ssz // 8
+        p = G.acquire(k, off, sp)
+        chain.run_device(d_ts.data_ptr(), pitch, nch, nfr, 0, p, sp)
+        G.push(k, off, nb, sp)
+        if rank == 0:
+            slot = G.wait(k, cp)
+            G.release(k, cp)
+            return slot
+        return None
+
+    def plain_step():
+        chain.run_device(d_ts.data_ptr(), pitch, nch, nfr, 0, d_out.data_ptr(), sp)
+
+    def timed(step_fn, steps, end_stream):
+        """barrier, K steps, end event on `end_stream` (where the rank's last piece of work completes), max over ranks"""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            step_fn()
+        e1.record(stream if end_stream is None else end_stream)
+        barrier()
+        return allmax(e0.elapsed_time(e1)) / steps
+
     # clocks are sampled from before the warm-up until after the timed region (nvidia-smi needs ~0.1 s to
     # start; the timed region itself can be shorter than one sampling period)
     clocks = ClockSampler(local)
     clocks.start()
     chain.enable_timing(False)
-    t_w = time.perf_counter()
-    n_w = 0
+    main_step = gather_step if G is not None else plain_step
+    t_w, n_w = time.perf_counter(), 0
     while n_w < max(3, args.warmup) or time.perf_counter() - t_w < 0.4:
-        step()
+        main_step()
         n_w += 1
         if n_w % 8 == 0:
             torch.cuda.synchronize()
+    if world > 1:       # every rank does the same number of warm-up steps (the step counter must agree)
+        t = torch.tensor([n_w], device=dev, dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        for _ in range(int(t.item()) - n_w):
+            main_step()
+        n_w = int(t.item())
     barrier()
 
-    # ---- timed region: K steps, CUDA events on the launching stream, max over ranks
+    # ---- timed region: K steps, CUDA events on the launching streams, max over ranks
     chain.enable_timing(True)
     launches0 = T.kernel_launches()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    stage_acc = {}
-    barrier()
-    ev0.record(stream)
-    for _ in range(args.steps):
-        step()
-    ev1.record(stream)
-    barrier()
-    stage_n = min(args.steps, 64)
-    stage_acc = {k: v * stage_n for k, v in chain.stage_ms().items()}    # per-run CUDA events, read after the timed region
+    if G is None:
+        end_stream = None
+    else:
+        side = torch.cuda.ExternalStream(G.side_stream, device=dev)
+        end_stream = consumer if rank == 0 else side
+    ms_per_step = timed(main_step, args.steps, end_stream)
+    stage_ms = chain.stage_ms()          # per-run CUDA events, read after the timed region
     launches = T.kernel_launches() - launches0
-    ms = ev0.elapsed_time(ev1)
     clk = clocks.stop()
     chain.enable_timing(False)
-    if world > 1:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    ms_per_step = ms / args.steps
-    total_samples = frames * S * world
+    total_samples = args.channels * nfr * S
     value = total_samples / (ms_per_step * 1e-3) / 1e6
 
+    # ---- N > 1 extras: the same step without the reassembly, the int16-sink reassembly, weak scaling
+    multi = None
+    if G is not None:
+        # the gathered slot must be what the ranks produced: the root compares every rank's last channel of the final
+        # slot with the checker (untimed)
+        gather_ok = None
+        if rank == 0 and not args.no_parity:
+            torch.cuda.synchronize()
+            last_slot = G.wait(step_no[0] - 1, cp)
+            torch.cuda.synchronize()
+            gather_ok = True
+            worst = 1e9
+            for r in range(world):
+                c = shard.channels_for_rank(args.channels, world, r)[-1]
+                host = np.empty(S, np.complex64)
+                src_ptr = last_slot + (offs[r] + (counts[r] - 1) * part_bytes)
+                T.copy_to_host(host, src_ptr)
+                want, _ = reference_frame(cfg, K.make_ts(nfr * n_ts, seed=K.TS_SEED + c))
+                m = mer_db(host, want)
+                worst = min(worst, m)
+                gather_ok = gather_ok and m >= 90.0
+            if not gather_ok:
+                raise SystemExit("bench.py: reassembled slot differs from the checker (worst MER %.1f dB)" % worst)
+        compute_ms = timed(plain_step, args.steps, None)
+        # int16 I/Q sink: halves the bytes every rank pushes
+        chain.set_sink(1, 0.2)
+        for _ in range(3):
+            gather_step(4)
+        int16_ms = timed(lambda: gather_step(4), args.steps, end_stream)
+        chain.set_sink(0, 1.0)
+        # weak scaling: 64 channels on every GPU, no reassembly (round-1 headline, kept for continuity)
+        wts = torch.empty((weak_nch, pitch), dtype=torch.uint8)
+        wnp = wts.numpy()
+        for c in range(weak_nch):
+            wnp[c, :nfr * n_ts] = ts_np[c % max(nch, 1), :nfr * n_ts]
+        d_wts = wts.to(dev)
+        d_wout = torch.empty((weak_nch, nfr * S), dtype=torch.complex64, device=dev)
+
+        def weak_step():
+            chain.run_device(d_wts.data_ptr(), pitch, weak_nch, nfr, 0, d_wout.data_ptr(), sp)
+        for _ in range(3):
+            weak_step()
+        weak_ms = timed(weak_step, args.steps, None)
+        del d_wts, d_wout
+        into_root = slot_bytes - sizes[0]
+        multi = {
+            "reassembly": {"api": "dvbt2ll_gather_acquire/push/wait/release (NVLink peer copy per rank on a side stream, 2-slot ring on GPU 0, "
+                                  "device-side arrival/release counters)", "in_value": True,
+                           "bytes_into_root_per_step": int(into_root), "ingest_gbs_achieved": into_root / (ms_per_step * 1e-3) / 1e9,
+                           "ingest_gbs_bound": NVLINK_PEER_GBS, "ingest_bound_source": "B200_PROFILING.md: measured peer copy 770 GB/s per direction per GPU (900 nominal)",
+                           "ms_per_step_floor_from_ingest": into_root / (NVLINK_PEER_GBS * 1e9) * 1e3,
+                           "gather_parity_ok": gather_ok},
+            "compute_only": {"value": total_samples / (compute_ms * 1e-3) / 1e6, "ms_per_step": compute_ms,
+                             "note": "same sharded step, every rank keeps its frames (no reassembly)"},
+            "reassembly_int16_sink": {"value": total_samples / (int16_ms * 1e-3) / 1e6, "ms_per_step": int16_ms,
+                                      "bytes_into_root_per_step": int(into_root // 2),
+                                      "ingest_gbs_achieved": (into_root // 2) / (int16_ms * 1e-3) / 1e9},
+            "weak": {"value": world * weak_nch * nfr * S / (weak_ms * 1e-3) / 1e6, "ms_per_step": weak_ms,
+                     "channels_per_gpu": weak_nch, "note": "64 channels on every GPU, no reassembly (round-1 headline)"},
+            "limiter": "one GPU's NVLink ingest: all but 1/N of every step's samples must enter GPU 0",
+        }
+
     # ---- e2e: HOST TS in, HOST samples out through the C ABI (pinned buffers), copies inside the timed region
-    out_host = torch.empty((nch, nfr * S), dtype=torch.complex64).pin_memory()
+    out_host = torch.empty((max(nch, 1), nfr * S), dtype=torch.complex64).pin_memory()
     out_np = out_host.numpy()
     chain.run_host(ts_np, nch, nfr, 0, out=out_np)      # warm-up (allocates staging)
     barrier()
@@ -311,17 +612,13 @@ def run_ours(args):
     for _ in range(args.e2e_steps):
         chain.run_host(ts_np, nch, nfr, 0, out=out_np)
     torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / args.e2e_steps
-    if world > 1:
-        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+    e2e_s = allmax((time.perf_counter() - t0) / args.e2e_steps)
     e2e_value = total_samples / e2e_s / 1e6
     checksum = float(np.abs(out_np[0, :4096]).sum())
 
     # ---- extra: the flowgraph's sink side folded into the last kernel -- x0.2 gain and
     # 16-bit I/Q output, which halves the device-to-host bytes.  Reported beside e2e, not instead of it.
-    out16_host = torch.empty((nch, nfr * S, 2), dtype=torch.int16).pin_memory()
+    out16_host = torch.empty((max(nch, 1), nfr * S, 2), dtype=torch.int16).pin_memory()
     out16_np = out16_host.numpy()
     chain.set_sink(1, 0.2)
     chain.run_host(ts_np, nch, nfr, 0, out=out16_np)
@@ -330,32 +627,30 @@ def run_ours(args):
     for _ in range(args.e2e_steps):
         chain.run_host(ts_np, nch, nfr, 0, out=out16_np)
     torch.cuda.synchronize()
-    e2e16_s = (time.perf_counter() - t0) / args.e2e_steps
+    e2e16_s = allmax((time.perf_counter() - t0) / args.e2e_steps)
     chain.set_sink(0, 1.0)
-    if world > 1:
-        t = torch.tensor([e2e16_s], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e16_s = float(t.item())
     e2e16_value = total_samples / e2e16_s / 1e6
 
-    # ---- optional ordered gather of the finished frames to rank 0 (north_star: NCCL only for that)
-    gather = None
-    if world > 1:
-        d_real = torch.view_as_real(d_out)
-        bufs = [torch.empty_like(d_real) for _ in range(world)] if rank == 0 else None
-        torch.cuda.synchronize(); dist.barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        dist.gather(d_real, bufs, dst=0)
-        torch.cuda.synchronize(); dist.barrier()
-        g0.record()
-        for _ in range(3):
-            dist.gather(d_real, bufs, dst=0)
-        g1.record()
-        torch.cuda.synchronize()
-        gather = {"ms_per_step": g0.elapsed_time(g1) / 3.0, "bytes_into_root": (world - 1) * d_out.numel() * 8,
-                  "note": "ordered NCCL gather of all ranks' frames to rank 0, timed separately (not in value)"}
+    # ---- the box's device->host ceiling: every GPU copies 1 GB to pinned host memory at the same time, no kernels
+    probe_bytes = 1 << 30
+    d_probe = torch.empty(probe_bytes, dtype=torch.uint8, device=dev)
+    h_probe = torch.empty(probe_bytes, dtype=torch.uint8).pin_memory()
+    h_probe.copy_(d_probe, non_blocking=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        h_probe.copy_(d_probe, non_blocking=True)
+    torch.cuda.synchronize()
+    probe_s = allmax((time.perf_counter() - t0) / 3)
+    pcie_ceiling = world * probe_bytes / probe_s / 1e9
+    del d_probe, h_probe
+    e2e_d2h = args.channels * nfr * S * 8
+    e2e_gbs = (e2e_d2h + args.channels * nfr * n_ts) / e2e_s / 1e9
 
     if rank != 0:
+        if G is not None:
+            G.close()           # peers unmap the root's ring before the root frees it
+            barrier()
         if world > 1:
             dist.destroy_process_group()
         return
@@ -367,62 +662,74 @@ def run_ours(args):
             peak = float(json.load(f)["hbm_gbs"]); peak_src = "MEASURED_PEAKS.json hbm_gbs"
     except Exception:
         pass
-    dims = chain.plan("ofdm.dims", np.int32)
-    active_items = int(dims[15])
-    stage_ms = {k: v / stage_n for k, v in stage_acc.items()}
-    ofdm_bytes = frames * 8 * (active_items + S)              # 8*mapped_items + 8*samples per T2 frame
-    # mapper kernel in chain mode: packed codewords in, 16-bit cell codes out
-    map_bytes = frames * F * ((64800 if cfg["framesize"] else 16200) // 8 + 2 * cell_size)
-    ach = ofdm_bytes / (stage_ms["ofdm"] * 1e-3) / 1e9
-    traffic = None
+    roofline = stage_roofline(chain, cfg, frames, stage_ms, peak, peak_src)
+    traffic, traffic_src = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "ofdm_traffic.json")) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+            tj = json.load(f)
+            # measured once under `ncu --set full` for 64 T2 frames per launch; scaled to this launch's frame count
+            traffic = tj.get("dram_bytes_per_launch") * frames / float(tj.get("frames_per_launch", 64))
+            traffic_src = "profiles/ofdm_traffic.json (static: one ncu --set full capture, not measured in this run)"
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "k_ofdm (cell staging + carrier fill + IFFT + scale + guard interval + P1)",
-                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": ofdm_bytes,
-                "kernel_ms": stage_ms["ofdm"],
-                "stage_ms": stage_ms,
-                "map_kernel_gbs": map_bytes / (stage_ms["map"] * 1e-3) / 1e9}
+    roofline["traffic"] = traffic
+    roofline["traffic_source"] = traffic_src
+
+    extras = {}
+    if world == 1 and not args.no_extras:
+        try:
+            extras["dropin_e2e"] = dropin_extras(torch, T, K, args.config, 3)
+        except Exception as e:      # pragma: no cover  (an extra must never cost the headline line)
+            extras["dropin_e2e"] = {"error": str(e)[:300]}
+        try:
+            extras["per_config"] = per_config_extras(torch, T, K, dev, stream, peak, peak_src, max(5, args.steps // 2))
+        except Exception as e:      # pragma: no cover
+            extras["per_config"] = {"error": str(e)[:300]}
 
     cpu = None
-    if orig_affinity is not None:
-        os.sched_setaffinity(0, orig_affinity)
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_run(cfg, args.cpu_frames, 1)
+        r = cpu_reference_run(cfg, 1, args.cpu_frames, 1)
         if r is not None:
             v = r["samples"] / r["seconds"] / 1e6
+            fft_share = r["stage_seconds"].get("fft", 0.0) / max(1e-9, sum(x for k, x in r["stage_seconds"].items() if k != "fft"))
             cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "reference",
-                   "sample": "%d consecutive T2 frames of one %s channel, unmodified reference sources via oracle/_ref "
-                             "(GNU Radio shim, single-precision Stockham FFT stand-in for FFTW), one frame per general_work call; "
-                             "stage CPU-seconds %s" % (r["frames"], args.config, json.dumps(r["stage_seconds"]))}
+                   "fft_share_of_cpu_time": fft_share, "value_without_fft": v / (1 - fft_share) if fft_share < 1 else None,
+                   "sample": "%d consecutive T2 frames of one %s channel on %s, unmodified reference sources via oracle/_ref "
+                             "(GNU Radio shim, single-precision radix-4 FFT stand-in for FFTW), one frame per general_work call; "
+                             "stage CPU-seconds %s" % (r["frames"], args.config, cpu_model(), json.dumps(r["stage_seconds"]))}
 
+    cell_size = (64800 if cfg["framesize"] else 16200) // (2 * (cfg["constellation"] + 1))
+    conf = config_dict(args, S, F)
+    conf.update({"channels_per_gpu": counts, "l2": "working set per step per GPU (%.0f MB 16-bit cells + %.0f MB samples) %s the 126 MB L2; no explicit flush" % (
+        frames * F * cell_size * 2 / 1e6, frames * S * 8 / 1e6, "exceeds" if frames * S * 8 > 126e6 else "is below")})
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u8/f32", "data": "synthetic",
-        "config": {"workload": workload_name(args), "channels_per_gpu": nch, "t2_frames_per_channel_per_step": nfr,
-                   "fecframes_per_step": frames * F * world, "samples_per_step": total_samples,
-                   "l2": "working set per step (%.0f MB 16-bit cells + %.0f MB samples per GPU) exceeds the 126 MB L2; no explicit flush" % (
-                       frames * F * cell_size * 2 / 1e6, frames * S * 8 / 1e6)},
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": n_w,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u8/f32", "data": "synthetic", "config": conf,
         "x_realtime": value / K.REALTIME_MSPS, "x_realtime_per_gpu": value / K.REALTIME_MSPS / world,
-        "fecframes_per_s": frames * F * world / (ms_per_step * 1e-3),
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(nch * nfr * n_ts), "d2h_bytes_per_step": int(frames * S * 8),
-                "api": "dvbt2ll_chain_run_host (pinned host buffers)", "checksum": checksum,
-                "host_cores_local_to_gpu": numa_cores},
-        "e2e_int16_sink": {"value": e2e16_value, "unit": UNIT, "d2h_bytes_per_step": int(frames * S * 4),
+        "fecframes_per_s": args.channels * nfr * F / (ms_per_step * 1e-3),
+        "parity_ok_ranks": parity_ok_ranks, "parity": parity,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(args.channels * nfr * n_ts), "d2h_bytes_per_step": int(e2e_d2h),
+                "api": "dvbt2ll_chain_run_host (pinned host buffers), every rank on its own channels", "checksum": checksum,
+                "pcie_gbs_achieved": e2e_gbs, "pcie_ceiling_gbs": pcie_ceiling,
+                "pcie_ceiling_how": "all %d GPU(s) copying 1 GiB device->pinned host concurrently, no kernels (3 copies each, max over ranks)" % world,
+                "frac_of_ceiling": e2e_gbs / pcie_ceiling},
+        "e2e_int16_sink": {"value": e2e16_value, "unit": UNIT, "d2h_bytes_per_step": int(e2e_d2h // 2),
+                           "pcie_gbs_achieved": (e2e_d2h // 2 + args.channels * nfr * n_ts) / e2e16_s / 1e9,
                            "note": "same call with dvbt2ll_chain_set_sink(format=int16 I/Q, gain=0.2): the flowgraph's multiply_const + sc16 conversion fused into the last kernel"},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "clocks": clk,
     }
+    if multi is not None:
+        line["multi_gpu"] = multi
+    line.update(extras)
     if cpu is not None:
         line["cpu_baseline"] = cpu
-    if gather is not None:
-        line["gather"] = gather
     print(json.dumps(line))
+    if G is not None:
+        barrier()
+        G.close()
     if world > 1:
         dist.destroy_process_group()
 

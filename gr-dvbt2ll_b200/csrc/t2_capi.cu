@@ -8,7 +8,10 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -66,6 +69,15 @@ std::vector<t2::cfloat> make_twiddles(int n, int count)
 
 } // namespace
 
+// Device-resident hand-off between two adjacent drop-in blocks (dvbt2ll_link): what the producer last wrote, on the
+// host and where the same items still sit in HBM.  Both blocks hold the mutex for the whole of their work() call.
+struct LinkRec {
+  std::mutex m;
+  const uint8_t *host; size_t bytes; const uint8_t *dev;
+  long long hits, misses;
+  LinkRec() : host(0), bytes(0), dev(0), hits(0), misses(0) {}
+};
+
 // ------------------------------------------------------------------------------------------------
 struct dvbt2ll_handle {
   enum Kind { BB, LDPC, MAP, FRAME, OFDM, CHAIN } kind;
@@ -73,8 +85,47 @@ struct dvbt2ll_handle {
   bool dev_ready;
   int warnings;
   DevBuf stage_in, stage_out;   // device staging for host-buffer work()
-  explicit dvbt2ll_handle(Kind k) : kind(k), stream(0), dev_ready(false), warnings(0) {}
-  virtual ~dvbt2ll_handle() { if (stream) cudaStreamDestroy(stream); }
+  // host buffers registered with cudaHostRegister on first sight (the scheduler's buffers are long-lived and reused)
+  struct Pinned { const void *p; size_t n; };
+  std::vector<Pinned> pinned;
+  bool pin_enabled;
+  std::shared_ptr<LinkRec> link_in, link_out;     // set by dvbt2ll_link
+  explicit dvbt2ll_handle(Kind k) : kind(k), stream(0), dev_ready(false), warnings(0), pin_enabled(false)
+  {
+    // opt-in (dvbt2ll_set_host_register or the environment): only safe when the caller's buffers outlive the handle,
+    // as the GNU Radio scheduler's do -- a registration must never survive the munmap of its pages
+    const char *e = std::getenv("DVBT2LL_HOST_REGISTER");
+    if (e && e[0] == '1') pin_enabled = true;
+  }
+  virtual ~dvbt2ll_handle()
+  {
+    if (link_out) { std::lock_guard<std::mutex> g(link_out->m); link_out->dev = 0; link_out->bytes = 0; }
+    for (size_t i = 0; i < pinned.size(); i++) cudaHostUnregister(const_cast<void *>(pinned[i].p));
+    cudaGetLastError();
+    if (stream) cudaStreamDestroy(stream);
+  }
+  // Register [p, p + n) (page-granular) unless a registered range already covers it.  Failure is not an error:
+  // the copy then runs from pageable memory.  GNU Radio's circular buffers are mapped twice back to back; a call's
+  // span is one contiguous virtual range either way.
+  void pin(const void *p, size_t n)
+  {
+    if (!pin_enabled || !p || n < (1u << 16)) return;
+    const uintptr_t a0 = (uintptr_t)p & ~(uintptr_t)4095, a1 = ((uintptr_t)p + n + 4095) & ~(uintptr_t)4095;
+    for (size_t i = 0; i < pinned.size(); i++) {
+      const uintptr_t q0 = (uintptr_t)pinned[i].p, q1 = q0 + pinned[i].n;
+      if (a0 >= q0 && a1 <= q1) return;
+      if (a0 < q1 && q0 < a1) return;      // overlaps a registered range: leave it (partly pageable copy)
+    }
+    if (pinned.size() >= 16) return;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type != cudaMemoryTypeUnregistered) return;   // already pinned
+    cudaGetLastError();
+    if (cudaHostRegister((void *)a0, a1 - a0, cudaHostRegisterPortable) == cudaSuccess) {
+      Pinned e = { (const void *)a0, (size_t)(a1 - a0) };
+      pinned.push_back(e);
+    }
+    else cudaGetLastError();
+  }
   virtual int output_multiple() const = 0;
   virtual int forecast(int noutput) const = 0;
   virtual int in_item() const = 0;
@@ -85,6 +136,7 @@ struct dvbt2ll_handle {
   // host-side staging hooks: items that must be copied in for noutput outputs (default = forecast)
   virtual long long plan_get(const char *name, void *out, long long cap) const = 0;
 
+  virtual int enter() { return ensure_device(); }
   int ensure_device()
   {
     if (dev_ready) return 0;
@@ -121,12 +173,23 @@ long long dims_get(const t2::OfdmDims &d, void *out, long long cap)
 // ================================================================================================
 struct BbHandle : dvbt2ll_handle {
   t2::BbPlan plan;
-  DevBuf d_scr, d_crc, d_tab, d_cols, d_ib, d_ts, d_packed, d_err;
+  DevBuf d_scr, d_crc, d_tab, d_cols, d_ib, d_ts, d_packed;
   // streaming state (reference: count, crc via history, fec_block)
   int count, fec_block;
-  std::vector<uint8_t> history;   // last 187 TS bytes
-  int reported_errors;
-  BbHandle() : dvbt2ll_handle(BB), count(0), fec_block(0), history(187, 0), reported_errors(0) {}
+  uint8_t history[187];           // last 187 TS bytes consumed (CRC-8 of the packet in flight)
+  long long total_consumed;       // TS bytes consumed so far through work() / work_device()
+  int *h_err;                     // sync-error counter in mapped pinned host memory: no copy back per call
+  BbHandle() : dvbt2ll_handle(BB), count(0), fec_block(0), total_consumed(0), h_err(0) { std::memset(history, 0, sizeof(history)); }
+  ~BbHandle() { if (h_err) cudaFreeHost(h_err); }
+  // slide the 187-byte history window over `used` newly consumed bytes
+  void note_consumed(const uint8_t *in, long long used)
+  {
+    if (used >= 187) std::memcpy(history, in + used - 187, 187);
+    else if (used > 0) {
+      std::memmove(history, history + used, 187 - (size_t)used);
+      std::memcpy(history + 187 - used, in, (size_t)used);
+    }
+  }
 
   int output_multiple() const { return plan.fec.nbch; }
   int in_item() const { return 1; }
@@ -160,8 +223,10 @@ struct BbHandle : dvbt2ll_handle {
     CK(upload(d_tab, plan.bch_byte_tab));
     CK(upload(d_cols, plan.bch_shift_cols));
     CK(upload(d_ib, plan.inband_bytes));
-    CK(d_err.ensure(16));
-    CK(cudaMemset(d_err.p, 0, 16));
+    if (!h_err) {
+      CK(cudaHostAlloc((void **)&h_err, 16, cudaHostAllocMapped | cudaHostAllocPortable));
+      std::memset(h_err, 0, 16);
+    }
     return 0;
   }
   // payload bytes of `frames` FECFRAMEs starting at in-band phase fb0
@@ -190,7 +255,7 @@ struct BbHandle : dvbt2ll_handle {
     a.scramble = d_scr.as<uint8_t>(); a.crc8_tab = d_crc.as<uint8_t>(); a.bch_tab = d_tab.as<uint32_t>();
     for (int k = 0; k < 8; k++) a.crc8_mask[k] = crc_mask[k];
     a.bch_cols = d_cols.as<uint32_t>(); a.inband_bytes = d_ib.as<uint8_t>();
-    a.out = d_out; a.out_pitch = out_pitch; a.sync_errors = d_err.as<int>();
+    a.out = d_out; a.out_pitch = out_pitch; a.sync_errors = h_err;
   }
   // d_in must be preceded by 187 bytes of valid history on the device (work() arranges that)
   int work_device(const void *d_in, int ninput, void *d_out, int noutput, int *consumed, cudaStream_t s)
@@ -209,6 +274,7 @@ struct BbHandle : dvbt2ll_handle {
     CK(cudaGetLastError());
     count = (int)((count + need) % 188);
     if (plan.inband) fec_block = (fec_block + frames) % plan.fecblocks;
+    total_consumed += need;
     if (consumed) *consumed = (int)need;
     return frames * plan.fec.nbch;
   }
@@ -388,6 +454,7 @@ struct OfdmDevice {
   DevBuf d_code, d_pool, d_p1, d_sinc, d_tw, d_tw_split, d_scratch, d_sym_flags;
   int log2_m, split;
   long long pool_stride;
+  long long scratch_slot_elems;     // float2 elements per scratch slot (one slot per concurrently running batch)
   // c16: `code` holds staging slots (chain mode, 16-bit cells) and is re-encoded for the kernel's branch-free fill:
   //   data carrier         -> 2 * slot            (byte offset into the staging area, < 65536)
   //   small pool cell p<8  -> (p + 1) << 16       (zero / pilot amplitudes, kept in shared memory)
@@ -410,6 +477,7 @@ struct OfdmDevice {
     CK(upload(d_p1, op.p1));
     const int N = op.dims.fft_n;
     split = N > 16384 ? 2 : 1;
+    scratch_slot_elems = 0;
     const int M = N / split;
     log2_m = 0;
     while ((1 << log2_m) < M) log2_m++;
@@ -451,7 +519,10 @@ struct OfdmDevice {
       int dev = 0, sms = 148;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-      CK(d_scratch.ensure((size_t)(sms + 8) * 2 * M * sizeof(float2)));     // one slot per resident CTA
+      // parking space of the int16-sink 32K path: one M-point region per resident CTA, two slots so that two batches
+      // can be in flight on two streams (dvbt2ll_chain_run_host)
+      scratch_slot_elems = (long long)(sms + 8) * M;
+      CK(d_scratch.ensure((size_t)2 * scratch_slot_elems * sizeof(float2)));
     }
     return 0;
   }
@@ -531,11 +602,12 @@ struct ChainHandle : dvbt2ll_handle {
   float sink_gain;       // the flowgraph's multiply_const stage folded into the last kernel
   cudaStream_t stream2;
   int last_frames;
+  long long next_frame;  // stream position of the generic work() / work_device() path (T2 frames consumed so far)
   bool timing;
   enum { TIMING_SLOTS = 64 };
   cudaEvent_t ev[TIMING_SLOTS][5];     // per-run event sets so the timed loop never has to synchronise
   long long n_timed;
-  ChainHandle() : dvbt2ll_handle(CHAIN), max_frames(0), device(0), sink_fmt(0), sink_gain(1.0f), stream2(0), last_frames(0), timing(false)
+  ChainHandle() : dvbt2ll_handle(CHAIN), max_frames(0), device(0), sink_fmt(0), sink_gain(1.0f), stream2(0), last_frames(0), next_frame(0), timing(false)
   {
     n_timed = 0;
     for (int s = 0; s < TIMING_SLOTS; s++) for (int i = 0; i < 5; i++) ev[s][i] = 0;
@@ -544,6 +616,13 @@ struct ChainHandle : dvbt2ll_handle {
   {
     for (int s = 0; s < TIMING_SLOTS; s++) for (int i = 0; i < 5; i++) if (ev[s][i]) cudaEventDestroy(ev[s][i]);
     if (stream2) cudaStreamDestroy(stream2);
+  }
+  // every entry point: make the handle's device current for the calling thread (handles may be driven from any
+  // thread, and one process may hold chains on several devices), then lazy device initialisation
+  int enter() override
+  {
+    if (device >= 0) CK(cudaSetDevice(device));
+    return ensure_device();
   }
   int F() const { return fplan.prm.fecblocks; }
   // cells per T2 frame in the 16-bit cell memory, padded so every frame starts on an 8-byte boundary
@@ -585,9 +664,10 @@ struct ChainHandle : dvbt2ll_handle {
     for (int s = 0; s < TIMING_SLOTS; s++) for (int i = 0; i < 5; i++) CK(cudaEventCreate(&ev[s][i]));
     return 0;
   }
-  // buf_frame: first T2-frame slot of the intermediate buffers to use (lets two batches be in flight on two streams)
+  // buf_frame: first T2-frame slot of the intermediate buffers to use, scratch_slot: which half of the 32K parking
+  // scratch (two batches may be in flight on two streams); hist_valid < 0: history is present iff first_frame > 0
   int run(const void *d_ts, long long ts_pitch, int n_channels, int n_frames, long long first_frame, void *d_out, cudaStream_t s,
-          int buf_frame = 0)
+          int buf_frame = 0, int scratch_slot = 0, int hist_valid = -1)
   {
     const int frames = n_channels * n_frames;
     if (frames < 1) return 0;
@@ -605,8 +685,8 @@ struct ChainHandle : dvbt2ll_handle {
     uint8_t *bch_buf = d_bch.as<uint8_t>() + (size_t)buf_frame * F() * bp;
     uint8_t *fec_buf = d_fec.as<uint8_t>() + (size_t)buf_frame * F() * fp;
     uint16_t *cell_buf = d_cells.as<uint16_t>() + (size_t)buf_frame * cells16_stride();
-    bb.fill_args(ba, (const uint8_t *)d_ts, ts_pitch, n_channels, n_frames * F(), count0, fb0, first_frame > 0 ? 1 : 0,
-                 bch_buf, bp);
+    bb.fill_args(ba, (const uint8_t *)d_ts, ts_pitch, n_channels, n_frames * F(), count0, fb0,
+                 hist_valid >= 0 ? hist_valid : (first_frame > 0 ? 1 : 0), bch_buf, bp);
     t2k::launch_bb_bch(ba, s);
     if (timing) cudaEventRecord(tev[1], s);
     t2k::LdpcArgs la;
@@ -626,6 +706,7 @@ struct ChainHandle : dvbt2ll_handle {
     oa.lut = map.d_lut.as<float2>(); oa.lut_n = 1 << map.plan.mod;
     oa.out = d_out; oa.out_stride = oplan.samples_per_frame;
     oa.out_fmt = sink_fmt; oa.sink_gain = sink_gain; oa.norm = oplan.normalization * sink_gain;
+    if (oa.scratch && scratch_slot) oa.scratch += odev.scratch_slot_elems;
     oa.frames = frames; oa.frames_per_channel = n_frames;
     oa.frame_idx0 = (int)(first_frame % (tables.pool.l1post_variants > 0 ? tables.pool.l1post_variants : 1));
     t2k::launch_ofdm(oa, s);
@@ -639,10 +720,14 @@ struct ChainHandle : dvbt2ll_handle {
     const int frames = noutput / oplan.samples_per_frame;
     if (consumed) *consumed = 0;
     if (frames < 1) return 0;
-    if ((long long)ninput < ts_bytes(0, frames)) return fail(DVBT2LL_ERR_SHORT, "chain: not enough input items");
-    int r = run(d_in, 0, 1, frames, 0, d_out, s);
+    // streams like the first stage: frame counter carried across calls, 187 history bytes in front of d_in once
+    // anything has been consumed (normal input mode)
+    const long long need = ts_bytes(next_frame, frames);
+    if ((long long)ninput < need) return fail(DVBT2LL_ERR_SHORT, "chain: not enough input items");
+    int r = run(d_in, 0, 1, frames, next_frame, d_out, s);
     if (r < 0) return r;
-    if (consumed) *consumed = (int)ts_bytes(0, frames);
+    next_frame += frames;
+    if (consumed) *consumed = (int)need;
     return frames * oplan.samples_per_frame;
   }
   long long plan_get(const char *name, void *out, long long cap) const
@@ -697,11 +782,13 @@ long long dvbt2ll_plan_get(const dvbt2ll_handle *h, const char *name, void *out,
 int dvbt2ll_work_device(dvbt2ll_handle *h, const void *d_in, int ninput, void *d_out, int noutput, int *consumed, void *stream)
 {
   if (!h) return fail(DVBT2LL_ERR_INVALID, "null handle");
-  int r = h->ensure_device();
+  int r = h->enter();
   if (r) return r;
   if (h->kind == dvbt2ll_handle::BB) {
-    // device-resident callers must keep 187 bytes of history in front of d_in themselves
-    static_cast<BbHandle *>(h)->hist_on_device = 0;
+    // device-resident callers keep the 187 stream bytes before d_in in front of it (see the header): they are read
+    // once anything has been consumed; at the very start of the stream the history is all zero by definition
+    BbHandle *b = static_cast<BbHandle *>(h);
+    b->hist_on_device = b->total_consumed > 0 ? 1 : 0;
   }
   cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
   r = h->work_device(d_in, ninput, d_out, noutput, consumed, s);
@@ -713,50 +800,121 @@ int dvbt2ll_work(dvbt2ll_handle *h, const void *in, int ninput, void *out, int n
 {
   if (!h) return fail(DVBT2LL_ERR_INVALID, "null handle");
   if (consumed) *consumed = 0;
-  int r = h->ensure_device();
+  int r = h->enter();
   if (r) return r;
   const int om = h->output_multiple();
   const int frames = noutput / om;
   if (frames < 1) return 0;
   const int nout = frames * om;
+  BbHandle *b = h->kind == dvbt2ll_handle::BB ? static_cast<BbHandle *>(h) : 0;
+  ChainHandle *ch = h->kind == dvbt2ll_handle::CHAIN ? static_cast<ChainHandle *>(h) : 0;
+  if (ch) b = &ch->bb;          // the chain streams like its first stage: history + frame counter carried across calls
   // items to stage in
   long long need;
-  if (h->kind == dvbt2ll_handle::BB) need = static_cast<BbHandle *>(h)->ts_needed(frames);
-  else if (h->kind == dvbt2ll_handle::CHAIN) need = static_cast<ChainHandle *>(h)->ts_bytes(0, frames);
+  if (ch) need = ch->ts_bytes(ch->next_frame, frames);
+  else if (b) need = b->ts_needed(frames);
   else need = (long long)h->forecast(nout);
   if (ninput < need) return fail(DVBT2LL_ERR_SHORT, "not enough input items for the requested output");
+  if (ch && frames > ch->max_frames) return fail(DVBT2LL_ERR_INVALID, "chain: more frames requested than max_frames given at create");
   DevBuf &d_in = h->stage_in, &d_out = h->stage_out;
   const size_t in_bytes = (size_t)need * h->in_item(), out_bytes = (size_t)nout * h->out_item();
   const size_t prefix = 192;
-  CK(d_in.ensure(prefix + in_bytes + 256));
+  // linked neighbours (dvbt2ll_link): upstream record first, then downstream -- one global lock order
+  std::unique_lock<std::mutex> lk_in, lk_out;
+  if (h->link_in) lk_in = std::unique_lock<std::mutex>(h->link_in->m);
+  if (h->link_out) lk_out = std::unique_lock<std::mutex>(h->link_out->m);
+  const uint8_t *resident = 0;           // the input items, if the upstream block left them in HBM
+  if (h->link_in && !b) {
+    LinkRec &L = *h->link_in;
+    const uint8_t *ip = (const uint8_t *)in;
+    if (L.dev && ip >= L.host && ip + in_bytes <= L.host + L.bytes) { resident = L.dev + (ip - L.host); L.hits++; }
+    else L.misses++;
+  }
+  if (!resident) CK(d_in.ensure(prefix + in_bytes + 256));
+  if (h->link_out) h->link_out->dev = 0;                       // about to be overwritten (and possibly reallocated)
   CK(d_out.ensure(out_bytes + 256));
-  uint8_t *din = d_in.as<uint8_t>() + prefix;
+  uint8_t *din = resident ? const_cast<uint8_t *>(resident) : d_in.as<uint8_t>() + prefix;
   cudaStream_t s = h->stream;
-  if (h->kind == dvbt2ll_handle::BB) {
-    BbHandle *b = static_cast<BbHandle *>(h);
-    CK(cudaMemcpyAsync(din - 187, b->history.data(), 187, cudaMemcpyHostToDevice, s));
+  // GNU Radio hands over pageable buffers; registering them (once per distinct buffer, they are reused call after
+  // call) turns the two copies into DMA transfers at full PCIe rate instead of staged pageable copies
+  if (!resident) h->pin(in, in_bytes);
+  h->pin(out, out_bytes);
+  if (b) {
+    CK(cudaMemcpyAsync(din - 187, b->history, 187, cudaMemcpyHostToDevice, s));
     b->hist_on_device = 1;
   }
-  CK(cudaMemcpyAsync(din, in, in_bytes, cudaMemcpyHostToDevice, s));
+  if (!resident) CK(cudaMemcpyAsync(din, in, in_bytes, cudaMemcpyHostToDevice, s));
   int used = 0;
-  r = h->work_device(din, (int)need, d_out.p, nout, &used, s);
+  if (ch) {
+    r = ch->run(din, 0, 1, frames, ch->next_frame, d_out.p, s, 0, 0, 1);
+    if (r >= 0) { r = nout; used = (int)need; ch->next_frame += frames; }
+  }
+  else r = h->work_device(din, (int)need, d_out.p, nout, &used, s);
   if (r < 0) return r;
   CK(cudaMemcpyAsync(out, d_out.p, out_bytes, cudaMemcpyDeviceToHost, s));
-  if (h->kind == dvbt2ll_handle::BB) {
-    BbHandle *b = static_cast<BbHandle *>(h);
-    int errs = 0;
-    CK(cudaMemcpyAsync(&errs, b->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    h->warnings = errs;
-    // keep the last 187 consumed bytes as history for the CRC-8 of the packet in flight
-    std::vector<uint8_t> joined(b->history);
-    joined.insert(joined.end(), (const uint8_t *)in, (const uint8_t *)in + used);
-    b->history.assign(joined.end() - 187, joined.end());
+  CK(cudaStreamSynchronize(s));
+  if (b) {
+    h->warnings = *b->h_err;         // mapped host counter, complete after the synchronize
+    b->note_consumed((const uint8_t *)in, used);
   }
-  else CK(cudaStreamSynchronize(s));
+  if (h->link_out) { LinkRec &L = *h->link_out; L.host = (const uint8_t *)out; L.bytes = out_bytes; L.dev = d_out.as<uint8_t>(); }
   if (consumed) *consumed = used;
   return r;
 }
+
+// plain synchronous copies between host and device memory, for hosts (tests, bench.py, language bindings) that hold raw
+// device pointers handed out by this library (dvbt2ll_gather_wait) and have no CUDA runtime binding of their own
+int dvbt2ll_copy_to_host(void *dst, const void *d_src, size_t bytes)
+{
+  CK(cudaMemcpy(dst, d_src, bytes, cudaMemcpyDeviceToHost));
+  return 0;
+}
+int dvbt2ll_copy_to_device(void *d_dst, const void *src, size_t bytes)
+{
+  CK(cudaMemcpy(d_dst, src, bytes, cudaMemcpyHostToDevice));
+  return 0;
+}
+void *dvbt2ll_device_alloc(size_t bytes)
+{
+  void *p = 0;
+  if (cudaMalloc(&p, bytes) != cudaSuccess) { fail(DVBT2LL_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(cudaGetLastError())); return 0; }
+  return p;
+}
+void dvbt2ll_device_free(void *p) { if (p) cudaFree(p); }
+int dvbt2ll_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+int dvbt2ll_set_device(int device) { CK(cudaSetDevice(device)); return 0; }
+void *dvbt2ll_stream_create(void)
+{
+  cudaStream_t s = 0;
+  if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) { fail(DVBT2LL_ERR_CUDA, "cudaStreamCreate failed"); cudaGetLastError(); return 0; }
+  return (void *)s;
+}
+void dvbt2ll_stream_destroy(void *stream) { if (stream) cudaStreamDestroy((cudaStream_t)stream); }
+int dvbt2ll_stream_synchronize(void *stream) { CK(cudaStreamSynchronize((cudaStream_t)stream)); return 0; }
+int dvbt2ll_device_synchronize(void) { CK(cudaDeviceSynchronize()); return 0; }
+
+void dvbt2ll_set_overfull_policy(int policy) { t2::set_overfull_policy(policy); }
+
+void dvbt2ll_set_host_register(dvbt2ll_handle *h, int on) { if (h) h->pin_enabled = on != 0; }
+
+int dvbt2ll_link(dvbt2ll_handle *producer, dvbt2ll_handle *consumer)
+{
+  if (!producer || !consumer || producer == consumer) return fail(DVBT2LL_ERR_INVALID, "link: two distinct handles needed");
+  if (producer->out_item() != consumer->in_item()) return fail(DVBT2LL_ERR_INVALID, "link: item sizes differ");
+  if (consumer->kind == dvbt2ll_handle::BB || consumer->kind == dvbt2ll_handle::CHAIN)
+    return fail(DVBT2LL_ERR_INVALID, "link: a TS-consuming block keeps stream history in front of its input and cannot be a consumer");
+  std::shared_ptr<LinkRec> L = std::make_shared<LinkRec>();
+  producer->link_out = L;
+  consumer->link_in = L;
+  return 0;
+}
+
+long long dvbt2ll_link_hits(const dvbt2ll_handle *consumer) { return (consumer && consumer->link_in) ? consumer->link_in->hits : 0; }
 
 // ---- factories -----------------------------------------------------------------------------------
 dvbt2ll_handle *dvbt2ll_bbheaderbch_create(int framesize, int rate, int mode, int inband, int fecblocks, int tsrate)
@@ -796,6 +954,7 @@ dvbt2ll_handle *dvbt2ll_framemapperfint_create(int framesize, int rate, int cons
                         l1constellation, pilotpattern, t2frames, numdatasyms, paprmode, version, preamble, inputmode,
                         reservedbiasbits, l1scrambled, inband };
   if (!t2::build_frame_plan(p, &h->plan, &err)) { delete h; fail(DVBT2LL_ERR_INVALID, err); return 0; }
+  if (h->plan.overfull) { h->warnings = 1; g_err = "Frame Mapper, too many FEC blocks in T2 frame."; }
   return h;
 }
 
@@ -830,6 +989,7 @@ dvbt2ll_handle *dvbt2ll_chain_create(const dvbt2ll_chain_params *c, int max_fram
   ok = ok && t2::build_ofdm_plan(op, &h->oplan, &err);
   ok = ok && t2::compose_chain16(h->fplan, h->oplan, &h->tables, &err);
   if (!ok) { delete h; fail(DVBT2LL_ERR_INVALID, err); return 0; }
+  if (h->fplan.overfull) { h->warnings = 1; g_err = "Frame Mapper, too many FEC blocks in T2 frame."; }
   return h;
 }
 
@@ -852,9 +1012,10 @@ int dvbt2ll_chain_run_device(dvbt2ll_handle *h, const void *d_ts, long long ts_p
 {
   ChainHandle *c = as_chain(h);
   if (!c) return fail(DVBT2LL_ERR_INVALID, "not a chain handle");
-  if (c->device >= 0 && !c->dev_ready) CK(cudaSetDevice(c->device));
-  int r = c->ensure_device();
+  int r = c->enter();
   if (r) return r;
+  if (n_channels < 0 || n_frames < 0) return fail(DVBT2LL_ERR_INVALID, "chain: negative batch size");
+  if (n_channels == 0 || n_frames == 0) return 0;
   return c->run(d_ts, ts_pitch, n_channels, n_frames, first_frame, d_out, stream ? (cudaStream_t)stream : c->stream);
 }
 
@@ -863,13 +1024,15 @@ int dvbt2ll_chain_run_host(dvbt2ll_handle *h, const void *ts, long long ts_pitch
 {
   ChainHandle *c = as_chain(h);
   if (!c) return fail(DVBT2LL_ERR_INVALID, "not a chain handle");
-  if (c->device >= 0 && !c->dev_ready) CK(cudaSetDevice(c->device));
-  int r = c->ensure_device();
+  int r = c->enter();
   if (r) return r;
+  if (n_channels < 0 || n_frames < 0) return fail(DVBT2LL_ERR_INVALID, "chain: negative batch size");
+  if (n_channels == 0 || n_frames == 0) return 0;
   const long long per_ch = c->ts_bytes(first_frame, n_frames);
   // normal input mode: the CRC-8 that replaces the first sync byte covers the 187 bytes before the pointer
   const long long hist = (first_frame > 0 && c->bb.plan.mode == t2::INPUTMODE_NORMAL) ? 187 : 0;
-  if (n_channels < 0 || n_frames < 0 || (n_channels > 1 && ts_pitch < per_ch + hist))
+  if (n_channels == 1 && ts_pitch < per_ch + hist) ts_pitch = per_ch + hist;      // a single row: the pitch is never used to step
+  if (ts_pitch < per_ch + hist)
     return fail(DVBT2LL_ERR_INVALID, "chain: ts_pitch smaller than the TS bytes (+ 187 history bytes) of one channel");
   const long long dpitch = (per_ch + hist + 255) & ~255LL;
   const size_t ssz = c->sink_fmt ? 4 : 8;                                        // bytes per output sample
@@ -894,7 +1057,7 @@ int dvbt2ll_chain_run_host(dvbt2ll_handle *h, const void *ts, long long ts_pitch
     CK(cudaMemcpy2DAsync(base + (size_t)c0 * dpitch - hist, (size_t)dpitch, (const uint8_t *)ts + (size_t)c0 * ts_pitch - hist,
                          (size_t)ts_pitch, (size_t)(per_ch + hist), (size_t)nc, cudaMemcpyHostToDevice, s));
     r = c->run(base + (size_t)c0 * dpitch, dpitch, nc, n_frames, first_frame, dout + (size_t)c0 * ch_out * ssz, s,
-               groups == 1 ? 0 : (gi & 1) * per * n_frames);
+               groups == 1 ? 0 : (gi & 1) * per * n_frames, gi & 1);
     if (r < 0) return r;
     CK(cudaMemcpyAsync((uint8_t *)out + (size_t)c0 * ch_out * ssz, dout + (size_t)c0 * ch_out * ssz, (size_t)nc * ch_out * ssz,
                        cudaMemcpyDeviceToHost, s));

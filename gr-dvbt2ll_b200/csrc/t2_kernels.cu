@@ -22,17 +22,38 @@ namespace t2k {
 static std::atomic<long long> g_launches(0);
 long long kernel_launch_count() { return g_launches.load(); }
 static inline void count_launch() { g_launches.fetch_add(1); }
+void count_extra_launch() { count_launch(); }      // kernels of other translation units (t2_gather.cu)
+
+// Per-device caches: function attributes and the SM count belong to a device, and one process may drive several
+// (dvbt2ll_chain_create takes a device index).  Racing writers store the same value.
+constexpr int MAX_DEVICES = 64;
+static inline int current_device()
+{
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev < 0 || dev >= MAX_DEVICES) ? 0 : dev;
+}
 
 static inline int sm_count()
 {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  static int n[MAX_DEVICES];
+  const int dev = current_device();
+  if (!n[dev]) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    n[dev] = v > 0 ? v : 148;
   }
-  return n;
+  return n[dev];
+}
+
+// opt in to `bytes` of dynamic shared memory for kernel `k` once per device
+template <class K>
+static inline void allow_smem(K k, int bytes, bool (&done)[MAX_DEVICES])
+{
+  const int dev = current_device();
+  if (done[dev]) return;
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  done[dev] = true;
 }
 
 __device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
@@ -320,12 +341,9 @@ void launch_bb_bch(const BbArgs &a, cudaStream_t s)
   const size_t fixed = (size_t)4 * 16 * (w6 ? 6 : 5) * 32 * 4 + 6 * 32 * 6 * 4 + 256;
   const int total = a.n_channels * a.frames;
   if (total < 1) return;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(k_bb_bch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(k_bb_bch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    attr = true;
-  }
+  static bool attr6[MAX_DEVICES], attr5[MAX_DEVICES];
+  allow_smem(k_bb_bch<true>, 227 * 1024, attr6);
+  allow_smem(k_bb_bch<false>, 227 * 1024, attr5);
   // one CTA per SM (the lane-private tables take 40-48 KB), as many warps as frame buffers fit
   int warps = BB_MAX_WARPS;
   while (warps > 4 && fixed + (size_t)warps * buf_pitch > 227 * 1024) warps -= 4;
@@ -469,8 +487,8 @@ void launch_ldpc(const LdpcArgs &a, cudaStream_t s)
   const int warp_words = (a.groups * 13 + cw_words + 3) & ~3;
   const size_t smem = (size_t)LDPC_WARPS * warp_words * 4;
   if (a.frames < 1) return;
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(k_ldpc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+  static bool attr[MAX_DEVICES];
+  allow_smem(k_ldpc, 200 * 1024, attr);
   int per_sm = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ldpc, LDPC_WARPS * 32, smem);
   if (per_sm < 1) per_sm = 1;
@@ -710,11 +728,8 @@ void launch_map(const MapArgs &a, cudaStream_t s)
   // one FECFRAME per CTA: the hardware scheduler balances the tail at frame granularity
   const int blocks = a.frames;
   if (blocks < 1) return;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(k_map, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);   // QPSK normal: 32400 cell codes
-    attr = true;
-  }
+  static bool attr[MAX_DEVICES];
+  allow_smem(k_map, 100 * 1024, attr);      // QPSK normal: 32400 cell codes
   k_map<<<blocks, MAP_THREADS, smem, s>>>(a);
   count_launch();
 }
@@ -1403,11 +1418,8 @@ static void launch_ofdm_t(const OfdmArgs &a, cudaStream_t s)
   constexpr int M = 1 << LOG2M;
   const size_t smem = (size_t)padx(M) * sizeof(float2) + (C16 ? (size_t)a.stage_cap * 3 + ((size_t)2048 << a.lut_rep_shift) + 64 : 0);
   const int units = a.frames * a.num_symbols;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(k_ofdm<LOG2M, T, C16, FMT, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    attr = true;
-  }
+  static bool attr[MAX_DEVICES];
+  allow_smem(k_ofdm<LOG2M, T, C16, FMT, SPLIT>, 227 * 1024, attr);
   int per_sm = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ofdm<LOG2M, T, C16, FMT, SPLIT>, T, smem);
   if (per_sm < 1) per_sm = 1;

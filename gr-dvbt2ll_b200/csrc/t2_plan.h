@@ -160,6 +160,9 @@ struct FramePlan {
   int pool_l1pre, pool_dummy, pool_zero;
 };
 bool build_frame_plan(const FrameParams &prm, FramePlan *p, std::string *err);
+// over-full T2 frames: 0 = refuse at plan time (default), 1 = warn and truncate like the reference (:1138-1141)
+void set_overfull_policy(int policy);
+bool overfull_warn_policy();
 
 // ---- block 5: pilots + IFFT + guard interval + P1 (reference lib/pilotgenp1insert_cc_impl.cc) ---
 struct OfdmParams {

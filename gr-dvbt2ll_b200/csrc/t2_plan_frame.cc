@@ -2,6 +2,8 @@
 // time interleaver, frame assembly (incl. the multi-P2 zig-zag) and frequency interleaver, all
 // folded into ONE gather table per T2 frame (block 4 of the reference,
 // lib/framemapperfint_cc_impl.cc).  Host only, runs once per make().
+#include <atomic>
+#include <cstdlib>
 #include "t2_plan.h"
 
 #include <cmath>
@@ -10,6 +12,20 @@
 #include "t2_std_tables.inc"
 
 namespace t2 {
+
+static std::atomic<int> g_overfull_policy(-1);
+void set_overfull_policy(int policy) { g_overfull_policy.store(policy ? 1 : 0); }
+bool overfull_warn_policy()
+{
+  int v = g_overfull_policy.load();
+  if (v < 0) {
+    const char *e = std::getenv("DVBT2LL_OVERFULL");
+    v = (e && (e[0] == 'w' || e[0] == 'W' || e[0] == '1')) ? 1 : 0;
+    g_overfull_policy.store(v);
+  }
+  return v == 1;
+}
+
 
 // ------------------------------------------------------------------------------------------------
 // OFDM dimensions (EN 302 755 Tables 47-49, 51, 67; reference framemapper :290-915, pilotgen :56-666)
@@ -373,13 +389,19 @@ bool build_frame_plan(const FrameParams &prm, FramePlan *p, std::string *err)
   p->mapped_items = d.active_items;
   const int fixed = 1840 + l1post_cells + (d.n_fc - d.c_fc);
   p->overfull = p->mapped_items < p->stream_items + fixed;
+  // Length of the linear frame before truncation.  Reference :1138-1141: an over-full frame only logs a warning,
+  // grows its private frame buffers to stream_items + fixed "to avoid segfault" and carries on; the frequency
+  // interleaver then reads the physical frame only, so the cells that do not fit are dropped.  By default creation
+  // fails with the reference's message; with the opt-in policy the same truncated frame is produced.
+  int linear_items = p->mapped_items;
   if (p->overfull) {
-    // reference :1138-1141 only warns ("too many FEC blocks in T2 frame") and then emits a
-    // malformed frame; a plan for that is not defined, so creation fails with the same message.
-    if (err) *err = "Frame Mapper, too many FEC blocks in T2 frame.";
-    return false;
+    if (!overfull_warn_policy()) {
+      if (err) *err = "Frame Mapper, too many FEC blocks in T2 frame.";
+      return false;
+    }
+    linear_items = p->stream_items + fixed;
   }
-  p->dummy_cells = p->mapped_items - p->stream_items - fixed;
+  p->dummy_cells = linear_items - p->stream_items - fixed;
 
   // ---- cell interleaver permutation (EN 302 755 6.4; reference :999-1107)
   {
@@ -492,7 +514,7 @@ bool build_frame_plan(const FrameParams &prm, FramePlan *p, std::string *err)
   { cfloat z; z.re = 0.0f; z.im = 0.0f; pool.cells.push_back(z); }
 
   // ---- linear frame (before zig-zag): [L1-pre][L1-post][data][dummy][unmodulated]
-  std::vector<int32_t> linear((size_t)p->mapped_items);
+  std::vector<int32_t> linear((size_t)linear_items);
   {
     size_t k = 0;
     for (int i = 0; i < 1840; i++) linear[k++] = -(1 + p->pool_l1pre + i);
@@ -502,7 +524,7 @@ bool build_frame_plan(const FrameParams &prm, FramePlan *p, std::string *err)
     for (int i = 0; i < d.n_fc - d.c_fc; i++) linear[k++] = -(1 + p->pool_zero);
   }
   // ---- P2 zig-zag when N_P2 > 1 (reference :2047-2103)
-  std::vector<int32_t> framed((size_t)p->mapped_items);
+  std::vector<int32_t> framed((size_t)linear_items);
   if (d.n_p2 == 1) framed = linear;
   else {
     const int NP = d.n_p2, CP = d.c_p2;
@@ -515,7 +537,7 @@ bool build_frame_plan(const FrameParams &prm, FramePlan *p, std::string *err)
     const int rest = CP - pre_per - post_per;
     for (int n = 0; n < NP; n++)
       for (int j = 0; j < rest; j++) framed[(size_t)n * CP + pre_per + post_per + j] = linear[read++];
-    for (size_t i = (size_t)NP * CP; i < (size_t)p->mapped_items; i++) framed[i] = linear[read++];
+    for (size_t i = (size_t)NP * CP; i < (size_t)linear_items; i++) framed[i] = linear[read++];
   }
   // ---- frequency interleaver, symbol parity counted from 0 in every T2 frame (reference :2104-2142)
   std::vector<int32_t> He, Ho, HeP2, HoP2, HeFC, HoFC;
@@ -548,6 +570,7 @@ bool build_frame_plan(const FrameParams &prm, FramePlan *p, std::string *err)
     if (d.n_fc) emit((sym & 1) ? HoFC : HeFC, d.n_fc);
     if (off != (size_t)p->mapped_items) { if (err) *err = "internal: frame size"; return false; }
   }
+  framed.resize((size_t)p->mapped_items);      // over-full: what lies beyond the physical frame is never transmitted
   p->framed.swap(framed);
   return true;
 }

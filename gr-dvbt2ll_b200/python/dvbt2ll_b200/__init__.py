@@ -29,7 +29,15 @@ EXPORTED_SYMBOLS = [
     "dvbt2ll_chain_create", "dvbt2ll_chain_ts_bytes_per_frame", "dvbt2ll_chain_ts_bytes", "dvbt2ll_chain_samples_per_frame",
     "dvbt2ll_chain_fecframes_per_frame", "dvbt2ll_chain_run_device", "dvbt2ll_chain_run_host",
     "dvbt2ll_chain_tap", "dvbt2ll_chain_stage_ms", "dvbt2ll_chain_enable_timing", "dvbt2ll_chain_set_sink",
+    "dvbt2ll_set_overfull_policy", "dvbt2ll_set_host_register", "dvbt2ll_link", "dvbt2ll_link_hits",
+    "dvbt2ll_gather_last_error", "dvbt2ll_gather_create", "dvbt2ll_gather_export", "dvbt2ll_gather_connect",
+    "dvbt2ll_gather_acquire", "dvbt2ll_gather_push", "dvbt2ll_gather_wait", "dvbt2ll_gather_release",
+    "dvbt2ll_gather_side_stream", "dvbt2ll_gather_destroy",
+    "dvbt2ll_copy_to_host", "dvbt2ll_copy_to_device", "dvbt2ll_device_alloc", "dvbt2ll_device_free",
+    "dvbt2ll_device_count", "dvbt2ll_set_device", "dvbt2ll_device_synchronize",
+    "dvbt2ll_stream_create", "dvbt2ll_stream_destroy", "dvbt2ll_stream_synchronize",
 ]
+GATHER_BLOB_BYTES = 256
 
 
 class ChainParams(C.Structure):
@@ -82,6 +90,38 @@ def lib():
         L.dvbt2ll_chain_stage_ms.argtypes = [vp, C.POINTER(C.c_float)]
         L.dvbt2ll_chain_enable_timing.argtypes = [vp, ci]
         L.dvbt2ll_chain_set_sink.argtypes = [vp, ci, C.c_float]
+        L.dvbt2ll_set_overfull_policy.argtypes = [ci]
+        L.dvbt2ll_set_overfull_policy.restype = None
+        L.dvbt2ll_set_host_register.argtypes = [vp, ci]
+        L.dvbt2ll_set_host_register.restype = None
+        L.dvbt2ll_link.argtypes = [vp, vp]
+        L.dvbt2ll_link_hits.argtypes = [vp]
+        L.dvbt2ll_link_hits.restype = cll
+        sz = C.c_size_t
+        L.dvbt2ll_gather_last_error.restype = C.c_char_p
+        L.dvbt2ll_gather_create.restype = vp
+        L.dvbt2ll_gather_create.argtypes = [ci, ci, ci, ci, sz, sz, ci]
+        L.dvbt2ll_gather_export.argtypes = [vp, vp, sz]
+        L.dvbt2ll_gather_connect.argtypes = [vp, vp, sz]
+        L.dvbt2ll_gather_acquire.argtypes = [vp, cll, sz, vp, C.POINTER(vp)]
+        L.dvbt2ll_gather_push.argtypes = [vp, cll, sz, sz, vp]
+        L.dvbt2ll_gather_wait.argtypes = [vp, cll, vp, C.POINTER(vp)]
+        L.dvbt2ll_gather_release.argtypes = [vp, cll, vp]
+        L.dvbt2ll_gather_side_stream.restype = vp
+        L.dvbt2ll_gather_side_stream.argtypes = [vp]
+        L.dvbt2ll_gather_destroy.argtypes = [vp]
+        L.dvbt2ll_gather_destroy.restype = None
+        L.dvbt2ll_copy_to_host.argtypes = [vp, vp, sz]
+        L.dvbt2ll_copy_to_device.argtypes = [vp, vp, sz]
+        L.dvbt2ll_device_alloc.restype = vp
+        L.dvbt2ll_device_alloc.argtypes = [sz]
+        L.dvbt2ll_device_free.argtypes = [vp]
+        L.dvbt2ll_device_free.restype = None
+        L.dvbt2ll_set_device.argtypes = [ci]
+        L.dvbt2ll_stream_create.restype = vp
+        L.dvbt2ll_stream_destroy.argtypes = [vp]
+        L.dvbt2ll_stream_destroy.restype = None
+        L.dvbt2ll_stream_synchronize.argtypes = [vp]
         _lib = L
     return _lib
 
@@ -96,6 +136,68 @@ def device_available():
 
 def kernel_launches():
     return int(lib().dvbt2ll_kernel_launches())
+
+
+def device_count():
+    return int(lib().dvbt2ll_device_count())
+
+
+def set_device(device):
+    if lib().dvbt2ll_set_device(int(device)) < 0:
+        raise RuntimeError(last_error())
+
+
+def stream_create():
+    """A non-blocking stream on the current device (raw handle)."""
+    s = lib().dvbt2ll_stream_create()
+    if not s:
+        raise RuntimeError(last_error())
+    return s
+
+
+def stream_destroy(s):
+    lib().dvbt2ll_stream_destroy(s)
+
+
+def device_synchronize():
+    if lib().dvbt2ll_device_synchronize() < 0:
+        raise RuntimeError(last_error())
+
+
+def copy_to_host(dst, d_ptr):
+    """Fill the numpy array `dst` from device memory at raw pointer d_ptr (synchronous)."""
+    if lib().dvbt2ll_copy_to_host(dst.ctypes.data, d_ptr, dst.nbytes) < 0:
+        raise RuntimeError(last_error())
+    return dst
+
+
+class DeviceBuffer(object):
+    """A plain device allocation on the current device (tests and hosts without their own CUDA binding)."""
+
+    def __init__(self, nbytes, data=None):
+        self.nbytes = int(nbytes)
+        self.ptr = lib().dvbt2ll_device_alloc(self.nbytes)
+        if not self.ptr:
+            raise MemoryError(last_error())
+        if data is not None:
+            data = np.ascontiguousarray(data)
+            if lib().dvbt2ll_copy_to_device(self.ptr, data.ctypes.data, data.nbytes) < 0:
+                raise RuntimeError(last_error())
+
+    def to_host(self, dtype, count=None):
+        out = np.empty(self.nbytes // np.dtype(dtype).itemsize if count is None else count, dtype=dtype)
+        return copy_to_host(out, self.ptr)
+
+    def free(self):
+        p, self.ptr = self.ptr, None
+        if p:
+            lib().dvbt2ll_device_free(p)
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 class _Block(object):
@@ -136,6 +238,30 @@ class _Block(object):
         if r < 0:
             raise RuntimeError("dvbt2ll_work failed (%d): %s" % (r, last_error()))
         return out[:r], consumed.value
+
+    def work_into(self, data, out, nframes):
+        """general_work() into a caller-owned output array (long-lived buffers, as the scheduler's are).
+        Returns (items produced, consumed)."""
+        nout = nframes * self.output_multiple
+        consumed = C.c_int(0)
+        r = lib().dvbt2ll_work(self._h, data.ctypes.data, data.size, out.ctypes.data, nout, C.byref(consumed))
+        if r < 0:
+            raise RuntimeError("dvbt2ll_work failed (%d): %s" % (r, last_error()))
+        return r, consumed.value
+
+    def set_host_register(self, on=True):
+        """Register the host buffers handed to work() with CUDA on first sight (only for long-lived buffers)."""
+        lib().dvbt2ll_set_host_register(self._h, 1 if on else 0)
+
+    def link_to(self, consumer):
+        """Device-resident hand-off: `consumer` takes its input from HBM when it is handed what this block last wrote."""
+        r = lib().dvbt2ll_link(self._h, consumer._h)
+        if r < 0:
+            raise ValueError(last_error())
+
+    @property
+    def link_hits(self):
+        return int(lib().dvbt2ll_link_hits(self._h))
 
     def plan(self, name, dtype):
         """Host-side plan table by name (see dvbt2ll_plan_get)."""
@@ -247,16 +373,27 @@ class Chain(_Block):
             raise ValueError(last_error())
         self.sink_format = int(fmt)
 
+    def history_bytes(self, first_frame):
+        """Stream bytes that must precede the first TS byte of `first_frame` in every row handed to run_host():
+        187 in normal input mode once the stream has started (CRC-8 of the packet in flight), else 0."""
+        return 187 if (first_frame > 0 and self.cfg["inputmode"] == configs.INPUTMODE_NORMAL) else 0
+
     def run_host(self, ts, n_channels, n_frames, first_frame=0, out=None):
-        """ts: uint8 array [n_channels, >= n_frames*ts_bytes_per_frame] (host). Returns complex64 [n_channels, n_frames*samples]
+        """ts: uint8 array [n_channels, history_bytes(first_frame) + >= ts_bytes(first_frame, n_frames)] (host): each row
+        starts with the history bytes (the 187 stream bytes before the first frame; none for first_frame = 0 or in
+        high-efficiency mode), followed by the TS bytes of the frames.  Returns complex64 [n_channels, n_frames*samples]
         (int16 [n_channels, n_frames*samples, 2] with sink format 1)."""
         ts = np.ascontiguousarray(ts, dtype=np.uint8).reshape(n_channels, -1)
+        hist = self.history_bytes(first_frame)
+        if ts.shape[1] < hist + self.ts_bytes(first_frame, n_frames):
+            raise ValueError("run_host: each TS row needs %d history bytes + %d TS bytes, got %d" % (
+                hist, self.ts_bytes(first_frame, n_frames), ts.shape[1]))
         if out is None:
             if self.sink_format:
                 out = np.empty((n_channels, n_frames * self.samples_per_frame, 2), dtype=np.int16)
             else:
                 out = np.empty((n_channels, n_frames * self.samples_per_frame), dtype=np.complex64)
-        r = lib().dvbt2ll_chain_run_host(self._h, ts.ctypes.data, ts.shape[1], n_channels, n_frames, first_frame,
+        r = lib().dvbt2ll_chain_run_host(self._h, ts.ctypes.data + hist, ts.shape[1], n_channels, n_frames, first_frame,
                                          out.ctypes.data)
         if r < 0:
             raise RuntimeError("dvbt2ll_chain_run_host failed (%d): %s" % (r, last_error()))
@@ -286,3 +423,67 @@ class Chain(_Block):
         if r < 0:
             raise RuntimeError(last_error())
         return dict(zip(("bb_bch", "ldpc", "map", "ofdm", "total"), [float(x) for x in ms]))
+
+
+def set_overfull_policy(warn):
+    """False (default): creating a frame mapper / chain whose T2 frame is over-full fails; True: warn and truncate
+    like the reference (lib/framemapperfint_cc_impl.cc:1138-1141)."""
+    lib().dvbt2ll_set_overfull_policy(1 if warn else 0)
+
+
+class Gather(object):
+    """Ordered multi-GPU reassembly on the root GPU (dvbt2ll_gather_*): see include/dvbt2ll_cuda.h.
+    `exchange(blob_bytes) -> list of every rank's blob in rank order` is the only host-side collective (done once);
+    bench.py passes a torch.distributed all_gather."""
+
+    def __init__(self, rank, world, root, device, slot_bytes, local_bytes, n_slots=2):
+        self.rank, self.world, self.root = rank, world, root
+        h = lib().dvbt2ll_gather_create(rank, world, root, device, slot_bytes, local_bytes, n_slots)
+        if not h:
+            raise RuntimeError("dvbt2ll_gather_create: %s" % lib().dvbt2ll_gather_last_error().decode())
+        self._h = C.c_void_p(h)
+
+    def _ck(self, r, what):
+        if r < 0:
+            raise RuntimeError("%s failed (%d): %s" % (what, r, lib().dvbt2ll_gather_last_error().decode()))
+        return r
+
+    def export(self):
+        buf = (C.c_ubyte * GATHER_BLOB_BYTES)()
+        self._ck(lib().dvbt2ll_gather_export(self._h, buf, GATHER_BLOB_BYTES), "gather_export")
+        return bytes(buf)
+
+    def connect(self, blobs):
+        raw = b"".join(blobs)
+        self._ck(lib().dvbt2ll_gather_connect(self._h, raw, len(raw)), "gather_connect")
+
+    def acquire(self, step, offset, producer_stream):
+        p = C.c_void_p(0)
+        self._ck(lib().dvbt2ll_gather_acquire(self._h, step, offset, producer_stream, C.byref(p)), "gather_acquire")
+        return p.value
+
+    def push(self, step, offset, nbytes, producer_stream):
+        self._ck(lib().dvbt2ll_gather_push(self._h, step, offset, nbytes, producer_stream), "gather_push")
+
+    def wait(self, step, consumer_stream):
+        p = C.c_void_p(0)
+        self._ck(lib().dvbt2ll_gather_wait(self._h, step, consumer_stream, C.byref(p)), "gather_wait")
+        return p.value
+
+    def release(self, step, consumer_stream):
+        self._ck(lib().dvbt2ll_gather_release(self._h, step, consumer_stream), "gather_release")
+
+    @property
+    def side_stream(self):
+        return lib().dvbt2ll_gather_side_stream(self._h)
+
+    def close(self):
+        h, self._h = self._h, None
+        if h:
+            lib().dvbt2ll_gather_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

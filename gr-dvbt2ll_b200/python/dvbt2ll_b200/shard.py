@@ -23,11 +23,28 @@ def frames_for_rank(n_frames, world, rank):
     return start, base + (1 if rank < extra else 0)
 
 
-def ts_slice_for_frames(ts_bytes_per_frame, first_frame, count):
-    """Byte range of a channel's TS needed for frames [first_frame, first_frame + count): the payload bytes
-    plus up to 187 bytes of history for the CRC-8 that replaces the first sync byte."""
-    lo = first_frame * ts_bytes_per_frame
-    return max(0, lo - 187), lo + count * ts_bytes_per_frame
+def ts_slice_for_frames(chain, first_frame, count):
+    """Byte range [lo, hi) of a channel's TS that chain.run_host(row, 1, count, first_frame) must be handed for frames
+    [first_frame, first_frame + count): the history bytes (187 in normal input mode once the stream has started: the
+    CRC-8 that replaces the first sync byte covers the packet in flight) followed by the frames' TS bytes.  The bytes
+    per frame come from the chain (chain.ts_bytes): in high-efficiency mode they depend on the stream position.
+    `chain` may also be the constant bytes per T2 frame of a normal-mode stream (int)."""
+    if isinstance(chain, (int, np.integer)):
+        n = int(chain)
+        lo = first_frame * n
+        return max(0, lo - 187), lo + count * n
+    lo = chain.ts_bytes(0, first_frame) if first_frame > 0 else 0
+    return lo - chain.history_bytes(first_frame), lo + chain.ts_bytes(first_frame, count)
+
+
+def slot_layout(parts_per_rank, bytes_per_part):
+    """Ordered reassembly layout of one step: rank r's parts follow rank r-1's.  Returns (offsets, sizes, slot_bytes)."""
+    offs, sizes, o = [], [], 0
+    for n in parts_per_rank:
+        offs.append(o)
+        sizes.append(n * bytes_per_part)
+        o += n * bytes_per_part
+    return offs, sizes, o
 
 
 def gather_frames(local, dst=0, group=None):

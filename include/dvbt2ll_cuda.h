@@ -128,12 +128,72 @@ DVBT2LL_API_EXPORT int dvbt2ll_chain_run_host(dvbt2ll_handle *h, const void *ts,
  * With format 1 the output buffers of dvbt2ll_chain_run_* hold 4 bytes per sample. */
 DVBT2LL_API_EXPORT int dvbt2ll_chain_set_sink(dvbt2ll_handle *h, int format, float gain);
 /* Stage taps of the most recent chain run, for parity tests: "bch" (packed bits), "fec" (packed, parity
- * in interleaved-row order), "cells" (complex64).  Copies to HOST; returns bytes or negative error. */
+ * in interleaved-row order), "cells" (uint16 cell codes in cell-interleaved order: own constellation word |
+ * word supplying the imaginary part << 8, frame stride padded to a multiple of 4 cells).  Copies to HOST; returns
+ * bytes or negative error. */
 DVBT2LL_API_EXPORT long long dvbt2ll_chain_tap(dvbt2ll_handle *h, const char *stage, void *out, long long cap);
 /* Device time in ms of each stage kernel (bb_bch, ldpc, map, ofdm, total), averaged over the chain runs issued since
  * timing was enabled (at most the last 64); events are recorded per run, so the caller's timed loop needs no sync. */
 DVBT2LL_API_EXPORT int dvbt2ll_chain_stage_ms(dvbt2ll_handle *h, float *ms5);
 DVBT2LL_API_EXPORT void dvbt2ll_chain_enable_timing(dvbt2ll_handle *h, int on);
+
+/* ---- small device utilities for hosts without a CUDA runtime binding of their own (tests, language bindings):
+ * synchronous copies, allocation and device selection for the raw device pointers the *_device entry points take. */
+DVBT2LL_API_EXPORT int dvbt2ll_copy_to_host(void *dst, const void *d_src, size_t bytes);
+DVBT2LL_API_EXPORT int dvbt2ll_copy_to_device(void *d_dst, const void *src, size_t bytes);
+DVBT2LL_API_EXPORT void *dvbt2ll_device_alloc(size_t bytes);
+DVBT2LL_API_EXPORT void dvbt2ll_device_free(void *p);
+DVBT2LL_API_EXPORT int dvbt2ll_device_count(void);
+DVBT2LL_API_EXPORT int dvbt2ll_set_device(int device);
+DVBT2LL_API_EXPORT int dvbt2ll_device_synchronize(void);
+/* a non-blocking stream on the current device, usable wherever an entry point takes a `stream` */
+DVBT2LL_API_EXPORT void *dvbt2ll_stream_create(void);
+DVBT2LL_API_EXPORT void dvbt2ll_stream_destroy(void *stream);
+DVBT2LL_API_EXPORT int dvbt2ll_stream_synchronize(void *stream);
+
+/* ---- behaviour switches --------------------------------------------------------------------------- */
+/* Over-full T2 frame (more FEC blocks than the frame has cells for).  The reference logs "Frame Mapper, too many FEC
+ * blocks in T2 frame." and keeps running, dropping the cells that do not fit (lib/framemapperfint_cc_impl.cc:1138-1141).
+ * policy 0 (default): *_create() fails with that message; policy 1: reproduce the reference -- the handle is created,
+ * dvbt2ll_warnings() reports 1 and the frames carry what the reference's frames carry.  Also settable through the
+ * environment (DVBT2LL_OVERFULL=warn).  Process-wide; affects handles created afterwards. */
+DVBT2LL_API_EXPORT void dvbt2ll_set_overfull_policy(int policy);
+/* dvbt2ll_work() on HOST buffers: when on, the buffers are registered with cudaHostRegister the first time they are
+ * seen, so both copies run as DMA at PCIe rate (GNU Radio hands over pageable memory).  Only for callers whose buffers
+ * outlive the handle (the scheduler's do); default off, or DVBT2LL_HOST_REGISTER=1 in the environment. */
+DVBT2LL_API_EXPORT void dvbt2ll_set_host_register(dvbt2ll_handle *h, int on);
+/* Device-resident hand-off between adjacent drop-in blocks of one process: after dvbt2ll_work() the producer keeps
+ * its output in HBM; a consumer linked to it takes its input from there when the host pointer/length it is handed
+ * matches what the producer last wrote (the scheduler passes the very buffer on), skipping the D2H/H2D pair. */
+DVBT2LL_API_EXPORT int dvbt2ll_link(dvbt2ll_handle *producer, dvbt2ll_handle *consumer);
+/* Number of work() calls of `consumer` that found their input resident in HBM (tests, tuning). */
+DVBT2LL_API_EXPORT long long dvbt2ll_link_hits(const dvbt2ll_handle *consumer);
+
+/* ---- ordered multi-GPU reassembly on one GPU ------------------------------------------------------
+ * T2 frames shard across GPUs with no data-path collective; the one exchange is putting the ranks' finished frames
+ * back into ONE ordered stream on the root GPU -- the single sink of the reference flowgraph
+ * (apps/vv009-4kshort.grc:1696-1697).  A "step" is one batch of every rank; its ordered output is one slot of
+ * slot_bytes in a ring of n_slots on the root.  The root's chain writes into the slot in place; the other ranks
+ * produce into a local buffer and push it with one peer copy over NVLink (copy engine, side stream), overlapping
+ * their next step.  Arrival and slot release are device-side counters waited on with stream memory operations:
+ * no host synchronisation anywhere.  Ranks are processes (CUDA IPC) or several handles of one process.
+ *   every rank:  g = create(); export(blob); <all ranks' blobs, rank order> -> connect();
+ *   every step:  acquire(step, offset, producer, &p); dvbt2ll_chain_run_device(..., p, producer); push(step, offset, bytes, producer);
+ *   root only:   wait(step, consumer, &slot); <consume slot on consumer>; release(step, consumer). */
+#define DVBT2LL_GATHER_BLOB_BYTES 256
+typedef struct dvbt2ll_gather dvbt2ll_gather;
+DVBT2LL_API_EXPORT const char *dvbt2ll_gather_last_error(void);
+/* local_bytes: largest part this rank pushes per step (ignored on the root). 1 <= n_slots <= 8, world <= 64. */
+DVBT2LL_API_EXPORT dvbt2ll_gather *dvbt2ll_gather_create(int rank, int world, int root, int device, size_t slot_bytes,
+                                                         size_t local_bytes, int n_slots);
+DVBT2LL_API_EXPORT int dvbt2ll_gather_export(dvbt2ll_gather *g, void *blob, size_t cap);
+DVBT2LL_API_EXPORT int dvbt2ll_gather_connect(dvbt2ll_gather *g, const void *blobs, size_t bytes);
+DVBT2LL_API_EXPORT int dvbt2ll_gather_acquire(dvbt2ll_gather *g, long long step, size_t offset, void *producer_stream, void **ptr);
+DVBT2LL_API_EXPORT int dvbt2ll_gather_push(dvbt2ll_gather *g, long long step, size_t offset, size_t bytes, void *producer_stream);
+DVBT2LL_API_EXPORT int dvbt2ll_gather_wait(dvbt2ll_gather *g, long long step, void *consumer_stream, void **slot);
+DVBT2LL_API_EXPORT int dvbt2ll_gather_release(dvbt2ll_gather *g, long long step, void *consumer_stream);
+DVBT2LL_API_EXPORT void *dvbt2ll_gather_side_stream(dvbt2ll_gather *g);
+DVBT2LL_API_EXPORT void dvbt2ll_gather_destroy(dvbt2ll_gather *g);
 
 #ifdef __cplusplus
 }

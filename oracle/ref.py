@@ -68,6 +68,8 @@ def lib():
         L.ref_byte_table.argtypes = [C.c_char_p, C.POINTER(C.c_int)]
         L.ref_set_quiet.argtypes = [C.c_int]
         L.ref_set_fft_fast.argtypes = [C.c_int]
+        L.ref_fft_seconds.restype = C.c_double
+        L.ref_fft_seconds.argtypes = [C.c_int]
         _lib = L
     return _lib
 

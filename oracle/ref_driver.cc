@@ -34,9 +34,11 @@ extern "C" {
 
 int oracle_shim_quiet = 0;
 int oracle_shim_fft_fast = 0;
+double oracle_shim_fft_seconds = 0.0;
 
 void ref_set_quiet(int q) { oracle_shim_quiet = q; }
 void ref_set_fft_fast(int f) { oracle_shim_fft_fast = f; }
+double ref_fft_seconds(int reset) { const double v = oracle_shim_fft_seconds; if (reset) oracle_shim_fft_seconds = 0.0; return v; }
 
 enum { REF_BBHEADERBCH = 1, REF_INTERLEAVERMOD = 2, REF_FRAMEMAPPER = 3, REF_PILOTGEN = 4 };
 

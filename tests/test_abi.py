@@ -74,3 +74,38 @@ def test_no_cpu_fallback():
     ch = T.Chain(cfg, max_frames=1)
     with pytest.raises(RuntimeError):
         ch.run_host(K.make_ts(ch.ts_bytes_per_frame), 1, 1)
+
+
+def test_overfull_policy_is_opt_in():
+    """Reference lib/framemapperfint_cc_impl.cc:1138-1141 warns and keeps going; here that is an explicit opt-in."""
+    from common import fm_args
+    cfg = K.resolve(dict(K.CONFIGS["c1"], fecblocks=9))
+    T.set_overfull_policy(False)
+    with pytest.raises(ValueError):
+        T.framemapperfint_cc(*fm_args(cfg))
+    T.set_overfull_policy(True)
+    try:
+        fm = T.framemapperfint_cc(*fm_args(cfg))
+        assert fm.warnings == 1
+        ok = T.framemapperfint_cc(*fm_args(K.resolve("c1")))
+        assert ok.warnings == 0
+        assert fm.output_multiple == ok.output_multiple          # the physical frame does not grow
+        code = fm.plan("frame.code", np.int32)
+        info = fm.plan("frame.info", np.int32)
+        assert code.size == fm.output_multiple and info[6] == 0   # no dummy cells
+        # every input cell index that survives the truncation is unique, and some cells are dropped
+        data = code[code >= 0]
+        assert np.unique(data).size == data.size and data.size < fm.forecast(fm.output_multiple)
+    finally:
+        T.set_overfull_policy(False)
+
+
+def test_link_rejects_ts_consumers_and_mismatched_items():
+    cfg = K.resolve("c1")
+    B = T.blocks_for(cfg)
+    B["bb"].link_to(B["ldpc"])
+    B["im"].link_to(B["fm"])
+    with pytest.raises(ValueError):
+        B["ldpc"].link_to(B["fm"])           # bytes -> complex cells
+    with pytest.raises(ValueError):
+        B["ldpc"].link_to(B["bb"])           # the TS consumer keeps stream history in front of its input

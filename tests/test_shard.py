@@ -22,6 +22,29 @@ def test_partitions_cover_everything_in_order():
     lo, hi = shard.ts_slice_for_frames(12352, 2, 3)
     assert (lo, hi) == (2 * 12352 - 187, 5 * 12352)
     assert shard.ts_slice_for_frames(12352, 0, 1) == (0, 12352)
+    assert shard.slot_layout([3, 2, 2], 10) == ([0, 30, 50], [30, 20, 20], 70)
+
+
+def test_ts_slices_follow_the_chain_in_both_input_modes():
+    """The TS range of a run of T2 frames comes from the chain: constant per frame in normal mode (+187 history bytes
+    once the stream has started), position dependent and history-free in high-efficiency mode."""
+    import dvbt2ll_b200 as T
+    from dvbt2ll_b200 import configs as K
+    ch = T.Chain(K.resolve("c1"), max_frames=1)
+    n = ch.ts_bytes_per_frame
+    assert shard.ts_slice_for_frames(ch, 0, 2) == (0, 2 * n)
+    assert shard.ts_slice_for_frames(ch, 3, 2) == (3 * n - 187, 5 * n)
+    hem = T.Chain(K.resolve(dict(K.CONFIGS["c1"], inputmode=1, inband=1, version=2, fecblocks=7)), max_frames=1)
+    sizes = [hem.ts_bytes(f, 1) for f in range(6)]
+    assert len(set(sizes)) > 1
+    pos = 0
+    for f in range(6):
+        assert shard.ts_slice_for_frames(hem, f, 1) == (pos, pos + sizes[f])
+        pos += sizes[f]
+    # consecutive rank slices tile the stream
+    runs = [shard.frames_for_rank(6, 4, r) for r in range(4)]
+    edges = [shard.ts_slice_for_frames(hem, a, c) for a, c in runs]
+    assert edges[0][0] == 0 and all(edges[i][1] == edges[i + 1][0] for i in range(3)) and edges[-1][1] == pos
 
 
 def _worker(rank, world, port, n_channels, q):
