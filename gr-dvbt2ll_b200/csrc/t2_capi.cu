@@ -27,8 +27,10 @@ int fail(int code, const std::string &msg) { g_err = msg; return code; }
 #define CK(call)                                                                                  \
   do {                                                                                            \
     cudaError_t e_ = (call);                                                                      \
-    if (e_ != cudaSuccess)                                                                        \
+    if (e_ != cudaSuccess) {                                                                      \
+      cudaGetLastError(); /* not sticky: the next call must not inherit it */                     \
       return fail(DVBT2LL_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));          \
+    }                                                                                             \
   } while (0)
 
 struct DevBuf {
@@ -78,6 +80,70 @@ struct LinkRec {
   LinkRec() : host(0), bytes(0), dev(0), hits(0), misses(0) {}
 };
 
+// Process-wide registry of host page ranges registered by this library (cudaHostRegister), shared by all handles.
+struct PinRegistry {
+  struct Iv { uintptr_t a0, a1; std::vector<const void *> users; };
+  std::mutex m;
+  std::vector<Iv> ivs;            // disjoint page ranges registered by us
+  static PinRegistry &get() { static PinRegistry r; return r; }
+  static void add_user(Iv &iv, const void *u)
+  {
+    for (size_t i = 0; i < iv.users.size(); i++) if (iv.users[i] == u) return;
+    iv.users.push_back(u);
+  }
+  void acquire(const void *user, uintptr_t p0, uintptr_t p1)
+  {
+    std::lock_guard<std::mutex> g(m);
+    // gaps of [p0, p1) not covered by our ranges
+    std::vector<Iv> sorted(ivs);
+    std::sort(sorted.begin(), sorted.end(), [](const Iv &x, const Iv &y) { return x.a0 < y.a0; });
+    std::vector<std::pair<uintptr_t, uintptr_t> > gaps;
+    uintptr_t cur = p0;
+    for (size_t i = 0; i < sorted.size() && cur < p1; i++) {
+      if (sorted[i].a1 <= cur) continue;
+      if (sorted[i].a0 >= p1) break;
+      if (sorted[i].a0 > cur) gaps.push_back(std::make_pair(cur, sorted[i].a0));
+      cur = sorted[i].a1;
+    }
+    if (cur < p1) gaps.push_back(std::make_pair(cur, p1));
+    size_t done = 0;
+    for (; done < gaps.size(); done++) {
+      cudaPointerAttributes at;
+      const bool foreign = cudaPointerGetAttributes(&at, (const void *)gaps[done].first) == cudaSuccess && at.type != cudaMemoryTypeUnregistered;
+      cudaGetLastError();
+      if (foreign || cudaHostRegister((void *)gaps[done].first, gaps[done].second - gaps[done].first, cudaHostRegisterPortable) != cudaSuccess) {
+        cudaGetLastError();
+        break;
+      }
+    }
+    if (done < gaps.size()) {      // could not cover everything: undo this call's pieces, the range stays as it was
+      for (size_t i = 0; i < done; i++) cudaHostUnregister((void *)gaps[i].first);
+      cudaGetLastError();
+      return;
+    }
+    for (size_t i = 0; i < gaps.size(); i++) {
+      Iv iv; iv.a0 = gaps[i].first; iv.a1 = gaps[i].second;
+      ivs.push_back(iv);
+    }
+    for (size_t i = 0; i < ivs.size(); i++)
+      if (ivs[i].a0 < p1 && p0 < ivs[i].a1) add_user(ivs[i], user);
+  }
+  void release_all(const void *user)
+  {
+    std::lock_guard<std::mutex> g(m);
+    for (size_t i = 0; i < ivs.size();) {
+      std::vector<const void *> &u = ivs[i].users;
+      u.erase(std::remove(u.begin(), u.end(), user), u.end());
+      if (u.empty()) {
+        cudaHostUnregister((void *)ivs[i].a0);
+        cudaGetLastError();
+        ivs.erase(ivs.begin() + i);
+      }
+      else i++;
+    }
+  }
+};
+
 // ------------------------------------------------------------------------------------------------
 struct dvbt2ll_handle {
   enum Kind { BB, LDPC, MAP, FRAME, OFDM, CHAIN } kind;
@@ -86,8 +152,8 @@ struct dvbt2ll_handle {
   int warnings;
   DevBuf stage_in, stage_out;   // device staging for host-buffer work()
   // host buffers registered with cudaHostRegister on first sight (the scheduler's buffers are long-lived and reused)
-  struct Pinned { const void *p; size_t n; };
-  std::vector<Pinned> pinned;
+  struct Pinned { uintptr_t a0, a1; };
+  std::vector<Pinned> pinned;   // page ranges this handle has already asked the registry for (lock-free fast path)
   bool pin_enabled;
   std::shared_ptr<LinkRec> link_in, link_out;     // set by dvbt2ll_link
   explicit dvbt2ll_handle(Kind k) : kind(k), stream(0), dev_ready(false), warnings(0), pin_enabled(false)
@@ -100,31 +166,23 @@ struct dvbt2ll_handle {
   virtual ~dvbt2ll_handle()
   {
     if (link_out) { std::lock_guard<std::mutex> g(link_out->m); link_out->dev = 0; link_out->bytes = 0; }
-    for (size_t i = 0; i < pinned.size(); i++) cudaHostUnregister(const_cast<void *>(pinned[i].p));
-    cudaGetLastError();
+    if (!pinned.empty()) PinRegistry::get().release_all(this);
     if (stream) cudaStreamDestroy(stream);
   }
-  // Register [p, p + n) (page-granular) unless a registered range already covers it.  Failure is not an error:
-  // the copy then runs from pageable memory.  GNU Radio's circular buffers are mapped twice back to back; a call's
-  // span is one contiguous virtual range either way.
+  // Make [p, p + n) page-locked (page granular).  Adjacent blocks share buffers (one's output is the next one's input)
+  // and heap buffers share pages, so registrations are kept in one process-wide registry that only ever registers
+  // the pages nobody registered yet: a copy never sees a partly registered range (CUDA rejects those).  Failure is
+  // not an error: the copy then runs from pageable memory.
   void pin(const void *p, size_t n)
   {
     if (!pin_enabled || !p || n < (1u << 16)) return;
     const uintptr_t a0 = (uintptr_t)p & ~(uintptr_t)4095, a1 = ((uintptr_t)p + n + 4095) & ~(uintptr_t)4095;
-    for (size_t i = 0; i < pinned.size(); i++) {
-      const uintptr_t q0 = (uintptr_t)pinned[i].p, q1 = q0 + pinned[i].n;
-      if (a0 >= q0 && a1 <= q1) return;
-      if (a0 < q1 && q0 < a1) return;      // overlaps a registered range: leave it (partly pageable copy)
-    }
-    if (pinned.size() >= 16) return;
-    cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type != cudaMemoryTypeUnregistered) return;   // already pinned
-    cudaGetLastError();
-    if (cudaHostRegister((void *)a0, a1 - a0, cudaHostRegisterPortable) == cudaSuccess) {
-      Pinned e = { (const void *)a0, (size_t)(a1 - a0) };
-      pinned.push_back(e);
-    }
-    else cudaGetLastError();
+    for (size_t i = 0; i < pinned.size(); i++)
+      if (a0 >= pinned[i].a0 && a1 <= pinned[i].a1) return;
+    if (pinned.size() >= 64) return;
+    PinRegistry::get().acquire(this, a0, a1);
+    Pinned e = { a0, a1 };
+    pinned.push_back(e);
   }
   virtual int output_multiple() const = 0;
   virtual int forecast(int noutput) const = 0;
@@ -366,6 +424,7 @@ struct MapHandle : dvbt2ll_handle {
     a.bit_src = d_bitsrc.as<uint16_t>(); a.lut = d_lut.as<float2>();
     a.ci_inv = 0; a.fec_shift = 0; a.fecblocks = 1; a.out16 = 0; a.out16_frame_stride = 0;
     a.ncol = plan.ncol;
+    a.im_from_re = plan.im_from_re; a.im_mask_i = plan.im_mask_i; a.im_mask_q = plan.im_mask_q; a.im_flip = plan.im_flip;
     std::memcpy(a.col_of_bit, plan.col_of_bit, 16);
     std::memcpy(a.twist_of_col, plan.twist_of_col, 16);
   }
@@ -390,6 +449,7 @@ struct MapHandle : dvbt2ll_handle {
     std::string n(name);
     if (n == "map.bit_src") return copy_vec(plan.bit_src, out, cap);
     if (n == "map.lut") return copy_vec(plan.lut, out, cap);
+    if (n == "map.im_from_re") { const int v[4] = { plan.im_from_re, (int)plan.im_mask_i, (int)plan.im_mask_q, (int)plan.im_flip }; return copy_out(v, sizeof(v), out, cap); }
     return -1;
   }
 };
@@ -456,8 +516,8 @@ struct OfdmDevice {
   long long pool_stride;
   long long scratch_slot_elems;     // float2 elements per scratch slot (one slot per concurrently running batch)
   // c16: `code` holds staging slots (chain mode, 16-bit cells) and is re-encoded for the kernel's branch-free fill:
-  //   data carrier         -> 2 * slot            (byte offset into the staging area, < 65536)
-  //   small pool cell p<8  -> (p + 1) << 16       (zero / pilot amplitudes, kept in shared memory)
+  //   data carrier         -> 2 * slot            (byte offset into the staging area, < 131072)
+  //   small pool cell p<8  -> (p + 1) << 17       (zero / pilot amplitudes, kept in shared memory)
   //   other pool cell      -> 0x80000000 | index  (L1 signalling, dummy cells; symbols holding any are flagged)
   int init(const std::vector<int32_t> &code, const t2::CellPool &pool, const t2::OfdmPlan &op, bool c16 = false)
   {
@@ -497,10 +557,10 @@ struct OfdmDevice {
           int32_t v = (k >= 0 && k < cps) ? code[(size_t)l * cps + k] : -1;
           if (c16) {
             if (v >= 0) {
-              if (v >= 32768) return fail(DVBT2LL_ERR_INVALID, "chain: staging slot out of range");
+              if (v >= 65536) return fail(DVBT2LL_ERR_INVALID, "chain: staging slot out of range");
               v = 2 * v;
             }
-            else if (~v < 8) v = (~v + 1) << 16;
+            else if (~v < 8) v = (~v + 1) << 17;
             else { v = (int32_t)(0x80000000u | (uint32_t)(~v)); sym_flags[l] = 1; }
           }
           code_pos[((size_t)l * split + p) * M + pos[m]] = v;
@@ -535,7 +595,7 @@ struct OfdmDevice {
     a.fft_n = op.dims.fft_n; a.log2_m = log2_m; a.split = split;
     a.c_ps = op.dims.c_ps; a.left_nulls = op.left_nulls; a.gi = op.dims.gi; a.num_symbols = op.dims.num_symbols;
     a.norm = op.normalization;
-    a.cells16 = 0; a.chunk_src = 0; a.chunk_ptr = 0; a.stage_cap = 0; a.lut = 0; a.lut_n = 0;
+    a.cells16 = 0; a.run_desc = 0; a.run_ptr = 0; a.stage_bytes = 0; a.stage_cap = 0; a.lut = 0; a.lut_n = 0; a.lut_single = 0;
     a.sym_flags = d_sym_flags.as<int32_t>();
     a.out_fmt = 0; a.sink_gain = 1.0f; a.scratch = d_scratch.as<float2>();
   }
@@ -595,7 +655,7 @@ struct ChainHandle : dvbt2ll_handle {
   t2::OfdmPlan oplan;
   t2::Chain16Tables tables;
   OfdmDevice odev;
-  DevBuf d_bch, d_fec, d_cells, d_ts_stage, d_out_stage, d_ci_inv, d_fec_shift, d_chunk_src, d_chunk_ptr;
+  DevBuf d_bch, d_fec, d_cells, d_ts_stage, d_out_stage, d_ci_inv, d_fec_shift, d_run_desc, d_run_ptr, d_stage_bytes;
   int stage_cap;
   int max_frames, device;
   int sink_fmt;          // 0 complex64 (what pilotgenp1insert_cc emits), 1 interleaved int16 I/Q
@@ -625,8 +685,8 @@ struct ChainHandle : dvbt2ll_handle {
     return ensure_device();
   }
   int F() const { return fplan.prm.fecblocks; }
-  // cells per T2 frame in the 16-bit cell memory, padded so every frame starts on an 8-byte boundary
-  long long cells16_stride() const { return ((long long)F() * map.plan.cell_size + 3) & ~3LL; }
+  // cells per T2 frame in the 16-bit cell memory, padded so every frame starts on a 16-byte boundary (bulk copies)
+  long long cells16_stride() const { return ((long long)F() * map.plan.cell_size + 7) & ~7LL; }
   // TS byte index (per channel, stream starts on a packet boundary) at which T2 frame `frame` begins
   long long stream_pos(long long frame) const
   {
@@ -654,9 +714,12 @@ struct ChainHandle : dvbt2ll_handle {
     if ((r = odev.init(tables.code, tables.pool, oplan, true))) return r;
     CK(upload(d_ci_inv, fplan.cell_perm_inv));
     CK(upload(d_fec_shift, fplan.fec_shift));
-    CK(upload(d_chunk_src, tables.chunk_src));
-    CK(upload(d_chunk_ptr, tables.chunk_ptr));
+    CK(upload(d_run_desc, tables.run_desc));
+    CK(upload(d_run_ptr, tables.run_ptr));
+    CK(upload(d_stage_bytes, tables.stage_bytes));
     stage_cap = (tables.max_slots + 7) & ~7;
+    if ((size_t)(1 << odev.log2_m) * 8 * 17 / 16 + (size_t)stage_cap * 2 + 2048 + 80 > 227 * 1024)
+      return fail(DVBT2LL_ERR_INVALID, "chain: the cells of one OFDM symbol do not fit the shared-memory staging area");
     const size_t nfec = (size_t)max_frames * F();
     CK(d_bch.ensure(nfec * align16(bb.plan.fec.nbch / 8) + 64));
     CK(d_fec.ensure(nfec * align16(bb.plan.fec.nldpc / 8) + 64));
@@ -702,7 +765,8 @@ struct ChainHandle : dvbt2ll_handle {
     t2k::OfdmArgs oa;
     odev.fill(oa, oplan, tables.pool);
     oa.cells = 0; oa.cells_stride = cells16_stride();
-    oa.cells16 = cell_buf; oa.chunk_src = d_chunk_src.as<int32_t>(); oa.chunk_ptr = d_chunk_ptr.as<int32_t>(); oa.stage_cap = stage_cap;
+    oa.cells16 = cell_buf; oa.run_desc = d_run_desc.as<int2>(); oa.run_ptr = d_run_ptr.as<int32_t>();
+    oa.stage_bytes = d_stage_bytes.as<int32_t>(); oa.stage_cap = stage_cap; oa.lut_single = map.plan.im_from_re;
     oa.lut = map.d_lut.as<float2>(); oa.lut_n = 1 << map.plan.mod;
     oa.out = d_out; oa.out_stride = oplan.samples_per_frame;
     oa.out_fmt = sink_fmt; oa.sink_gain = sink_gain; oa.norm = oplan.normalization * sink_gain;
@@ -735,8 +799,9 @@ struct ChainHandle : dvbt2ll_handle {
     std::string n(name);
     if (n == "chain.code") return copy_vec(tables.code, out, cap);
     if (n == "chain.pool") return copy_vec(tables.pool.cells, out, cap);
-    if (n == "chain.chunk_src") return copy_vec(tables.chunk_src, out, cap);
-    if (n == "chain.chunk_ptr") return copy_vec(tables.chunk_ptr, out, cap);
+    if (n == "chain.run_desc") return copy_vec(tables.run_desc, out, cap);
+    if (n == "chain.run_ptr") return copy_vec(tables.run_ptr, out, cap);
+    if (n == "chain.stage_bytes") return copy_vec(tables.stage_bytes, out, cap);
     if (n == "ofdm.sym_data_start") return copy_vec(oplan.sym_data_start, out, cap);
     if (n == "frame.framed") return copy_vec(fplan.framed, out, cap);
     if (n == "frame.fi_src") return copy_vec(fplan.fi_src, out, cap);

@@ -542,6 +542,11 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map(const MapArgs a)
   uint16_t *cw = reinterpret_cast<uint16_t *>(lut + (1 << a.mod));
   for (int i = threadIdx.x; i < (1 << a.mod); i += blockDim.x) lut[i] = a.lut[i];
   const int mod = a.mod, Nc = a.cell_size;
+  // single-table constellation (MapPlan::im_from_re): the byte that supplies the imaginary part is kept as w~
+  const bool tilde = a.im_from_re != 0;
+  const uint32_t tI = a.im_mask_i * 0x01010101u, tQ = a.im_mask_q * 0x01010101u, tF = a.im_flip * 0x01010101u;
+  auto tilde4 = [&](uint32_t w) -> uint32_t { return tilde ? ((((w << 1) & tI) | ((w >> 1) & tQ)) ^ tF) : w; };   // four packed cell words
+  auto tilde1 = [&](uint32_t w) -> uint32_t { return tilde4(w) & 0xFFu; };
   __shared__ int s_base[16], s_twist[16];      // per output bit: first codeword bit of its column, twist
   if (threadIdx.x < 16) {
     const int rho = threadIdx.x;
@@ -599,7 +604,8 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map(const MapArgs a)
         // the Q delay [c0 | prev << 8, c1 | c0 << 8], [c2 | c1 << 8, c3 | c2 << 8] (prev = c3 of the previous
         // four; the first cell of the thread is patched below), without it [c0 | c0 << 8, ...].
         const uint32_t mask = (1u << mod) - 1u;
-        const uint32_t sel0 = a.cyclic_delay ? 0x0170u : 0x1100u, sel1 = a.cyclic_delay ? 0x2312u : 0x3322u;
+        // X = the four words supplying the imaginary parts (as w~): the previous cell's under the Q delay, else the own
+        const int xs = a.cyclic_delay ? 8 : 0;
         uint32_t wprev = 0;
         if (a.ncol == 2 * mod) {
           uint32_t *dst = reinterpret_cast<uint32_t *>(cw + 2 * d0 + 2 * g);      // 64 cells + 1 pad word per thread
@@ -607,9 +613,10 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map(const MapArgs a)
           for (int i = 0; i < 32; i += 2) {
             const uint32_t p0 = A[i], p1 = A[i + 1];
             const uint32_t w = (p0 >> mod) | ((p0 & mask) << 8) | ((p1 >> mod) << 16) | ((p1 & mask) << 24);
-            dst[i] = __byte_perm(w, wprev, sel0);
-            dst[i + 1] = __byte_perm(w, wprev, sel1);
-            wprev = w;
+            const uint32_t wt = tilde4(w), X = __funnelshift_l(wprev, wt, xs);
+            dst[i] = __byte_perm(w, X, 0x5140u);
+            dst[i + 1] = __byte_perm(w, X, 0x7362u);
+            wprev = wt;
           }
         }
         else {
@@ -617,9 +624,10 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map(const MapArgs a)
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
             const uint32_t w = (A[i] & mask) | ((A[i + 1] & mask) << 8) | ((A[i + 2] & mask) << 16) | ((A[i + 3] & mask) << 24);
-            dst[i >> 1] = __byte_perm(w, wprev, sel0);
-            dst[(i >> 1) + 1] = __byte_perm(w, wprev, sel1);
-            wprev = w;
+            const uint32_t wt = tilde4(w), X = __funnelshift_l(wprev, wt, xs);
+            dst[i >> 1] = __byte_perm(w, X, 0x5140u);
+            dst[(i >> 1) + 1] = __byte_perm(w, X, 0x7362u);
+            wprev = wt;
           }
         }
       }
@@ -629,7 +637,7 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map(const MapArgs a)
         const int run = a.ncol == 2 * mod ? 64 : 32;
         for (int c = threadIdx.x * run; c < Nc; c += blockDim.x * run) {
           const int pc = c == 0 ? Nc - 1 : c - 1;
-          reinterpret_cast<uint8_t *>(cw)[2 * (c + 2 * (c >> 6)) + 1] = (uint8_t)cw[pc + 2 * (pc >> 6)];
+          reinterpret_cast<uint8_t *>(cw)[2 * (c + 2 * (c >> 6)) + 1] = (uint8_t)tilde1(cw[pc + 2 * (pc >> 6)]);
         }
       }
     }
@@ -644,7 +652,7 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map(const MapArgs a)
         for (int k = 0; k < 4; k++) {
           const uint32_t p0 = w[k] & 0xFFFFu, p1 = w[k] >> 16;
           const uint32_t v = (((ub[p0 >> 3] >> (7 - (p0 & 7))) & 1u) << 1) | ((ub[p1 >> 3] >> (7 - (p1 & 7))) & 1u);
-          code[k] = v | (v << 8);
+          code[k] = v | (tilde1(v) << 8);
         }
         uint32_t *dst = reinterpret_cast<uint32_t *>(cw + c + 2 * (c >> 6));
         dst[0] = code[0] | (code[1] << 16);
@@ -654,7 +662,7 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map(const MapArgs a)
         __syncthreads();
         for (int c = threadIdx.x; c < Nc; c += blockDim.x) {
           const int pc = c == 0 ? Nc - 1 : c - 1;
-          reinterpret_cast<uint8_t *>(cw)[2 * (c + 2 * (c >> 6)) + 1] = (uint8_t)cw[pc + 2 * (pc >> 6)];
+          reinterpret_cast<uint8_t *>(cw)[2 * (c + 2 * (c >> 6)) + 1] = (uint8_t)tilde1(cw[pc + 2 * (pc >> 6)]);
         }
       }
     }
@@ -666,14 +674,14 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map(const MapArgs a)
           const int p = __ldg(src + b);
           v = (v << 1) | ((reinterpret_cast<const uint8_t *>(u)[p >> 3] >> (7 - (p & 7))) & 1u);
         }
-        cw[c + 2 * (c >> 6)] = (uint16_t)(v | (v << 8));
+        cw[c + 2 * (c >> 6)] = (uint16_t)(v | (tilde1(v) << 8));
       }
       if (a.cyclic_delay) {
         __syncthreads();
         // only high bytes are written and only low bytes read: no ordering needed between the threads
         for (int c = threadIdx.x; c < Nc; c += blockDim.x) {
           const int pc = c == 0 ? Nc - 1 : c - 1;
-          reinterpret_cast<uint8_t *>(cw)[2 * (c + 2 * (c >> 6)) + 1] = (uint8_t)cw[pc + 2 * (pc >> 6)];
+          reinterpret_cast<uint8_t *>(cw)[2 * (c + 2 * (c >> 6)) + 1] = (uint8_t)tilde1(cw[pc + 2 * (pc >> 6)]);
         }
       }
     }
@@ -709,13 +717,13 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map(const MapArgs a)
         int y = xo - shift;
         if (y < 0) y += Nc;
         const unsigned cd = code(__ldg(a.ci_inv + y));
-        out[xo] = make_float2(lut[cd & 255u].x, lut[cd >> 8].y);
+        out[xo] = make_float2(lut[cd & 255u].x, tilde ? lut[cd >> 8].x : lut[cd >> 8].y);
       }
     }
     else {
       for (int c = threadIdx.x; c < Nc; c += blockDim.x) {
         const unsigned cd = code(c);
-        out[c] = make_float2(lut[cd & 255u].x, lut[cd >> 8].y);
+        out[c] = make_float2(lut[cd & 255u].x, tilde ? lut[cd >> 8].x : lut[cd >> 8].y);
       }
     }
   }
@@ -1045,10 +1053,10 @@ __device__ __forceinline__ void store_sample(short2 *p, int idx, float2 v)
 //      the odd-bin half of a 32K symbol, the in-place recombination with the even-bin half.
 //
 // C16 (chain mode): data cells arrive as 16-bit codes in cell-interleaved order.  Per symbol the CTA first
-// copies the symbol's cells into a shared-memory staging area in aligned 8-byte chunks (chunk_src names the
-// source chunk of every staging chunk; runs of consecutive source cells stay contiguous, so global memory is
-// read in contiguous pieces); the carrier fill then gathers from shared memory and decodes through the
-// constellation LUT (real part from the low byte's entry, imaginary from the high byte's).
+// copies the symbol's cells into a shared-memory staging area with bulk asynchronous copies (TMA), one per run of
+// consecutive source cells (run_desc; for a time-interleaved PLP a run is a time-interleaver column); the carrier
+// fill then gathers from shared memory and decodes through the constellation LUT (real part from the low byte's
+// entry, imaginary from the high byte's -- in the same real-part table when the codes carry w~, see k_map).
 
 // geometry of the carrier fill: a thread handles GPB first-pass butterflies (groups of R0 consecutive positions) per batch
 template <int LOG2M, int T>
@@ -1121,15 +1129,15 @@ __device__ __forceinline__ void ofdm_fill(float2 *x, const int32_t *__restrict__
         const int cc = c[b][r];
         if (C16) {
           // data cell: 16-bit code from the staging area through the LUT (a dummy read of offset 0 for the others);
-          // small pool cell (null, pilots): (p + 1) << 16 -> spool[p]; big pool cell: sign bit set (POOL symbols only)
-          const unsigned off = POOL && cc < 0 ? 0u : (unsigned)cc & 0xFFFFu;
+          // small pool cell (null, pilots): (p + 1) << 17 -> spool[p]; big pool cell: sign bit set (POOL symbols only)
+          const unsigned off = POOL && cc < 0 ? 0u : (unsigned)cc & 0x1FFFFu;
           const unsigned sc = *reinterpret_cast<const uint16_t *>(stage + off);
           // the LUTs are replicated 2^lut_rep_shift times (entry e, copy c at e * copies + c) and a lane reads copy
           // lane mod copies: with 16 copies only lanes l and l + 16 can collide (2 wavefronts instead of ~3.4)
           const unsigned esh = 2 + lut_rep_shift, emask = 255u << esh, lane_off = (threadIdx.x & ((1u << lut_rep_shift) - 1u)) << 2;
           float2 val = make_float2(*reinterpret_cast<const float *>(reinterpret_cast<const uint8_t *>(lut_re) + (((sc << esh) & emask) | lane_off)),
                                    *reinterpret_cast<const float *>(reinterpret_cast<const uint8_t *>(lut_im) + ((((sc >> 8) << esh) & emask) | lane_off)));
-          if (cc >= 0x10000) val = *reinterpret_cast<const float2 *>(spool_m8 + ((unsigned)cc >> 13));
+          if (cc >= 0x20000) val = *reinterpret_cast<const float2 *>(spool_m8 + ((unsigned)cc >> 14));
           if (POOL && cc < 0) val = __ldg(pool + (cc & 0x7FFFFFFF));
           v[b][r] = val;
         }
@@ -1166,12 +1174,23 @@ __global__ void __launch_bounds__(T, (LOG2M == 14 ? 1 : 1024 / T)) k_ofdm(const 
   uint8_t *stage = reinterpret_cast<uint8_t *>(x + padx(M));
   float *lut_re = reinterpret_cast<float *>(stage + 2 * a.stage_cap);
   const int lut_rep_shift = a.lut_rep_shift, lut_rep = 1 << lut_rep_shift;
-  float *lut_im = lut_re + 256 * lut_rep;
-  float2 *spool = reinterpret_cast<float2 *>(lut_im + 256 * lut_rep);      // first 8 pool cells: zero and the pilot values
-  int *idxbuf = reinterpret_cast<int *>(spool + 8);                         // [stage_cap / 4] source chunk of every staging chunk
+  // one table when the cell codes carry w~ (Im = Re lut[w~]), else a second one for the imaginary parts
+  float *lut_im = a.lut_single ? lut_re : lut_re + 256 * lut_rep;
+  float2 *spool = reinterpret_cast<float2 *>(lut_re + (a.lut_single ? 256 : 512) * lut_rep);      // first 8 pool cells: zero and the pilot values
+  uint64_t *mbar = reinterpret_cast<uint64_t *>(spool + 8);                 // completion barrier of the staging copies
+  const uint32_t mbar_s = (uint32_t)__cvta_generic_to_shared(mbar);
   if (C16) {
-    for (int i = threadIdx.x; i < a.lut_n * lut_rep; i += T) { const float2 v = __ldg(a.lut + (i >> lut_rep_shift)); lut_re[i] = v.x; lut_im[i] = v.y; }
+    for (int i = threadIdx.x; i < a.lut_n * lut_rep; i += T) {
+      const float2 v = __ldg(a.lut + (i >> lut_rep_shift));
+      lut_re[i] = v.x;
+      if (!a.lut_single) lut_im[i] = v.y;
+    }
     if (threadIdx.x < 8) spool[threadIdx.x] = __ldg(a.pool + threadIdx.x);
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(mbar_s) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
   }
   constexpr int R0 = 1 << (LOG2M & 3);       // first radix (1 = no first pass)
   constexpr int NLAST = M / 16;              // NPREV of the last radix-16 pass
@@ -1192,43 +1211,48 @@ __global__ void __launch_bounds__(T, (LOG2M == 14 ? 1 : 1024 / T)) k_ofdm(const 
     if (SPLIT == 2) tw_rec = __fmul2_rn(__ldg(a.tw_split + threadIdx.x), make_float2(a.norm, a.norm));   // W_N^{tid} * norm
   }
 
-  // C16: copy the cells of symbol `u` into the staging area in aligned 8-byte chunks (4 cells), asynchronously
-  // (cp.async; the caller waits before the fill).  Issued for symbol u + gridDim.x as soon as symbol u's last fill
-  // has finished reading the staging area, so the copy runs under the FFT passes.
-  // The source-chunk indices (chunk_src) come from L2 (~700 cycles) and every copy needs its own, so they are
-  // pipelined one symbol further ahead than the data: idx_prefetch copies the indices of a symbol into idxbuf
-  // asynchronously (4-byte cp.async, no registers), stage_copy later reads them from shared memory and starts the data
-  // copies.  Slot i of idxbuf / chunk i of the staging area always belong to thread i mod T.
-  const uint32_t idx_s = (uint32_t)__cvta_generic_to_shared(idxbuf);
-  // (first chunk, chunk count) of a symbol's staging list; requested a symbol ahead of their use (cp1, cp2 below)
-  auto chunk_range = [&](int u) {
+  // C16: the cells of symbol `u` go to the staging area by bulk asynchronous copies (TMA, cp.async.bulk): one copy
+  // per run of consecutive source cells -- the enclosing 16-byte aligned span of the frame's cell memory -- spread over
+  // the threads, all completing on one mbarrier whose transaction count is the symbol's byte total.  Issued for symbol
+  // u + gridDim.x as soon as symbol u's last fill has finished reading the staging area, so the copies run under the
+  // FFT passes without occupying the load/store pipe.
+  uint32_t mphase = 0;
+  // (first run, run count) of a symbol's copy list; requested a symbol ahead of its use (cp1 below)
+  auto run_range = [&](int u) {
     const int ul = u % a.num_symbols;
-    const int c0 = __ldg(a.chunk_ptr + ul);
-    return make_int2(c0, __ldg(a.chunk_ptr + ul + 1) - c0);
+    const int r0 = __ldg(a.run_ptr + ul);
+    return make_int2(r0, __ldg(a.run_ptr + ul + 1) - r0);
   };
-  auto idx_prefetch = [&](int2 cr) {
-    const int n_chunks = cr.y;
-    const int32_t *csrc = a.chunk_src + cr.x;
-#pragma unroll 4
-    for (int i = threadIdx.x; i < n_chunks; i += T)
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(idx_s + 4u * (uint32_t)i), "l"(csrc + i) : "memory");
-  };
-  auto stage_copy = [&](int u, int2 cr, bool from_idxbuf) {
-    const int uf = u / a.num_symbols;
+  auto stage_issue = [&](int u, int2 rr) {
+    if (rr.y <= 0) return;
+    const int uf = u / a.num_symbols, ul = u - uf * a.num_symbols;
     const uint8_t *src = reinterpret_cast<const uint8_t *>(a.cells16 + (long long)uf * a.cells_stride);
-    const int c0 = cr.x, n_chunks = cr.y;
-#pragma unroll 4
-    for (int i = threadIdx.x; i < n_chunks; i += T) {
-      const int sidx = from_idxbuf ? idxbuf[i] : __ldg(a.chunk_src + c0 + i);
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(stage_s + 8u * (uint32_t)i), "l"(src + 8ll * sidx) : "memory");
+    // the fill's reads of the staging area (generic proxy) are ordered before these writes (async proxy)
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    if (threadIdx.x == 0)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(mbar_s), "r"(__ldg(a.stage_bytes + ul)) : "memory");
+    const int2 *rd = a.run_desc + rr.x;
+#pragma unroll 2
+    for (int i = threadIdx.x; i < rr.y; i += T) {
+      const int2 d = __ldg(rd + i);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                   ::"r"(stage_s + 16u * ((uint32_t)d.y >> 16)), "l"(src + 16ll * d.x), "r"(16u * ((uint32_t)d.y & 0xFFFFu)), "r"(mbar_s) : "memory");
     }
   };
+  auto stage_wait = [&]() {
+    uint32_t done;
+    do {
+      asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                   : "=r"(done) : "r"(mbar_s), "r"(mphase) : "memory");
+    } while (!done);
+    mphase ^= 1u;
+  };
 
-  int2 cp1 = make_int2(0, 0), cp2 = cp1;      // staging lists of the next symbol of this CTA and of the one after it
-  if (C16 && (int)(blockIdx.x + gridDim.x) < units) cp1 = chunk_range(blockIdx.x + gridDim.x);
+  int2 cp0 = make_int2(0, 0), cp1 = cp0;      // copy lists of this CTA's current and next symbol
+  if (C16 && (int)blockIdx.x < units) cp0 = run_range(blockIdx.x);
   for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
     const int f = unit / a.num_symbols, l = unit - f * a.num_symbols;
-    if (C16 && unit + 2 * (int)gridDim.x < units) cp2 = chunk_range(unit + 2 * gridDim.x);
+    if (C16 && unit + (int)gridDim.x < units) cp1 = run_range(unit + gridDim.x);
     const int variant = (a.frame_idx0 + (f % a.frames_per_channel)) % a.l1post_variants;
     const float2 *cells = a.cells + (long long)f * a.cells_stride;
     const float2 *pool = a.pool + (long long)variant * a.pool_stride;
@@ -1252,11 +1276,8 @@ __global__ void __launch_bounds__(T, (LOG2M == 14 ? 1 : 1024 / T)) k_ofdm(const 
     int c[FillGeom<LOG2M, T>::GPB][FillGeom<LOG2M, T>::R0];
     fill_load_codes<LOG2M, T>(a.code_pos + (long long)l * SPLIT * M, threadIdx.x, c);
     if (C16) {
-      if (unit == (int)blockIdx.x) {      // first symbol of this CTA: indices straight from global memory
-        stage_copy(unit, chunk_range(unit), false);
-        if (unit + (int)gridDim.x < units) idx_prefetch(cp1);
-      }
-      asm volatile("cp.async.wait_all;\n" ::: "memory");
+      if (unit == (int)blockIdx.x) stage_issue(unit, cp0);      // first symbol of this CTA
+      if (cp0.y > 0) stage_wait();
     }
 
     for (int phase = 0; phase < SPLIT; phase++) {
@@ -1275,12 +1296,10 @@ __global__ void __launch_bounds__(T, (LOG2M == 14 ? 1 : 1024 / T)) k_ofdm(const 
         else ofdm_fill<LOG2M, T, C16, false, false>(x, code, sinc, c, stage, lut_re, lut_im, lut_rep_shift, spool_m8, cells, pool);
       }
       __syncthreads();
-      // every fill of the symbol has read its cells: the next symbol's cells may replace them (under the passes), and
-      // the indices of the symbol after that may replace the ones just used
-      if (C16 && phase == SPLIT - 1 && unit + (int)gridDim.x < units) {
-        stage_copy(unit + gridDim.x, cp1, true);
-        if (unit + 2 * (int)gridDim.x < units) idx_prefetch(cp2);
-        cp1 = cp2;
+      // every fill of the symbol has read its cells: the next symbol's cells may replace them (under the passes)
+      if (C16 && phase == SPLIT - 1) {
+        if (unit + (int)gridDim.x < units) stage_issue(unit + gridDim.x, cp1);
+        cp0 = cp1;
       }
       // ---- 2. middle radix-16 passes
       if (REGTW) {
@@ -1416,7 +1435,8 @@ template <int LOG2M, int T, bool C16, int FMT, int SPLIT>
 static void launch_ofdm_t(const OfdmArgs &a, cudaStream_t s)
 {
   constexpr int M = 1 << LOG2M;
-  const size_t smem = (size_t)padx(M) * sizeof(float2) + (C16 ? (size_t)a.stage_cap * 3 + ((size_t)2048 << a.lut_rep_shift) + 64 : 0);
+  const size_t smem = (size_t)padx(M) * sizeof(float2) +
+                      (C16 ? (size_t)a.stage_cap * 2 + ((size_t)(a.lut_single ? 1024 : 2048) << a.lut_rep_shift) + 64 + 16 : 0);
   const int units = a.frames * a.num_symbols;
   static bool attr[MAX_DEVICES];
   allow_smem(k_ofdm<LOG2M, T, C16, FMT, SPLIT>, 227 * 1024, attr);
@@ -1450,16 +1470,17 @@ void launch_ofdm(const OfdmArgs &a0, cudaStream_t s)
 {
   if (a0.frames * a0.num_symbols < 1) return;
   OfdmArgs a = a0;
-  // up to 16 copies of the constellation LUTs, as many as shared memory allows (chain mode)
+  // up to 32 copies of the constellation table(s) (conflict-free: copy = lane), as many as shared memory allows (chain mode)
   // (without lowering the number of CTAs per SM that fit without replication; 2 resident CTAs at most are useful below 16K)
   a.lut_rep_shift = 0;
   if (a.cells16) {
-    const size_t base = (size_t)padx(1 << a.log2_m) * sizeof(float2) + (size_t)a.stage_cap * 3 + 64, sm_bytes = 227 * 1024;
-    size_t ctas = sm_bytes / (base + 2048 + 1024);
+    const size_t base = (size_t)padx(1 << a.log2_m) * sizeof(float2) + (size_t)a.stage_cap * 2 + 64 + 16, sm_bytes = 227 * 1024;
+    const size_t one = a.lut_single ? 1024 : 2048;
+    size_t ctas = sm_bytes / (base + one + 1024);
     if (ctas < 1) ctas = 1;
     if (ctas > 2) ctas = 2;
-    for (int sh = 4; sh > 0; sh--)
-      if (base + ((size_t)2048 << sh) + 1024 <= sm_bytes / ctas) { a.lut_rep_shift = sh; break; }
+    for (int sh = 5; sh > 0; sh--)
+      if (base + (one << sh) + 1024 <= sm_bytes / ctas) { a.lut_rep_shift = sh; break; }
   }
   if (a.cells16) {
     if (a.out_fmt) launch_ofdm_c<true, 1>(a, s);

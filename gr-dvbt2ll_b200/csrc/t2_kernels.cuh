@@ -60,6 +60,10 @@ struct MapArgs {
   const uint16_t *ci_inv;    // inverse of the cell permutation, or NULL for natural order
   const int32_t *fec_shift;  // [fecblocks] cyclic shift per FEC block of the T2 frame
   int fecblocks;
+  // single-table constellation (MapPlan::im_from_re): the word supplying the imaginary part is stored as
+  // w~ = (((w << 1) & im_mask_i) | ((w >> 1) & im_mask_q)) ^ im_flip, and Im = Re lut[w~]
+  int im_from_re;
+  uint32_t im_mask_i, im_mask_q, im_flip;
 };
 void launch_map(const MapArgs &a, cudaStream_t s);
 
@@ -90,13 +94,17 @@ void launch_gather(const GatherArgs &a, cudaStream_t s);
 struct OfdmArgs {
   const float2 *cells; long long cells_stride;   // per T2 frame (stride in cells for both cell formats)
   // chain mode with 16-bit cells: cells16 != NULL selects it; then `code_pos` holds the encoding described at
-  // OfdmDevice::init (2 * staging slot | (small pool cell + 1) << 16 | 0x80000000 + pool cell)
-  const uint16_t *cells16;   // [frame][fecblocks * cell_size] cell-interleaved 16-bit codes
-  const int32_t *chunk_src;  // source chunk (8 bytes = 4 cells) of every staging chunk, symbols back to back
-  const int32_t *chunk_ptr;  // [num_symbols + 1]
+  // OfdmDevice::init (2 * staging slot | (small pool cell + 1) << 17 | 0x80000000 + pool cell)
+  const uint16_t *cells16;   // [frame][fecblocks * cell_size] cell-interleaved 16-bit codes; frames start 16-byte aligned
+  // bulk copies (cp.async.bulk) that stage a symbol's cells in shared memory: run i = { source 16-byte unit from the
+  // frame's first cell, (staging 16-byte unit << 16) | length in units }, symbols back to back
+  const int2 *run_desc;
+  const int32_t *run_ptr;    // [num_symbols + 1]
+  const int32_t *stage_bytes;// [num_symbols] bytes delivered by the symbol's copies
   const int32_t *sym_flags;  // [num_symbols] bit 0: the symbol has carriers coded 0x80000000 + pool cell
-  int stage_cap;             // staging slots reserved in shared memory (multiple of 8)
+  int stage_cap;             // staging slots (cells) reserved in shared memory (multiple of 8)
   const float2 *lut; int lut_n;   // constellation LUT
+  int lut_single;            // 1: imaginary parts come from the real-part table (the cell codes carry w~, see MapArgs)
   int lut_rep_shift;         // set by launch_ofdm: log2 of the number of LUT copies kept in shared memory
   void *out;           long long out_stride;     // samples per T2 frame (complex64, or short2 when out_fmt = 1)
   int out_fmt;               // 0 = complex64, 1 = interleaved 16-bit I/Q (x * 32767, saturated)

@@ -107,6 +107,9 @@ struct MapPlan {
   int ncol;
   uint8_t col_of_bit[16];             // twist-matrix column feeding output bit p of the demux word (p = 0 MSB)
   uint8_t twist_of_col[16];
+  // single-table form of the constellation: Im lut[w] == Re lut[w~], w~ = (((w << 1) & im_mask_i) | ((w >> 1) & im_mask_q)) ^ im_flip
+  int im_from_re;                     // 1 when that identity holds bit for bit for every word (checked at plan time)
+  uint32_t im_mask_i, im_mask_q, im_flip;
 };
 bool build_map_plan(int framesize, int rate, int constellation, int rotation, MapPlan *p, std::string *err);
 
@@ -200,15 +203,18 @@ bool compose_chain(const FramePlan &fp, const OfdmPlan &op, bool cells_cell_inte
 
 // Chain mode with 16-bit cells: the mapper kernel stores every data cell as (own cell word | previous cell
 // word << 8) in cell-interleaved order; the OFDM kernel first copies the cells of one symbol into a shared-
-// memory staging area in aligned 8-byte CHUNKS (4 cells): the symbol's source cells are sorted by address and
-// grouped into runs of consecutive cells (for a time-interleaved PLP: one run per TI column); staging chunk i of
-// symbol l is a copy of source chunk chunk_src[chunk_ptr[l] + i] of the frame's cell memory (up to 3 unused cells
-// at either end of a run).  The carriers are then filled from the staging area.
+// memory staging area with bulk asynchronous copies (TMA, cp.async.bulk): the symbol's source cells are sorted by
+// address and grouped into runs of consecutive cells (for a time-interleaved PLP: one run per TI column); each run
+// is copied as its enclosing 16-byte aligned span (up to 7 unused cells at either end).  The carriers are then
+// filled from the staging area.
 struct Chain16Tables {
   std::vector<int32_t> code;        // [num_symbols * c_ps]: >= 0 staging slot of the symbol, < 0 pool cell
-  std::vector<int32_t> chunk_src;   // all symbols, grouped: source chunk of each staging chunk
-  std::vector<int32_t> chunk_ptr;   // [num_symbols + 1]
-  int max_slots;                    // largest number of staging slots of any symbol
+  // bulk copies that stage a symbol's cells: 2 words per run = { source 16-byte unit (from the frame's first cell),
+  // (staging 16-byte unit << 16) | length in 16-byte units }, symbols back to back
+  std::vector<int32_t> run_desc;
+  std::vector<int32_t> run_ptr;     // [num_symbols + 1] in runs
+  std::vector<int32_t> stage_bytes; // [num_symbols] bytes the symbol's copies deliver (mbarrier transaction count)
+  int max_slots;                    // largest number of staging slots (cells) of any symbol
   CellPool pool;
 };
 bool compose_chain16(const FramePlan &fp, const OfdmPlan &op, Chain16Tables *out, std::string *err);

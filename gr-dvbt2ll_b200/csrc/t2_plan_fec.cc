@@ -394,6 +394,24 @@ bool build_map_plan(int framesize, int rate, int constellation, int rotation, Ma
       p->lut[i].re = re; p->lut[i].im = im;
     }
   }
+  // ---- one table instead of two.  With a = level of the I bits and b = level of the Q bits a point is
+  // (a c - b s, a s + b c); the word w~ whose I bits are w's Q bits and whose Q bits are w's I bits with the sign bit
+  // flipped has levels (b, -a), so Re lut[w~] = b c + a s = Im lut[w] -- bit for bit, the same two rounded products
+  // added in the other order.  The kernels keep "word supplying the imaginary part" as w~ and look both parts up in
+  // the real-part table; verified here for every word, otherwise the two-table form stays in use.
+  {
+    uint32_t im = 0, qm = 0;
+    for (int b = 0; b < half; b++) { im |= 1u << (p->mod - 1 - 2 * b); qm |= 1u << (p->mod - 2 - 2 * b); }
+    p->im_mask_i = im; p->im_mask_q = qm; p->im_flip = 1u << (p->mod - 2);
+    p->im_from_re = 1;
+    for (int w = 0; w < npts; w++) {
+      const uint32_t wt = ((((uint32_t)w << 1) & im) | (((uint32_t)w >> 1) & qm)) ^ p->im_flip;
+      uint32_t x, y;
+      std::memcpy(&x, &p->lut[wt].re, 4);
+      std::memcpy(&y, &p->lut[w].im, 4);
+      if (x != y) p->im_from_re = 0;
+    }
+  }
   return true;
 }
 

@@ -326,15 +326,17 @@ bool compose_chain16(const FramePlan &fp, const OfdmPlan &op, Chain16Tables *out
   out->pool.l1post_variants = fp.pool.l1post_variants;
   const int L = op.dims.num_symbols, cps = op.dims.c_ps;
   out->code.assign(op.code.size(), 0);
-  out->chunk_src.clear();
-  out->chunk_ptr.assign(L + 1, 0);
+  out->run_desc.clear();
+  out->run_ptr.assign(L + 1, 0);
+  out->stage_bytes.assign(L, 0);
   out->max_slots = 0;
   for (int l = 0; l < L; l++) {
     const int s0 = op.sym_data_start[l], s1 = op.sym_data_start[l + 1];     // frame positions of this symbol
-    // staging layout: the symbol's source cells sorted by source address, copied run by run in 8-byte
-    // chunks (4 cells).  A run is a maximal stretch of consecutive source cells; its first staging slot
-    // has the same position inside a chunk as its first source cell, so whole aligned chunks can be
-    // copied (up to 3 unused cells at either end).
+    // staging layout: the symbol's source cells sorted by source address, copied run by run with bulk
+    // asynchronous copies (cp.async.bulk: 16-byte aligned source, destination and size).  A run is a maximal
+    // stretch of consecutive source cells (2 bytes each); its copy is the enclosing 16-byte aligned span of the
+    // frame's cell memory, landed at the next 16-byte aligned staging offset, so a cell keeps its position inside
+    // its 16-byte unit (up to 7 unused cells at either end of a run).
     std::vector<std::pair<int32_t, int32_t> > ps;      // (source cell, frame-order position - s0)
     for (int pos = s0; pos < s1; pos++) {
       const int32_t f = fp.framed[pos];
@@ -342,21 +344,31 @@ bool compose_chain16(const FramePlan &fp, const OfdmPlan &op, Chain16Tables *out
     }
     std::sort(ps.begin(), ps.end());
     std::vector<int32_t> slot_of_pos(s1 - s0, -1);
-    out->chunk_ptr[l] = (int32_t)out->chunk_src.size();
-    int32_t next_chunk = 0;                             // staging chunks used so far
+    out->run_ptr[l] = (int32_t)(out->run_desc.size() / 2);
+    int32_t next_unit = 0;                              // 16-byte staging units used so far
     size_t i = 0;
     while (i < ps.size()) {
-      const int32_t src = ps[i].first;
-      const int32_t first_chunk = src >> 2;
+      const int32_t first_unit = ps[i].first >> 3;      // 8 cells per 16-byte unit
       size_t j = i + 1;
       while (j < ps.size() && ps[j].first == ps[j - 1].first + 1) j++;
-      const int32_t last_chunk = ps[j - 1].first >> 2;
-      for (size_t k = i; k < j; k++) slot_of_pos[ps[k].second] = 4 * next_chunk + (ps[k].first - 4 * first_chunk);
-      for (int32_t c = first_chunk; c <= last_chunk; c++) out->chunk_src.push_back(c);
-      next_chunk += last_chunk - first_chunk + 1;
+      const int32_t last_unit = ps[j - 1].first >> 3;
+      int32_t u0 = first_unit;
+      while (u0 <= last_unit) {                         // a copy carries at most 65535 units (1 MB): split longer runs
+        const int32_t n = std::min<int32_t>(last_unit - u0 + 1, 65535);
+        if (next_unit + (u0 - first_unit) + n > 8191) {      // staging byte offsets are 17-bit
+          if (err) *err = "chain: a symbol's cells do not fit the staging address range";
+          return false;
+        }
+        out->run_desc.push_back(u0);
+        out->run_desc.push_back((int32_t)(((uint32_t)(next_unit + (u0 - first_unit)) << 16) | (uint32_t)n));
+        u0 += n;
+      }
+      for (size_t k = i; k < j; k++) slot_of_pos[ps[k].second] = 8 * next_unit + (ps[k].first - 8 * first_unit);
+      next_unit += last_unit - first_unit + 1;
       i = j;
     }
-    if (4 * next_chunk > out->max_slots) out->max_slots = 4 * next_chunk;
+    out->stage_bytes[l] = 16 * next_unit;
+    if (8 * next_unit > out->max_slots) out->max_slots = 8 * next_unit;
     // carrier codes: data carrier -> staging slot of its cell
     for (int k = 0; k < cps; k++) {
       const int32_t c = op.code[(size_t)l * cps + k];
@@ -370,7 +382,7 @@ bool compose_chain16(const FramePlan &fp, const OfdmPlan &op, Chain16Tables *out
       out->code[(size_t)l * cps + k] = v;
     }
   }
-  out->chunk_ptr[L] = (int32_t)out->chunk_src.size();
+  out->run_ptr[L] = (int32_t)(out->run_desc.size() / 2);
   return true;
 }
 

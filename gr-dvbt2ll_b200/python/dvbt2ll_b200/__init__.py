@@ -17,7 +17,8 @@ from .configs import *  # noqa: F401,F403  (enum constants, CONFIGS, make_ts)
 from . import configs
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "..", "libdvbt2ll_cuda.so"))
+# DVBT2LL_LIB selects another build of the same library (A/B timing of kernel variants, the bounds-checking debug build)
+LIB_PATH = os.environ.get("DVBT2LL_LIB") or os.path.normpath(os.path.join(_HERE, "..", "..", "libdvbt2ll_cuda.so"))
 
 _lib = None
 

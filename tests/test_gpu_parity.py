@@ -135,14 +135,15 @@ def test_chain_matches_reference(reflib, name):
     codes = ch.tap("cells", np.uint16)             # chain mode keeps cells as 16-bit codes, cell-interleaved
     ci_dst = ch.plan("frame.ci_dst", np.int32)
     lut = ch.plan("map.lut", np.complex64)
+    single = int(ch.plan("map.im_from_re", np.int32)[0])      # 1: the high byte is w~ and Im = Re lut[w~]
     for fr in range(nframes):
         r = refs[fr]
         got = np.unpackbits(bch[fr * F:(fr + 1) * F, :nbch // 8], axis=1).reshape(-1)
         assert bits_equal(got, r["bch"])
         n = r["cells"].size
-        stride = (n + 3) & ~3                          # frames are padded to a multiple of 4 cells
+        stride = (n + 7) & ~7                          # frames are padded to a multiple of 8 cells (16 bytes)
         fc = codes[fr * stride:fr * stride + n][ci_dst]
-        cells = (lut[fc & 255].real + 1j * lut[fc >> 8].imag).astype(np.complex64)
+        cells = (lut[fc & 255].real + 1j * (lut[fc >> 8].real if single else lut[fc >> 8].imag)).astype(np.complex64)
         assert cells_equal(cells, r["cells"])
         s = out[fr * S:(fr + 1) * S]
         assert mer_db(s, r["samples"]) >= MER_MIN_DB

@@ -107,15 +107,17 @@ def test_frame_and_ofdm_plans(name, cfg):
 
 @pytest.mark.parametrize("name", ["c1", "c2", "c3"])
 def test_chain16_tables(name):
-    """Chain mode: staging chunks + per-carrier slots reproduce exactly the composition
-    frequency interleaver o frame o time interleaver o cell interleaver of the drop-in tables."""
+    """Chain mode: the bulk-copy list (16-byte aligned spans of the frame's 16-bit cell memory, landed at 16-byte
+    aligned staging offsets) + per-carrier slots reproduce exactly the composition frequency interleaver o frame o time
+    interleaver o cell interleaver of the drop-in tables; copies never overlap in the staging area."""
     cfg = K.resolve(name)
     ch = T.Chain(cfg, max_frames=1)
     oc, fc = ch.plan("ofdm.code", np.int32), ch.plan("frame.code", np.int32)
     cc = ch.plan("chain.code", np.int32)
     ci_dst = ch.plan("frame.ci_dst", np.int32)
-    chunk_src = ch.plan("chain.chunk_src", np.int32)
-    chunk_ptr = ch.plan("chain.chunk_ptr", np.int32)
+    run_desc = ch.plan("chain.run_desc", np.int32).reshape(-1, 2)
+    run_ptr = ch.plan("chain.run_ptr", np.int32)
+    stage_bytes = ch.plan("chain.stage_bytes", np.int32)
     starts = ch.plan("ofdm.sym_data_start", np.int32)
     dims = ch.plan("ofdm.dims", np.int32)
     cps, L = int(dims[8]), int(dims[14])
@@ -123,11 +125,17 @@ def test_chain16_tables(name):
     rng = np.random.default_rng(3)
     cells16 = rng.integers(0, 65536, ci_dst.size).astype(np.int64)       # cell-interleaved memory of one T2 frame
     oc, cc = oc.reshape(L, cps), cc.reshape(L, cps)
-    pad = (-ci_dst.size) % 4
-    mem = np.concatenate([cells16, np.zeros(pad + 4, dtype=np.int64)])
+    pad = (-ci_dst.size) % 8
+    mem = np.concatenate([cells16, np.zeros(pad + 8, dtype=np.int64)])
     for l in range(L):
-        src = chunk_src[chunk_ptr[l]:chunk_ptr[l + 1]].astype(np.int64)     # aligned 8-byte chunks = 4 cells
-        stage = mem[(4 * src[:, None] + np.arange(4)[None, :]).reshape(-1)]
+        runs = run_desc[run_ptr[l]:run_ptr[l + 1]].astype(np.int64)
+        src_u, dst_u, n_u = runs[:, 0], (runs[:, 1] >> 16) & 0xFFFF, runs[:, 1] & 0xFFFF
+        assert int(16 * n_u.sum()) == int(stage_bytes[l])
+        stage = np.full(int(8 * (dst_u + n_u).max()) if len(runs) else 0, -1, dtype=np.int64)
+        for s_, d_, n_ in zip(src_u, dst_u, n_u):                          # 8 cells per 16-byte unit
+            assert np.all(stage[8 * d_:8 * (d_ + n_)] == -1), "staging copies overlap"
+            assert 8 * (s_ + n_) <= mem.size
+            stage[8 * d_:8 * (d_ + n_)] = mem[8 * s_:8 * (s_ + n_)]
         data = oc[l] >= 0
         assert np.array_equal(cc[l][~data], oc[l][~data])                  # pilots / nulls untouched
         f = fc[oc[l][data]]                                                # drop-in frame mapper code of each data carrier
@@ -136,3 +144,17 @@ def test_chain16_tables(name):
         assert np.all(got[from_cells] >= 0) and np.all(got[~from_cells] < 0)
         assert np.array_equal(stage[got[from_cells]], cells16[ci_dst[f[from_cells]]])
     assert ch.ts_bytes_per_frame == {"c1": 12352, "c2": 76304, "c3": 1084740}[name]
+
+
+def test_single_table_constellation_identity():
+    """Im lut[w] == Re lut[w~] bit for bit for every constellation, rotated or not (MapPlan::im_from_re): the kernels
+    rely on it to look both parts of a cell up in one table."""
+    for con in range(4):
+        for rot in (0, 1):
+            im = T.interleavermod_bc(K.FECFRAME_SHORT, K.C1_2, con, rot)
+            flag, mi, mq, fl = [int(x) & 0xFFFFFFFF for x in im.plan("map.im_from_re", np.int32)]
+            assert flag == 1, (con, rot)
+            lut = im.plan("map.lut", np.complex64)
+            w = np.arange(lut.size)
+            wt = (((w << 1) & mi) | ((w >> 1) & mq)) ^ fl
+            assert np.array_equal(lut[wt].real.view(np.uint32), lut.imag.copy().view(np.uint32))
