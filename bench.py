@@ -262,7 +262,8 @@ def stage_roofline(chain, cfg, frames, stage_ms, peak, peak_src):
     return {"bound": "hbm", "kernel": "k_ofdm (cell staging + carrier fill + IFFT + scale + guard interval + P1)",
             "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": ofdm_bytes, "kernel_ms": stage_ms["ofdm"], "stage_ms": stage_ms,
-            "map_kernel_gbs": map_bytes / (stage_ms["map"] * 1e-3) / 1e9}
+            "fec_frontend_ms": sum(v for k, v in stage_ms.items() if k in ("bb_bch", "ldpc", "map", "ldpc_map")),
+            "map_kernel_gbs": (map_bytes / (stage_ms["map"] * 1e-3) / 1e9) if "map" in stage_ms else None}
 
 
 def time_chain(torch, chain, stream, d_ts, pitch, nch, nfr, d_out, steps, min_warm_s=0.2):

@@ -128,6 +128,18 @@ struct PinRegistry {
     for (size_t i = 0; i < ivs.size(); i++)
       if (ivs[i].a0 < p1 && p0 < ivs[i].a1) add_user(ivs[i], user);
   }
+  // boundaries of our registered ranges that fall strictly inside [p0, p1), ascending: a copy must not span two
+  // separately registered ranges (or a registered and a pageable one), so it is issued piece by piece
+  void cuts(uintptr_t p0, uintptr_t p1, std::vector<uintptr_t> &out)
+  {
+    std::lock_guard<std::mutex> g(m);
+    for (size_t i = 0; i < ivs.size(); i++) {
+      if (ivs[i].a0 > p0 && ivs[i].a0 < p1) out.push_back(ivs[i].a0);
+      if (ivs[i].a1 > p0 && ivs[i].a1 < p1) out.push_back(ivs[i].a1);
+    }
+    std::sort(out.begin(), out.end());
+    out.erase(std::unique(out.begin(), out.end()), out.end());
+  }
   void release_all(const void *user)
   {
     std::lock_guard<std::mutex> g(m);
@@ -183,6 +195,23 @@ struct dvbt2ll_handle {
     PinRegistry::get().acquire(this, a0, a1);
     Pinned e = { a0, a1 };
     pinned.push_back(e);
+  }
+  // host <-> device copy of a caller buffer on `s`, split at the boundaries of registered ranges when registration is on
+  cudaError_t copy_host(void *dst, const void *src, size_t bytes, cudaMemcpyKind kind, cudaStream_t s)
+  {
+    if (!pin_enabled || pinned.empty()) return cudaMemcpyAsync(dst, src, bytes, kind, s);
+    const uintptr_t h0 = (uintptr_t)(kind == cudaMemcpyHostToDevice ? src : dst);
+    std::vector<uintptr_t> cut;
+    PinRegistry::get().cuts(h0, h0 + bytes, cut);
+    cut.push_back(h0 + bytes);
+    size_t off = 0;
+    for (size_t i = 0; i < cut.size(); i++) {
+      const size_t end = cut[i] - h0;
+      cudaError_t e = cudaMemcpyAsync((char *)dst + off, (const char *)src + off, end - off, kind, s);
+      if (e != cudaSuccess) return e;
+      off = end;
+    }
+    return cudaSuccess;
   }
   virtual int output_multiple() const = 0;
   virtual int forecast(int noutput) const = 0;
@@ -259,6 +288,7 @@ struct BbHandle : dvbt2ll_handle {
     return plan.mode == t2::INPUTMODE_NORMAL ? base : base + ((plan.fec.kbch - 80) / 8) / 187 + 1;
   }
   uint32_t crc_mask[8];
+  uint32_t crc_pos_mask[47][8];
   int dev_init()
   {
     std::vector<uint8_t> scr(plan.scramble);
@@ -277,6 +307,19 @@ struct BbHandle : dvbt2ll_handle {
       for (int i = 0; i < 4; i++)
         for (int j = 0; j < 8; j++)
           if ((crc[(3 - i) * 256 + (1 << j)] >> k) & 1) crc_mask[k] |= 1u << (8 * i + j);
+    }
+    // the whole packet at once: word j (of 47) contributes M4 followed by 46 - j further four-byte steps of its
+    // 8-bit image; mask[j][k] collects the input bits that reach CRC bit k; the leading byte of word 0 is not data
+    {
+      auto step = [&](uint32_t t) { uint32_t c = 0; for (int k = 0; k < 8; k++) c |= (uint32_t)(__builtin_popcount(t & crc_mask[k]) & 1) << k; return c; };
+      std::memset(crc_pos_mask, 0, sizeof(crc_pos_mask));
+      for (int j = 0; j < 47; j++)
+        for (int bit = 0; bit < 32; bit++) {
+          uint32_t v = step(1u << bit);
+          for (int r = 0; r < 46 - j; r++) v = step(v);
+          for (int k = 0; k < 8; k++) if ((v >> k) & 1u) crc_pos_mask[j][k] |= 1u << bit;
+        }
+      for (int k = 0; k < 8; k++) crc_pos_mask[0][k] &= 0xFFFFFF00u;
     }
     CK(upload(d_tab, plan.bch_byte_tab));
     CK(upload(d_cols, plan.bch_shift_cols));
@@ -312,6 +355,7 @@ struct BbHandle : dvbt2ll_handle {
     a.chunk_bytes = plan.chunk_bytes; a.lead_zero_bytes = plan.lead_zero_bytes;
     a.scramble = d_scr.as<uint8_t>(); a.crc8_tab = d_crc.as<uint8_t>(); a.bch_tab = d_tab.as<uint32_t>();
     for (int k = 0; k < 8; k++) a.crc8_mask[k] = crc_mask[k];
+    std::memcpy(a.crc8_pos_mask, crc_pos_mask, sizeof(crc_pos_mask));
     a.bch_cols = d_cols.as<uint32_t>(); a.inband_bytes = d_ib.as<uint8_t>();
     a.out = d_out; a.out_pitch = out_pitch; a.sync_errors = h_err;
   }
@@ -663,12 +707,18 @@ struct ChainHandle : dvbt2ll_handle {
   cudaStream_t stream2;
   int last_frames;
   long long next_frame;  // stream position of the generic work() / work_device() path (T2 frames consumed so far)
+  bool fuse_fec;         // LDPC and mapper as one kernel (DVBT2LL_FUSE_FEC=1).  Off by default: measured on B200 the fused
+                         // kernel takes 0.320 ms for 64 x c3 against 0.127 + 0.162 ms for the two kernels -- its phases are
+                         // short and separated by CTA barriers, the warp-per-FECFRAME LDPC kernel has none
+  bool taps;             // keep the packed LDPC codewords for dvbt2ll_chain_tap("fec") (parity tests)
   bool timing;
   enum { TIMING_SLOTS = 64 };
   cudaEvent_t ev[TIMING_SLOTS][5];     // per-run event sets so the timed loop never has to synchronise
   long long n_timed;
-  ChainHandle() : dvbt2ll_handle(CHAIN), max_frames(0), device(0), sink_fmt(0), sink_gain(1.0f), stream2(0), last_frames(0), next_frame(0), timing(false)
+  ChainHandle() : dvbt2ll_handle(CHAIN), max_frames(0), device(0), sink_fmt(0), sink_gain(1.0f), stream2(0), last_frames(0), next_frame(0), fuse_fec(false), taps(false), timing(false)
   {
+    const char *e = std::getenv("DVBT2LL_FUSE_FEC");
+    if (e && e[0] == '1') fuse_fec = true;
     n_timed = 0;
     for (int s = 0; s < TIMING_SLOTS; s++) for (int i = 0; i < 5; i++) ev[s][i] = 0;
   }
@@ -722,7 +772,6 @@ struct ChainHandle : dvbt2ll_handle {
       return fail(DVBT2LL_ERR_INVALID, "chain: the cells of one OFDM symbol do not fit the shared-memory staging area");
     const size_t nfec = (size_t)max_frames * F();
     CK(d_bch.ensure(nfec * align16(bb.plan.fec.nbch / 8) + 64));
-    CK(d_fec.ensure(nfec * align16(bb.plan.fec.nldpc / 8) + 64));
     CK(d_cells.ensure((size_t)max_frames * cells16_stride() * sizeof(uint16_t) + 64));   // 16-bit cell codes
     for (int s = 0; s < TIMING_SLOTS; s++) for (int i = 0; i < 5; i++) CK(cudaEventCreate(&ev[s][i]));
     return 0;
@@ -746,7 +795,8 @@ struct ChainHandle : dvbt2ll_handle {
     if (timing) cudaEventRecord(tev[0], s);
     t2k::BbArgs ba;
     uint8_t *bch_buf = d_bch.as<uint8_t>() + (size_t)buf_frame * F() * bp;
-    uint8_t *fec_buf = d_fec.as<uint8_t>() + (size_t)buf_frame * F() * fp;
+    if (!fuse_fec || taps) CK(d_fec.ensure((size_t)max_frames * F() * fp + 64));
+    uint8_t *fec_buf = d_fec.as<uint8_t>() ? d_fec.as<uint8_t>() + (size_t)buf_frame * F() * fp : 0;
     uint16_t *cell_buf = d_cells.as<uint16_t>() + (size_t)buf_frame * cells16_stride();
     bb.fill_args(ba, (const uint8_t *)d_ts, ts_pitch, n_channels, n_frames * F(), count0, fb0,
                  hist_valid >= 0 ? hist_valid : (first_frame > 0 ? 1 : 0), bch_buf, bp);
@@ -754,13 +804,21 @@ struct ChainHandle : dvbt2ll_handle {
     if (timing) cudaEventRecord(tev[1], s);
     t2k::LdpcArgs la;
     ldpc.fill_args(la, bch_buf, bp, fec_buf, fp, nfec);
-    t2k::launch_ldpc(la, s);
-    if (timing) cudaEventRecord(tev[2], s);
     t2k::MapArgs ma;
     map.fill_args(ma, fec_buf, fp, 0, nfec);
     ma.out16 = cell_buf; ma.out16_frame_stride = cells16_stride();                                        // 16-bit cell codes,
     ma.ci_inv = d_ci_inv.as<uint16_t>(); ma.fec_shift = d_fec_shift.as<int32_t>(); ma.fecblocks = F();   // cell-interleaved
-    t2k::launch_map(ma, s);
+    if (fuse_fec) {
+      // LDPC + bit interleaver / mapper in one kernel: the LDPC codeword stays in shared memory (the packed codewords
+      // reach HBM only when the parity-test tap is on)
+      if (timing) cudaEventRecord(tev[2], s);
+      t2k::launch_fec(la, ma, taps ? fec_buf : 0, fp, s);
+    }
+    else {
+      t2k::launch_ldpc(la, s);
+      if (timing) cudaEventRecord(tev[2], s);
+      t2k::launch_map(ma, s);
+    }
     if (timing) cudaEventRecord(tev[3], s);
     t2k::OfdmArgs oa;
     odev.fill(oa, oplan, tables.pool);
@@ -908,7 +966,7 @@ int dvbt2ll_work(dvbt2ll_handle *h, const void *in, int ninput, void *out, int n
     CK(cudaMemcpyAsync(din - 187, b->history, 187, cudaMemcpyHostToDevice, s));
     b->hist_on_device = 1;
   }
-  if (!resident) CK(cudaMemcpyAsync(din, in, in_bytes, cudaMemcpyHostToDevice, s));
+  if (!resident) CK(h->copy_host(din, in, in_bytes, cudaMemcpyHostToDevice, s));
   int used = 0;
   if (ch) {
     r = ch->run(din, 0, 1, frames, ch->next_frame, d_out.p, s, 0, 0, 1);
@@ -916,7 +974,7 @@ int dvbt2ll_work(dvbt2ll_handle *h, const void *in, int ninput, void *out, int n
   }
   else r = h->work_device(din, (int)need, d_out.p, nout, &used, s);
   if (r < 0) return r;
-  CK(cudaMemcpyAsync(out, d_out.p, out_bytes, cudaMemcpyDeviceToHost, s));
+  CK(h->copy_host(out, d_out.p, out_bytes, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   if (b) {
     h->warnings = *b->h_err;         // mapped host counter, complete after the synchronize
@@ -1141,7 +1199,10 @@ long long dvbt2ll_chain_tap(dvbt2ll_handle *h, const char *stage, void *out, lon
   const void *src; size_t bytes;
   std::string n(stage);
   if (n == "bch") { src = c->d_bch.p; bytes = nfec * align16(c->bb.plan.fec.nbch / 8); }
-  else if (n == "fec") { src = c->d_fec.p; bytes = nfec * align16(c->bb.plan.fec.nldpc / 8); }
+  else if (n == "fec") {
+    if (c->fuse_fec && !c->taps) return fail(DVBT2LL_ERR_INVALID, "chain: the LDPC codewords stay on chip; call dvbt2ll_chain_enable_taps before the run");
+    src = c->d_fec.p; bytes = nfec * align16(c->bb.plan.fec.nldpc / 8);
+  }
   else if (n == "cells") { src = c->d_cells.p; bytes = (size_t)c->last_frames * c->cells16_stride() * sizeof(uint16_t); }
   else return fail(DVBT2LL_ERR_INVALID, "chain: unknown tap");
   CK(cudaStreamSynchronize(c->stream));
@@ -1159,6 +1220,14 @@ int dvbt2ll_chain_set_sink(dvbt2ll_handle *h, int format, float gain)
   c->sink_gain = gain;
   return 0;
 }
+
+void dvbt2ll_chain_enable_taps(dvbt2ll_handle *h, int on)
+{
+  ChainHandle *c = as_chain(h);
+  if (c) c->taps = on != 0;
+}
+
+int dvbt2ll_chain_fused_fec(const dvbt2ll_handle *h) { ChainHandle *c = as_chain(h); return c ? (c->fuse_fec ? 1 : 0) : 0; }
 
 void dvbt2ll_chain_enable_timing(dvbt2ll_handle *h, int on)
 {

@@ -191,24 +191,26 @@ __global__ void __launch_bounds__(BB_MAX_WARPS * 32) k_bb_bch(const BbArgs a)
         const int si = i0 + 188 * (lane + 32 * rnd);
         if (si < Dj) {
           if (buf[10 + si] != 0x47) atomicAdd(a.sync_errors, 1);
-          // CRC-8 of the 187 bytes before the sync byte, four bytes per step: 47 unaligned little-endian words
-          // starting one byte early (that byte zeroed: leading zeros leave a zero state alone); the step is
-          // GF(2)-linear in (word ^ state), evaluated as eight parities -- no table look-ups
+          // CRC-8 of the 187 bytes before the sync byte: 47 unaligned little-endian words starting one byte early
+          // (that byte masked off).  The CRC is GF(2)-linear in the data: each of its bits is the parity of the XOR of
+          // (word & position mask) over the words, the masks being constant-bank operands -- no table look-ups, no
+          // serial state
           const uint8_t *p = buf + 10 + si - 188;
           const uint32_t *pw = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
           const int sh = (int)(reinterpret_cast<uintptr_t>(p) & 3) * 8;
-          uint32_t crc = 0, lo = pw[0];
-#pragma unroll 4
+          uint32_t lo = pw[0];
+          uint32_t acc[8] = { 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u };
+#pragma unroll
           for (int st = 0; st < 47; st++) {
             const uint32_t hi = pw[st + 1];
-            uint32_t t = __funnelshift_r(lo, hi, sh);
+            const uint32_t t = __funnelshift_r(lo, hi, sh);
             lo = hi;
-            if (st == 0) t &= 0xFFFFFF00u;
-            t ^= crc;
-            crc = 0;
 #pragma unroll
-            for (int k = 0; k < 8; k++) crc |= (__popc(t & a.crc8_mask[k]) & 1u) << k;
+            for (int k = 0; k < 8; k++) acc[k] ^= t & a.crc8_pos_mask[st][k];
           }
+          uint32_t crc = 0;
+#pragma unroll
+          for (int k = 0; k < 8; k++) crc |= (__popc(acc[k]) & 1u) << k;
           my_crc[rnd] = (uint8_t)crc;
         }
       }
@@ -347,9 +349,14 @@ void launch_bb_bch(const BbArgs &a, cudaStream_t s)
   // one CTA per SM (the lane-private tables take 40-48 KB), as many warps as frame buffers fit
   int warps = BB_MAX_WARPS;
   while (warps > 4 && fixed + (size_t)warps * buf_pitch > 227 * 1024) warps -= 4;
-  // small batches: spread the FECFRAMEs over all SMs instead of filling a few CTAs
+  // spread the FECFRAMEs evenly: with `spread` FECFRAMEs per SM the warps make ceil(spread / warps) rounds, and a
+  // last round that is nearly empty runs latency-bound -- use just enough warps for that many equal rounds
   const int spread = (total + sm_count() - 1) / sm_count();
   if (spread < warps) warps = spread < 1 ? 1 : spread;
+  else {
+    const int rounds = (spread + warps - 1) / warps;
+    warps = (spread + rounds - 1) / rounds;
+  }
   const size_t smem = fixed + (size_t)warps * buf_pitch;
   int blocks = (total + warps - 1) / warps;
   const int cap = sm_count();                 // one resident wave; warps loop over the remaining FECFRAMEs
@@ -531,23 +538,11 @@ __device__ __forceinline__ void transpose32(uint32_t (&A)[32])
   transpose32_stage<1>(A);
 }
 
-__global__ void __launch_bounds__(MAP_THREADS) k_map(const MapArgs a)
+// Geometry of the column-twist path kept in shared memory: per output bit of the demux word, the first codeword bit
+// of the column that feeds it and that column's twist; plus the constellation table
+__device__ __forceinline__ void map_setup(const MapArgs &a, float2 *lut, int *s_base, int *s_twist)
 {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  const int nwords = (a.nldpc + 31) / 32;
-  uint32_t *u = reinterpret_cast<uint32_t *>(smem_raw);                   // packed codeword, raw byte order, + slack
-  float2 *lut = reinterpret_cast<float2 *>(u + ((nwords + 11) & ~3));     // [1 << mod]
-  // cell codes of the FECFRAME: own cell word | (word supplying the imaginary part << 8), i.e. the previous cell's
-  // word under the cyclic Q delay, the cell's own otherwise.  Padded: cell c at index c + 2 (c / 64).
-  uint16_t *cw = reinterpret_cast<uint16_t *>(lut + (1 << a.mod));
   for (int i = threadIdx.x; i < (1 << a.mod); i += blockDim.x) lut[i] = a.lut[i];
-  const int mod = a.mod, Nc = a.cell_size;
-  // single-table constellation (MapPlan::im_from_re): the byte that supplies the imaginary part is kept as w~
-  const bool tilde = a.im_from_re != 0;
-  const uint32_t tI = a.im_mask_i * 0x01010101u, tQ = a.im_mask_q * 0x01010101u, tF = a.im_flip * 0x01010101u;
-  auto tilde4 = [&](uint32_t w) -> uint32_t { return tilde ? ((((w << 1) & tI) | ((w >> 1) & tQ)) ^ tF) : w; };   // four packed cell words
-  auto tilde1 = [&](uint32_t w) -> uint32_t { return tilde4(w) & 0xFFu; };
-  __shared__ int s_base[16], s_twist[16];      // per output bit: first codeword bit of its column, twist
   if (threadIdx.x < 16) {
     const int rho = threadIdx.x;
     int col = 0;
@@ -559,6 +554,187 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map(const MapArgs a)
     s_base[rho] = a.ncol ? (a.nldpc / a.ncol) * col : 0;
     s_twist[rho] = tw;
   }
+}
+
+// Bit interleaver + demux + cell codes + output of FECFRAME f whose packed "u"-order codeword sits in shared memory
+// (raw byte order, zero slack words behind it).  The caller has synchronised the CTA on `u`; ends without a barrier.
+__device__ __forceinline__ void map_body(const MapArgs &a, const int f, const uint32_t *u, const float2 *lut, uint16_t *cw,
+                                         const int *s_base, const int *s_twist, const int shift)
+{
+  const int mod = a.mod, Nc = a.cell_size;
+  // single-table constellation (MapPlan::im_from_re): the byte that supplies the imaginary part is kept as w~
+  const bool tilde = a.im_from_re != 0;
+  const uint32_t tI = a.im_mask_i * 0x01010101u, tQ = a.im_mask_q * 0x01010101u, tF = a.im_flip * 0x01010101u;
+  auto tilde4 = [&](uint32_t w) -> uint32_t { return tilde ? ((((w << 1) & tI) | ((w >> 1) & tQ)) ^ tF) : w; };   // four packed cell words
+  auto tilde1 = [&](uint32_t w) -> uint32_t { return tilde4(w) & 0xFFu; };
+  if (a.ncol) {
+    const int rows = a.nldpc / a.ncol;
+    const int groups = (rows + 31) >> 5;
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+      const int d0 = g << 5;
+      uint32_t A[32];
+#pragma unroll
+      for (int y = 0; y < 32; y++) A[y] = 0;
+#pragma unroll
+      for (int y = 16; y < 32; y++) {
+        const int rho = y - (32 - a.ncol);     // output bit (0 = MSB of the ncol-bit demux word) held by row y
+        if (rho >= 0) {
+          int s0 = d0 - s_twist[rho];
+          if (s0 < 0) s0 += rows;
+          const int base = s_base[rho];
+          const int n1 = rows - s0;
+          uint32_t w = window32_be(u, base + s0);
+          if (n1 < 32) w = (w & ~(0xFFFFFFFFu >> n1)) | (window32_be(u, base) >> n1);
+          A[y] = w;
+        }
+      }
+      transpose32(A);
+      // transpose32 uses (row, MSB-first column) coordinates: window bit i (from the MSB) of row y moves to
+      // bit y (from the MSB) of A[i], so A[i] is the ncol-bit word of row d0 + i of the twist matrix.
+      // Emit cells (two per word when ncol = 2 mod, else one) as packed bytes.
+      // Four consecutive cells as bytes w = [c0 c1 c2 c3] (c0 lowest), then their codes by byte permutes: with
+      // the Q delay [c0 | prev << 8, c1 | c0 << 8], [c2 | c1 << 8, c3 | c2 << 8] (prev = c3 of the previous
+      // four; the first cell of the thread is patched below), without it [c0 | c0 << 8, ...].
+      const uint32_t mask = (1u << mod) - 1u;
+      // X = the four words supplying the imaginary parts (as w~): the previous cell's under the Q delay, else the own
+      const int xs = a.cyclic_delay ? 8 : 0;
+      uint32_t wprev = 0;
+      if (a.ncol == 2 * mod) {
+        uint32_t *dst = reinterpret_cast<uint32_t *>(cw + 2 * d0 + 2 * g);      // 64 cells + 1 pad word per thread
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const uint32_t p0 = A[i], p1 = A[i + 1];
+          const uint32_t w = (p0 >> mod) | ((p0 & mask) << 8) | ((p1 >> mod) << 16) | ((p1 & mask) << 24);
+          const uint32_t wt = tilde4(w), X = __funnelshift_l(wprev, wt, xs);
+          dst[i] = __byte_perm(w, X, 0x5140u);
+          dst[i + 1] = __byte_perm(w, X, 0x7362u);
+          wprev = wt;
+        }
+      }
+      else {
+        uint32_t *dst = reinterpret_cast<uint32_t *>(cw + d0 + 2 * (g >> 1));   // 32 cells per thread, pad per 64
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const uint32_t w = (A[i] & mask) | ((A[i + 1] & mask) << 8) | ((A[i + 2] & mask) << 16) | ((A[i + 3] & mask) << 24);
+          const uint32_t wt = tilde4(w), X = __funnelshift_l(wprev, wt, xs);
+          dst[i >> 1] = __byte_perm(w, X, 0x5140u);
+          dst[(i >> 1) + 1] = __byte_perm(w, X, 0x7362u);
+          wprev = wt;
+        }
+      }
+    }
+    if (a.cyclic_delay) {
+      // first cell of every thread's run: the imaginary part comes from the last cell of the previous run
+      __syncthreads();
+      const int run = a.ncol == 2 * mod ? 64 : 32;
+      for (int c = threadIdx.x * run; c < Nc; c += blockDim.x * run) {
+        const int pc = c == 0 ? Nc - 1 : c - 1;
+        reinterpret_cast<uint8_t *>(cw)[2 * (c + 2 * (c >> 6)) + 1] = (uint8_t)tilde1(cw[pc + 2 * (pc >> 6)]);
+      }
+    }
+  }
+  else if (mod == 2 && (Nc & 3) == 0) {
+    // QPSK: four cells per step -- their eight source bit positions are one 16-byte load
+    const uint8_t *ub = reinterpret_cast<const uint8_t *>(u);
+    for (int c = 4 * threadIdx.x; c < Nc; c += 4 * blockDim.x) {
+      const uint4 pp = __ldg(reinterpret_cast<const uint4 *>(a.bit_src) + (c >> 2));
+      const uint32_t w[4] = { pp.x, pp.y, pp.z, pp.w };
+      uint32_t code[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const uint32_t p0 = w[k] & 0xFFFFu, p1 = w[k] >> 16;
+        const uint32_t v = (((ub[p0 >> 3] >> (7 - (p0 & 7))) & 1u) << 1) | ((ub[p1 >> 3] >> (7 - (p1 & 7))) & 1u);
+        code[k] = v | (tilde1(v) << 8);
+      }
+      uint32_t *dst = reinterpret_cast<uint32_t *>(cw + c + 2 * (c >> 6));
+      dst[0] = code[0] | (code[1] << 16);
+      dst[1] = code[2] | (code[3] << 16);
+    }
+    if (a.cyclic_delay) {
+      __syncthreads();
+      for (int c = threadIdx.x; c < Nc; c += blockDim.x) {
+        const int pc = c == 0 ? Nc - 1 : c - 1;
+        reinterpret_cast<uint8_t *>(cw)[2 * (c + 2 * (c >> 6)) + 1] = (uint8_t)tilde1(cw[pc + 2 * (pc >> 6)]);
+      }
+    }
+  }
+  else {
+    for (int c = threadIdx.x; c < Nc; c += blockDim.x) {
+      const uint16_t *src = a.bit_src + c * mod;
+      uint32_t v = 0;
+      for (int b = 0; b < mod; b++) {
+        const int p = __ldg(src + b);
+        v = (v << 1) | ((reinterpret_cast<const uint8_t *>(u)[p >> 3] >> (7 - (p & 7))) & 1u);
+      }
+      cw[c + 2 * (c >> 6)] = (uint16_t)(v | (tilde1(v) << 8));
+    }
+    if (a.cyclic_delay) {
+      __syncthreads();
+      // only high bytes are written and only low bytes read: no ordering needed between the threads
+      for (int c = threadIdx.x; c < Nc; c += blockDim.x) {
+        const int pc = c == 0 ? Nc - 1 : c - 1;
+        reinterpret_cast<uint8_t *>(cw)[2 * (c + 2 * (c >> 6)) + 1] = (uint8_t)tilde1(cw[pc + 2 * (pc >> 6)]);
+      }
+    }
+  }
+  __syncthreads();
+  auto code = [&](int c) -> unsigned { return cw[c + 2 * (c >> 6)]; };     // padded layout, see above
+  float2 *out = a.out + (long long)f * Nc;
+  if (a.out16) {
+    // chain mode: the 16-bit codes in cell-interleaved order: cell ci_inv[y] goes to position (y + shift) mod Nc.
+    // Two segments with a constant position - y, so table reads and stores are a base pointer + constant offsets.
+    uint16_t *o16 = a.out16 + (long long)(f / a.fecblocks) * a.out16_frame_stride + (long long)(f % a.fecblocks) * Nc;
+#pragma unroll 1
+    for (int seg = 0; seg < 2; seg++) {
+      const int y_end = seg ? Nc : Nc - shift;
+      uint16_t *o = o16 + (seg ? shift - Nc : shift);
+      // eight permutation look-ups in flight per thread
+#pragma unroll 1
+      for (int y0 = (seg ? Nc - shift : 0) + threadIdx.x; y0 < y_end; y0 += 8 * MAP_THREADS) {
+        const uint16_t *ci = a.ci_inv + y0;
+        uint16_t *oy = o + y0;
+        const int left = y_end - y0;
+        int c[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) c[k] = k * MAP_THREADS < left ? __ldg(ci + k * MAP_THREADS) : 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+          if (k * MAP_THREADS < left) oy[k * MAP_THREADS] = (uint16_t)code(c[k]);
+      }
+    }
+  }
+  else if (a.ci_inv) {
+    // fused cell interleaver with complex output
+    for (int xo = threadIdx.x; xo < Nc; xo += blockDim.x) {
+      int y = xo - shift;
+      if (y < 0) y += Nc;
+      const unsigned cd = code(__ldg(a.ci_inv + y));
+      out[xo] = make_float2(lut[cd & 255u].x, tilde ? lut[cd >> 8].x : lut[cd >> 8].y);
+    }
+  }
+  else {
+    for (int c = threadIdx.x; c < Nc; c += blockDim.x) {
+      const unsigned cd = code(c);
+      out[c] = make_float2(lut[cd & 255u].x, tilde ? lut[cd >> 8].x : lut[cd >> 8].y);
+    }
+  }
+}
+
+// shared-memory words of the mapper part: codeword (+ slack), constellation table, padded cell codes
+__host__ __device__ inline int map_u_words(int nldpc) { return (((nldpc + 31) / 32) + 11) & ~3; }
+__host__ __device__ inline int map_cw_halfwords(int cell_size) { return ((cell_size + 127) & ~63) + 2 * (cell_size / 64 + 2); }
+
+__global__ void __launch_bounds__(MAP_THREADS) k_map(const MapArgs a)
+{
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int nwords = (a.nldpc + 31) / 32;
+  uint32_t *u = reinterpret_cast<uint32_t *>(smem_raw);                   // packed codeword, raw byte order, + slack
+  float2 *lut = reinterpret_cast<float2 *>(u + map_u_words(a.nldpc));     // [1 << mod]
+  // cell codes of the FECFRAME: own cell word | (word supplying the imaginary part << 8), i.e. the previous cell's
+  // word under the cyclic Q delay, the cell's own otherwise.  Padded: cell c at index c + 2 (c / 64).
+  uint16_t *cw = reinterpret_cast<uint16_t *>(lut + (1 << a.mod));
+  __shared__ int s_base[16], s_twist[16];
+  map_setup(a, lut, s_base, s_twist);
 
   for (int f = blockIdx.x; f < a.frames; f += gridDim.x) {
     const uint32_t *in = reinterpret_cast<const uint32_t *>(a.in + (long long)f * a.in_pitch);
@@ -575,170 +751,170 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map(const MapArgs a)
       if (threadIdx.x < 4) u[4 * n16 + threadIdx.x] = 0u;
     }
     __syncthreads();
-    if (a.ncol) {
-      const int rows = a.nldpc / a.ncol;
-      const int groups = (rows + 31) >> 5;
-      for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-        const int d0 = g << 5;
-        uint32_t A[32];
-#pragma unroll
-        for (int y = 0; y < 32; y++) A[y] = 0;
-#pragma unroll
-        for (int y = 16; y < 32; y++) {
-          const int rho = y - (32 - a.ncol);     // output bit (0 = MSB of the ncol-bit demux word) held by row y
-          if (rho >= 0) {
-            int s0 = d0 - s_twist[rho];
-            if (s0 < 0) s0 += rows;
-            const int base = s_base[rho];
-            const int n1 = rows - s0;
-            uint32_t w = window32_be(u, base + s0);
-            if (n1 < 32) w = (w & ~(0xFFFFFFFFu >> n1)) | (window32_be(u, base) >> n1);
-            A[y] = w;
-          }
-        }
-        transpose32(A);
-        // transpose32 uses (row, MSB-first column) coordinates: window bit i (from the MSB) of row y moves to
-        // bit y (from the MSB) of A[i], so A[i] is the ncol-bit word of row d0 + i of the twist matrix.
-        // Emit cells (two per word when ncol = 2 mod, else one) as packed bytes.
-        // Four consecutive cells as bytes w = [c0 c1 c2 c3] (c0 lowest), then their codes by byte permutes: with
-        // the Q delay [c0 | prev << 8, c1 | c0 << 8], [c2 | c1 << 8, c3 | c2 << 8] (prev = c3 of the previous
-        // four; the first cell of the thread is patched below), without it [c0 | c0 << 8, ...].
-        const uint32_t mask = (1u << mod) - 1u;
-        // X = the four words supplying the imaginary parts (as w~): the previous cell's under the Q delay, else the own
-        const int xs = a.cyclic_delay ? 8 : 0;
-        uint32_t wprev = 0;
-        if (a.ncol == 2 * mod) {
-          uint32_t *dst = reinterpret_cast<uint32_t *>(cw + 2 * d0 + 2 * g);      // 64 cells + 1 pad word per thread
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const uint32_t p0 = A[i], p1 = A[i + 1];
-            const uint32_t w = (p0 >> mod) | ((p0 & mask) << 8) | ((p1 >> mod) << 16) | ((p1 & mask) << 24);
-            const uint32_t wt = tilde4(w), X = __funnelshift_l(wprev, wt, xs);
-            dst[i] = __byte_perm(w, X, 0x5140u);
-            dst[i + 1] = __byte_perm(w, X, 0x7362u);
-            wprev = wt;
-          }
-        }
-        else {
-          uint32_t *dst = reinterpret_cast<uint32_t *>(cw + d0 + 2 * (g >> 1));   // 32 cells per thread, pad per 64
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const uint32_t w = (A[i] & mask) | ((A[i + 1] & mask) << 8) | ((A[i + 2] & mask) << 16) | ((A[i + 3] & mask) << 24);
-            const uint32_t wt = tilde4(w), X = __funnelshift_l(wprev, wt, xs);
-            dst[i >> 1] = __byte_perm(w, X, 0x5140u);
-            dst[(i >> 1) + 1] = __byte_perm(w, X, 0x7362u);
-            wprev = wt;
-          }
-        }
-      }
-      if (a.cyclic_delay) {
-        // first cell of every thread's run: the imaginary part comes from the last cell of the previous run
-        __syncthreads();
-        const int run = a.ncol == 2 * mod ? 64 : 32;
-        for (int c = threadIdx.x * run; c < Nc; c += blockDim.x * run) {
-          const int pc = c == 0 ? Nc - 1 : c - 1;
-          reinterpret_cast<uint8_t *>(cw)[2 * (c + 2 * (c >> 6)) + 1] = (uint8_t)tilde1(cw[pc + 2 * (pc >> 6)]);
-        }
-      }
-    }
-    else if (mod == 2 && (Nc & 3) == 0) {
-      // QPSK: four cells per step -- their eight source bit positions are one 16-byte load
-      const uint8_t *ub = reinterpret_cast<const uint8_t *>(u);
-      for (int c = 4 * threadIdx.x; c < Nc; c += 4 * blockDim.x) {
-        const uint4 pp = __ldg(reinterpret_cast<const uint4 *>(a.bit_src) + (c >> 2));
-        const uint32_t w[4] = { pp.x, pp.y, pp.z, pp.w };
-        uint32_t code[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const uint32_t p0 = w[k] & 0xFFFFu, p1 = w[k] >> 16;
-          const uint32_t v = (((ub[p0 >> 3] >> (7 - (p0 & 7))) & 1u) << 1) | ((ub[p1 >> 3] >> (7 - (p1 & 7))) & 1u);
-          code[k] = v | (tilde1(v) << 8);
-        }
-        uint32_t *dst = reinterpret_cast<uint32_t *>(cw + c + 2 * (c >> 6));
-        dst[0] = code[0] | (code[1] << 16);
-        dst[1] = code[2] | (code[3] << 16);
-      }
-      if (a.cyclic_delay) {
-        __syncthreads();
-        for (int c = threadIdx.x; c < Nc; c += blockDim.x) {
-          const int pc = c == 0 ? Nc - 1 : c - 1;
-          reinterpret_cast<uint8_t *>(cw)[2 * (c + 2 * (c >> 6)) + 1] = (uint8_t)tilde1(cw[pc + 2 * (pc >> 6)]);
-        }
-      }
-    }
-    else {
-      for (int c = threadIdx.x; c < Nc; c += blockDim.x) {
-        const uint16_t *src = a.bit_src + c * mod;
-        uint32_t v = 0;
-        for (int b = 0; b < mod; b++) {
-          const int p = __ldg(src + b);
-          v = (v << 1) | ((reinterpret_cast<const uint8_t *>(u)[p >> 3] >> (7 - (p & 7))) & 1u);
-        }
-        cw[c + 2 * (c >> 6)] = (uint16_t)(v | (tilde1(v) << 8));
-      }
-      if (a.cyclic_delay) {
-        __syncthreads();
-        // only high bytes are written and only low bytes read: no ordering needed between the threads
-        for (int c = threadIdx.x; c < Nc; c += blockDim.x) {
-          const int pc = c == 0 ? Nc - 1 : c - 1;
-          reinterpret_cast<uint8_t *>(cw)[2 * (c + 2 * (c >> 6)) + 1] = (uint8_t)tilde1(cw[pc + 2 * (pc >> 6)]);
-        }
-      }
+    map_body(a, f, u, lut, cw, s_base, s_twist, shift);
+  }
+}
+
+// ================================================================================================
+// K2+K3 fused (chain mode): LDPC parity and bit interleaver / mapper of one FECFRAME per CTA.  The BCH codeword comes
+// in by asynchronous copies, the parity rows are computed by the whole CTA, laid behind the info bits in shared
+// memory in "u" order, and the mapper stages run from there: the LDPC codeword never travels through HBM.
+// ================================================================================================
+// big-endian 32-bit value at byte offset `off` of a byte stream held as raw (little-endian loaded) words in shared memory
+__device__ __forceinline__ uint32_t be32_at_smem(const uint32_t *w, int off)
+{
+  const int k = off >> 2;
+  return __byte_perm(w[k], w[k + 1], 0x0123u + 0x1111u * (unsigned)(off & 3));
+}
+
+#ifndef FEC_MIN_BLOCKS
+#define FEC_MIN_BLOCKS 6
+#endif
+__global__ void __launch_bounds__(MAP_THREADS, FEC_MIN_BLOCKS) k_fec(const LdpcArgs l, const MapArgs a, uint8_t *fec_tap, int fec_tap_pitch)
+{
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int nwords = (a.nldpc + 31) / 32;
+  uint32_t *u = reinterpret_cast<uint32_t *>(smem_raw);
+  float2 *lut = reinterpret_cast<float2 *>(u + map_u_words(a.nldpc));
+  uint16_t *cw = reinterpret_cast<uint16_t *>(lut + (1 << a.mod));
+  const int q = l.q, G = l.groups;
+  uint32_t *ext = reinterpret_cast<uint32_t *>(cw + ((map_cw_halfwords(a.cell_size) + 1) & ~1));   // [groups][13]
+  uint32_t *rows = ext + G * 13;                                                                     // [q][12] (+ 12 spare)
+  uint32_t *s_E = rows + q * 12 + 12;                                                                // [12] + one zero word
+  __shared__ int s_base[16], s_twist[16];
+  map_setup(a, lut, s_base, s_twist);
+  const int info_bytes = l.nbch / 8;
+  const int tid = threadIdx.x, lane = tid & 31;
+
+  for (int f = blockIdx.x; f < l.frames; f += gridDim.x) {
+    const uint8_t *in = l.in + (long long)f * l.in_pitch;
+    const int shift = a.fec_shift ? __ldg(a.fec_shift + f % a.fecblocks) : 0;
+    __syncthreads();
+    {
+      // the BCH codeword (= the info bits of the LDPC codeword) as raw bytes, 16-byte asynchronous copies
+      const int n16 = (info_bytes + 15) >> 4;
+      const unsigned dst0 = (unsigned)__cvta_generic_to_shared(u);
+      for (int i = tid; i < n16; i += MAP_THREADS)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst0 + 16u * i), "l"(in + 16 * i));
+      asm volatile("cp.async.commit_group;\n" ::);
+      asm volatile("cp.async.wait_group 0;\n" ::);
     }
     __syncthreads();
-    auto code = [&](int c) -> unsigned { return cw[c + 2 * (c >> 6)]; };     // padded layout, see above
-    float2 *out = a.out + (long long)f * Nc;
-    if (a.out16) {
-      // chain mode: the 16-bit codes in cell-interleaved order: cell ci_inv[y] goes to position (y + shift) mod Nc.
-      // Two segments with a constant position - y, so table reads and stores are a base pointer + constant offsets.
-      uint16_t *o16 = a.out16 + (long long)(f / a.fecblocks) * a.out16_frame_stride + (long long)(f % a.fecblocks) * Nc;
-#pragma unroll 1
-      for (int seg = 0; seg < 2; seg++) {
-        const int y_end = seg ? Nc : Nc - shift;
-        uint16_t *o = o16 + (seg ? shift - Nc : shift);
-        // eight permutation look-ups in flight per thread
-#pragma unroll 1
-        for (int y0 = (seg ? Nc - shift : 0) + threadIdx.x; y0 < y_end; y0 += 8 * MAP_THREADS) {
-          const uint16_t *ci = a.ci_inv + y0;
-          uint16_t *oy = o + y0;
-          const int left = y_end - y0;
-          int c[8];
-#pragma unroll
-          for (int k = 0; k < 8; k++) c[k] = k * MAP_THREADS < left ? __ldg(ci + k * MAP_THREADS) : 0;
-#pragma unroll
-          for (int k = 0; k < 8; k++)
-            if (k * MAP_THREADS < left) oy[k * MAP_THREADS] = (uint16_t)code(c[k]);
-        }
-      }
+    // ---- wrap-extended groups: 13 words = circular bits [0, 416) of each 360-bit group (see k_ldpc)
+    for (int idx = tid; idx < G * 13; idx += MAP_THREADS) {
+      const int g = idx / 13, w = idx - g * 13;
+      uint32_t v = be32_at_smem(u, 45 * g + (w == 12 ? 3 : 4 * w));
+      if (w == 11) v = (v & 0xFF000000u) | (be32_at_smem(u, 45 * g) >> 8);
+      ext[idx] = v;
     }
-    else if (a.ci_inv) {
-      // fused cell interleaver with complex output
-      for (int xo = threadIdx.x; xo < Nc; xo += blockDim.x) {
-        int y = xo - shift;
-        if (y < 0) y += Nc;
-        const unsigned cd = code(__ldg(a.ci_inv + y));
-        out[xo] = make_float2(lut[cd & 255u].x, tilde ? lut[cd >> 8].x : lut[cd >> 8].y);
+    __syncthreads();
+    // ---- pre-accumulator parity rows: R_t = XOR of rotated info groups
+    for (int idx = tid; idx < q * 12; idx += MAP_THREADS) {
+      const int t = idx / 12, w = idx - t * 12;
+      uint32_t acc = 0;
+      const int e1 = l.row_ptr[t + 1];
+      for (int e = l.row_ptr[t]; e < e1; e++) {
+        const uint32_t en = __ldg(l.entries + e);
+        int p = 32 * w - (int)(en >> 16);
+        if (p < 0) p += 360;
+        acc ^= window32(ext + (en & 0xffffu) * 13, p);
+      }
+      if (w == 11) acc &= 0xFF000000u;
+      rows[idx] = acc;
+    }
+    if (tid < 13) { rows[q * 12 + (tid < 12 ? tid : 0)] = 0u; s_E[12] = 0u; }
+    __syncthreads();
+    // ---- accumulator, part 1: T_t = XOR_{t' <= t} R_t' (prefix over rows, per word): ten row segments scanned side
+    // by side by 120 threads, then offset by the totals of the segments before them
+    const int seg_rows = (q + 9) / 10;
+    const int sw = tid % 12, sg = tid / 12;
+    const int t0 = sg * seg_rows, t1 = min(q, t0 + seg_rows);
+    if (tid < 120) {
+      uint32_t run = 0;
+      for (int t = t0; t < t1; t++) { run ^= rows[t * 12 + sw]; rows[t * 12 + sw] = run; }
+    }
+    __syncthreads();
+    uint32_t offs = 0;
+    if (tid < 120)
+      for (int s2 = 0; s2 < sg; s2++) {
+        const int last = min(q, (s2 + 1) * seg_rows) - 1;
+        if (last >= s2 * seg_rows) offs ^= rows[last * 12 + sw];
+      }
+    __syncthreads();
+    if (tid < 120 && offs)
+      for (int t = t0; t < t1; t++) rows[t * 12 + sw] ^= offs;
+    __syncthreads();
+    // ---- part 2: E = exclusive prefix-XOR along the 360 bit positions of T_{q-1} (first warp)
+    if (tid < 32) {
+      uint32_t x = lane < 12 ? rows[(q - 1) * 12 + lane] : 0;
+      x ^= x >> 1; x ^= x >> 2; x ^= x >> 4; x ^= x >> 8; x ^= x >> 16;   // inclusive, MSB first
+      uint32_t par = x & 1u, carry = par;
+#pragma unroll
+      for (int d = 1; d < 16; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, carry, d);
+        if (lane >= d) carry ^= o;
+      }
+      carry ^= par;     // exclusive over words
+      uint32_t E = (x >> 1) ^ (carry ? 0xFFFFFFFFu : 0u);
+      if (lane == 11) E &= 0xFF000000u;
+      if (lane < 12) s_E[lane] = E;
+    }
+    __syncthreads();
+    // ---- parity rows (T_t ^ E) laid end to end behind the info bits, in raw byte order
+    if ((info_bytes & 3) == 0) {
+      uint32_t *pw = u + (info_bytes >> 2);
+      const int nwp = (q * 360) >> 5;
+      for (int j = tid; j < nwp; j += MAP_THREADS) {
+        const int P = j << 5;
+        const int t = P / 360, o = P - t * 360;
+        uint32_t v = window32(rows + t * 12, o) ^ window32(s_E, o);
+        const int n1 = 360 - o;                        // bits left in row t
+        if (n1 < 32) v = (v & ~(0xFFFFFFFFu >> n1)) | ((rows[(t + 1) * 12] ^ s_E[0]) >> n1);
+        pw[j] = bswap32(v);
+      }
+      uint8_t *ub = reinterpret_cast<uint8_t *>(u);
+      for (int b = (nwp << 2) + tid; b < q * 45; b += MAP_THREADS) {
+        const int t = b / 45, bb = b - t * 45;
+        ub[info_bytes + b] = (uint8_t)((rows[t * 12 + (bb >> 2)] ^ s_E[bb >> 2]) >> (24 - 8 * (bb & 3)));
       }
     }
     else {
-      for (int c = threadIdx.x; c < Nc; c += blockDim.x) {
-        const unsigned cd = code(c);
-        out[c] = make_float2(lut[cd & 255u].x, tilde ? lut[cd >> 8].x : lut[cd >> 8].y);
+      uint8_t *ub = reinterpret_cast<uint8_t *>(u);
+      for (int b = tid; b < q * 45; b += MAP_THREADS) {
+        const int t = b / 45, bb = b - t * 45;
+        ub[info_bytes + b] = (uint8_t)((rows[t * 12 + (bb >> 2)] ^ s_E[bb >> 2]) >> (24 - 8 * (bb & 3)));
       }
     }
+    if (tid < 4) u[4 * ((nwords + 3) >> 2) + tid] = 0u;
+    __syncthreads();
+    if (fec_tap) {        // parity-test tap of the codeword (not part of the product path)
+      uint32_t *o = reinterpret_cast<uint32_t *>(fec_tap + (long long)f * fec_tap_pitch);
+      for (int i = tid; i < (a.nldpc / 8 + 3) / 4; i += MAP_THREADS) o[i] = u[i];
+    }
+    map_body(a, f, u, lut, cw, s_base, s_twist, shift);
   }
 }
 
 void launch_map(const MapArgs &a, cudaStream_t s)
 {
-  const int nwords = (a.nldpc + 31) / 32;
-  const size_t smem = (size_t)((nwords + 11) & ~3) * 4 + (size_t)(1 << a.mod) * 8 + 2 * (((a.cell_size + 127) & ~63) + 2 * (a.cell_size / 64 + 2));
+  const size_t smem = (size_t)map_u_words(a.nldpc) * 4 + (size_t)(1 << a.mod) * 8 + 2 * (size_t)map_cw_halfwords(a.cell_size);
   // one FECFRAME per CTA: the hardware scheduler balances the tail at frame granularity
   const int blocks = a.frames;
   if (blocks < 1) return;
   static bool attr[MAX_DEVICES];
   allow_smem(k_map, 100 * 1024, attr);      // QPSK normal: 32400 cell codes
   k_map<<<blocks, MAP_THREADS, smem, s>>>(a);
+  count_launch();
+}
+
+void launch_fec(const LdpcArgs &l, const MapArgs &a, uint8_t *fec_tap, int fec_tap_pitch, cudaStream_t s)
+{
+  if (l.frames < 1) return;
+  const size_t smem = (size_t)map_u_words(a.nldpc) * 4 + (size_t)(1 << a.mod) * 8 + 2 * (size_t)((map_cw_halfwords(a.cell_size) + 1) & ~1) +
+                      (size_t)(l.groups * 13 + l.q * 12 + 12 + 16) * 4;
+  static bool attr[MAX_DEVICES];
+  allow_smem(k_fec, 160 * 1024, attr);
+  k_fec<<<l.frames, MAP_THREADS, smem, s>>>(l, a, fec_tap, fec_tap_pitch);      // one FECFRAME per CTA
   count_launch();
 }
 

@@ -1,10 +1,14 @@
-// Minimal single-threaded stand-in for the GNU Radio scheduler: drives the four blocks in the order of the
+// Minimal single-threaded stand-in for the GNU Radio scheduler: drives the blocks in the order of the
 // shipped flowgraph (apps/vv009-4kshort.grc of the reference: bbheaderbch -> LDPC -> interleavermod ->
 // framemapper -> pilotgen) through their gr::block interface (make / forecast / general_work), with the
 // parameters of that flowgraph (4K, short FECFRAME, 256QAM rotated, CR 4/5, PP7, GI 1/32).  The LDPC stage,
-// which the flowgraph takes from GNU Radio's gr-dtv, is called through the C ABI directly.
-// Usage: gr_flowgraph_demo [n_t2_frames]   -- prints a checksum of the baseband; needs a CUDA device.
+// which the flowgraph takes from GNU Radio's gr-dtv, is this module's own ldpc_bb block here.
+// Usage: gr_flowgraph_demo [n_t2_frames] [link]   -- prints a checksum of the baseband; needs a CUDA device.
+// With "link" adjacent blocks hand their items over in HBM (dvbt2ll/cuda_link.h); the buffers between the blocks
+// are then kept at fixed addresses, as the scheduler's are.
 #include <dvbt2ll/bbheaderbch_bb.h>
+#include <dvbt2ll/cuda_link.h>
+#include <dvbt2ll/ldpc_bb.h>
 #include <dvbt2ll/framemapperfint_cc.h>
 #include <dvbt2ll/interleavermod_bc.h>
 #include <dvbt2ll/pilotgenp1insert_cc.h>
@@ -12,30 +16,32 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "../../../include/dvbt2ll_cuda.h"
 
 using namespace gr::dvbt2ll;
 
+// one general_work() call producing `noutput` items into `out` (a buffer that keeps its address between calls)
 template <class In, class Out>
-static std::vector<Out> run_block(gr::block &b, const std::vector<In> &in, size_t &in_pos, int noutput)
+static void run_block(gr::block &b, const std::vector<In> &in, size_t &in_pos, std::vector<Out> &out, int noutput)
 {
   gr_vector_int need(1, 0);
   b.forecast(noutput, need);
-  std::vector<Out> out(noutput);
+  if (out.size() < (size_t)noutput) out.resize(noutput);
   gr_vector_int nin(1, (int)(in.size() - in_pos));
   gr_vector_const_void_star ins(1, (const void *)(in.data() + in_pos));
   gr_vector_void_star outs(1, (void *)out.data());
   const int produced = b.general_work(noutput, nin, ins, outs);
+  if (produced != noutput) { fprintf(stderr, "block produced %d of %d items\n", produced, noutput); exit(1); }
   in_pos += b.last_consumed();
-  out.resize(produced);
-  return out;
 }
 
 int main(int argc, char **argv)
 {
   const int nframes = argc > 1 ? atoi(argv[1]) : 2;
+  const bool linked = argc > 2 && !strcmp(argv[2], "link");
   const int fecblocks = 8;
   bbheaderbch_bb::sptr bb = bbheaderbch_bb::make(FECFRAME_SHORT, C4_5, INPUTMODE_NORMAL, INBAND_OFF, fecblocks, 4000000);
   interleavermod_bc::sptr im = interleavermod_bc::make(FECFRAME_SHORT, C4_5, MOD_256QAM, ROTATION_ON);
@@ -44,7 +50,13 @@ int main(int argc, char **argv)
       L1_SCRAMBLED_OFF, INBAND_OFF);
   pilotgenp1insert_cc::sptr pg = pilotgenp1insert_cc::make(CARRIERS_NORMAL, FFTSIZE_4K, PILOT_PP7, GI_1_32, 3, PAPR_OFF, VERSION_111,
       PREAMBLE_T2_SISO, MISO_TX1, EQUALIZATION_OFF, BANDWIDTH_8_0_MHZ, 4096);
-  dvbt2ll_handle *ldpc = dvbt2ll_ldpc_create(FECFRAME_SHORT, C4_5);
+  ldpc_bb::sptr ldpc = ldpc_bb::make(FECFRAME_SHORT, C4_5);
+  if (linked) {
+    if (!link(bb.get(), ldpc.get()) || !link(ldpc.get(), im.get()) || !link(im.get(), fm.get()) || !link(fm.get(), pg.get())) {
+      fprintf(stderr, "link failed: %s\n", dvbt2ll_last_error());
+      return 1;
+    }
+  }
 
   // synthetic TS (xorshift32, sync byte every 188 bytes), as in bench.py / the tests
   std::vector<unsigned char> ts((size_t)nframes * fecblocks * 1544 + 1000);
@@ -53,21 +65,23 @@ int main(int argc, char **argv)
 
   size_t ts_pos = 0;
   double acc = 0.0;
+  std::vector<unsigned char> bch, fec;
+  std::vector<gr_complex> cells, mapped, samples;
   for (int f = 0; f < nframes; f++) {
-    std::vector<unsigned char> bch = run_block<unsigned char, unsigned char>(*bb, ts, ts_pos, fecblocks * 12600);
-    std::vector<unsigned char> fec((size_t)fecblocks * 16200);
-    int used = 0;
-    if (dvbt2ll_work(ldpc, bch.data(), (int)bch.size(), fec.data(), (int)fec.size(), &used) < 0) { fprintf(stderr, "%s\n", dvbt2ll_last_error()); return 1; }
     size_t p = 0;
-    std::vector<gr_complex> cells = run_block<unsigned char, gr_complex>(*im, fec, p, fecblocks * 2025);
+    run_block(*bb, ts, ts_pos, bch, fecblocks * 12600);
+    run_block(*ldpc, bch, p, fec, fecblocks * 16200);
     p = 0;
-    std::vector<gr_complex> mapped = run_block<gr_complex, gr_complex>(*fm, cells, p, 18866);
+    run_block(*im, fec, p, cells, fecblocks * 2025);
     p = 0;
-    std::vector<gr_complex> samples = run_block<gr_complex, gr_complex>(*pg, mapped, p, 31616);
+    run_block(*fm, cells, p, mapped, 18866);
+    p = 0;
+    run_block(*pg, mapped, p, samples, 31616);
     for (size_t i = 0; i < samples.size(); i++) acc += std::abs(samples[i]);
     printf("T2 frame %d: %zu samples, TS consumed so far %zu bytes\n", f, samples.size(), ts_pos);
   }
   printf("sum |x| = %.6f, kernel launches = %lld\n", acc, dvbt2ll_kernel_launches());
-  dvbt2ll_destroy(ldpc);
+  // the blocks (and with them the registrations of these buffers) go before the buffers do
+  bb.reset(); ldpc.reset(); im.reset(); fm.reset(); pg.reset();
   return 0;
 }

@@ -9,7 +9,7 @@
 namespace gr {
 namespace dvbt2ll {
 
-class bbheaderbch_bb_impl : public bbheaderbch_bb
+class bbheaderbch_bb_impl : public bbheaderbch_bb, public cuda_block_base
 {
 public:
   bbheaderbch_bb_impl(dvbt2_framesize_t framesize, dvbt2_code_rate_t rate, dvbt2_inputmode_t mode, dvbt2_inband_t inband, int fecblocks, int tsrate);
@@ -17,6 +17,8 @@ public:
   void forecast(int noutput_items, gr_vector_int &ninput_items_required);
   int general_work(int noutput_items, gr_vector_int &ninput_items, gr_vector_const_void_star &input_items,
                    gr_vector_void_star &output_items);
+
+  cuda_block_core &core() { return d_core; }
 
 private:
   cuda_block_core d_core;

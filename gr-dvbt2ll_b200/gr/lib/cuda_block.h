@@ -1,4 +1,4 @@
-// Shared plumbing of the four GNU Radio blocks: each block owns one dvbt2ll_handle of libdvbt2ll_cuda.so and
+// Shared plumbing of the five GNU Radio blocks: each block owns one dvbt2ll_handle of libdvbt2ll_cuda.so and
 // forwards forecast() / general_work() to the C ABI (include/dvbt2ll_cuda.h).  Host code stays a plain
 // gr::block; all DSP runs in CUDA kernels; there is no CPU fallback (a CUDA failure is logged as FATAL and
 // thrown, like the reference's allocation failures, lib/framemapperfint_cc_impl.cc:1121-1124).
@@ -8,6 +8,7 @@
 #include <gnuradio/block.h>
 #include <gnuradio/io_signature.h>
 
+#include <cstdlib>
 #include <new>
 #include <stdexcept>
 #include <string>
@@ -33,7 +34,12 @@ public:
       throw std::invalid_argument(msg);
     }
     d_h = h;
+    // the scheduler's buffers are long-lived and reused call after call: let the library page-lock them on first
+    // sight, so both copies of general_work() run as DMA at PCIe rate (DVBT2LL_HOST_REGISTER=0 turns it off)
+    const char *e = std::getenv("DVBT2LL_HOST_REGISTER");
+    dvbt2ll_set_host_register(d_h, (e && e[0] == '0') ? 0 : 1);
   }
+  dvbt2ll_handle *handle() const { return d_h; }
   int output_multiple() const { return dvbt2ll_output_multiple(d_h); }
   int forecast(int noutput) const { return dvbt2ll_forecast(d_h, noutput); }
 
@@ -55,6 +61,14 @@ public:
 private:
   dvbt2ll_handle *d_h;
   int d_warned;
+};
+
+// every GPU-backed block of the module exposes its core (dvbt2ll/cuda_link.h: device-resident hand-off)
+class cuda_block_base
+{
+public:
+  virtual ~cuda_block_base() {}
+  virtual cuda_block_core &core() = 0;
 };
 
 } // namespace dvbt2ll

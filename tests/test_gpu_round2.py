@@ -40,6 +40,7 @@ def test_chain_short_codes_reference_cannot_encode(rate):
     cfg = K.resolve(dict(K.CONFIGS["c1"], rate=rate))
     nframes = 2
     ch = T.Chain(cfg, max_frames=nframes)
+    ch.enable_taps()                                   # keep the LDPC codewords the fused kernel otherwise never stores
     ts = K.make_ts(ch.ts_bytes(0, nframes) + 16, seed=K.TS_SEED + rate)
     out = ch.run_host(ts[:ch.ts_bytes(0, nframes)], 1, nframes)[0]
     want = O.chain(cfg, ts, nframes)
