@@ -358,6 +358,7 @@ struct BbHandle : dvbt2ll_handle {
     std::memcpy(a.crc8_pos_mask, crc_pos_mask, sizeof(crc_pos_mask));
     a.bch_cols = d_cols.as<uint32_t>(); a.inband_bytes = d_ib.as<uint8_t>();
     a.out = d_out; a.out_pitch = out_pitch; a.sync_errors = h_err;
+    a.ts_len = 0; a.out_len = (long long)channels * frames * out_pitch;
   }
   // d_in must be preceded by 187 bytes of valid history on the device (work() arranges that)
   int work_device(const void *d_in, int ninput, void *d_out, int noutput, int *consumed, cudaStream_t s)
@@ -371,6 +372,7 @@ struct BbHandle : dvbt2ll_handle {
     CK(d_packed.ensure((size_t)frames * pitch));
     t2k::BbArgs a;
     fill_args(a, (const uint8_t *)d_in, 0, 1, frames, count, fec_block, hist_on_device, d_packed.as<uint8_t>(), pitch);
+    a.ts_len = ninput;
     t2k::launch_bb_bch(a, s);
     t2k::launch_unpack_bits(d_packed.as<uint8_t>(), pitch, plan.fec.nbch, (uint8_t *)d_out, frames, s);
     CK(cudaGetLastError());
@@ -418,6 +420,7 @@ struct LdpcHandle : dvbt2ll_handle {
     a.in = in; a.in_pitch = in_pitch; a.out = out; a.out_pitch = out_pitch; a.frames = frames;
     a.nbch = plan.fec.nbch; a.nldpc = plan.fec.nldpc; a.q = plan.fec.q; a.groups = plan.groups;
     a.row_ptr = d_rowptr.as<uint16_t>(); a.entries = d_entries.as<uint32_t>();
+    a.in_len = (long long)frames * in_pitch + 64; a.out_len = (long long)frames * out_pitch;
   }
   int work_device(const void *d_in, int ninput, void *d_out, int noutput, int *consumed, cudaStream_t s)
   {
@@ -466,7 +469,8 @@ struct MapHandle : dvbt2ll_handle {
     a.in = in; a.in_pitch = in_pitch; a.out = out; a.frames = frames;
     a.nldpc = plan.fec.nldpc; a.mod = plan.mod; a.cell_size = plan.cell_size; a.cyclic_delay = plan.cyclic_delay;
     a.bit_src = d_bitsrc.as<uint16_t>(); a.lut = d_lut.as<float2>();
-    a.ci_inv = 0; a.fec_shift = 0; a.fecblocks = 1; a.out16 = 0; a.out16_frame_stride = 0;
+    a.ci_inv = 0; a.ci_inv4 = 0; a.ci_inv4_stride = 0; a.fec_shift = 0; a.fecblocks = 1; a.out16 = 0; a.out16_frame_stride = 0;
+    a.in_len = (long long)frames * in_pitch; a.out_len = 0;
     a.ncol = plan.ncol;
     a.im_from_re = plan.im_from_re; a.im_mask_i = plan.im_mask_i; a.im_mask_q = plan.im_mask_q; a.im_flip = plan.im_flip;
     std::memcpy(a.col_of_bit, plan.col_of_bit, 16);
@@ -639,9 +643,10 @@ struct OfdmDevice {
     a.fft_n = op.dims.fft_n; a.log2_m = log2_m; a.split = split;
     a.c_ps = op.dims.c_ps; a.left_nulls = op.left_nulls; a.gi = op.dims.gi; a.num_symbols = op.dims.num_symbols;
     a.norm = op.normalization;
-    a.cells16 = 0; a.run_desc = 0; a.run_ptr = 0; a.stage_bytes = 0; a.stage_cap = 0; a.lut = 0; a.lut_n = 0; a.lut_single = 0;
+    a.cells16 = 0; a.run_desc = 0; a.run_ptr = 0; a.run_cnt = 0; a.desc_cap = 0; a.stage_bytes = 0; a.stage_cap = 0; a.lut = 0; a.lut_n = 0; a.lut_single = 0;
     a.sym_flags = d_sym_flags.as<int32_t>();
     a.out_fmt = 0; a.sink_gain = 1.0f; a.scratch = d_scratch.as<float2>();
+    a.cells_len = 0; a.out_len = 0; a.pool_len = pool_stride;
   }
 };
 
@@ -665,6 +670,7 @@ struct OfdmHandle : dvbt2ll_handle {
     dev.fill(a, plan, plan.pool);
     a.cells = (const float2 *)d_in; a.cells_stride = plan.dims.active_items;
     a.out = d_out; a.out_stride = plan.samples_per_frame;
+    a.cells_len = (long long)frames * plan.dims.active_items; a.out_len = (long long)frames * plan.samples_per_frame;
     a.frames = frames; a.frame_idx0 = 0; a.frames_per_channel = frames;
     t2k::launch_ofdm(a, s);
     CK(cudaGetLastError());
@@ -699,8 +705,8 @@ struct ChainHandle : dvbt2ll_handle {
   t2::OfdmPlan oplan;
   t2::Chain16Tables tables;
   OfdmDevice odev;
-  DevBuf d_bch, d_fec, d_cells, d_ts_stage, d_out_stage, d_ci_inv, d_fec_shift, d_run_desc, d_run_ptr, d_stage_bytes;
-  int stage_cap;
+  DevBuf d_bch, d_fec, d_cells, d_ts_stage, d_out_stage, d_ci_inv, d_ci_inv4, d_fec_shift, d_run_desc, d_run_ptr, d_run_cnt, d_stage_bytes;
+  int stage_cap, ci4_stride;
   int max_frames, device;
   int sink_fmt;          // 0 complex64 (what pilotgenp1insert_cc emits), 1 interleaved int16 I/Q
   float sink_gain;       // the flowgraph's multiply_const stage folded into the last kernel
@@ -763,12 +769,22 @@ struct ChainHandle : dvbt2ll_handle {
     if ((r = map.dev_init())) return r;
     if ((r = odev.init(tables.code, tables.pool, oplan, true))) return r;
     CK(upload(d_ci_inv, fplan.cell_perm_inv));
+    {
+      // the same table shifted by 0..3 entries: four consecutive entries at any phase become one aligned 8-byte load
+      const int nc = (int)fplan.cell_perm_inv.size();
+      ci4_stride = (nc + 8 + 3) & ~3;
+      std::vector<uint16_t> c4((size_t)4 * ci4_stride, 0);
+      for (int k = 0; k < 4; k++)
+        for (int j = 0; j + k < nc; j++) c4[(size_t)k * ci4_stride + j] = fplan.cell_perm_inv[j + k];
+      CK(upload(d_ci_inv4, c4));
+    }
     CK(upload(d_fec_shift, fplan.fec_shift));
     CK(upload(d_run_desc, tables.run_desc));
     CK(upload(d_run_ptr, tables.run_ptr));
+    CK(upload(d_run_cnt, tables.run_cnt));
     CK(upload(d_stage_bytes, tables.stage_bytes));
     stage_cap = (tables.max_slots + 7) & ~7;
-    if ((size_t)(1 << odev.log2_m) * 8 * 17 / 16 + (size_t)stage_cap * 2 + 2048 + 80 > 227 * 1024)
+    if ((size_t)(1 << odev.log2_m) * 8 * 17 / 16 + (size_t)stage_cap * 2 + 2048 + 96 + (size_t)(tables.max_runs + 2) * 8 > 227 * 1024)
       return fail(DVBT2LL_ERR_INVALID, "chain: the cells of one OFDM symbol do not fit the shared-memory staging area");
     const size_t nfec = (size_t)max_frames * F();
     CK(d_bch.ensure(nfec * align16(bb.plan.fec.nbch / 8) + 64));
@@ -800,6 +816,7 @@ struct ChainHandle : dvbt2ll_handle {
     uint16_t *cell_buf = d_cells.as<uint16_t>() + (size_t)buf_frame * cells16_stride();
     bb.fill_args(ba, (const uint8_t *)d_ts, ts_pitch, n_channels, n_frames * F(), count0, fb0,
                  hist_valid >= 0 ? hist_valid : (first_frame > 0 ? 1 : 0), bch_buf, bp);
+    ba.ts_len = ts_bytes(first_frame, n_frames);
     t2k::launch_bb_bch(ba, s);
     if (timing) cudaEventRecord(tev[1], s);
     t2k::LdpcArgs la;
@@ -808,6 +825,8 @@ struct ChainHandle : dvbt2ll_handle {
     map.fill_args(ma, fec_buf, fp, 0, nfec);
     ma.out16 = cell_buf; ma.out16_frame_stride = cells16_stride();                                        // 16-bit cell codes,
     ma.ci_inv = d_ci_inv.as<uint16_t>(); ma.fec_shift = d_fec_shift.as<int32_t>(); ma.fecblocks = F();   // cell-interleaved
+    ma.ci_inv4 = d_ci_inv4.as<uint16_t>(); ma.ci_inv4_stride = ci4_stride;
+    ma.out_len = (long long)frames * cells16_stride();
     if (fuse_fec) {
       // LDPC + bit interleaver / mapper in one kernel: the LDPC codeword stays in shared memory (the packed codewords
       // reach HBM only when the parity-test tap is on)
@@ -824,9 +843,11 @@ struct ChainHandle : dvbt2ll_handle {
     odev.fill(oa, oplan, tables.pool);
     oa.cells = 0; oa.cells_stride = cells16_stride();
     oa.cells16 = cell_buf; oa.run_desc = d_run_desc.as<int2>(); oa.run_ptr = d_run_ptr.as<int32_t>();
+    oa.run_cnt = d_run_cnt.as<int32_t>(); oa.desc_cap = (tables.max_runs + 2) & ~1;
     oa.stage_bytes = d_stage_bytes.as<int32_t>(); oa.stage_cap = stage_cap; oa.lut_single = map.plan.im_from_re;
     oa.lut = map.d_lut.as<float2>(); oa.lut_n = 1 << map.plan.mod;
     oa.out = d_out; oa.out_stride = oplan.samples_per_frame;
+    oa.cells_len = (long long)frames * cells16_stride(); oa.out_len = (long long)frames * oplan.samples_per_frame;
     oa.out_fmt = sink_fmt; oa.sink_gain = sink_gain; oa.norm = oplan.normalization * sink_gain;
     if (oa.scratch && scratch_slot) oa.scratch += odev.scratch_slot_elems;
     oa.frames = frames; oa.frames_per_channel = n_frames;
@@ -859,6 +880,7 @@ struct ChainHandle : dvbt2ll_handle {
     if (n == "chain.pool") return copy_vec(tables.pool.cells, out, cap);
     if (n == "chain.run_desc") return copy_vec(tables.run_desc, out, cap);
     if (n == "chain.run_ptr") return copy_vec(tables.run_ptr, out, cap);
+    if (n == "chain.run_cnt") return copy_vec(tables.run_cnt, out, cap);
     if (n == "chain.stage_bytes") return copy_vec(tables.stage_bytes, out, cap);
     if (n == "ofdm.sym_data_start") return copy_vec(oplan.sym_data_start, out, cap);
     if (n == "frame.framed") return copy_vec(fplan.framed, out, cap);
@@ -881,7 +903,11 @@ struct ChainHandle : dvbt2ll_handle {
 extern "C" {
 
 const char *dvbt2ll_last_error(void) { return g_err.c_str(); }
-const char *dvbt2ll_version(void) { return "dvbt2ll-b200 0.1 (sm_100a)"; }
+#ifdef DVBT2LL_DEBUG_BOUNDS
+const char *dvbt2ll_version(void) { return "dvbt2ll-b200 0.2 (sm_100a, bounds-checking debug build)"; }
+#else
+const char *dvbt2ll_version(void) { return "dvbt2ll-b200 0.2 (sm_100a)"; }
+#endif
 long long dvbt2ll_kernel_launches(void) { return t2k::kernel_launch_count(); }
 
 int dvbt2ll_device_available(void)

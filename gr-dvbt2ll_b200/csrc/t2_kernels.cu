@@ -17,6 +17,23 @@
 
 #include <atomic>
 
+// Bounds-checking debug build (make -C gr-dvbt2ll_b200/csrc debug -> libdvbt2ll_cuda_dbg.so, selected with
+// DVBT2LL_LIB): every index the kernels derive from tables or stream positions is checked against the extent of
+// the buffer it addresses; a violation prints its source line and traps.  compute-sanitizer is closed on the GPU
+// pool, so the parity suite is run once under this build instead.
+#ifdef DVBT2LL_DEBUG_BOUNDS
+#include <cstdio>
+#define BND(ok)                                                                                                   \
+  do {                                                                                                            \
+    if (!(ok)) {                                                                                                  \
+      printf("DVBT2LL bounds violation: %s (t2_kernels.cu:%d, block %d thread %d)\n", #ok, __LINE__, (int)blockIdx.x, (int)threadIdx.x); \
+      __trap();                                                                                                   \
+    }                                                                                                             \
+  } while (0)
+#else
+#define BND(ok) do { } while (0)
+#endif
+
 namespace t2k {
 
 static std::atomic<long long> g_launches(0);
@@ -144,9 +161,12 @@ __global__ void __launch_bounds__(BB_MAX_WARPS * 32) k_bb_bch(const BbArgs a)
     else t_start = P0 == 0 ? 0 : hem_ts_index(P0 - 1, a.count0) + 1;
     const int count = (int)((a.count0 + t_start) % 188);
 
+    BND(10 + Dj + (ib ? 13 : 0) <= msg_bytes && msg_bytes + a.bch_r / 8 == nbytes && nbytes <= buf_pitch - HIST);
+    BND(a.out_len == 0 || (long long)(job + 1) * a.out_pitch <= a.out_len + (a.out_pitch - nbytes));
     // ---- stage the raw payload in shared memory (buf byte 10 + i = payload byte i)
     if (!hem) {
       const uint8_t *src = ts + P0;
+      BND(a.ts_len == 0 || (P0 >= 0 && P0 + Dj <= a.ts_len));
       {
         // the TS is read once, from DRAM: ask L2 for the payload of this warp's NEXT FECFRAME now
         const int nj = job + gridDim.x * nwarps;
@@ -173,6 +193,7 @@ __global__ void __launch_bounds__(BB_MAX_WARPS * 32) k_bb_bch(const BbArgs a)
       for (int k = 1 + lane; k <= 187; k += 32) buf[10 - k] = (P0 - k >= 0 || a.hist_valid) ? src[-k] : (uint8_t)0;
     }
     else {
+      BND(a.ts_len == 0 || hem_ts_index(P0 + Dj - 1, a.count0) < a.ts_len);
       for (int i = lane; i < Dj; i += 32) buf[10 + i] = ts[hem_ts_index(P0 + i, a.count0)];
       // sync bytes skipped by this frame: positions between t_start and the last payload byte
       const long long t_end = hem_ts_index(P0 + Dj - 1, a.count0);
@@ -196,6 +217,7 @@ __global__ void __launch_bounds__(BB_MAX_WARPS * 32) k_bb_bch(const BbArgs a)
           // (word & position mask) over the words, the masks being constant-bank operands -- no table look-ups, no
           // serial state
           const uint8_t *p = buf + 10 + si - 188;
+          BND(10 + si - 188 >= -HIST && si < Dj);
           const uint32_t *pw = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
           const int sh = (int)(reinterpret_cast<uintptr_t>(p) & 3) * 8;
           uint32_t lo = pw[0];
@@ -399,6 +421,9 @@ __global__ void __launch_bounds__(LDPC_WARPS * 32, 8) k_ldpc(const LdpcArgs a, i
     const uint8_t *in = a.in + (long long)job * a.in_pitch;
     uint8_t *out = a.out + (long long)job * a.out_pitch;
     const uint32_t *cw = reinterpret_cast<const uint32_t *>(in);      // packed BCH codeword, read through L1
+    BND(a.in_len == 0 || (long long)job * a.in_pitch + 45 * G + 8 <= a.in_len);
+    BND(a.out_len == 0 || (long long)job * a.out_pitch + a.nldpc / 8 <= a.out_len);
+    BND(45 * G == info_bytes && warp_words >= G * 13 + q * 12);
     // ---- info bits pass through to the output
     {
       uint32_t *ow = reinterpret_cast<uint32_t *>(out);
@@ -417,6 +442,32 @@ __global__ void __launch_bounds__(LDPC_WARPS * 32, 8) k_ldpc(const LdpcArgs a, i
     }
     __syncwarp();
     // ---- pre-accumulator parity rows: R_t = XOR of rotated info groups
+    if (q >= 24) {
+      // a lane per row, all twelve words of it: a table entry is fetched and decoded once per row instead of once
+      // per word, and the window position just advances by 32 bits (mod 360) from word to word
+      for (int t = lane; t < q; t += 32) {
+        uint32_t acc[12];
+#pragma unroll
+        for (int w = 0; w < 12; w++) acc[w] = 0u;
+        const int e1 = a.row_ptr[t + 1];
+        for (int e = a.row_ptr[t]; e < e1; e++) {
+          const uint32_t en = __ldg(a.entries + e);
+          BND((int)(en & 0xffffu) < G && (en >> 16) < 360u);
+          const uint32_t *eg = ext + (en & 0xffffu) * 13;
+          int p = (en >> 16) ? 360 - (int)(en >> 16) : 0;
+#pragma unroll
+          for (int w = 0; w < 12; w++) {
+            acc[w] ^= window32(eg, p);
+            p += 32;
+            if (p >= 360) p -= 360;
+          }
+        }
+        acc[11] &= 0xFF000000u;
+#pragma unroll
+        for (int w = 0; w < 12; w++) rows[t * 12 + w] = acc[w];
+      }
+    }
+    else
     for (int idx = lane; idx < q * 12; idx += 32) {
       const int t = idx / 12, w = idx - t * 12;
       uint32_t acc = 0;
@@ -425,6 +476,7 @@ __global__ void __launch_bounds__(LDPC_WARPS * 32, 8) k_ldpc(const LdpcArgs a, i
         const uint32_t en = __ldg(a.entries + e);
         int p = 32 * w - (int)(en >> 16);
         if (p < 0) p += 360;
+        BND((int)(en & 0xffffu) < G && (en >> 16) < 360u && p >= 0 && p < 360);
         acc ^= window32(ext + (en & 0xffffu) * 13, p);
       }
       if (w == 11) acc &= 0xFF000000u;
@@ -684,6 +736,40 @@ __device__ __forceinline__ void map_body(const MapArgs &a, const int f, const ui
     // chain mode: the 16-bit codes in cell-interleaved order: cell ci_inv[y] goes to position (y + shift) mod Nc.
     // Two segments with a constant position - y, so table reads and stores are a base pointer + constant offsets.
     uint16_t *o16 = a.out16 + (long long)(f / a.fecblocks) * a.out16_frame_stride + (long long)(f % a.fecblocks) * Nc;
+    if (a.ci_inv4) {
+      // four cells per step: destinations taken in aligned groups of four (one 8-byte store); their four permutation
+      // entries are one 8-byte load from the copy of the table that is shifted by the group's source phase
+      // (ci_inv4[k][j] = ci_inv[j + k]); ragged ends of a segment go cell by cell
+      const long long a0 = o16 - a.out16;                     // absolute cell index of destination 0 (a.out16 is 16-byte aligned)
+#pragma unroll 1
+      for (int seg = 0; seg < 2; seg++) {
+        const int y_beg = seg ? Nc - shift : 0, y_end = seg ? Nc : Nc - shift;
+        const int dofs = seg ? shift - Nc : shift;            // destination = y + dofs
+        if (y_end <= y_beg) continue;
+        const int head = (int)((4 - ((a0 + y_beg + dofs) & 3)) & 3);
+        const int yv = min(y_end, y_beg + head);              // first y of the aligned part
+        const int ngrp = (y_end - yv) >> 2;
+        const int k = yv & 3;                                 // source phase of every group
+        const uint2 *ci4 = reinterpret_cast<const uint2 *>(a.ci_inv4 + (long long)k * a.ci_inv4_stride + (yv - k));
+        uint2 *ov = reinterpret_cast<uint2 *>(o16 + yv + dofs);
+#pragma unroll 2
+        for (int g = threadIdx.x; g < ngrp; g += MAP_THREADS) {
+          const uint2 ci = __ldg(ci4 + g);
+          const unsigned c0 = ci.x & 0xFFFFu, c1 = ci.x >> 16, c2 = ci.y & 0xFFFFu, c3 = ci.y >> 16;
+          BND((int)c0 < Nc && (int)c1 < Nc && (int)c2 < Nc && (int)c3 < Nc);
+          BND(a.out_len == 0 || (a0 + yv + dofs + 4ll * g >= 0 && a0 + yv + dofs + 4ll * g + 4 <= a.out_len));
+          ov[g] = make_uint2(code(c0) | (code(c1) << 16), code(c2) | (code(c3) << 16));
+        }
+        // ragged ends: up to 3 cells before and after the aligned part
+        const int tail0 = yv + 4 * ngrp;
+        const int nrag = (yv - y_beg) + (y_end - tail0);
+        if ((int)threadIdx.x < nrag) {
+          const int y = (int)threadIdx.x < yv - y_beg ? y_beg + threadIdx.x : tail0 + (threadIdx.x - (yv - y_beg));
+          o16[y + dofs] = (uint16_t)code(__ldg(a.ci_inv + y));
+        }
+      }
+    }
+    else {
 #pragma unroll 1
     for (int seg = 0; seg < 2; seg++) {
       const int y_end = seg ? Nc : Nc - shift;
@@ -701,6 +787,7 @@ __device__ __forceinline__ void map_body(const MapArgs &a, const int f, const ui
         for (int k = 0; k < 8; k++)
           if (k * MAP_THREADS < left) oy[k * MAP_THREADS] = (uint16_t)code(c[k]);
       }
+    }
     }
   }
   else if (a.ci_inv) {
@@ -1291,7 +1378,7 @@ __device__ __forceinline__ void ofdm_fill(float2 *x, const int32_t *__restrict__
                                           int (&c)[FillGeom<LOG2M, T>::GPB][FillGeom<LOG2M, T>::R0],
                                           const uint8_t *stage, const float *lut_re, const float *lut_im, int lut_rep_shift,
                                           const uint8_t *spool_m8, const float2 *__restrict__ cells,
-                                          const float2 *__restrict__ pool)
+                                          const float2 *__restrict__ pool, int stage_cap_dbg = 0)
 {
   typedef FillGeom<LOG2M, T> G;
   constexpr int R0 = G::R0, GPB = G::GPB;
@@ -1307,6 +1394,7 @@ __device__ __forceinline__ void ofdm_fill(float2 *x, const int32_t *__restrict__
           // data cell: 16-bit code from the staging area through the LUT (a dummy read of offset 0 for the others);
           // small pool cell (null, pilots): (p + 1) << 17 -> spool[p]; big pool cell: sign bit set (POOL symbols only)
           const unsigned off = POOL && cc < 0 ? 0u : (unsigned)cc & 0x1FFFFu;
+          BND(cc < 0 || cc >= 0x20000 || off + 2 <= 2u * (unsigned)stage_cap_dbg);
           const unsigned sc = *reinterpret_cast<const uint16_t *>(stage + off);
           // the LUTs are replicated 2^lut_rep_shift times (entry e, copy c at e * copies + c) and a lane reads copy
           // lane mod copies: with 16 copies only lanes l and l + 16 can collide (2 wavefronts instead of ~3.4)
@@ -1353,18 +1441,24 @@ __global__ void __launch_bounds__(T, (LOG2M == 14 ? 1 : 1024 / T)) k_ofdm(const 
   // one table when the cell codes carry w~ (Im = Re lut[w~]), else a second one for the imaginary parts
   float *lut_im = a.lut_single ? lut_re : lut_re + 256 * lut_rep;
   float2 *spool = reinterpret_cast<float2 *>(lut_re + (a.lut_single ? 256 : 512) * lut_rep);      // first 8 pool cells: zero and the pilot values
-  uint64_t *mbar = reinterpret_cast<uint64_t *>(spool + 8);                 // completion barrier of the staging copies
-  const uint32_t mbar_s = (uint32_t)__cvta_generic_to_shared(mbar);
+  uint64_t *mbar = reinterpret_cast<uint64_t *>(spool + 8);                 // completion barriers: [0] staging copies, [1] descriptors
+  const uint32_t mbar_s = (uint32_t)__cvta_generic_to_shared(mbar), dbar_s = mbar_s + 8;
+  const int2 *descbuf = reinterpret_cast<const int2 *>(mbar + 2);           // the next symbol's copy descriptors
+  const uint32_t desc_s = mbar_s + 16;
   if (C16) {
-    for (int i = threadIdx.x; i < a.lut_n * lut_rep; i += T) {
-      const float2 v = __ldg(a.lut + (i >> lut_rep_shift));
-      lut_re[i] = v.x;
-      if (!a.lut_single) lut_im[i] = v.y;
-    }
+    // the constellation table goes through the (still unused) transform buffer: one L2 round trip, then replication
+    if (threadIdx.x < a.lut_n) x[threadIdx.x] = __ldg(a.lut + threadIdx.x);
     if (threadIdx.x < 8) spool[threadIdx.x] = __ldg(a.pool + threadIdx.x);
     if (threadIdx.x == 0) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(mbar_s) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(dbar_s) : "memory");
       asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < a.lut_n * lut_rep; i += T) {
+      const float2 v = x[i >> lut_rep_shift];
+      lut_re[i] = v.x;
+      if (!a.lut_single) lut_im[i] = v.y;
     }
     __syncthreads();
   }
@@ -1392,25 +1486,44 @@ __global__ void __launch_bounds__(T, (LOG2M == 14 ? 1 : 1024 / T)) k_ofdm(const 
   // the threads, all completing on one mbarrier whose transaction count is the symbol's byte total.  Issued for symbol
   // u + gridDim.x as soon as symbol u's last fill has finished reading the staging area, so the copies run under the
   // FFT passes without occupying the load/store pipe.
-  uint32_t mphase = 0;
+  // The descriptors themselves (8 bytes per run, from L2) are fetched one symbol further ahead, by one more bulk copy
+  // into shared memory, so issuing a symbol's copies never waits on global memory.
+  uint32_t mphase = 0, dphase = 0;
   // (first run, run count) of a symbol's copy list; requested a symbol ahead of its use (cp1 below)
   auto run_range = [&](int u) {
     const int ul = u % a.num_symbols;
-    const int r0 = __ldg(a.run_ptr + ul);
-    return make_int2(r0, __ldg(a.run_ptr + ul + 1) - r0);
+    return make_int2(__ldg(a.run_ptr + ul), __ldg(a.run_cnt + ul));
+  };
+  // one thread: fetch the descriptors of a symbol into descbuf (lists are 16-byte aligned and padded)
+  auto desc_issue = [&](int2 rr) {
+    if (rr.y <= 0) return;
+    const uint32_t bytes = (uint32_t)((rr.y + 1) >> 1) * 16u;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(dbar_s), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(desc_s), "l"(a.run_desc + rr.x), "r"(bytes), "r"(dbar_s) : "memory");
   };
   auto stage_issue = [&](int u, int2 rr) {
     if (rr.y <= 0) return;
+    {
+      uint32_t done;
+      do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(done) : "r"(dbar_s), "r"(dphase) : "memory");
+      } while (!done);
+      dphase ^= 1u;
+    }
     const int uf = u / a.num_symbols, ul = u - uf * a.num_symbols;
     const uint8_t *src = reinterpret_cast<const uint8_t *>(a.cells16 + (long long)uf * a.cells_stride);
     // the fill's reads of the staging area (generic proxy) are ordered before these writes (async proxy)
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     if (threadIdx.x == 0)
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(mbar_s), "r"(__ldg(a.stage_bytes + ul)) : "memory");
-    const int2 *rd = a.run_desc + rr.x;
 #pragma unroll 2
     for (int i = threadIdx.x; i < rr.y; i += T) {
-      const int2 d = __ldg(rd + i);
+      const int2 d = descbuf[i];
+      BND(i < a.desc_cap);
+      BND(((unsigned)d.y >> 16) + ((unsigned)d.y & 0xFFFFu) <= (unsigned)a.stage_cap / 8u && d.x >= 0);
+      BND(a.cells_len == 0 || (long long)uf * a.cells_stride * 2 + 16ll * (d.x + (d.y & 0xFFFF)) <= a.cells_len * 2 + 64);
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
                    ::"r"(stage_s + 16u * ((uint32_t)d.y >> 16)), "l"(src + 16ll * d.x), "r"(16u * ((uint32_t)d.y & 0xFFFFu)), "r"(mbar_s) : "memory");
     }
@@ -1425,7 +1538,10 @@ __global__ void __launch_bounds__(T, (LOG2M == 14 ? 1 : 1024 / T)) k_ofdm(const 
   };
 
   int2 cp0 = make_int2(0, 0), cp1 = cp0;      // copy lists of this CTA's current and next symbol
-  if (C16 && (int)blockIdx.x < units) cp0 = run_range(blockIdx.x);
+  if (C16 && (int)blockIdx.x < units) {
+    cp0 = run_range(blockIdx.x);
+    if (threadIdx.x == 0) desc_issue(cp0);
+  }
   for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
     const int f = unit / a.num_symbols, l = unit - f * a.num_symbols;
     if (C16 && unit + (int)gridDim.x < units) cp1 = run_range(unit + gridDim.x);
@@ -1436,6 +1552,7 @@ __global__ void __launch_bounds__(T, (LOG2M == 14 ? 1 : 1024 / T)) k_ofdm(const 
     typedef typename SinkT<FMT>::type sample_t;
     sample_t *out = reinterpret_cast<sample_t *>(a.out) + (long long)f * a.out_stride;
     sample_t *sym = out + 2048 + (long long)l * (N + a.gi);
+    BND(a.out_len == 0 || (long long)f * a.out_stride + 2048 + (long long)(l + 1) * (N + a.gi) <= a.out_len);
     // parking space for the even-bin half of a 32K symbol: the first half of the symbol itself when the output is
     // complex64 (the odd-bin phase overwrites it in place, the lines are still in L2), a per-CTA scratch slot otherwise
     float2 *park = FMT == 0 ? reinterpret_cast<float2 *>(sym) + a.gi : a.scratch + (long long)blockIdx.x * M;
@@ -1462,14 +1579,16 @@ __global__ void __launch_bounds__(T, (LOG2M == 14 ? 1 : 1024 / T)) k_ofdm(const 
       const uint8_t *spool_m8 = reinterpret_cast<const uint8_t *>(spool) - 8;
       if (phase) fill_load_codes<LOG2M, T>(code, threadIdx.x, c);
       __syncthreads();      // staging area landed (phase 0) / previous phase has finished reading x
+      // every thread is past its reads of the descriptor buffer: the next symbol's list may come in
+      if (C16 && phase == 0 && threadIdx.x == 0 && unit + (int)gridDim.x < units) desc_issue(cp1);
       // ---- 1. carrier fill (+ first pass)
       if (sinc) {
-        if (pool_sym) ofdm_fill<LOG2M, T, C16, true, true>(x, code, sinc, c, stage, lut_re, lut_im, lut_rep_shift, spool_m8, cells, pool);
-        else ofdm_fill<LOG2M, T, C16, false, true>(x, code, sinc, c, stage, lut_re, lut_im, lut_rep_shift, spool_m8, cells, pool);
+        if (pool_sym) ofdm_fill<LOG2M, T, C16, true, true>(x, code, sinc, c, stage, lut_re, lut_im, lut_rep_shift, spool_m8, cells, pool, a.stage_cap);
+        else ofdm_fill<LOG2M, T, C16, false, true>(x, code, sinc, c, stage, lut_re, lut_im, lut_rep_shift, spool_m8, cells, pool, a.stage_cap);
       }
       else {
-        if (pool_sym) ofdm_fill<LOG2M, T, C16, true, false>(x, code, sinc, c, stage, lut_re, lut_im, lut_rep_shift, spool_m8, cells, pool);
-        else ofdm_fill<LOG2M, T, C16, false, false>(x, code, sinc, c, stage, lut_re, lut_im, lut_rep_shift, spool_m8, cells, pool);
+        if (pool_sym) ofdm_fill<LOG2M, T, C16, true, false>(x, code, sinc, c, stage, lut_re, lut_im, lut_rep_shift, spool_m8, cells, pool, a.stage_cap);
+        else ofdm_fill<LOG2M, T, C16, false, false>(x, code, sinc, c, stage, lut_re, lut_im, lut_rep_shift, spool_m8, cells, pool, a.stage_cap);
       }
       __syncthreads();
       // every fill of the symbol has read its cells: the next symbol's cells may replace them (under the passes)
@@ -1612,7 +1731,7 @@ static void launch_ofdm_t(const OfdmArgs &a, cudaStream_t s)
 {
   constexpr int M = 1 << LOG2M;
   const size_t smem = (size_t)padx(M) * sizeof(float2) +
-                      (C16 ? (size_t)a.stage_cap * 2 + ((size_t)(a.lut_single ? 1024 : 2048) << a.lut_rep_shift) + 64 + 16 : 0);
+                      (C16 ? (size_t)a.stage_cap * 2 + ((size_t)(a.lut_single ? 1024 : 2048) << a.lut_rep_shift) + 64 + 16 + (size_t)a.desc_cap * 8 : 0);
   const int units = a.frames * a.num_symbols;
   static bool attr[MAX_DEVICES];
   allow_smem(k_ofdm<LOG2M, T, C16, FMT, SPLIT>, 227 * 1024, attr);
@@ -1650,7 +1769,7 @@ void launch_ofdm(const OfdmArgs &a0, cudaStream_t s)
   // (without lowering the number of CTAs per SM that fit without replication; 2 resident CTAs at most are useful below 16K)
   a.lut_rep_shift = 0;
   if (a.cells16) {
-    const size_t base = (size_t)padx(1 << a.log2_m) * sizeof(float2) + (size_t)a.stage_cap * 2 + 64 + 16, sm_bytes = 227 * 1024;
+    const size_t base = (size_t)padx(1 << a.log2_m) * sizeof(float2) + (size_t)a.stage_cap * 2 + 64 + 16 + (size_t)a.desc_cap * 8, sm_bytes = 227 * 1024;
     const size_t one = a.lut_single ? 1024 : 2048;
     size_t ctas = sm_bytes / (base + one + 1024);
     if (ctas < 1) ctas = 1;

@@ -31,6 +31,9 @@ struct BbArgs {
   uint8_t *out;               // packed codewords, pitch out_pitch bytes per FECFRAME
   int out_pitch;
   int *sync_errors;           // counter of payload sync bytes != 0x47 (reference logs a warning)
+  // buffer extents for the bounds-checking debug build (DVBT2LL_DEBUG_BOUNDS); 0 = unknown, not checked
+  long long ts_len;           // valid TS bytes per channel from ts + c * ts_pitch on
+  long long out_len;          // bytes behind `out`
 };
 void launch_bb_bch(const BbArgs &a, cudaStream_t s);
 
@@ -42,6 +45,7 @@ struct LdpcArgs {
   int nbch, nldpc, q, groups;
   const uint16_t *row_ptr;   // q + 1
   const uint32_t *entries;   // (shift << 16) | group
+  long long in_len, out_len; // bytes behind in / out (debug build bounds checks; 0 = not checked)
 };
 void launch_ldpc(const LdpcArgs &a, cudaStream_t s);
 
@@ -62,12 +66,17 @@ struct MapArgs {
   uint16_t *out16;           // chain mode: 16-bit cell codes (own word | imaginary-part word << 8) instead of `out`
   long long out16_frame_stride;   // cells between T2 frames in out16 (multiple of 4: frames stay 8-byte aligned)
   const uint16_t *ci_inv;    // inverse of the cell permutation, or NULL for natural order
+  // chain mode, optional: four copies of ci_inv shifted by 0..3 entries (copy k, entry j = ci_inv[j + k], copies
+  // ci_inv4_stride entries apart, 8-byte aligned) so that any four consecutive entries are one aligned 8-byte load
+  const uint16_t *ci_inv4;
+  int ci_inv4_stride;
   const int32_t *fec_shift;  // [fecblocks] cyclic shift per FEC block of the T2 frame
   int fecblocks;
   // single-table constellation (MapPlan::im_from_re): the word supplying the imaginary part is stored as
   // w~ = (((w << 1) & im_mask_i) | ((w >> 1) & im_mask_q)) ^ im_flip, and Im = Re lut[w~]
   int im_from_re;
   uint32_t im_mask_i, im_mask_q, im_flip;
+  long long in_len, out_len; // bytes behind in, cells behind out / out16 (debug build bounds checks; 0 = not checked)
 };
 void launch_map(const MapArgs &a, cudaStream_t s);
 // K2 + K3 fused, one FECFRAME per CTA: l.in = packed BCH codewords (l.out unused), a = mapper arguments (a.in unused);
@@ -106,7 +115,9 @@ struct OfdmArgs {
   // bulk copies (cp.async.bulk) that stage a symbol's cells in shared memory: run i = { source 16-byte unit from the
   // frame's first cell, (staging 16-byte unit << 16) | length in units }, symbols back to back
   const int2 *run_desc;
-  const int32_t *run_ptr;    // [num_symbols + 1]
+  const int32_t *run_ptr;    // [num_symbols + 1] first run of each symbol (even)
+  const int32_t *run_cnt;    // [num_symbols] number of runs
+  int desc_cap;              // run descriptors the shared-memory descriptor buffer holds (even, >= the longest list)
   const int32_t *stage_bytes;// [num_symbols] bytes delivered by the symbol's copies
   const int32_t *sym_flags;  // [num_symbols] bit 0: the symbol has carriers coded 0x80000000 + pool cell
   int stage_cap;             // staging slots (cells) reserved in shared memory (multiple of 8)
@@ -130,6 +141,9 @@ struct OfdmArgs {
   float norm;
   int frames; int frame_idx0;         // t2 frame number of the first frame, reduced mod l1post_variants by the host
   int frames_per_channel;    // frame f -> t2 frame number frame_idx0 + (f % frames_per_channel)
+  // extents for the debug build bounds checks (0 = not checked): cells behind cells / cells16, samples behind out,
+  // cells in one copy of the pool
+  long long cells_len, out_len, pool_len;
 };
 void launch_ofdm(const OfdmArgs &a, cudaStream_t s);
 // shared-memory position (before swizzle) at which the carrier-fill stage must store bin m of an

@@ -212,7 +212,9 @@ struct Chain16Tables {
   // bulk copies that stage a symbol's cells: 2 words per run = { source 16-byte unit (from the frame's first cell),
   // (staging 16-byte unit << 16) | length in 16-byte units }, symbols back to back
   std::vector<int32_t> run_desc;
-  std::vector<int32_t> run_ptr;     // [num_symbols + 1] in runs
+  std::vector<int32_t> run_ptr;     // [num_symbols + 1] first run of each symbol (even: lists are 16-byte aligned, padded with a zero entry)
+  std::vector<int32_t> run_cnt;     // [num_symbols] runs of each symbol
+  int max_runs;                     // longest list
   std::vector<int32_t> stage_bytes; // [num_symbols] bytes the symbol's copies deliver (mbarrier transaction count)
   int max_slots;                    // largest number of staging slots (cells) of any symbol
   CellPool pool;

@@ -329,7 +329,9 @@ bool compose_chain16(const FramePlan &fp, const OfdmPlan &op, Chain16Tables *out
   out->run_desc.clear();
   out->run_ptr.assign(L + 1, 0);
   out->stage_bytes.assign(L, 0);
+  out->run_cnt.assign(L, 0);
   out->max_slots = 0;
+  out->max_runs = 0;
   for (int l = 0; l < L; l++) {
     const int s0 = op.sym_data_start[l], s1 = op.sym_data_start[l + 1];     // frame positions of this symbol
     // staging layout: the symbol's source cells sorted by source address, copied run by run with bulk
@@ -344,6 +346,7 @@ bool compose_chain16(const FramePlan &fp, const OfdmPlan &op, Chain16Tables *out
     }
     std::sort(ps.begin(), ps.end());
     std::vector<int32_t> slot_of_pos(s1 - s0, -1);
+    if ((out->run_desc.size() / 2) & 1) { out->run_desc.push_back(0); out->run_desc.push_back(0); }   // lists start 16-byte aligned
     out->run_ptr[l] = (int32_t)(out->run_desc.size() / 2);
     int32_t next_unit = 0;                              // 16-byte staging units used so far
     size_t i = 0;
@@ -368,6 +371,8 @@ bool compose_chain16(const FramePlan &fp, const OfdmPlan &op, Chain16Tables *out
       i = j;
     }
     out->stage_bytes[l] = 16 * next_unit;
+    out->run_cnt[l] = (int32_t)(out->run_desc.size() / 2) - out->run_ptr[l];
+    if (out->run_cnt[l] > out->max_runs) out->max_runs = out->run_cnt[l];
     if (8 * next_unit > out->max_slots) out->max_slots = 8 * next_unit;
     // carrier codes: data carrier -> staging slot of its cell
     for (int k = 0; k < cps; k++) {
@@ -383,6 +388,7 @@ bool compose_chain16(const FramePlan &fp, const OfdmPlan &op, Chain16Tables *out
     }
   }
   out->run_ptr[L] = (int32_t)(out->run_desc.size() / 2);
+  out->run_desc.push_back(0); out->run_desc.push_back(0);      // the kernel fetches lists in 16-byte units
   return true;
 }
 

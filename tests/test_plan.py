@@ -117,6 +117,8 @@ def test_chain16_tables(name):
     ci_dst = ch.plan("frame.ci_dst", np.int32)
     run_desc = ch.plan("chain.run_desc", np.int32).reshape(-1, 2)
     run_ptr = ch.plan("chain.run_ptr", np.int32)
+    run_cnt = ch.plan("chain.run_cnt", np.int32)
+    assert np.all(run_ptr[:-1] % 2 == 0)                    # every list starts 16-byte aligned (fetched by a bulk copy)
     stage_bytes = ch.plan("chain.stage_bytes", np.int32)
     starts = ch.plan("ofdm.sym_data_start", np.int32)
     dims = ch.plan("ofdm.dims", np.int32)
@@ -128,7 +130,8 @@ def test_chain16_tables(name):
     pad = (-ci_dst.size) % 8
     mem = np.concatenate([cells16, np.zeros(pad + 8, dtype=np.int64)])
     for l in range(L):
-        runs = run_desc[run_ptr[l]:run_ptr[l + 1]].astype(np.int64)
+        runs = run_desc[run_ptr[l]:run_ptr[l] + run_cnt[l]].astype(np.int64)
+        assert run_ptr[l] + run_cnt[l] <= run_ptr[l + 1] <= run_ptr[l] + run_cnt[l] + 1
         src_u, dst_u, n_u = runs[:, 0], (runs[:, 1] >> 16) & 0xFFFF, runs[:, 1] & 0xFFFF
         assert int(16 * n_u.sum()) == int(stage_bytes[l])
         stage = np.full(int(8 * (dst_u + n_u).max()) if len(runs) else 0, -1, dtype=np.int64)
