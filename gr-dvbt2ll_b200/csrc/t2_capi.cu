@@ -404,7 +404,8 @@ struct BbHandle : dvbt2ll_handle {
 struct LdpcHandle : dvbt2ll_handle {
   t2::LdpcPlan plan;
   DevBuf d_rowptr, d_entries, d_in_packed, d_out_packed;
-  LdpcHandle() : dvbt2ll_handle(LDPC) {}
+  int lane_per_row;         // accumulation scheme of k_ldpc, chosen per code in dev_init (DVBT2LL_LDPC_MODE=0|1 overrides)
+  LdpcHandle() : dvbt2ll_handle(LDPC), lane_per_row(0) {}
   int output_multiple() const { return plan.fec.nldpc; }
   int in_item() const { return 1; }
   int out_item() const { return 1; }
@@ -413,13 +414,24 @@ struct LdpcHandle : dvbt2ll_handle {
   {
     CK(upload(d_rowptr, plan.row_ptr));
     CK(upload(d_entries, plan.entries));
+    // measured on B200 (tools/ldpc_mode_sweep.py, profiles/r2_ldpc_modes.txt)
+    lane_per_row = ldpc_lane_per_row_default(plan.fec.nldpc, plan.fec.q);
+    const char *e = std::getenv("DVBT2LL_LDPC_MODE");
+    if (e && (e[0] == '0' || e[0] == '1')) lane_per_row = e[0] - '0';
     return 0;
+  }
+  static int ldpc_lane_per_row_default(int nldpc, int q)
+  {
+    // a lane per row wins for the low-rate codes (few table entries per row: the per-(row, word) bookkeeping dominates),
+    // a lane per (row, word) for the others (consecutive lanes read consecutive words: fewer bank conflicts)
+    return nldpc == 64800 ? (q >= 90 ? 1 : 0) : (q >= 18 ? 1 : 0);
   }
   void fill_args(t2k::LdpcArgs &a, const uint8_t *in, int in_pitch, uint8_t *out, int out_pitch, int frames)
   {
     a.in = in; a.in_pitch = in_pitch; a.out = out; a.out_pitch = out_pitch; a.frames = frames;
     a.nbch = plan.fec.nbch; a.nldpc = plan.fec.nldpc; a.q = plan.fec.q; a.groups = plan.groups;
     a.row_ptr = d_rowptr.as<uint16_t>(); a.entries = d_entries.as<uint32_t>();
+    a.lane_per_row = lane_per_row;
     a.in_len = (long long)frames * in_pitch + 64; a.out_len = (long long)frames * out_pitch;
   }
   int work_device(const void *d_in, int ninput, void *d_out, int noutput, int *consumed, cudaStream_t s)

@@ -442,7 +442,7 @@ __global__ void __launch_bounds__(LDPC_WARPS * 32, 8) k_ldpc(const LdpcArgs a, i
     }
     __syncwarp();
     // ---- pre-accumulator parity rows: R_t = XOR of rotated info groups
-    if (q >= 24) {
+    if (a.lane_per_row) {
       // a lane per row, all twelve words of it: a table entry is fetched and decoded once per row instead of once
       // per word, and the window position just advances by 32 bits (mod 360) from word to word
       for (int t = lane; t < q; t += 32) {

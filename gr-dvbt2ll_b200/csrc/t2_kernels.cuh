@@ -45,6 +45,8 @@ struct LdpcArgs {
   int nbch, nldpc, q, groups;
   const uint16_t *row_ptr;   // q + 1
   const uint32_t *entries;   // (shift << 16) | group
+  int lane_per_row;          // 1: a lane accumulates all 12 words of a parity row (fewer instructions, more bank conflicts);
+                             // 0: a lane per (row, word).  Which is faster depends on the code: set from the plan.
   long long in_len, out_len; // bytes behind in / out (debug build bounds checks; 0 = not checked)
 };
 void launch_ldpc(const LdpcArgs &a, cudaStream_t s);
