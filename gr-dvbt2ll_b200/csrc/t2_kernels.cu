@@ -1369,6 +1369,15 @@ __device__ __forceinline__ void fill_load_codes(const int32_t *__restrict__ code
   }
 }
 
+// shared-window addresses the chain-mode fill works with (see ofdm_fill)
+struct FillSmem {
+  uint32_t stage_s;        // staging area
+  uint32_t lut_lane_s;     // real-part table + 4 * (lane mod copies)
+  uint32_t im_ofs;         // distance of the imaginary-part table (0 with the single-table cell codes)
+  uint32_t spool_m8_s;     // small pool - 8 bytes
+  uint32_t esh;            // log2 of the bytes between table entries
+};
+
 // carrier fill of one (symbol, phase), fused with the first pass of radix R0.  POOL: the symbol has carriers taken
 // from the big pool (L1 signalling / dummy cells); SINC: inverse-sinc equalisation factors are applied.
 // `c` holds the codes of the thread's first batch (loaded by the caller ahead of the barrier that precedes the fill);
@@ -1378,7 +1387,7 @@ __device__ __forceinline__ void ofdm_fill(float2 *x, const int32_t *__restrict__
                                           int (&c)[FillGeom<LOG2M, T>::GPB][FillGeom<LOG2M, T>::R0],
                                           const uint8_t *stage, const float *lut_re, const float *lut_im, int lut_rep_shift,
                                           const uint8_t *spool_m8, const float2 *__restrict__ cells,
-                                          const float2 *__restrict__ pool, int stage_cap_dbg = 0)
+                                          const float2 *__restrict__ pool, const FillSmem fs, int stage_cap_dbg = 0)
 {
   typedef FillGeom<LOG2M, T> G;
   constexpr int R0 = G::R0, GPB = G::GPB;
@@ -1395,6 +1404,18 @@ __device__ __forceinline__ void ofdm_fill(float2 *x, const int32_t *__restrict__
           // small pool cell (null, pilots): (p + 1) << 17 -> spool[p]; big pool cell: sign bit set (POOL symbols only)
           const unsigned off = POOL && cc < 0 ? 0u : (unsigned)cc & 0x1FFFFu;
           BND(cc < 0 || cc >= 0x20000 || off + 2 <= 2u * (unsigned)stage_cap_dbg);
+#ifndef OFDM_FILL_GENERIC
+          // explicit 32-bit shared-window addresses (one base register + the lane's table column): the generic-pointer
+          // form made the compiler rebuild the window base and the lane offset for every carrier (≈ 10 instructions)
+          unsigned sc;
+          asm volatile("ld.shared.u16 %0, [%1];" : "=r"(sc) : "r"(fs.stage_s + off));
+          // the tables are replicated 2^rep_shift times (entry e, copy c at (e << esh) + 4 c) and a lane reads copy
+          // lane mod copies: with 32 copies no two lanes share a bank, with 16 only lanes l and l + 16 can collide
+          float2 val;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(val.x) : "r"(fs.lut_lane_s + ((sc & 255u) << fs.esh)));
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(val.y) : "r"(fs.lut_lane_s + fs.im_ofs + ((sc >> 8) << fs.esh)));
+          if (cc >= 0x20000) asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(val.x), "=f"(val.y) : "r"(fs.spool_m8_s + ((unsigned)cc >> 14)));
+#else
           const unsigned sc = *reinterpret_cast<const uint16_t *>(stage + off);
           // the LUTs are replicated 2^lut_rep_shift times (entry e, copy c at e * copies + c) and a lane reads copy
           // lane mod copies: with 16 copies only lanes l and l + 16 can collide (2 wavefronts instead of ~3.4)
@@ -1402,6 +1423,7 @@ __device__ __forceinline__ void ofdm_fill(float2 *x, const int32_t *__restrict__
           float2 val = make_float2(*reinterpret_cast<const float *>(reinterpret_cast<const uint8_t *>(lut_re) + (((sc << esh) & emask) | lane_off)),
                                    *reinterpret_cast<const float *>(reinterpret_cast<const uint8_t *>(lut_im) + ((((sc >> 8) << esh) & emask) | lane_off)));
           if (cc >= 0x20000) val = *reinterpret_cast<const float2 *>(spool_m8 + ((unsigned)cc >> 14));
+#endif
           if (POOL && cc < 0) val = __ldg(pool + (cc & 0x7FFFFFFF));
           v[b][r] = val;
         }
@@ -1468,6 +1490,12 @@ __global__ void __launch_bounds__(T, (LOG2M == 14 ? 1 : 1024 / T)) k_ofdm(const 
   const int units = a.frames * a.num_symbols;
   const int cp_from = N - a.gi;
   const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
+  FillSmem fs;
+  fs.stage_s = stage_s;
+  fs.esh = 2u + (uint32_t)lut_rep_shift;
+  fs.lut_lane_s = (uint32_t)__cvta_generic_to_shared(lut_re) + ((threadIdx.x & (uint32_t)(lut_rep - 1)) << 2);
+  fs.im_ofs = a.lut_single ? 0u : 1024u * (uint32_t)lut_rep;
+  fs.spool_m8_s = (uint32_t)__cvta_generic_to_shared(spool) - 8u;
   // 16K sub-transform with 512 threads: every thread runs the same butterflies for every symbol, so their twiddle
   // bases stay in registers for the whole kernel (no L2 round trip at the start of each pass: L1 is ~2 KB here)
   // Pass schedule of the 16K sub-transform: radix 16 (in the fill, no twiddles), 16, 16, 4 (in the output).
@@ -1583,12 +1611,12 @@ __global__ void __launch_bounds__(T, (LOG2M == 14 ? 1 : 1024 / T)) k_ofdm(const 
       if (C16 && phase == 0 && threadIdx.x == 0 && unit + (int)gridDim.x < units) desc_issue(cp1);
       // ---- 1. carrier fill (+ first pass)
       if (sinc) {
-        if (pool_sym) ofdm_fill<LOG2M, T, C16, true, true>(x, code, sinc, c, stage, lut_re, lut_im, lut_rep_shift, spool_m8, cells, pool, a.stage_cap);
-        else ofdm_fill<LOG2M, T, C16, false, true>(x, code, sinc, c, stage, lut_re, lut_im, lut_rep_shift, spool_m8, cells, pool, a.stage_cap);
+        if (pool_sym) ofdm_fill<LOG2M, T, C16, true, true>(x, code, sinc, c, stage, lut_re, lut_im, lut_rep_shift, spool_m8, cells, pool, fs, a.stage_cap);
+        else ofdm_fill<LOG2M, T, C16, false, true>(x, code, sinc, c, stage, lut_re, lut_im, lut_rep_shift, spool_m8, cells, pool, fs, a.stage_cap);
       }
       else {
-        if (pool_sym) ofdm_fill<LOG2M, T, C16, true, false>(x, code, sinc, c, stage, lut_re, lut_im, lut_rep_shift, spool_m8, cells, pool, a.stage_cap);
-        else ofdm_fill<LOG2M, T, C16, false, false>(x, code, sinc, c, stage, lut_re, lut_im, lut_rep_shift, spool_m8, cells, pool, a.stage_cap);
+        if (pool_sym) ofdm_fill<LOG2M, T, C16, true, false>(x, code, sinc, c, stage, lut_re, lut_im, lut_rep_shift, spool_m8, cells, pool, fs, a.stage_cap);
+        else ofdm_fill<LOG2M, T, C16, false, false>(x, code, sinc, c, stage, lut_re, lut_im, lut_rep_shift, spool_m8, cells, pool, fs, a.stage_cap);
       }
       __syncthreads();
       // every fill of the symbol has read its cells: the next symbol's cells may replace them (under the passes)

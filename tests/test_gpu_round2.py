@@ -314,3 +314,42 @@ def test_two_devices_in_one_process(reflib):
     slots, want = _run_gather([0, 1], cfg_name="c4", nch_total=4, nfr=1, steps=5)
     for s in slots:
         assert np.array_equal(s.view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.parametrize("name,over", [("c1", {}), ("c2", {}), ("c4", {"fecblocks": 20}), ("c3", {"rate": K.C1_2})])
+def test_fused_fec_kernel_matches_two_kernel_path(name, over, monkeypatch):
+    """The optional fused LDPC + mapper kernel (DVBT2LL_FUSE_FEC=1) gives bit-identical cells and samples, and its
+    codeword tap equals the two-kernel path's LDPC output."""
+    cfg = K.resolve(dict(K.CONFIGS[name], **over))
+    nfr = 2
+    two = T.Chain(cfg, max_frames=nfr)
+    assert not two.fused_fec
+    ts = K.make_ts(two.ts_bytes(0, nfr), seed=11)
+    want = two.run_host(ts, 1, nfr).copy()
+    want_fec, want_cells = two.tap("fec").copy(), two.tap("cells", np.uint16).copy()
+    monkeypatch.setenv("DVBT2LL_FUSE_FEC", "1")
+    one = T.Chain(cfg, max_frames=nfr)
+    assert one.fused_fec
+    one.enable_taps()
+    got = one.run_host(ts, 1, nfr)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert np.array_equal(one.tap("cells", np.uint16), want_cells)
+    F = cfg["fecblocks"]
+    nbytes = (64800 if cfg["framesize"] else 16200) // 8
+    a = one.tap("fec").reshape(nfr * F, -1)[:, :nbytes]
+    b = want_fec.reshape(nfr * F, -1)[:, :nbytes]
+    assert np.array_equal(a, b)
+
+
+def test_ldpc_both_accumulation_schemes(monkeypatch):
+    """k_ldpc picks a lane per (row, word) or a lane per row by code; both must give the oracle's codewords."""
+    from oracle import t2oracle as O
+    rng = np.random.default_rng(12)
+    for fs, rate in ((1, K.C1_2), (1, K.C2_3), (0, K.C1_3), (0, K.C4_5)):
+        p = O.fec_params(fs, rate)
+        info = rng.integers(0, 2, 3 * p["nbch"], dtype=np.uint8)
+        want = O.ldpc_encode(info.reshape(3, p["nbch"]), fs, rate).reshape(-1)
+        for mode in ("0", "1"):
+            monkeypatch.setenv("DVBT2LL_LDPC_MODE", mode)
+            fec, _ = T.ldpc_bb(fs, rate).work(info, 3)
+            assert bits_equal(fec, want), (fs, rate, mode)
