@@ -168,7 +168,7 @@ struct dvbt2ll_handle {
   std::vector<Pinned> pinned;   // page ranges this handle has already asked the registry for (lock-free fast path)
   bool pin_enabled;
   std::shared_ptr<LinkRec> link_in, link_out;     // set by dvbt2ll_link
-  explicit dvbt2ll_handle(Kind k) : kind(k), stream(0), dev_ready(false), warnings(0), pin_enabled(false)
+  explicit dvbt2ll_handle(Kind k) : kind(k), stream(0), dev_ready(false), warnings(0), pin_enabled(false), bounce(0), bounce_cap(0), bounced_copies(0)
   {
     // opt-in (dvbt2ll_set_host_register or the environment): only safe when the caller's buffers outlive the handle,
     // as the GNU Radio scheduler's do -- a registration must never survive the munmap of its pages
@@ -179,6 +179,7 @@ struct dvbt2ll_handle {
   {
     if (link_out) { std::lock_guard<std::mutex> g(link_out->m); link_out->dev = 0; link_out->bytes = 0; }
     if (!pinned.empty()) PinRegistry::get().release_all(this);
+    if (bounce) cudaFreeHost(bounce);
     if (stream) cudaStreamDestroy(stream);
   }
   // Make [p, p + n) page-locked (page granular).  Adjacent blocks share buffers (one's output is the next one's input)
@@ -196,7 +197,38 @@ struct dvbt2ll_handle {
     Pinned e = { a0, a1 };
     pinned.push_back(e);
   }
-  // host <-> device copy of a caller buffer on `s`, split at the boundaries of registered ranges when registration is on
+  // host <-> device copy of a caller buffer on `s`, split at the boundaries of registered ranges when registration is on.
+  // CUDA refuses a copy whose host range is only partly page-locked (e.g. pages some other component registered or
+  // unregistered behind our back): such a piece goes through a page-locked bounce buffer of our own instead.
+  void *bounce;
+  size_t bounce_cap;
+  long long bounced_copies;
+  cudaError_t copy_piece(void *dst, const void *src, size_t bytes, cudaMemcpyKind kind, cudaStream_t s)
+  {
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, kind, s);
+    if (e == cudaSuccess || !pin_enabled) return e;
+    cudaGetLastError();
+    const size_t chunk = (size_t)4 << 20;
+    if (!bounce) {
+      if (cudaHostAlloc(&bounce, chunk, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return e; }
+      bounce_cap = chunk;
+    }
+    bounced_copies++;
+    for (size_t off = 0; off < bytes; off += bounce_cap) {
+      const size_t n = bytes - off < bounce_cap ? bytes - off : bounce_cap;
+      if (kind == cudaMemcpyHostToDevice) {
+        std::memcpy(bounce, (const char *)src + off, n);
+        if ((e = cudaMemcpyAsync((char *)dst + off, bounce, n, kind, s)) != cudaSuccess) return e;
+        if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+      }
+      else {
+        if ((e = cudaMemcpyAsync(bounce, (const char *)src + off, n, kind, s)) != cudaSuccess) return e;
+        if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+        std::memcpy((char *)dst + off, bounce, n);
+      }
+    }
+    return cudaSuccess;
+  }
   cudaError_t copy_host(void *dst, const void *src, size_t bytes, cudaMemcpyKind kind, cudaStream_t s)
   {
     if (!pin_enabled || pinned.empty()) return cudaMemcpyAsync(dst, src, bytes, kind, s);
@@ -207,7 +239,7 @@ struct dvbt2ll_handle {
     size_t off = 0;
     for (size_t i = 0; i < cut.size(); i++) {
       const size_t end = cut[i] - h0;
-      cudaError_t e = cudaMemcpyAsync((char *)dst + off, (const char *)src + off, end - off, kind, s);
+      cudaError_t e = copy_piece((char *)dst + off, (const char *)src + off, end - off, kind, s);
       if (e != cudaSuccess) return e;
       off = end;
     }
@@ -597,6 +629,11 @@ struct OfdmDevice {
     CK(upload(d_p1, op.p1));
     const int N = op.dims.fft_n;
     split = N > 16384 ? 2 : 1;
+    {
+      // experiment: 16K symbols as two 8K halves recombined through L2 (like 32K), which fits two CTAs per SM
+      const char *e = std::getenv("DVBT2LL_OFDM_SPLIT16K");
+      if (c16 && N == 16384 && e && e[0] == '1') split = 2;
+    }
     scratch_slot_elems = 0;
     const int M = N / split;
     log2_m = 0;
@@ -641,7 +678,7 @@ struct OfdmDevice {
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
       // parking space of the int16-sink 32K path: one M-point region per resident CTA, two slots so that two batches
       // can be in flight on two streams (dvbt2ll_chain_run_host)
-      scratch_slot_elems = (long long)(sms + 8) * M;
+      scratch_slot_elems = (long long)(4 * sms + 8) * M;      // up to 4 resident CTAs per SM below 16K sub-transforms
       CK(d_scratch.ensure((size_t)2 * scratch_slot_elems * sizeof(float2)));
     }
     return 0;
@@ -801,6 +838,9 @@ struct ChainHandle : dvbt2ll_handle {
     const size_t nfec = (size_t)max_frames * F();
     CK(d_bch.ensure(nfec * align16(bb.plan.fec.nbch / 8) + 64));
     CK(d_cells.ensure((size_t)max_frames * cells16_stride() * sizeof(uint16_t) + 64));   // 16-bit cell codes
+    // the padding cells between frames and the slack behind the last one are never written by the mapper but travel
+    // with the aligned bulk copies: give them a valid code once
+    CK(cudaMemset(d_cells.p, 0, (size_t)max_frames * cells16_stride() * sizeof(uint16_t) + 64));
     for (int s = 0; s < TIMING_SLOTS; s++) for (int i = 0; i < 5; i++) CK(cudaEventCreate(&ev[s][i]));
     return 0;
   }

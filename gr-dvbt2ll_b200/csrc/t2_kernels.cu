@@ -1461,8 +1461,9 @@ __global__ void __launch_bounds__(T, (LOG2M == 14 ? 1 : 1024 / T)) k_ofdm(const 
   float *lut_re = reinterpret_cast<float *>(stage + 2 * a.stage_cap);
   const int lut_rep_shift = a.lut_rep_shift, lut_rep = 1 << lut_rep_shift;
   // one table when the cell codes carry w~ (Im = Re lut[w~]), else a second one for the imaginary parts
-  float *lut_im = a.lut_single ? lut_re : lut_re + 256 * lut_rep;
-  float2 *spool = reinterpret_cast<float2 *>(lut_re + (a.lut_single ? 256 : 512) * lut_rep);      // first 8 pool cells: zero and the pilot values
+  const int lut_e = a.lut_n < 16 ? 16 : a.lut_n;      // table entries kept (a multiple of 16: the small pool behind stays 64-byte aligned)
+  float *lut_im = a.lut_single ? lut_re : lut_re + lut_e * lut_rep;
+  float2 *spool = reinterpret_cast<float2 *>(lut_re + (a.lut_single ? lut_e : 2 * lut_e) * lut_rep);      // first 8 pool cells: zero and the pilot values
   uint64_t *mbar = reinterpret_cast<uint64_t *>(spool + 8);                 // completion barriers: [0] staging copies, [1] descriptors
   const uint32_t mbar_s = (uint32_t)__cvta_generic_to_shared(mbar), dbar_s = mbar_s + 8;
   const int2 *descbuf = reinterpret_cast<const int2 *>(mbar + 2);           // the next symbol's copy descriptors
@@ -1471,6 +1472,9 @@ __global__ void __launch_bounds__(T, (LOG2M == 14 ? 1 : 1024 / T)) k_ofdm(const 
     // the constellation table goes through the (still unused) transform buffer: one L2 round trip, then replication
     if (threadIdx.x < a.lut_n) x[threadIdx.x] = __ldg(a.lut + threadIdx.x);
     if (threadIdx.x < 8) spool[threadIdx.x] = __ldg(a.pool + threadIdx.x);
+    // carriers that are not data cells do a dummy read of staging slot 0 and look its code up: until a symbol with
+    // data cells has been staged that slot must hold a valid code (the tables only have lut_n entries)
+    if (threadIdx.x < 4) reinterpret_cast<uint32_t *>(stage)[threadIdx.x] = 0u;
     if (threadIdx.x == 0) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(mbar_s) : "memory");
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(dbar_s) : "memory");
@@ -1494,7 +1498,7 @@ __global__ void __launch_bounds__(T, (LOG2M == 14 ? 1 : 1024 / T)) k_ofdm(const 
   fs.stage_s = stage_s;
   fs.esh = 2u + (uint32_t)lut_rep_shift;
   fs.lut_lane_s = (uint32_t)__cvta_generic_to_shared(lut_re) + ((threadIdx.x & (uint32_t)(lut_rep - 1)) << 2);
-  fs.im_ofs = a.lut_single ? 0u : 1024u * (uint32_t)lut_rep;
+  fs.im_ofs = a.lut_single ? 0u : 4u * (uint32_t)(lut_e * lut_rep);
   fs.spool_m8_s = (uint32_t)__cvta_generic_to_shared(spool) - 8u;
   // 16K sub-transform with 512 threads: every thread runs the same butterflies for every symbol, so their twiddle
   // bases stay in registers for the whole kernel (no L2 round trip at the start of each pass: L1 is ~2 KB here)
@@ -1754,12 +1758,15 @@ __global__ void __launch_bounds__(T, (LOG2M == 14 ? 1 : 1024 / T)) k_ofdm(const 
   }
 }
 
+// bytes of one copy of the constellation table(s) in shared memory
+static inline size_t lut_table_bytes(const OfdmArgs &a) { return (size_t)(a.lut_n < 16 ? 16 : a.lut_n) * 4 * (a.lut_single ? 1 : 2); }
+
 template <int LOG2M, int T, bool C16, int FMT, int SPLIT>
 static void launch_ofdm_t(const OfdmArgs &a, cudaStream_t s)
 {
   constexpr int M = 1 << LOG2M;
   const size_t smem = (size_t)padx(M) * sizeof(float2) +
-                      (C16 ? (size_t)a.stage_cap * 2 + ((size_t)(a.lut_single ? 1024 : 2048) << a.lut_rep_shift) + 64 + 16 + (size_t)a.desc_cap * 8 : 0);
+                      (C16 ? (size_t)a.stage_cap * 2 + ((size_t)lut_table_bytes(a) << a.lut_rep_shift) + 64 + 16 + (size_t)a.desc_cap * 8 : 0);
   const int units = a.frames * a.num_symbols;
   static bool attr[MAX_DEVICES];
   allow_smem(k_ofdm<LOG2M, T, C16, FMT, SPLIT>, 227 * 1024, attr);
@@ -1779,7 +1786,11 @@ static void launch_ofdm_c(const OfdmArgs &a, cudaStream_t s)
     case 10: launch_ofdm_t<10, 256, C16, FMT, 1>(a, s); break;
     case 11: launch_ofdm_t<11, 256, C16, FMT, 1>(a, s); break;
     case 12: launch_ofdm_t<12, 256, C16, FMT, 1>(a, s); break;
-    case 13: launch_ofdm_t<13, 512, C16, FMT, 1>(a, s); break;
+    case 13:
+      // 8K symbols, or 16K symbols as two 8K halves (two CTAs per SM instead of one: OfdmDevice::init decides)
+      if (a.split == 2) launch_ofdm_t<13, 512, C16, FMT, 2>(a, s);
+      else launch_ofdm_t<13, 512, C16, FMT, 1>(a, s);
+      break;
     case 14:
       // 512 threads with up to 128 registers each: two butterflies per thread and pass, interleaved by the compiler
       if (a.split == 2) launch_ofdm_t<14, 512, C16, FMT, 2>(a, s);
@@ -1798,7 +1809,7 @@ void launch_ofdm(const OfdmArgs &a0, cudaStream_t s)
   a.lut_rep_shift = 0;
   if (a.cells16) {
     const size_t base = (size_t)padx(1 << a.log2_m) * sizeof(float2) + (size_t)a.stage_cap * 2 + 64 + 16 + (size_t)a.desc_cap * 8, sm_bytes = 227 * 1024;
-    const size_t one = a.lut_single ? 1024 : 2048;
+    const size_t one = lut_table_bytes(a);
     size_t ctas = sm_bytes / (base + one + 1024);
     if (ctas < 1) ctas = 1;
     if (ctas > 2) ctas = 2;
