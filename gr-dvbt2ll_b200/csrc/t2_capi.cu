@@ -391,6 +391,7 @@ struct BbHandle : dvbt2ll_handle {
     a.bch_cols = d_cols.as<uint32_t>(); a.inband_bytes = d_ib.as<uint8_t>();
     a.out = d_out; a.out_pitch = out_pitch; a.sync_errors = h_err;
     a.ts_len = 0; a.out_len = (long long)channels * frames * out_pitch;
+    a.out_group = 0; a.out_group_stride = 0; a.out_group_off = 0;
   }
   // d_in must be preceded by 187 bytes of valid history on the device (work() arranges that)
   int work_device(const void *d_in, int ninput, void *d_out, int noutput, int *consumed, cudaStream_t s)
@@ -790,20 +791,29 @@ struct ChainHandle : dvbt2ll_handle {
     return ensure_device();
   }
   int F() const { return fplan.prm.fecblocks; }
+  int P() const { return fplan.num_plp; }
+  int Fp(int plp) const { return fplan.plp_first_block[plp + 1] - fplan.plp_first_block[plp]; }
   // cells per T2 frame in the 16-bit cell memory, padded so every frame starts on a 16-byte boundary (bulk copies)
   long long cells16_stride() const { return ((long long)F() * map.plan.cell_size + 7) & ~7LL; }
   // TS byte index (per channel, stream starts on a packet boundary) at which T2 frame `frame` begins
-  long long stream_pos(long long frame) const
+  long long stream_pos(long long frame, int plp = 0) const
   {
-    const long long j0 = frame * F();
+    const int fpl = Fp(plp);            // the PLP's FEC blocks per T2 frame = its in-band signalling cycle
+    const long long j0 = frame * fpl;
     long long nb0 = 0;
-    if (bb.plan.inband) nb0 = (j0 + bb.plan.fecblocks - 1) / bb.plan.fecblocks;
+    if (bb.plan.inband) nb0 = (j0 + fpl - 1) / fpl;
     const long long P = j0 * bb.plan.payload_bytes - 13 * nb0;          // payload bytes before the frame
     if (bb.plan.mode == t2::INPUTMODE_NORMAL || P == 0) return P;
     const long long last = P - 1;                                       // high efficiency mode: sync bytes are skipped,
     return 1 + last + last / 187 + 1;                                   // packets = 1 sync + 187 payload bytes
   }
-  long long ts_bytes(long long first_frame, int n_frames) const { return stream_pos(first_frame + n_frames) - stream_pos(first_frame); }
+  long long ts_bytes(long long first_frame, int n_frames, int plp = 0) const { return stream_pos(first_frame + n_frames, plp) - stream_pos(first_frame, plp); }
+  long long ts_bytes_max(long long first_frame, int n_frames) const
+  {
+    long long m = 0;
+    for (int pl = 0; pl < P(); pl++) m = std::max(m, ts_bytes(first_frame, n_frames, pl));
+    return m;
+  }
   long long ts_per_frame() const { return ts_bytes(0, 1); }
   int output_multiple() const { return oplan.samples_per_frame; }
   int in_item() const { return 1; }
@@ -854,22 +864,29 @@ struct ChainHandle : dvbt2ll_handle {
     if (buf_frame + frames > max_frames) return fail(DVBT2LL_ERR_INVALID, "chain: batch larger than max_frames given at create");
     const int nfec = frames * F();
     const int bp = align16(bb.plan.fec.nbch / 8), fp = align16(bb.plan.fec.nldpc / 8);
-    // stream position of the batch start (streams begin on a packet boundary at frame 0)
-    const long long j0 = first_frame * F();
-    const int fb0 = bb.plan.inband ? (int)(j0 % bb.plan.fecblocks) : 0;
-    const int count0 = (int)(stream_pos(first_frame) % 188);
-
     cudaEvent_t *tev = ev[n_timed % TIMING_SLOTS];
     if (timing) cudaEventRecord(tev[0], s);
-    t2k::BbArgs ba;
     uint8_t *bch_buf = d_bch.as<uint8_t>() + (size_t)buf_frame * F() * bp;
     if (!fuse_fec || taps) CK(d_fec.ensure((size_t)max_frames * F() * fp + 64));
     uint8_t *fec_buf = d_fec.as<uint8_t>() ? d_fec.as<uint8_t>() + (size_t)buf_frame * F() * fp : 0;
     uint16_t *cell_buf = d_cells.as<uint16_t>() + (size_t)buf_frame * cells16_stride();
-    bb.fill_args(ba, (const uint8_t *)d_ts, ts_pitch, n_channels, n_frames * F(), count0, fb0,
-                 hist_valid >= 0 ? hist_valid : (first_frame > 0 ? 1 : 0), bch_buf, bp);
-    ba.ts_len = ts_bytes(first_frame, n_frames);
-    t2k::launch_bb_bch(ba, s);
+    // BB framing + BCH, PLP by PLP: row c * P + p of the TS holds PLP p of channel c; every PLP has its own stream
+    // position (packet phase, in-band cycle = its FEC blocks per frame), and its codewords go to their place inside
+    // the frame's block list (streams begin on a packet boundary at frame 0)
+    for (int pl = 0; pl < P(); pl++) {
+      const int fpl = Fp(pl);
+      const long long j0 = first_frame * fpl;
+      const int fb0 = bb.plan.inband ? (int)(j0 % fpl) : 0;
+      const int count0 = (int)(stream_pos(first_frame, pl) % 188);
+      t2k::BbArgs ba;
+      bb.fill_args(ba, (const uint8_t *)d_ts + (long long)pl * ts_pitch, ts_pitch * P(), n_channels, n_frames * fpl, count0, fb0,
+                   hist_valid >= 0 ? hist_valid : (first_frame > 0 ? 1 : 0), bch_buf, bp);
+      ba.fecblocks = fpl;
+      ba.ts_len = ts_bytes(first_frame, n_frames, pl);
+      ba.out_len = (long long)frames * F() * bp;
+      if (P() > 1) { ba.out_group = fpl; ba.out_group_stride = F(); ba.out_group_off = fplan.plp_first_block[pl]; }
+      t2k::launch_bb_bch(ba, s);
+    }
     if (timing) cudaEventRecord(tev[1], s);
     t2k::LdpcArgs la;
     ldpc.fill_args(la, bch_buf, bp, fec_buf, fp, nfec);
@@ -936,6 +953,18 @@ struct ChainHandle : dvbt2ll_handle {
     if (n == "chain.stage_bytes") return copy_vec(tables.stage_bytes, out, cap);
     if (n == "ofdm.sym_data_start") return copy_vec(oplan.sym_data_start, out, cap);
     if (n == "frame.framed") return copy_vec(fplan.framed, out, cap);
+    if (n == "frame.pool") return copy_vec(fplan.pool.cells, out, cap);
+    if (n == "frame.info") {
+      const int v[12] = { fplan.cell_size, fplan.stream_items, fplan.mapped_items, fplan.eta_mod, fplan.n_post, fplan.n_punc,
+                          fplan.dummy_cells, fplan.pool.l1post_base, fplan.pool.l1post_cells, fplan.pool.l1post_variants,
+                          fplan.pool_dummy, fplan.pool_zero };
+      return copy_out(v, sizeof(v), out, cap);
+    }
+    if (n == "frame.plp") {
+      int v[2 + t2::MAX_PLP + 1] = { fplan.num_plp, fplan.l1post_sig_bits };
+      for (int i = 0; i <= fplan.num_plp; i++) v[2 + i] = fplan.plp_first_block[i];
+      return copy_out(v, sizeof(int) * (3 + fplan.num_plp), out, cap);
+    }
     if (n == "frame.fi_src") return copy_vec(fplan.fi_src, out, cap);
     long long r;
     if ((r = bb.plan_get(name, out, cap)) >= 0) return r;
@@ -1009,6 +1038,7 @@ int dvbt2ll_work(dvbt2ll_handle *h, const void *in, int ninput, void *out, int n
   const int nout = frames * om;
   BbHandle *b = h->kind == dvbt2ll_handle::BB ? static_cast<BbHandle *>(h) : 0;
   ChainHandle *ch = h->kind == dvbt2ll_handle::CHAIN ? static_cast<ChainHandle *>(h) : 0;
+  if (ch && ch->P() > 1) return fail(DVBT2LL_ERR_INVALID, "chain: a multi-PLP chain takes one TS per PLP: use dvbt2ll_chain_run_host / _run_device");
   if (ch) b = &ch->bb;          // the chain streams like its first stage: history + frame counter carried across calls
   // items to stage in
   long long need;
@@ -1171,19 +1201,27 @@ dvbt2ll_handle *dvbt2ll_pilotgenp1insert_create(int carriermode, int fftsize, in
   return h;
 }
 
-dvbt2ll_handle *dvbt2ll_chain_create(const dvbt2ll_chain_params *c, int max_frames, int device)
+static dvbt2ll_handle *chain_create(const dvbt2ll_chain_params *c, int num_plp, const int *plp_fecblocks, int max_frames, int device)
 {
   if (!c || max_frames < 1) { fail(DVBT2LL_ERR_INVALID, "chain: bad arguments"); return 0; }
+  if (num_plp < 1 || num_plp > t2::MAX_PLP || (num_plp > 1 && !plp_fecblocks)) { fail(DVBT2LL_ERR_INVALID, "chain: number of PLPs out of range"); return 0; }
   ChainHandle *h = new ChainHandle();
   std::string err;
   h->max_frames = max_frames; h->device = device;
-  t2::FrameParams fp = { c->framesize, c->rate, c->constellation, c->rotation, c->fecblocks, c->tiblocks, c->carriermode,
+  int fecblocks = c->fecblocks;
+  if (num_plp > 1) {
+    fecblocks = 0;
+    for (int p = 0; p < num_plp; p++) fecblocks += plp_fecblocks[p];
+  }
+  t2::FrameParams fp = { c->framesize, c->rate, c->constellation, c->rotation, fecblocks, c->tiblocks, c->carriermode,
                          c->fftsize, c->guardinterval, c->l1constellation, c->pilotpattern, c->t2frames, c->numdatasyms,
                          c->paprmode, c->version, c->preamble, c->inputmode, c->reservedbiasbits, c->l1scrambled, c->inband };
+  fp.num_plp = num_plp;
+  for (int p = 0; p < num_plp && num_plp > 1; p++) fp.plp_fecblocks[p] = plp_fecblocks[p];
   t2::OfdmParams op = { c->carriermode, c->fftsize, c->pilotpattern, c->guardinterval, c->numdatasyms, c->paprmode,
                         c->version, c->preamble, c->misogroup, c->equalization, c->bandwidth, c->vlength };
   bool ok = true;
-  ok = ok && t2::build_bb_plan(c->framesize, c->rate, c->inputmode, c->inband, c->fecblocks, c->tsrate, &h->bb.plan, &err);
+  ok = ok && t2::build_bb_plan(c->framesize, c->rate, c->inputmode, c->inband, fecblocks, c->tsrate, &h->bb.plan, &err);
   ok = ok && t2::build_ldpc_plan(c->framesize, c->rate, &h->ldpc.plan, &err);
   ok = ok && t2::build_map_plan(c->framesize, c->rate, c->constellation, c->rotation, &h->map.plan, &err);
   ok = ok && t2::build_frame_plan(fp, &h->fplan, &err);
@@ -1192,6 +1230,16 @@ dvbt2ll_handle *dvbt2ll_chain_create(const dvbt2ll_chain_params *c, int max_fram
   if (!ok) { delete h; fail(DVBT2LL_ERR_INVALID, err); return 0; }
   if (h->fplan.overfull) { h->warnings = 1; g_err = "Frame Mapper, too many FEC blocks in T2 frame."; }
   return h;
+}
+
+dvbt2ll_handle *dvbt2ll_chain_create(const dvbt2ll_chain_params *c, int max_frames, int device)
+{
+  return chain_create(c, 1, 0, max_frames, device);
+}
+
+dvbt2ll_handle *dvbt2ll_chain_create_multiplp(const dvbt2ll_chain_params *c, int num_plp, const int *plp_fecblocks, int max_frames, int device)
+{
+  return chain_create(c, num_plp, plp_fecblocks, max_frames, device);
 }
 
 static ChainHandle *as_chain(const dvbt2ll_handle *h)
@@ -1205,6 +1253,13 @@ long long dvbt2ll_chain_ts_bytes(const dvbt2ll_handle *h, long long first_frame,
   ChainHandle *c = as_chain(h);
   return c ? c->ts_bytes(first_frame, n_frames) : -1;
 }
+int dvbt2ll_chain_num_plp(const dvbt2ll_handle *h) { ChainHandle *c = as_chain(h); return c ? c->P() : -1; }
+long long dvbt2ll_chain_plp_ts_bytes(const dvbt2ll_handle *h, int plp, long long first_frame, int n_frames)
+{
+  ChainHandle *c = as_chain(h);
+  if (!c || plp < 0 || plp >= c->P()) return -1;
+  return c->ts_bytes(first_frame, n_frames, plp);
+}
 long long dvbt2ll_chain_samples_per_frame(const dvbt2ll_handle *h) { ChainHandle *c = as_chain(h); return c ? c->oplan.samples_per_frame : -1; }
 int dvbt2ll_chain_fecframes_per_frame(const dvbt2ll_handle *h) { ChainHandle *c = as_chain(h); return c ? c->F() : -1; }
 
@@ -1217,6 +1272,8 @@ int dvbt2ll_chain_run_device(dvbt2ll_handle *h, const void *d_ts, long long ts_p
   if (r) return r;
   if (n_channels < 0 || n_frames < 0) return fail(DVBT2LL_ERR_INVALID, "chain: negative batch size");
   if (n_channels == 0 || n_frames == 0) return 0;
+  if (c->P() > 1 && ts_pitch < c->ts_bytes_max(first_frame, n_frames))
+    return fail(DVBT2LL_ERR_INVALID, "chain: with several PLPs the TS rows (channel * num_plp + plp) need a pitch of at least the longest PLP's bytes");
   return c->run(d_ts, ts_pitch, n_channels, n_frames, first_frame, d_out, stream ? (cudaStream_t)stream : c->stream);
 }
 
@@ -1229,16 +1286,17 @@ int dvbt2ll_chain_run_host(dvbt2ll_handle *h, const void *ts, long long ts_pitch
   if (r) return r;
   if (n_channels < 0 || n_frames < 0) return fail(DVBT2LL_ERR_INVALID, "chain: negative batch size");
   if (n_channels == 0 || n_frames == 0) return 0;
-  const long long per_ch = c->ts_bytes(first_frame, n_frames);
+  const int P = c->P();                      // TS rows per channel (row = channel * P + plp)
+  const long long per_ch = c->ts_bytes_max(first_frame, n_frames);
   // normal input mode: the CRC-8 that replaces the first sync byte covers the 187 bytes before the pointer
   const long long hist = (first_frame > 0 && c->bb.plan.mode == t2::INPUTMODE_NORMAL) ? 187 : 0;
-  if (n_channels == 1 && ts_pitch < per_ch + hist) ts_pitch = per_ch + hist;      // a single row: the pitch is never used to step
+  if (n_channels * P == 1 && ts_pitch < per_ch + hist) ts_pitch = per_ch + hist;      // a single row: the pitch is never used to step
   if (ts_pitch < per_ch + hist)
     return fail(DVBT2LL_ERR_INVALID, "chain: ts_pitch smaller than the TS bytes (+ 187 history bytes) of one channel");
   const long long dpitch = (per_ch + hist + 255) & ~255LL;
   const size_t ssz = c->sink_fmt ? 4 : 8;                                        // bytes per output sample
   const size_t out_bytes = (size_t)n_channels * n_frames * c->oplan.samples_per_frame * ssz;
-  CK(c->d_ts_stage.ensure((size_t)n_channels * dpitch + 512));
+  CK(c->d_ts_stage.ensure((size_t)n_channels * P * dpitch + 512));
   CK(c->d_out_stage.ensure(out_bytes));
   uint8_t *base = c->d_ts_stage.as<uint8_t>() + 256;
   uint8_t *dout = c->d_out_stage.as<uint8_t>();
@@ -1255,9 +1313,9 @@ int dvbt2ll_chain_run_host(dvbt2ll_handle *h, const void *ts, long long ts_pitch
   for (int c0 = 0; c0 < n_channels; c0 += (groups == 1 ? n_channels : per), gi++) {
     const int nc = groups == 1 ? n_channels : (c0 + per <= n_channels ? per : n_channels - c0);
     cudaStream_t s = (gi & 1) ? c->stream2 : c->stream;
-    CK(cudaMemcpy2DAsync(base + (size_t)c0 * dpitch - hist, (size_t)dpitch, (const uint8_t *)ts + (size_t)c0 * ts_pitch - hist,
-                         (size_t)ts_pitch, (size_t)(per_ch + hist), (size_t)nc, cudaMemcpyHostToDevice, s));
-    r = c->run(base + (size_t)c0 * dpitch, dpitch, nc, n_frames, first_frame, dout + (size_t)c0 * ch_out * ssz, s,
+    CK(cudaMemcpy2DAsync(base + (size_t)c0 * P * dpitch - hist, (size_t)dpitch, (const uint8_t *)ts + (size_t)c0 * P * ts_pitch - hist,
+                         (size_t)ts_pitch, (size_t)(per_ch + hist), (size_t)nc * P, cudaMemcpyHostToDevice, s));
+    r = c->run(base + (size_t)c0 * P * dpitch, dpitch, nc, n_frames, first_frame, dout + (size_t)c0 * ch_out * ssz, s,
                groups == 1 ? 0 : (gi & 1) * per * n_frames, gi & 1);
     if (r < 0) return r;
     CK(cudaMemcpyAsync((uint8_t *)out + (size_t)c0 * ch_out * ssz, dout + (size_t)c0 * ch_out * ssz, (size_t)nc * ch_out * ssz,

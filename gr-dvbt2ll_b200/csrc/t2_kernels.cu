@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(BB_MAX_WARPS * 32) k_bb_bch(const BbArgs a)
     const int count = (int)((a.count0 + t_start) % 188);
 
     BND(10 + Dj + (ib ? 13 : 0) <= msg_bytes && msg_bytes + a.bch_r / 8 == nbytes && nbytes <= buf_pitch - HIST);
-    BND(a.out_len == 0 || (long long)(job + 1) * a.out_pitch <= a.out_len + (a.out_pitch - nbytes));
+    BND(a.out_len == 0 || a.out_group != 0 || (long long)(job + 1) * a.out_pitch <= a.out_len + (a.out_pitch - nbytes));
     // ---- stage the raw payload in shared memory (buf byte 10 + i = payload byte i)
     if (!hem) {
       const uint8_t *src = ts + P0;
@@ -348,7 +348,8 @@ __global__ void __launch_bounds__(BB_MAX_WARPS * 32) k_bb_bch(const BbArgs a)
     }
     __syncwarp();
     // ---- store the packed codeword
-    uint8_t *o = a.out + (long long)job * a.out_pitch;
+    const long long oslot = a.out_group ? (long long)(job / a.out_group) * a.out_group_stride + a.out_group_off + job % a.out_group : job;
+    uint8_t *o = a.out + oslot * a.out_pitch;
     const int nw = nbytes >> 2;
     uint32_t *ow = reinterpret_cast<uint32_t *>(o);
     for (int i = lane; i < nw; i += 32) ow[i] = bufw[i];

@@ -30,6 +30,10 @@ struct BbArgs {
   const uint8_t *inband_bytes;// 13
   uint8_t *out;               // packed codewords, pitch out_pitch bytes per FECFRAME
   int out_pitch;
+  // FECFRAME job (= channel * frames + j) -> output slot: job itself, or -- several PLPs per T2 frame, one launch per
+  // PLP -- (job / out_group) * out_group_stride + out_group_off + job % out_group: the PLP's out_group FEC blocks of
+  // every T2 frame land at their place inside the frame's list of out_group_stride blocks
+  int out_group, out_group_stride, out_group_off;
   int *sync_errors;           // counter of payload sync bytes != 0x47 (reference logs a warning)
   // buffer extents for the bounds-checking debug build (DVBT2LL_DEBUG_BOUNDS); 0 = unknown, not checked
   long long ts_len;           // valid TS bytes per channel from ts + c * ts_pitch on

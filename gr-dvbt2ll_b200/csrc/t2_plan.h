@@ -140,10 +140,16 @@ struct CellPool {
 // (reference lib/framemapperfint_cc_impl.cc).  The whole block is ONE static gather: code[j] >= 0 is
 // an input cell index inside the T2 frame's fecblocks*cell_size cells, code[j] < 0 is pool cell
 // -(1+code[j]) (L1-post cells additionally offset by (frame_idx % t2_frames) * l1post_cells).
+enum { MAX_PLP = 16 };
 struct FrameParams {
   int framesize, rate, constellation, rotation, fecblocks, tiblocks, carriermode, fftsize,
       guardinterval, l1constellation, pilotpattern, t2frames, numdatasyms, paprmode, version,
       preamble, inputmode, reservedbiasbits, l1scrambled, inband;
+  // Beyond the reference (single PLP, lib/framemapperfint_cc_impl.cc:152 num_plp = 1): num_plp > 1 type-1 data PLPs of
+  // the same modulation / code / time-interleaving parameters, PLP p carrying plp_fecblocks[p] FEC blocks per T2 frame
+  // (fecblocks = their sum), laid one after the other in the frame.  num_plp = 0 or 1 is the reference's case.
+  int num_plp;
+  int plp_fecblocks[MAX_PLP];
 };
 struct FramePlan {
   FrameParams prm;
@@ -151,6 +157,9 @@ struct FramePlan {
   int cell_size, stream_items, mapped_items;
   int eta_mod, n_post, n_punc, dummy_cells;
   bool overfull;                       // reference warns "too many FEC blocks in T2 frame"
+  int num_plp;                         // >= 1
+  int plp_first_block[MAX_PLP + 1];    // first FEC block of each PLP inside the T2 frame's block list
+  int l1post_sig_bits;                 // K_sig of L1-post (350 for one PLP)
   std::vector<int32_t> cell_perm;      // cell interleaver permutation (reference :1087-1107)
   std::vector<int32_t> fec_shift;      // per FEC block cyclic shift (reference :1981-1992)
   std::vector<int32_t> ti_src;         // time-interleaver read-out position -> input cell index (cell int. composed)

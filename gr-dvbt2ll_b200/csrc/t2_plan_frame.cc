@@ -156,7 +156,7 @@ int l1_ldpc_code(bool pre)
   return -1;
 }
 
-void build_l1pre(const FrameParams &prm, int l1_post_size, std::vector<cfloat> &cells)
+void build_l1pre(const FrameParams &prm, int l1_post_size, int l1_post_info_size, std::vector<cfloat> &cells)
 {
   BitWriter w;
   w.put(0, 8);                                   // TYPE: TS only
@@ -170,7 +170,7 @@ void build_l1pre(const FrameParams &prm, int l1_post_size, std::vector<cfloat> &
   w.put(0, 2);                                   // L1_COD
   w.put(0, 2);                                   // L1_FEC_TYPE
   w.put(l1_post_size, 18);
-  w.put(350 - 32, 18);                           // L1_POST_INFO_SIZE
+  w.put(l1_post_info_size, 18);                  // L1_POST_INFO_SIZE (350 - 32 for one PLP)
   w.put(prm.pilotpattern, 4);
   w.put(0, 8);                                   // TX_ID_AVAILABILITY
   w.put(0, 16);                                  // CELL_ID
@@ -204,7 +204,8 @@ void build_l1pre(const FrameParams &prm, int l1_post_size, std::vector<cfloat> &
   for (int i = 3240; i < 16200; i++) if (!punct[i]) bpsk(cw[i]);
 }
 
-void build_l1post(const FrameParams &prm, int frame_idx, int n_post, int n_punc, int eta, std::vector<cfloat> &cells)
+void build_l1post(const FrameParams &prm, const int *plp_blocks, int num_plp, int cell_size, int frame_idx, int n_post, int n_punc,
+                  int eta, std::vector<cfloat> &cells)
 {
   const bool v131 = prm.version == VERSION_131;
   const bool bias = prm.reservedbiasbits && v131;
@@ -216,32 +217,34 @@ void build_l1post(const FrameParams &prm, int frame_idx, int n_post, int n_punc,
   }
   BitWriter w;
   w.put(1, 15);                                  // SUB_SLICES_PER_FRAME
-  w.put(1, 8);                                   // NUM_PLP
+  w.put(num_plp, 8);                             // NUM_PLP
   w.put(0, 4);                                   // NUM_AUX
   w.put(0, 8);                                   // AUX_CONFIG_RFU
   w.put(0, 3);                                   // RF_IDX
   w.put(729833333u, 32);                         // FREQUENCY
-  w.put(0, 8);                                   // PLP_ID
-  w.put(1, 3);                                   // PLP_TYPE
-  w.put(3, 5);                                   // PLP_PAYLOAD_TYPE (TS)
-  w.put(0, 1);                                   // FF_FLAG
-  w.put(0, 3);                                   // FIRST_RF_IDX
-  w.put(0, 8);                                   // FIRST_FRAME_IDX
-  w.put(1, 8);                                   // PLP_GROUP_ID
-  w.put(plp_cod, 3);
-  w.put(prm.constellation, 3);
-  w.put(prm.rotation, 1);
-  w.put(prm.framesize, 2);                       // PLP_FEC_TYPE
-  w.put(prm.fecblocks, 10);                      // PLP_NUM_BLOCKS_MAX
-  w.put(1, 8);                                   // FRAME_INTERVAL
-  w.put(prm.tiblocks, 8);                        // TIME_IL_LENGTH
-  w.put(0, 1);                                   // TIME_IL_TYPE
-  w.put(0, 1);                                   // IN_BAND_A_FLAG
-  w.put((prm.inband && v131) ? 1 : 0, 1);        // IN_BAND_B_FLAG
-  w.put(bias ? 0x7ff : 0, 11);                   // RESERVED_1
-  w.put(prm.version == VERSION_111 ? 0 : prm.inputmode + 1, 2);   // PLP_MODE
-  w.put(0, 1);                                   // STATIC_FLAG
-  w.put(0, 1);                                   // STATIC_PADDING_FLAG
+  for (int pl = 0; pl < num_plp; pl++) {         // configurable part, 89 bits per PLP
+    w.put(pl, 8);                                // PLP_ID
+    w.put(1, 3);                                 // PLP_TYPE (data type 1)
+    w.put(3, 5);                                 // PLP_PAYLOAD_TYPE (TS)
+    w.put(0, 1);                                 // FF_FLAG
+    w.put(0, 3);                                 // FIRST_RF_IDX
+    w.put(0, 8);                                 // FIRST_FRAME_IDX
+    w.put(1, 8);                                 // PLP_GROUP_ID
+    w.put(plp_cod, 3);
+    w.put(prm.constellation, 3);
+    w.put(prm.rotation, 1);
+    w.put(prm.framesize, 2);                     // PLP_FEC_TYPE
+    w.put(plp_blocks[pl], 10);                   // PLP_NUM_BLOCKS_MAX
+    w.put(1, 8);                                 // FRAME_INTERVAL
+    w.put(prm.tiblocks, 8);                      // TIME_IL_LENGTH
+    w.put(0, 1);                                 // TIME_IL_TYPE
+    w.put(0, 1);                                 // IN_BAND_A_FLAG
+    w.put((prm.inband && v131) ? 1 : 0, 1);      // IN_BAND_B_FLAG
+    w.put(bias ? 0x7ff : 0, 11);                 // RESERVED_1
+    w.put(prm.version == VERSION_111 ? 0 : prm.inputmode + 1, 2);   // PLP_MODE
+    w.put(0, 1);                                 // STATIC_FLAG
+    w.put(0, 1);                                 // STATIC_PADDING_FLAG
+  }
   w.put(0, 2);                                   // FEF_LENGTH_MSB
   w.put(bias ? 0x3fffffff : 0, 30);              // RESERVED_2
   w.put(frame_idx, 8);                           // FRAME_IDX (dynamic)
@@ -250,12 +253,18 @@ void build_l1post(const FrameParams &prm, int frame_idx, int n_post, int n_punc,
   w.put(0, 8);                                   // L1_CHANGE_COUNTER
   w.put(0, 3);                                   // START_RF_IDX
   w.put(bias ? 0xff : 0, 8);                     // RESERVED_3
-  w.put(0, 8);                                   // PLP_ID (dynamic)
-  w.put(0, 22);                                  // PLP_START
-  w.put(prm.fecblocks, 10);                      // PLP_NUM_BLOCKS
-  w.put(bias ? 0xff : 0, 8);                     // RESERVED_4
+  {
+    int start = 0;                               // type-1 PLPs follow each other from cell address 0 of the frame's data
+    for (int pl = 0; pl < num_plp; pl++) {       // dynamic part, 48 bits per PLP
+      w.put(pl, 8);                              // PLP_ID (dynamic; the reference leaves its single one uninitialised = 0)
+      w.put(start, 22);                          // PLP_START
+      w.put(plp_blocks[pl], 10);                 // PLP_NUM_BLOCKS
+      w.put(bias ? 0xff : 0, 8);                 // RESERVED_4
+      start += plp_blocks[pl] * cell_size;
+    }
+  }
   w.put(bias ? 0xff : 0, 8);                     // RESERVED_5
-  append_crc32(w.b);                             // 350 bits = K_sig
+  append_crc32(w.b);                             // K_sig = 213 + 137 num_plp bits (350 for one PLP)
   std::vector<uint8_t> sig(w.b);
   const int ksig = (int)sig.size();
   if (v131 && prm.l1scrambled) {
@@ -373,13 +382,26 @@ bool build_frame_plan(const FrameParams &prm, FramePlan *p, std::string *err)
   if (!ofdm_dims(prm.carriermode, prm.fftsize, prm.pilotpattern, prm.guardinterval, prm.numdatasyms,
                  prm.paprmode, prm.preamble, &p->dims, err)) return false;
   const OfdmDims &d = p->dims;
+  // PLPs: the reference's single one, or several type-1 PLPs of the same parameters one after the other
+  const int P = p->num_plp = prm.num_plp > 1 ? prm.num_plp : 1;
+  if (P > MAX_PLP) { if (err) *err = "framemapperfint_cc: too many PLPs"; return false; }
+  int plp_blocks[MAX_PLP];
+  p->plp_first_block[0] = 0;
+  for (int pl = 0; pl < P; pl++) {
+    plp_blocks[pl] = P == 1 ? prm.fecblocks : prm.plp_fecblocks[pl];
+    if (plp_blocks[pl] < 1 || plp_blocks[pl] > 1023) { if (err) *err = "framemapperfint_cc: FEC blocks of a PLP out of range"; return false; }
+    p->plp_first_block[pl + 1] = p->plp_first_block[pl] + plp_blocks[pl];
+  }
+  if (p->plp_first_block[P] != prm.fecblocks) { if (err) *err = "framemapperfint_cc: fecblocks is not the sum over the PLPs"; return false; }
   const int Nc = p->cell_size, F = prm.fecblocks;
   static const int etas[4] = { 1, 2, 4, 6 };
   const int eta = p->eta_mod = etas[prm.l1constellation];
 
-  // N_post / N_punc (EN 302 755 7.3.1.2; reference :978-987 incl. its float ceil)
-  const int n_punc_temp = (6 * (7032 - 350)) / 5;
-  const int n_post_temp = 350 + 168 + 9000 - n_punc_temp;
+  // N_post / N_punc (EN 302 755 7.3.1.2; reference :978-987 incl. its float ceil) from K_sig = 213 + 137 NUM_PLP bits
+  // (configurable 35 + 35 + 89 P + 32, dynamic 71 + 48 P + 8, CRC-32; 350 for the reference's single PLP)
+  const int ksig = p->l1post_sig_bits = 213 + 137 * P;
+  const int n_punc_temp = (6 * (7032 - ksig)) / 5;
+  const int n_post_temp = ksig + 168 + 9000 - n_punc_temp;
   if (d.n_p2 == 1) p->n_post = (int)std::ceil((float)n_post_temp / (2 * (float)eta)) * 2 * eta;
   else p->n_post = (int)std::ceil((float)n_post_temp / ((float)eta * (float)d.n_p2)) * eta * d.n_p2;
   p->n_punc = n_punc_temp - (p->n_post - n_post_temp);
@@ -430,30 +452,33 @@ bool build_frame_plan(const FrameParams &prm, FramePlan *p, std::string *err)
     }
     if ((int)p->cell_perm.size() != Nc) { if (err) *err = "internal: cell permutation size"; return false; }
 
-    // TI block split (reference :1108-1119) and per-FEC-block shifts (restart per TI block, :1974-1992)
-    int small, big, nbig, nsmall;
-    if (prm.tiblocks == 0) { small = big = 1; nbig = 0; nsmall = F; }
-    else {
-      small = (int)std::floor((float)F / (float)prm.tiblocks);
-      big = (int)std::ceil((float)F / (float)prm.tiblocks);
-      nbig = F % prm.tiblocks;
-      nsmall = prm.tiblocks - nbig;
-    }
+    // TI block split (reference :1108-1119) and per-FEC-block shifts (restart per TI block, :1974-1992), PLP by PLP
     p->fec_shift.clear();
     std::vector<int> ti_block_sizes;
-    for (int s = 0; s < nsmall + nbig; s++) {
-      const int k = s < nsmall ? small : big;
-      ti_block_sizes.push_back(k);
-      unsigned n = 0;
-      for (int r = 0; r < k; r++) {
-        int shift = Nc;
-        while (shift >= Nc) {
-          unsigned t = n, sh = 0;
-          for (int b = 0; b < deg; b++) { sh |= t & 1u; sh <<= 1; t >>= 1; }
-          shift = (int)sh;
-          n++;
+    for (int pl = 0; pl < P; pl++) {
+      const int Fp = plp_blocks[pl];
+      int small, big, nbig, nsmall;
+      if (prm.tiblocks == 0) { small = big = 1; nbig = 0; nsmall = Fp; }
+      else {
+        small = (int)std::floor((float)Fp / (float)prm.tiblocks);
+        big = (int)std::ceil((float)Fp / (float)prm.tiblocks);
+        nbig = Fp % prm.tiblocks;
+        nsmall = prm.tiblocks - nbig;
+      }
+      for (int s = 0; s < nsmall + nbig; s++) {
+        const int k = s < nsmall ? small : big;
+        ti_block_sizes.push_back(k);
+        unsigned n = 0;
+        for (int r = 0; r < k; r++) {
+          int shift = Nc;
+          while (shift >= Nc) {
+            unsigned t = n, sh = 0;
+            for (int b = 0; b < deg; b++) { sh |= t & 1u; sh <<= 1; t >>= 1; }
+            shift = (int)sh;
+            n++;
+          }
+          p->fec_shift.push_back(shift);
         }
-        p->fec_shift.push_back(shift);
       }
     }
     if ((int)p->fec_shift.size() != F) { if (err) *err = "framemapperfint_cc: fecblocks/tiblocks combination leaves FEC blocks unassigned"; return false; }
@@ -491,7 +516,7 @@ bool build_frame_plan(const FrameParams &prm, FramePlan *p, std::string *err)
   p->pool_l1pre = 0;
   {
     std::vector<cfloat> c;
-    build_l1pre(prm, l1post_cells, c);
+    build_l1pre(prm, l1post_cells, ksig - 32, c);
     if ((int)c.size() != 1840) { if (err) *err = "internal: L1-pre size"; return false; }
     pool.cells.insert(pool.cells.end(), c.begin(), c.end());
   }
@@ -500,7 +525,7 @@ bool build_frame_plan(const FrameParams &prm, FramePlan *p, std::string *err)
   pool.l1post_variants = prm.t2frames;
   for (int v = 0; v < prm.t2frames; v++) {
     std::vector<cfloat> c;
-    build_l1post(prm, v, p->n_post, p->n_punc, eta, c);
+    build_l1post(prm, plp_blocks, P, Nc, v, p->n_post, p->n_punc, eta, c);
     if ((int)c.size() != l1post_cells) { if (err) *err = "internal: L1-post size"; return false; }
     pool.cells.insert(pool.cells.end(), c.begin(), c.end());
   }

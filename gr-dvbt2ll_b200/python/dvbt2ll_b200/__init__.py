@@ -38,6 +38,7 @@ EXPORTED_SYMBOLS = [
     "dvbt2ll_device_count", "dvbt2ll_set_device", "dvbt2ll_device_synchronize",
     "dvbt2ll_stream_create", "dvbt2ll_stream_destroy", "dvbt2ll_stream_synchronize",
     "dvbt2ll_chain_enable_taps", "dvbt2ll_chain_fused_fec",
+    "dvbt2ll_chain_create_multiplp", "dvbt2ll_chain_num_plp", "dvbt2ll_chain_plp_ts_bytes",
 ]
 GATHER_BLOB_BYTES = 256
 
@@ -127,6 +128,11 @@ def lib():
         L.dvbt2ll_chain_enable_taps.argtypes = [vp, ci]
         L.dvbt2ll_chain_enable_taps.restype = None
         L.dvbt2ll_chain_fused_fec.argtypes = [vp]
+        L.dvbt2ll_chain_create_multiplp.restype = vp
+        L.dvbt2ll_chain_create_multiplp.argtypes = [C.POINTER(ChainParams), ci, C.POINTER(ci), ci, ci]
+        L.dvbt2ll_chain_num_plp.argtypes = [vp]
+        L.dvbt2ll_chain_plp_ts_bytes.restype = cll
+        L.dvbt2ll_chain_plp_ts_bytes.argtypes = [vp, ci, cll, ci]
         _lib = L
     return _lib
 
@@ -350,8 +356,22 @@ class Chain(_Block):
         cfg = configs.resolve(cfg)
         self.cfg = cfg
         p = ChainParams(**{n: int(cfg[n]) for n, _ in ChainParams._fields_})
-        _Block.__init__(self, lib().dvbt2ll_chain_create(C.byref(p), int(max_frames), int(device)), "chain")
+        plps = cfg.get("plp_fecblocks")
+        if plps and len(plps) > 1:          # several PLPs of the same parameters (beyond the single-PLP reference)
+            arr = (C.c_int * len(plps))(*[int(x) for x in plps])
+            h = lib().dvbt2ll_chain_create_multiplp(C.byref(p), len(plps), arr, int(max_frames), int(device))
+        else:
+            h = lib().dvbt2ll_chain_create(C.byref(p), int(max_frames), int(device))
+        _Block.__init__(self, h, "chain")
         self.max_frames = max_frames
+
+    @property
+    def num_plp(self):
+        return int(lib().dvbt2ll_chain_num_plp(self._h))
+
+    def plp_ts_bytes(self, plp, first_frame, n_frames):
+        """TS bytes PLP `plp` of one channel consumes for T2 frames [first_frame, first_frame + n_frames)."""
+        return int(lib().dvbt2ll_chain_plp_ts_bytes(self._h, int(plp), int(first_frame), int(n_frames)))
 
     @property
     def ts_bytes_per_frame(self):
@@ -388,11 +408,12 @@ class Chain(_Block):
         starts with the history bytes (the 187 stream bytes before the first frame; none for first_frame = 0 or in
         high-efficiency mode), followed by the TS bytes of the frames.  Returns complex64 [n_channels, n_frames*samples]
         (int16 [n_channels, n_frames*samples, 2] with sink format 1)."""
-        ts = np.ascontiguousarray(ts, dtype=np.uint8).reshape(n_channels, -1)
+        P = self.num_plp
+        ts = np.ascontiguousarray(ts, dtype=np.uint8).reshape(n_channels * P, -1)      # row = channel * num_plp + plp
         hist = self.history_bytes(first_frame)
-        if ts.shape[1] < hist + self.ts_bytes(first_frame, n_frames):
-            raise ValueError("run_host: each TS row needs %d history bytes + %d TS bytes, got %d" % (
-                hist, self.ts_bytes(first_frame, n_frames), ts.shape[1]))
+        need = max(self.plp_ts_bytes(p, first_frame, n_frames) for p in range(P))
+        if ts.shape[1] < hist + need:
+            raise ValueError("run_host: each TS row needs %d history bytes + %d TS bytes, got %d" % (hist, need, ts.shape[1]))
         if out is None:
             if self.sink_format:
                 out = np.empty((n_channels, n_frames * self.samples_per_frame, 2), dtype=np.int16)

@@ -104,6 +104,17 @@ typedef struct dvbt2ll_chain_params {
 
 /* device < 0: current device.  max_frames = largest channels*frames batch a single run will be given. */
 DVBT2LL_API_EXPORT dvbt2ll_handle *dvbt2ll_chain_create(const dvbt2ll_chain_params *p, int max_frames, int device);
+/* Several PLPs (beyond the reference, which is single-PLP: lib/framemapperfint_cc_impl.cc:152 num_plp = 1): num_plp
+ * type-1 data PLPs that share the modulation / code / time-interleaving parameters of `p`, PLP i carrying
+ * plp_fecblocks[i] FEC blocks per T2 frame (p->fecblocks is ignored; their sum is used), laid one after the other in the
+ * frame and signalled in L1-post (NUM_PLP, the per-PLP configurable and dynamic fields, PLP_START; K_sig = 213 + 137
+ * num_plp bits).  Every PLP is its own transport stream: the TS rows handed to dvbt2ll_chain_run_* are then
+ * row = channel * num_plp + plp, each dvbt2ll_chain_plp_ts_bytes(h, plp, first_frame, n_frames) bytes long.
+ * num_plp = 1 is dvbt2ll_chain_create. */
+DVBT2LL_API_EXPORT dvbt2ll_handle *dvbt2ll_chain_create_multiplp(const dvbt2ll_chain_params *p, int num_plp,
+                                                                 const int *plp_fecblocks, int max_frames, int device);
+DVBT2LL_API_EXPORT int dvbt2ll_chain_num_plp(const dvbt2ll_handle *h);
+DVBT2LL_API_EXPORT long long dvbt2ll_chain_plp_ts_bytes(const dvbt2ll_handle *h, int plp, long long first_frame, int n_frames);
 DVBT2LL_API_EXPORT long long dvbt2ll_chain_ts_bytes_per_frame(const dvbt2ll_handle *h);
 /* TS bytes (per channel) consumed by T2 frames [first_frame, first_frame + n_frames): constant per frame in normal
  * input mode; in high-efficiency mode the dropped sync bytes make it depend on the stream position. */

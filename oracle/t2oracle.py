@@ -366,12 +366,26 @@ def _l1_fec(kbits, nbch, table, q):
     return ldpc_encode(bch, 0, 0, table=table, q=q, nbch=nbch, nldpc=16200)[0]
 
 
+def plp_blocks(c):
+    """FEC blocks per T2 frame of every PLP.  The reference is single-PLP (lib/framemapperfint_cc_impl.cc:152); a config
+    with "plp_fecblocks" describes several type-1 PLPs of the same parameters (EN 302 755 7.2.3: one configurable and one
+    dynamic entry per PLP in L1-post, the PLPs one after the other in the frame) -- restated here from the standard's
+    field list, not from the reference."""
+    p = c.get("plp_fecblocks")
+    return list(p) if p and len(p) > 1 else [c["fecblocks"]]
+
+
+def l1post_sig_bits(c):
+    """K_sig of L1-post: configurable 35 + 35 + 89 P + 32, dynamic 71 + 48 P + 8, CRC-32 (350 for one PLP, :978)."""
+    return 213 + 137 * len(plp_blocks(c))
+
+
 def l1pre_cells(c, l1_post_size):
     """add_l1pre :1366-1534 -> 1840 BPSK cells."""
     v131 = c["version"] == VERSION_131
     b = (_bits(0, 8) + [c["carriermode"]] + _bits(c["preamble"], 3) + _bits(c["fftsize"] & 7, 3) + [0] + [0] +
          _bits(c["guardinterval"], 3) + _bits(c["paprmode"], 4) + _bits(c["l1constellation"], 4) + _bits(0, 2) + _bits(0, 2) +
-         _bits(l1_post_size, 18) + _bits(350 - 32, 18) + _bits(c["pilotpattern"], 4) + _bits(0, 8) + _bits(0, 16) +
+         _bits(l1_post_size, 18) + _bits(l1post_sig_bits(c) - 32, 18) + _bits(c["pilotpattern"], 4) + _bits(0, 8) + _bits(0, 16) +
          _bits(0x3085, 16) + _bits(0x8001, 16) + _bits(c["t2frames"], 8) + _bits(c["numdatasyms"], 12) + _bits(0, 3) + [0] +
          _bits(1, 3) + _bits(0, 3) + _bits(c["version"], 4) + [c["l1scrambled"] if v131 else 0] + [0] +
          _bits(0xF if (c["reservedbiasbits"] and v131) else 0, 4))
@@ -393,14 +407,23 @@ def l1post_cells(c, frame_idx, n_post, n_punc):
     v131 = c["version"] == VERSION_131
     bias = bool(c["reservedbiasbits"]) and v131
     plp_cod = {C1_3: 6, C2_5: 7, C1_2: 0, C3_5: 1, C2_3: 2, C3_4: 3, C4_5: 4, C5_6: 5}[c["rate"]]
-    b = (_bits(1, 15) + _bits(1, 8) + _bits(0, 4) + _bits(0, 8) + _bits(0, 3) + _bits(729833333, 32) + _bits(0, 8) + _bits(1, 3) +
-         _bits(3, 5) + [0] + _bits(0, 3) + _bits(0, 8) + _bits(1, 8) + _bits(plp_cod, 3) + _bits(c["constellation"], 3) +
-         [c["rotation"]] + _bits(c["framesize"], 2) + _bits(c["fecblocks"], 10) + _bits(1, 8) + _bits(c["tiblocks"], 8) + [0, 0] +
-         [1 if (c["inband"] and v131) else 0] + _bits(0x7FF if bias else 0, 11) +
-         _bits(0 if c["version"] == VERSION_111 else c["inputmode"] + 1, 2) + [0, 0] + _bits(0, 2) +
-         _bits(0x3FFFFFFF if bias else 0, 30) + _bits(frame_idx, 8) + _bits(0, 22) + _bits(0, 22) + _bits(0, 8) + _bits(0, 3) +
-         _bits(0xFF if bias else 0, 8) + _bits(0, 8) + _bits(0, 22) + _bits(c["fecblocks"], 10) + _bits(0xFF if bias else 0, 8) +
-         _bits(0xFF if bias else 0, 8))
+    blocks = plp_blocks(c)
+    cell_size = (64800 if c["framesize"] else 16200) // (2 * (c["constellation"] + 1))
+    r1 = 0x7FF if bias else 0
+    ff = 0xFF if bias else 0
+    b = _bits(1, 15) + _bits(len(blocks), 8) + _bits(0, 4) + _bits(0, 8) + _bits(0, 3) + _bits(729833333, 32)
+    for pid, nb in enumerate(blocks):                 # configurable part, one entry per PLP (:1582-1672 for the single one)
+        b += (_bits(pid, 8) + _bits(1, 3) + _bits(3, 5) + [0] + _bits(0, 3) + _bits(0, 8) + _bits(1, 8) + _bits(plp_cod, 3) +
+              _bits(c["constellation"], 3) + [c["rotation"]] + _bits(c["framesize"], 2) + _bits(nb, 10) + _bits(1, 8) +
+              _bits(c["tiblocks"], 8) + [0, 0] + [1 if (c["inband"] and v131) else 0] + _bits(r1, 11) +
+              _bits(0 if c["version"] == VERSION_111 else c["inputmode"] + 1, 2) + [0, 0])
+    b += _bits(0, 2) + _bits(0x3FFFFFFF if bias else 0, 30)
+    b += _bits(frame_idx, 8) + _bits(0, 22) + _bits(0, 22) + _bits(0, 8) + _bits(0, 3) + _bits(ff, 8)
+    start = 0
+    for pid, nb in enumerate(blocks):                 # dynamic part: PLP_ID, PLP_START (cell address), PLP_NUM_BLOCKS, reserved
+        b += _bits(pid, 8) + _bits(start, 22) + _bits(nb, 10) + _bits(ff, 8)
+        start += nb * cell_size
+    b += _bits(ff, 8)
     b += crc32_bits(b)
     sig = np.array(b, dtype=np.uint8)
     if v131 and c["l1scrambled"]:
@@ -513,8 +536,9 @@ class FrameMapper(object):
                                c["paprmode"], c["preamble"])
         self.cell_size = (64800 if c["framesize"] else 16200) // (2 * (c["constellation"] + 1))
         self.eta = [1, 2, 4, 6][c["l1constellation"]]
-        npt = (6 * (7032 - 350)) // 5
-        nposttmp = 350 + 168 + 9000 - npt
+        ksig = l1post_sig_bits(c)
+        npt = (6 * (7032 - ksig)) // 5
+        nposttmp = ksig + 168 + 9000 - npt
         if d["n_p2"] == 1:                                              # :978-987 (float ceil in the reference)
             self.n_post = int(math.ceil(np.float32(nposttmp) / np.float32(2 * self.eta))) * 2 * self.eta
         else:
@@ -541,12 +565,14 @@ class FrameMapper(object):
     def work(self, cells):
         c, d, Nc, F = self.c, self.d, self.cell_size, self.c["fecblocks"]
         T = c["tiblocks"]
-        if T == 0:
-            blocks = [1] * F
-        else:
-            small, big = F // T, -(-F // T)
-            nbig = F % T
-            blocks = [small] * (T - nbig) + [big] * nbig
+        blocks = []                                                      # TI blocks, PLP after PLP
+        for Fp in plp_blocks(c):
+            if T == 0:
+                blocks += [1] * Fp
+            else:
+                small, big = Fp // T, -(-Fp // T)
+                nbig = Fp % T
+                blocks += [small] * (T - nbig) + [big] * nbig
         ti = np.empty(F * Nc, dtype=np.complex64)
         r_glob = 0
         for k in blocks:                                                 # cell interleaver :1973-1998
@@ -772,17 +798,24 @@ class PilotGen(object):
 
 # --------------------------------------------------------------------------------------------------
 def chain(cfg, ts, nframes):
-    """The shipped flowgraph order (apps/vv009-4kshort.grc) for nframes T2 frames of one channel."""
+    """The shipped flowgraph order (apps/vv009-4kshort.grc) for nframes T2 frames of one channel.  With several PLPs
+    (cfg["plp_fecblocks"]) `ts` is a list of transport streams, one per PLP, each with its own BB framing."""
     c = cfg
     p = fec_params(c["framesize"], c["rate"])
-    bb = BbHeaderBch(c["framesize"], c["rate"], c["inputmode"], c["inband"], c["fecblocks"], c["tsrate"])
+    pb = plp_blocks(c)
+    tss = list(ts) if len(pb) > 1 else [ts]
+    bbs = [BbHeaderBch(c["framesize"], c["rate"], c["inputmode"], c["inband"], nb, c["tsrate"]) for nb in pb]
     fm, pg = FrameMapper(c), PilotGen(c)
-    F = c["fecblocks"]
     res = dict(bch=[], fec=[], cells=[], mapped=[], samples=[])
-    pos = 0
+    pos = [0] * len(pb)
     for _ in range(nframes):
-        bch, used = bb.work(ts[pos:], F)
-        pos += used
+        parts = []
+        for i, nb in enumerate(pb):
+            part, used = bbs[i].work(tss[i][pos[i]:], nb)
+            pos[i] += used
+            parts.append(part)
+        bch = np.concatenate(parts)
+        F = sum(pb)
         fec = ldpc_encode(bch.reshape(F, p["nbch"]), c["framesize"], c["rate"])
         cells = interleavermod(fec, c["framesize"], c["rate"], c["constellation"], c["rotation"]).reshape(-1)
         mapped = fm.work(cells)
@@ -790,5 +823,5 @@ def chain(cfg, ts, nframes):
         for k, v in (("bch", bch), ("fec", fec.reshape(-1)), ("cells", cells), ("mapped", mapped), ("samples", samples)):
             res[k].append(v)
     out = {k: np.concatenate(v) for k, v in res.items()}
-    out["ts_used"] = pos
+    out["ts_used"] = pos[0] if len(pb) == 1 else pos
     return out
