@@ -1093,6 +1093,41 @@ int dvbt2ll_work(dvbt2ll_handle *h, const void *in, int ninput, void *out, int n
   return r;
 }
 
+// ---- transport-stream ingest helpers (host side) ---------------------------------------------
+// first offset at which 0x47 repeats every 188 bytes over 5 packets (or to the end of a shorter buffer), -1 if none
+long long dvbt2ll_ts_sync(const unsigned char *ts, size_t n)
+{
+  if (!ts) return -1;
+  for (size_t off = 0; off < 188 && off < n; off++) {
+    int ok = 0;
+    size_t q = off;
+    for (; q < n && ok < 5; q += 188, ok++)
+      if (ts[q] != 0x47) break;
+    if (ok == 5 || (ok > 0 && q >= n)) return (long long)off;
+  }
+  return -1;
+}
+// dst[0, dst_bytes) = bytes [pos, pos + dst_bytes) of the packet-aligned stream `src`, continued with null packets
+// (PID 0x1FFF: 47 1F FF 10, payload FF) where pos runs past the last whole packet of src; pos < 0 reads as zeros
+// (the history in front of the very first frame).  Returns the number of null-packet bytes written.
+long long dvbt2ll_ts_fill(unsigned char *dst, size_t dst_bytes, const unsigned char *src, size_t src_bytes, long long pos)
+{
+  if (!dst) return -1;
+  const long long whole = (long long)(src_bytes / 188) * 188;        // a trailing partial packet is dropped
+  long long nulls = 0;
+  for (size_t i = 0; i < dst_bytes; i++) {
+    const long long q = pos + (long long)i;
+    if (q < 0) dst[i] = 0;
+    else if (q < whole && src) dst[i] = src[q];
+    else {
+      const int k = (int)(q % 188);
+      dst[i] = k == 0 ? 0x47 : k == 1 ? 0x1F : k == 2 ? 0xFF : k == 3 ? 0x10 : 0xFF;
+      nulls++;
+    }
+  }
+  return nulls;
+}
+
 // plain synchronous copies between host and device memory, for hosts (tests, bench.py, language bindings) that hold raw
 // device pointers handed out by this library (dvbt2ll_gather_wait) and have no CUDA runtime binding of their own
 int dvbt2ll_copy_to_host(void *dst, const void *d_src, size_t bytes)
@@ -1252,6 +1287,13 @@ long long dvbt2ll_chain_ts_bytes(const dvbt2ll_handle *h, long long first_frame,
 {
   ChainHandle *c = as_chain(h);
   return c ? c->ts_bytes(first_frame, n_frames) : -1;
+}
+// stream bytes that must precede the first TS byte of `first_frame` in every row handed to dvbt2ll_chain_run_*
+long long dvbt2ll_chain_history_bytes(const dvbt2ll_handle *h, long long first_frame)
+{
+  ChainHandle *c = as_chain(h);
+  if (!c) return -1;
+  return (first_frame > 0 && c->bb.plan.mode == t2::INPUTMODE_NORMAL) ? 187 : 0;
 }
 int dvbt2ll_chain_num_plp(const dvbt2ll_handle *h) { ChainHandle *c = as_chain(h); return c ? c->P() : -1; }
 long long dvbt2ll_chain_plp_ts_bytes(const dvbt2ll_handle *h, int plp, long long first_frame, int n_frames)

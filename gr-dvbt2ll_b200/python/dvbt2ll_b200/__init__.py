@@ -39,6 +39,7 @@ EXPORTED_SYMBOLS = [
     "dvbt2ll_stream_create", "dvbt2ll_stream_destroy", "dvbt2ll_stream_synchronize",
     "dvbt2ll_chain_enable_taps", "dvbt2ll_chain_fused_fec",
     "dvbt2ll_chain_create_multiplp", "dvbt2ll_chain_num_plp", "dvbt2ll_chain_plp_ts_bytes",
+    "dvbt2ll_chain_history_bytes", "dvbt2ll_ts_sync", "dvbt2ll_ts_fill",
 ]
 GATHER_BLOB_BYTES = 256
 
@@ -133,6 +134,12 @@ def lib():
         L.dvbt2ll_chain_num_plp.argtypes = [vp]
         L.dvbt2ll_chain_plp_ts_bytes.restype = cll
         L.dvbt2ll_chain_plp_ts_bytes.argtypes = [vp, ci, cll, ci]
+        L.dvbt2ll_chain_history_bytes.restype = cll
+        L.dvbt2ll_chain_history_bytes.argtypes = [vp, cll]
+        L.dvbt2ll_ts_sync.restype = cll
+        L.dvbt2ll_ts_sync.argtypes = [vp, sz]
+        L.dvbt2ll_ts_fill.restype = cll
+        L.dvbt2ll_ts_fill.argtypes = [vp, sz, vp, sz, cll]
         _lib = L
     return _lib
 
@@ -461,6 +468,21 @@ class Chain(_Block):
             d["ldpc_map"] = d.pop("map")
             d.pop("ldpc")
         return d
+
+
+def ts_sync(ts):
+    """First offset at which 0x47 repeats every 188 bytes over 5 packets (-1: none)."""
+    ts = np.ascontiguousarray(ts, dtype=np.uint8)
+    return int(lib().dvbt2ll_ts_sync(ts.ctypes.data, ts.size))
+
+
+def ts_fill(src, pos, nbytes):
+    """Bytes [pos, pos + nbytes) of the packet-aligned stream `src`, continued with null packets past its last whole
+    packet (zeros for pos < 0). Returns (bytes, null-packet bytes inserted)."""
+    src = np.ascontiguousarray(src, dtype=np.uint8)
+    out = np.empty(nbytes, dtype=np.uint8)
+    n = lib().dvbt2ll_ts_fill(out.ctypes.data, nbytes, src.ctypes.data, src.size, int(pos))
+    return out, int(n)
 
 
 def set_overfull_policy(warn):

@@ -114,6 +114,9 @@ DVBT2LL_API_EXPORT dvbt2ll_handle *dvbt2ll_chain_create(const dvbt2ll_chain_para
 DVBT2LL_API_EXPORT dvbt2ll_handle *dvbt2ll_chain_create_multiplp(const dvbt2ll_chain_params *p, int num_plp,
                                                                  const int *plp_fecblocks, int max_frames, int device);
 DVBT2LL_API_EXPORT int dvbt2ll_chain_num_plp(const dvbt2ll_handle *h);
+/* Stream bytes that must precede the first TS byte of first_frame in every row handed to dvbt2ll_chain_run_*:
+ * 187 in normal input mode once the stream has started (CRC-8 of the packet in flight), else 0. */
+DVBT2LL_API_EXPORT long long dvbt2ll_chain_history_bytes(const dvbt2ll_handle *h, long long first_frame);
 DVBT2LL_API_EXPORT long long dvbt2ll_chain_plp_ts_bytes(const dvbt2ll_handle *h, int plp, long long first_frame, int n_frames);
 DVBT2LL_API_EXPORT long long dvbt2ll_chain_ts_bytes_per_frame(const dvbt2ll_handle *h);
 /* TS bytes (per channel) consumed by T2 frames [first_frame, first_frame + n_frames): constant per frame in normal
@@ -153,6 +156,15 @@ DVBT2LL_API_EXPORT int dvbt2ll_chain_fused_fec(const dvbt2ll_handle *h);
  * timing was enabled (at most the last 64); events are recorded per run, so the caller's timed loop needs no sync. */
 DVBT2LL_API_EXPORT int dvbt2ll_chain_stage_ms(dvbt2ll_handle *h, float *ms5);
 DVBT2LL_API_EXPORT void dvbt2ll_chain_enable_timing(dvbt2ll_handle *h, int on);
+
+/* ---- transport-stream ingest helpers (host side): what stands in front of the chain when the TS comes from a file
+ * or a socket instead of the flowgraph's ule_source (apps/vv009-4kshort.grc:1663).  dvbt2ll_ts_sync: first offset at which
+ * 0x47 repeats every 188 bytes over 5 packets, -1 if none.  dvbt2ll_ts_fill: dst = bytes [pos, pos + dst_bytes) of the
+ * packet-aligned stream src, continued with null packets (PID 0x1FFF) past its last whole packet -- rate adaptation when
+ * the multiplex runs dry; pos < 0 reads as zeros.  Returns the null-packet bytes written. */
+DVBT2LL_API_EXPORT long long dvbt2ll_ts_sync(const unsigned char *ts, size_t n);
+DVBT2LL_API_EXPORT long long dvbt2ll_ts_fill(unsigned char *dst, size_t dst_bytes, const unsigned char *src, size_t src_bytes,
+                                             long long pos);
 
 /* ---- small device utilities for hosts without a CUDA runtime binding of their own (tests, language bindings):
  * synchronous copies, allocation and device selection for the raw device pointers the *_device entry points take. */

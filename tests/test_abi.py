@@ -109,3 +109,25 @@ def test_link_rejects_ts_consumers_and_mismatched_items():
         B["ldpc"].link_to(B["fm"])           # bytes -> complex cells
     with pytest.raises(ValueError):
         B["ldpc"].link_to(B["bb"])           # the TS consumer keeps stream history in front of its input
+
+
+def test_ts_ingest_helpers():
+    """dvbt2ll_ts_sync / dvbt2ll_ts_fill: sync acquisition on a stream that starts inside a packet, and completion of a
+    stream that has run dry with null packets (PID 0x1FFF) on the packet grid."""
+    ts = K.make_ts(188 * 40)
+    junk = np.full(77, 0x47, np.uint8)
+    junk[::3] = 0x12                                  # stray 0x47 bytes that do not repeat at the packet stride
+    stream = np.concatenate([junk, ts[:188 * 20 + 50]])
+    assert T.ts_sync(stream) == 77
+    assert T.ts_sync(np.zeros(1000, np.uint8)) == -1
+    aligned = stream[77:]
+    out, nulls = T.ts_fill(aligned, 188 * 18 - 5, 188 * 5 + 5)
+    whole = 188 * 20                                  # the trailing partial packet (50 bytes) is dropped
+    assert np.array_equal(out[:188 * 2 + 5], aligned[188 * 18 - 5:whole])
+    rest = out[188 * 2 + 5:]
+    assert nulls == rest.size == 188 * 3
+    pk = rest.reshape(3, 188)
+    assert np.all(pk[:, 0] == 0x47) and np.all(pk[:, 1] == 0x1F) and np.all(pk[:, 2] == 0xFF) and np.all(pk[:, 3] == 0x10)
+    assert np.all(pk[:, 4:] == 0xFF)
+    hist, n0 = T.ts_fill(aligned, -187, 200)
+    assert n0 == 0 and not hist[:187].any() and np.array_equal(hist[187:], aligned[:13])

@@ -63,3 +63,36 @@ def test_flowgraph_demo_matches_oracle(mode):
     ts = K.make_ts(2 * 12352 + 1000)
     want = float(np.abs(O.chain(cfg, ts, 2)["samples"].astype(np.complex128)).sum())
     assert abs(got - want) <= 2e-5 * want
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("plps", [None, [3, 5]])
+def test_file_modulator(tmp_path, plps):
+    """TS file(s) -> t2_file_modulator -> baseband file: sync acquisition, null-packet completion of the last T2 frame
+    and batching with carried stream position give exactly what the Python face computes for the same stream."""
+    import dvbt2ll_b200 as T
+    exe = os.path.join(ROOT, "gr-dvbt2ll_b200", "t2_file_modulator")
+    if not os.path.exists(exe):
+        pytest.skip("t2_file_modulator not built")
+    cfg = K.resolve(dict(K.CONFIGS["c1"], **({"plp_fecblocks": plps, "fecblocks": sum(plps)} if plps else {})))
+    ch = T.Chain(cfg, max_frames=3)
+    P = ch.num_plp
+    nfr = 3
+    files, rows = [], []
+    width = max(ch.plp_ts_bytes(p, 0, nfr) for p in range(P))
+    for p in range(P):
+        n = ch.plp_ts_bytes(p, 0, nfr) - 188 * 7 - 40          # ends inside the third frame, inside a packet
+        ts = K.make_ts(n, seed=K.TS_SEED + p)
+        path = str(tmp_path / ("plp%d.ts" % p))
+        np.concatenate([np.full(33, 0x11, np.uint8), ts]).tofile(path)     # starts with junk: sync has to be found
+        files.append(path)
+        rows.append(T.ts_fill(ts, 0, width)[0])
+    want = ch.run_host(np.stack(rows), 1, nfr)[0]
+    out = str(tmp_path / "out.cf32")
+    cmd = [exe, "--config", "c1", "--batch", "2", "--out", out] + (["--plp-blocks", ",".join(map(str, plps))] if plps else []) + files
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr + r.stdout
+    assert "%d T2 frame(s)" % nfr in r.stdout
+    got = np.fromfile(out, dtype=np.complex64)
+    assert got.size == want.size
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))

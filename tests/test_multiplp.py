@@ -95,14 +95,16 @@ def test_chain_multiplp_matches_oracle(name):
             s = K.make_ts(width + 4000, seed=K.TS_SEED + 17 * c + p)
             streams[c, p] = s
             ts[c * P + p] = s[:width]
-    out = ch.run_host(ts, nch, nfr)
-    S = ch.samples_per_frame
+    out = ch.run_host(ts, nch, nfr).copy()
     F = cfg["fecblocks"]
     p_ = O.fec_params(cfg["framesize"], cfg["rate"])
-    bch = np.unpackbits(ch.tap("bch").reshape(nch * nfr * F, -1)[:, :p_["nbch"] // 8], axis=1)
     for c in range(nch):
         want = O.chain(cfg, [streams[c, p] for p in range(P)], nfr)
         assert [int(u) for u in want["ts_used"]] == [ch.plp_ts_bytes(p, 0, nfr) for p in range(P)]
-        assert bits_equal(bch[c * nfr * F:(c + 1) * nfr * F].reshape(-1), want["bch"])
         assert mer_db(out[c], want["samples"]) >= 90.0, (name, c)
         assert max_err_over_rms(out[c], want["samples"]) <= 1e-5
+        # the BCH codewords of this channel (taps hold the last single-group run: run the channel alone)
+        alone = ch.run_host(ts[c * P:(c + 1) * P], 1, nfr)[0]
+        assert np.array_equal(alone.view(np.uint32), out[c].view(np.uint32))
+        bch = np.unpackbits(ch.tap("bch").reshape(nfr * F, -1)[:, :p_["nbch"] // 8], axis=1)
+        assert bits_equal(bch.reshape(-1), want["bch"])
