@@ -834,7 +834,10 @@ struct ChainHandle : dvbt2ll_handle {
       ci4_stride = (nc + 8 + 3) & ~3;
       std::vector<uint16_t> c4((size_t)4 * ci4_stride, 0);
       for (int k = 0; k < 4; k++)
-        for (int j = 0; j + k < nc; j++) c4[(size_t)k * ci4_stride + j] = fplan.cell_perm_inv[j + k];
+        for (int j = 0; j + k < nc; j++) {
+          const int c = fplan.cell_perm_inv[j + k];
+          c4[(size_t)k * ci4_stride + j] = (uint16_t)(c + 2 * (c >> 6));      // index in the kernel's padded code array
+        }
       CK(upload(d_ci_inv4, c4));
     }
     CK(upload(d_fec_shift, fplan.fec_shift));

@@ -755,11 +755,12 @@ __device__ __forceinline__ void map_body(const MapArgs &a, const int f, const ui
         uint2 *ov = reinterpret_cast<uint2 *>(o16 + yv + dofs);
 #pragma unroll 2
         for (int g = threadIdx.x; g < ngrp; g += MAP_THREADS) {
+          // the shifted copies hold the PADDED index c + 2 (c / 64) of each cell: no index arithmetic per look-up
           const uint2 ci = __ldg(ci4 + g);
           const unsigned c0 = ci.x & 0xFFFFu, c1 = ci.x >> 16, c2 = ci.y & 0xFFFFu, c3 = ci.y >> 16;
-          BND((int)c0 < Nc && (int)c1 < Nc && (int)c2 < Nc && (int)c3 < Nc);
+          BND((int)c0 < Nc + 2 * (Nc >> 6) + 2 && (int)c1 < Nc + 2 * (Nc >> 6) + 2 && (int)c2 < Nc + 2 * (Nc >> 6) + 2 && (int)c3 < Nc + 2 * (Nc >> 6) + 2);
           BND(a.out_len == 0 || (a0 + yv + dofs + 4ll * g >= 0 && a0 + yv + dofs + 4ll * g + 4 <= a.out_len));
-          ov[g] = make_uint2(code(c0) | (code(c1) << 16), code(c2) | (code(c3) << 16));
+          ov[g] = make_uint2((unsigned)cw[c0] | ((unsigned)cw[c1] << 16), (unsigned)cw[c2] | ((unsigned)cw[c3] << 16));
         }
         // ragged ends: up to 3 cells before and after the aligned part
         const int tail0 = yv + 4 * ngrp;

@@ -72,8 +72,9 @@ struct MapArgs {
   uint16_t *out16;           // chain mode: 16-bit cell codes (own word | imaginary-part word << 8) instead of `out`
   long long out16_frame_stride;   // cells between T2 frames in out16 (multiple of 4: frames stay 8-byte aligned)
   const uint16_t *ci_inv;    // inverse of the cell permutation, or NULL for natural order
-  // chain mode, optional: four copies of ci_inv shifted by 0..3 entries (copy k, entry j = ci_inv[j + k], copies
-  // ci_inv4_stride entries apart, 8-byte aligned) so that any four consecutive entries are one aligned 8-byte load
+  // chain mode, optional: four copies of ci_inv shifted by 0..3 entries (copy k, entry j = ci_inv[j + k] as the PADDED
+  // index c + 2 (c / 64) of k_map's code array, copies ci_inv4_stride entries apart, 8-byte aligned) so that any four
+  // consecutive entries are one aligned 8-byte load
   const uint16_t *ci_inv4;
   int ci_inv4_stride;
   const int32_t *fec_shift;  // [fecblocks] cyclic shift per FEC block of the T2 frame
