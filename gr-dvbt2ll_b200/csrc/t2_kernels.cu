@@ -1231,6 +1231,33 @@ __device__ __forceinline__ void fft_pass16(float2 *x, const float2 *__restrict__
   }
 }
 
+// REGTW form of a radix-16 pass for NB = 2 T butterflies: a thread owns butterflies u = tid and tid + T, which share
+// their twiddle base (T is a multiple of NPREV), so every twiddle W^q is generated ONCE -- by the running product
+// W^q = W^(q-1) W, three live values instead of a fifteen-entry tree the compiler re-derives per butterfly at the
+// 128-register cap -- and applied to both butterflies' element q at once.
+template <int M, int NPREV, int T>
+__device__ __forceinline__ void fft_pass16x2(float2 *x, float2 w1)
+{
+  static_assert(M / 16 == 2 * T && T % NPREV == 0, "two butterflies per thread with a common twiddle base");
+  const int u = threadIdx.x, i = u & (NPREV - 1);
+  float2 *xa = x + padx((u - i) * 16 + i);
+  float2 *xc = xa + padx(T * 16);                // butterfly u + T: (u + T - i) * 16 + i, T * 16 a multiple of 16
+  float2 va[16], vb[16];
+#pragma unroll
+  for (int qd = 0; qd < 16; qd++) { va[qd] = xa[padx(qd * NPREV)]; vb[qd] = xc[padx(qd * NPREV)]; }
+  float2 w = w1;
+#pragma unroll
+  for (int qd = 1; qd < 16; qd++) {
+    va[qd] = cmul(va[qd], w);
+    vb[qd] = cmul(vb[qd], w);
+    if (qd < 15) w = cmul(w, w1);
+  }
+  dft_reg<16>(va);
+  dft_reg<16>(vb);
+#pragma unroll
+  for (int k = 0; k < 16; k++) { xa[padx(k * NPREV)] = va[bitrev_c(k, 16)]; xc[padx(k * NPREV)] = vb[bitrev_c(k, 16)]; }
+}
+
 // exp(+j 2 pi k / 32), k compile-time after unrolling
 __device__ __forceinline__ float2 w32(int k)
 {
@@ -1631,9 +1658,14 @@ __global__ void __launch_bounds__(T, (LOG2M == 14 ? 1 : 1024 / T)) k_ofdm(const 
         cp0 = cp1;
       }
       // ---- 2. middle radix-16 passes
-      if (REGTW) {
+      if constexpr (REGTW) {
+#ifdef OFDM_PASS_TREE
         fft_pass16<M, 16, T, REGTW>(x, a.tw, tw_p1); __syncthreads();
         fft_pass16<M, 256, T, REGTW>(x, a.tw, tw_p2); __syncthreads();
+#else
+        fft_pass16x2<M, 16, T>(x, tw_p1); __syncthreads();
+        fft_pass16x2<M, 256, T>(x, tw_p2); __syncthreads();
+#endif
       }
       else {
         if (R0 * 16 < NLAST * 16 && R0 < NLAST) { fft_pass16<M, R0, T>(x, a.tw); __syncthreads(); }
