@@ -129,12 +129,26 @@ __global__ void __launch_bounds__(BB_MAX_WARPS * 32) k_bb_bch(const BbArgs a)
   constexpr int HIST = 192;                                   // stream history kept in front of each frame buffer
   const int buf_pitch = ((nbytes + 15) & ~15) + HIST;
 
-  for (int i = threadIdx.x; i < 4 * 16 * NW * 32; i += blockDim.x) {
-    const int w = (i >> 5) % NW, kn = (i >> 5) / NW, k = kn >> 4, n = kn & 15;
-    // from the byte tables T0 = b x^r, T1 = b x^(r+8): nibble n at position k is byte (n << 4*(k&1)) of table k>>1
-    s_ntab[i] = a.bch_tab[((k >> 1) * 256 + (n << (4 * (k & 1)))) * 6 + w];
+  // (eight table words requested per round trip: with few warps per CTA -- small batches -- this prologue is otherwise a
+  // chain of ~30 dependent L2 latencies, a third of the kernel's time at 8 channels per GPU)
+#pragma unroll 1
+  for (int i0 = threadIdx.x; i0 < 4 * 16 * NW * 32; i0 += 8 * blockDim.x) {
+    uint32_t v[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int i = i0 + u * blockDim.x;
+      const int w = (i >> 5) % NW, kn = (i >> 5) / NW, k = kn >> 4, n = kn & 15;
+      // from the byte tables T0 = b x^r, T1 = b x^(r+8): nibble n at position k is byte (n << 4*(k&1)) of table k>>1
+      v[u] = i < 4 * 16 * NW * 32 ? __ldg(a.bch_tab + ((k >> 1) * 256 + (n << (4 * (k & 1)))) * 6 + w) : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int i = i0 + u * blockDim.x;
+      if (i < 4 * 16 * NW * 32) s_ntab[i] = v[u];
+    }
   }
-  for (int i = threadIdx.x; i < 6 * 32 * 6; i += blockDim.x) s_cols[i] = a.bch_cols[i];
+#pragma unroll 4
+  for (int i = threadIdx.x; i < 6 * 32 * 6; i += blockDim.x) s_cols[i] = __ldg(a.bch_cols + i);
   for (int i = threadIdx.x; i < 256; i += blockDim.x) s_crc8[i] = a.crc8_tab[i];
   __syncthreads();
   const uint8_t *S1 = s_crc8;
