@@ -1696,10 +1696,18 @@ __global__ void __launch_bounds__(T, (LOG2M == 14 ? 1 : 1024 / T)) k_ofdm(const 
         sample_t *o = sym + a.gi + threadIdx.x;
         const bool odd_phase = SPLIT == 2 && phase == 1;
         const float2 *pk = park + threadIdx.x;
-        float2 e[4], en[4];
+        // parked even-bin values: requested from L2 PARK_AHEAD butterflies before their use, kept in a ring of
+        // PARK_AHEAD + 1 register sets.  One ahead leaves ~10 % of the kernel's stall samples on the first use of e[];
+        // two or three ahead spill at the 128-register cap and are slower (0.601 -> 0.612 / 0.638 ms)
+#ifndef PARK_AHEAD
+#define PARK_AHEAD 1
+#endif
+        float2 e[PARK_AHEAD + 1][4];
         if (odd_phase) {
 #pragma unroll
-          for (int k = 0; k < 4; k++) e[k] = pk[k * NL];
+          for (int jj = 0; jj < PARK_AHEAD; jj++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) e[jj][k] = pk[jj * T + k * NL];
         }
 #pragma unroll
         for (int j = 0; j < NBT; j++) {
@@ -1708,9 +1716,9 @@ __global__ void __launch_bounds__(T, (LOG2M == 14 ? 1 : 1024 / T)) k_ofdm(const 
           float2 v[4];
 #pragma unroll
           for (int q = 0; q < 4; q++) v[q] = xb[q * XS];
-          if (odd_phase && j + 1 < NBT) {
+          if (odd_phase && j + PARK_AHEAD < NBT) {
 #pragma unroll
-            for (int k = 0; k < 4; k++) en[k] = pk[(j + 1) * T + k * NL];
+            for (int k = 0; k < 4; k++) e[(j + PARK_AHEAD) % (PARK_AHEAD + 1)][k] = pk[(j + PARK_AHEAD) * T + k * NL];
           }
           const float2 w1 = j ? cmul(tw_last, w32(j)) : tw_last;
           const float2 w2 = cmul(w1, w1), w3 = cmul(w2, w1);
@@ -1736,13 +1744,11 @@ __global__ void __launch_bounds__(T, (LOG2M == 14 ? 1 : 1024 / T)) k_ofdm(const 
 #pragma unroll
             for (int k = 0; k < 4; k++) {
               const float2 r = cmul(tw16(v[bitrev_c(k, 4)], 2 * k), wi);
-              store_sample(o, j * T + k * NL, cadd(e[k], r));
-              const float2 hi = csub(e[k], r);
+              store_sample(o, j * T + k * NL, cadd(e[j % (PARK_AHEAD + 1)][k], r));
+              const float2 hi = csub(e[j % (PARK_AHEAD + 1)][k], r);
               store_sample(o, j * T + k * NL + M, hi);
               if (i + k * NL + M >= cp_from) store_sample(ocp, j * T + k * NL, hi);
             }
-#pragma unroll
-            for (int k = 0; k < 4; k++) e[k] = en[k];
           }
         }
       }
