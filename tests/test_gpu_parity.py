@@ -151,15 +151,23 @@ def test_chain_matches_reference(reflib, name):
 
 
 def _fuzz_configs():
+    """The committed random parameter sets (tools/make_fuzz_configs.py: seed 20261018 x 16 and seed 777 x 40), or the
+    file named by DVBT2LL_FUZZ."""
     import json
     import os
-    with open(os.environ.get("DVBT2LL_FUZZ", os.path.join(os.path.dirname(__file__), "golden", "fuzz_configs.json"))) as f:
-        return json.load(f)
+    here = os.path.join(os.path.dirname(__file__), "golden")
+    paths = [os.environ["DVBT2LL_FUZZ"]] if os.environ.get("DVBT2LL_FUZZ") else [os.path.join(here, "fuzz_configs.json"),
+                                                                                os.path.join(here, "fuzz_configs_r2.json")]
+    out = []
+    for p in paths:
+        with open(p) as f:
+            out += json.load(f)
+    return out
 
 
-@pytest.mark.parametrize("idx", range(int(os.environ.get("DVBT2LL_FUZZ_N", "16"))))
+@pytest.mark.parametrize("idx", range(int(os.environ.get("DVBT2LL_FUZZ_N", "56"))))
 def test_chain_random_configs(reflib, idx):
-    """16 random valid parameter sets (tools/make_fuzz_configs.py: FFT / guard interval / pilot pattern per EN 302 755,
+    """56 random valid parameter sets (tools/make_fuzz_configs.py: FFT / guard interval / pilot pattern per EN 302 755,
     all constellations, rotation, both frame sizes, L1 modulations, reserved tones, in-band, both input modes, inverse
     sinc, extended carriers, v1.1.1 / v1.3.1) against the reference flowgraph, two channels x three T2 frames."""
     cfg = K.resolve(_fuzz_configs()[idx])
