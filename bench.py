@@ -347,19 +347,19 @@ def dropin_extras(torch, T, K, cfg_name, frames_timed):
     """The reference-facing per-block path: one T2 frame per round through the five dvbt2ll_work() handles
     (bbheaderbch -> ldpc -> interleavermod -> framemapper -> pilotgen) on PAGEABLE host buffers -- what a GNU Radio
     scheduler hands to general_work() -- then with the buffers registered on first sight, then with the device-resident
-    hand-off between adjacent handles."""
+    hand-off between adjacent handles, then with the host copies of the linked edges left out as well."""
     cfg = K.resolve(cfg_name)
     res = {}
-    for mode in ("pageable", "host_register", "host_register+link"):
+    for mode in ("pageable", "host_register", "host_register+link", "host_register+link_lazy_host"):
         b = T.blocks_for(cfg)
         order = [b["bb"], b["ldpc"], b["im"], b["fm"], b["pg"]]
         F = cfg["fecblocks"]
         if mode != "pageable":
             for blk in order:
                 blk.set_host_register(True)
-        if mode.endswith("link"):
+        if "link" in mode:
             for i in range(4):
-                order[i].link_to(order[i + 1])
+                order[i].link_to(order[i + 1], lazy_host=mode.endswith("lazy_host"))
         nframes = [F, F, F, 1, 1]
         bufs = [np.empty(n * blk.output_multiple, dtype=blk.out_dtype) for blk, n in zip(order, nframes)]
         need0 = b["bb"].forecast(F * b["bb"].output_multiple) + 1024

@@ -73,11 +73,16 @@ std::vector<t2::cfloat> make_twiddles(int n, int count)
 
 // Device-resident hand-off between two adjacent drop-in blocks (dvbt2ll_link): what the producer last wrote, on the
 // host and where the same items still sit in HBM.  Both blocks hold the mutex for the whole of their work() call.
+// lazy (dvbt2ll_link_lazy_host): the producer leaves the host buffer unwritten; `pending` says the record's items
+// exist only in HBM, `taken_to` how far from the start the consumer has taken them.  Whatever was not taken is written
+// to the host buffer before the device copy is overwritten, and at once when the consumer asks for the range some
+// other way (a miss), so the stream is never lost -- only late for readers other than the linked consumer.
 struct LinkRec {
   std::mutex m;
   const uint8_t *host; size_t bytes; const uint8_t *dev;
-  long long hits, misses;
-  LinkRec() : host(0), bytes(0), dev(0), hits(0), misses(0) {}
+  long long hits, misses, late_writes;
+  bool lazy, pending; size_t taken_to;
+  LinkRec() : host(0), bytes(0), dev(0), hits(0), misses(0), late_writes(0), lazy(false), pending(false), taken_to(0) {}
 };
 
 // Process-wide registry of host page ranges registered by this library (cudaHostRegister), shared by all handles.
@@ -177,7 +182,7 @@ struct dvbt2ll_handle {
   }
   virtual ~dvbt2ll_handle()
   {
-    if (link_out) { std::lock_guard<std::mutex> g(link_out->m); link_out->dev = 0; link_out->bytes = 0; }
+    if (link_out) { std::lock_guard<std::mutex> g(link_out->m); link_out->dev = 0; link_out->bytes = 0; link_out->pending = false; }
     if (!pinned.empty()) PinRegistry::get().release_all(this);
     if (bounce) cudaFreeHost(bounce);
     if (stream) cudaStreamDestroy(stream);
@@ -186,10 +191,15 @@ struct dvbt2ll_handle {
   // and heap buffers share pages, so registrations are kept in one process-wide registry that only ever registers
   // the pages nobody registered yet: a copy never sees a partly registered range (CUDA rejects those).  Failure is
   // not an error: the copy then runs from pageable memory.
+  // Only the pages that lie WHOLLY inside the buffer are registered: a page shared with some other heap object would
+  // leave that object half registered, and CUDA rejects any copy from such a range (seen as "invalid argument" on a
+  // plan-table upload whose std::vector happened to sit next to a registered buffer).  The up to two partial pages at
+  // the ends travel as small pageable pieces (copy_host splits at the boundaries).
   void pin(const void *p, size_t n)
   {
     if (!pin_enabled || !p || n < (1u << 16)) return;
-    const uintptr_t a0 = (uintptr_t)p & ~(uintptr_t)4095, a1 = ((uintptr_t)p + n + 4095) & ~(uintptr_t)4095;
+    const uintptr_t a0 = ((uintptr_t)p + 4095) & ~(uintptr_t)4095, a1 = ((uintptr_t)p + n) & ~(uintptr_t)4095;
+    if (a1 <= a0) return;
     for (size_t i = 0; i < pinned.size(); i++)
       if (a0 >= pinned[i].a0 && a1 <= pinned[i].a1) return;
     if (pinned.size() >= 64) return;
@@ -1057,15 +1067,37 @@ int dvbt2ll_work(dvbt2ll_handle *h, const void *in, int ninput, void *out, int n
   std::unique_lock<std::mutex> lk_in, lk_out;
   if (h->link_in) lk_in = std::unique_lock<std::mutex>(h->link_in->m);
   if (h->link_out) lk_out = std::unique_lock<std::mutex>(h->link_out->m);
+  // a lazily kept record goes to the host buffer it stands for (late, but before anyone can miss it)
+  auto write_back = [&](LinkRec &L) -> int {
+    if (L.pending && L.dev && L.bytes) {
+      CK(h->copy_host(const_cast<uint8_t *>(L.host), L.dev, L.bytes, cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      L.late_writes++;
+    }
+    L.pending = false;
+    return 0;
+  };
   const uint8_t *resident = 0;           // the input items, if the upstream block left them in HBM
   if (h->link_in && !b) {
     LinkRec &L = *h->link_in;
     const uint8_t *ip = (const uint8_t *)in;
-    if (L.dev && ip >= L.host && ip + in_bytes <= L.host + L.bytes) { resident = L.dev + (ip - L.host); L.hits++; }
-    else L.misses++;
+    if (L.dev && ip >= L.host && ip + in_bytes <= L.host + L.bytes) {
+      resident = L.dev + (ip - L.host);
+      L.hits++;
+      const size_t o = (size_t)(ip - L.host);
+      if (o <= L.taken_to && o + in_bytes > L.taken_to) L.taken_to = o + in_bytes;
+      if (L.taken_to >= L.bytes) L.pending = false;            // taken in full: the host copy is never needed
+    }
+    else {
+      L.misses++;
+      if (L.pending && ip < L.host + L.bytes && ip + in_bytes > L.host && (r = write_back(L)) < 0) return r;
+    }
   }
   if (!resident) CK(d_in.ensure(prefix + in_bytes + 256));
-  if (h->link_out) h->link_out->dev = 0;                       // about to be overwritten (and possibly reallocated)
+  if (h->link_out) {
+    if ((r = write_back(*h->link_out)) < 0) return r;          // what the consumer did not take, before it is overwritten
+    h->link_out->dev = 0;                                      // about to be overwritten (and possibly reallocated)
+  }
   CK(d_out.ensure(out_bytes + 256));
   uint8_t *din = resident ? const_cast<uint8_t *>(resident) : d_in.as<uint8_t>() + prefix;
   cudaStream_t s = h->stream;
@@ -1085,13 +1117,18 @@ int dvbt2ll_work(dvbt2ll_handle *h, const void *in, int ninput, void *out, int n
   }
   else r = h->work_device(din, (int)need, d_out.p, nout, &used, s);
   if (r < 0) return r;
-  CK(h->copy_host(out, d_out.p, out_bytes, cudaMemcpyDeviceToHost, s));
+  const bool lazy_out = h->link_out && h->link_out->lazy;
+  if (!lazy_out) CK(h->copy_host(out, d_out.p, out_bytes, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   if (b) {
     h->warnings = *b->h_err;         // mapped host counter, complete after the synchronize
     b->note_consumed((const uint8_t *)in, used);
   }
-  if (h->link_out) { LinkRec &L = *h->link_out; L.host = (const uint8_t *)out; L.bytes = out_bytes; L.dev = d_out.as<uint8_t>(); }
+  if (h->link_out) {
+    LinkRec &L = *h->link_out;
+    L.host = (const uint8_t *)out; L.bytes = out_bytes; L.dev = d_out.as<uint8_t>();
+    L.pending = lazy_out; L.taken_to = 0;
+  }
   if (consumed) *consumed = used;
   return r;
 }
@@ -1184,6 +1221,16 @@ int dvbt2ll_link(dvbt2ll_handle *producer, dvbt2ll_handle *consumer)
 }
 
 long long dvbt2ll_link_hits(const dvbt2ll_handle *consumer) { return (consumer && consumer->link_in) ? consumer->link_in->hits : 0; }
+
+int dvbt2ll_link_lazy_host(dvbt2ll_handle *producer, int on)
+{
+  if (!producer || !producer->link_out) return fail(DVBT2LL_ERR_INVALID, "link_lazy_host: the handle is not the producer of a link");
+  std::lock_guard<std::mutex> g(producer->link_out->m);
+  producer->link_out->lazy = on != 0;
+  return 0;
+}
+
+long long dvbt2ll_link_late_writes(const dvbt2ll_handle *producer) { return (producer && producer->link_out) ? producer->link_out->late_writes : 0; }
 
 // ---- factories -----------------------------------------------------------------------------------
 dvbt2ll_handle *dvbt2ll_bbheaderbch_create(int framesize, int rate, int mode, int inband, int fecblocks, int tsrate)

@@ -3,7 +3,7 @@
 // framemapper -> pilotgen) through their gr::block interface (make / forecast / general_work), with the
 // parameters of that flowgraph (4K, short FECFRAME, 256QAM rotated, CR 4/5, PP7, GI 1/32).  The LDPC stage,
 // which the flowgraph takes from GNU Radio's gr-dtv, is this module's own ldpc_bb block here.
-// Usage: gr_flowgraph_demo [n_t2_frames] [link]   -- prints a checksum of the baseband; needs a CUDA device.
+// Usage: gr_flowgraph_demo [n_t2_frames] [link|link-lazy]   -- prints a checksum of the baseband; needs a CUDA device.
 // With "link" adjacent blocks hand their items over in HBM (dvbt2ll/cuda_link.h); the buffers between the blocks
 // are then kept at fixed addresses, as the scheduler's are.
 #include <dvbt2ll/bbheaderbch_bb.h>
@@ -41,7 +41,8 @@ static void run_block(gr::block &b, const std::vector<In> &in, size_t &in_pos, s
 int main(int argc, char **argv)
 {
   const int nframes = argc > 1 ? atoi(argv[1]) : 2;
-  const bool linked = argc > 2 && !strcmp(argv[2], "link");
+  const bool lazy = argc > 2 && !strcmp(argv[2], "link-lazy");
+  const bool linked = lazy || (argc > 2 && !strcmp(argv[2], "link"));
   const int fecblocks = 8;
   bbheaderbch_bb::sptr bb = bbheaderbch_bb::make(FECFRAME_SHORT, C4_5, INPUTMODE_NORMAL, INBAND_OFF, fecblocks, 4000000);
   interleavermod_bc::sptr im = interleavermod_bc::make(FECFRAME_SHORT, C4_5, MOD_256QAM, ROTATION_ON);
@@ -52,7 +53,7 @@ int main(int argc, char **argv)
       PREAMBLE_T2_SISO, MISO_TX1, EQUALIZATION_OFF, BANDWIDTH_8_0_MHZ, 4096);
   ldpc_bb::sptr ldpc = ldpc_bb::make(FECFRAME_SHORT, C4_5);
   if (linked) {
-    if (!link(bb.get(), ldpc.get()) || !link(ldpc.get(), im.get()) || !link(im.get(), fm.get()) || !link(fm.get(), pg.get())) {
+    if (!link(bb.get(), ldpc.get(), lazy) || !link(ldpc.get(), im.get(), lazy) || !link(im.get(), fm.get(), lazy) || !link(fm.get(), pg.get(), lazy)) {
       fprintf(stderr, "link failed: %s\n", dvbt2ll_last_error());
       return 1;
     }

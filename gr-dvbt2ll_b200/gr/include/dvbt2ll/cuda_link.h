@@ -12,8 +12,10 @@
 namespace gr {
 namespace dvbt2ll {
 
-// returns false when either block is not a GPU-backed dvbt2ll block or their item sizes differ
-DVBT2LL_API bool link(gr::block *producer, gr::block *consumer);
+// returns false when either block is not a GPU-backed dvbt2ll block or their item sizes differ.
+// lazy_host: a no longer writes its host output buffer while b keeps taking the items from HBM (items b does not take
+// that way are written late, nothing is lost) -- only for an edge whose sole reader is b.
+DVBT2LL_API bool link(gr::block *producer, gr::block *consumer, bool lazy_host = false);
 
 } // namespace dvbt2ll
 } // namespace gr

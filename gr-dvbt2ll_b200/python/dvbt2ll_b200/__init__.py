@@ -30,7 +30,7 @@ EXPORTED_SYMBOLS = [
     "dvbt2ll_chain_create", "dvbt2ll_chain_ts_bytes_per_frame", "dvbt2ll_chain_ts_bytes", "dvbt2ll_chain_samples_per_frame",
     "dvbt2ll_chain_fecframes_per_frame", "dvbt2ll_chain_run_device", "dvbt2ll_chain_run_host",
     "dvbt2ll_chain_tap", "dvbt2ll_chain_stage_ms", "dvbt2ll_chain_enable_timing", "dvbt2ll_chain_set_sink",
-    "dvbt2ll_set_overfull_policy", "dvbt2ll_set_host_register", "dvbt2ll_link", "dvbt2ll_link_hits",
+    "dvbt2ll_set_overfull_policy", "dvbt2ll_set_host_register", "dvbt2ll_link", "dvbt2ll_link_hits", "dvbt2ll_link_lazy_host", "dvbt2ll_link_late_writes",
     "dvbt2ll_gather_last_error", "dvbt2ll_gather_create", "dvbt2ll_gather_export", "dvbt2ll_gather_connect",
     "dvbt2ll_gather_acquire", "dvbt2ll_gather_push", "dvbt2ll_gather_wait", "dvbt2ll_gather_release",
     "dvbt2ll_gather_side_stream", "dvbt2ll_gather_destroy",
@@ -101,6 +101,9 @@ def lib():
         L.dvbt2ll_link.argtypes = [vp, vp]
         L.dvbt2ll_link_hits.argtypes = [vp]
         L.dvbt2ll_link_hits.restype = cll
+        L.dvbt2ll_link_lazy_host.argtypes = [vp, ci]
+        L.dvbt2ll_link_late_writes.argtypes = [vp]
+        L.dvbt2ll_link_late_writes.restype = cll
         sz = C.c_size_t
         L.dvbt2ll_gather_last_error.restype = C.c_char_p
         L.dvbt2ll_gather_create.restype = vp
@@ -271,11 +274,19 @@ class _Block(object):
         """Register the host buffers handed to work() with CUDA on first sight (only for long-lived buffers)."""
         lib().dvbt2ll_set_host_register(self._h, 1 if on else 0)
 
-    def link_to(self, consumer):
-        """Device-resident hand-off: `consumer` takes its input from HBM when it is handed what this block last wrote."""
+    def link_to(self, consumer, lazy_host=False):
+        """Device-resident hand-off: `consumer` takes its input from HBM when it is handed what this block last wrote.
+        lazy_host: this block's host output is only written when the consumer did not take the items from HBM
+        (for edges whose only reader is `consumer`)."""
         r = lib().dvbt2ll_link(self._h, consumer._h)
+        if r >= 0 and lazy_host:
+            r = lib().dvbt2ll_link_lazy_host(self._h, 1)
         if r < 0:
             raise ValueError(last_error())
+
+    @property
+    def link_late_writes(self):
+        return int(lib().dvbt2ll_link_late_writes(self._h))
 
     @property
     def link_hits(self):

@@ -197,6 +197,15 @@ DVBT2LL_API_EXPORT void dvbt2ll_set_host_register(dvbt2ll_handle *h, int on);
 DVBT2LL_API_EXPORT int dvbt2ll_link(dvbt2ll_handle *producer, dvbt2ll_handle *consumer);
 /* Number of work() calls of `consumer` that found their input resident in HBM (tests, tuning). */
 DVBT2LL_API_EXPORT long long dvbt2ll_link_hits(const dvbt2ll_handle *consumer);
+/* Opt-in on top of dvbt2ll_link(): the producer no longer writes its host output buffer on every call; the items stay
+ * in HBM for the linked consumer.  Whatever the consumer has not taken from HBM is written to the host buffer late --
+ * at the producer's next call, before the device copy is overwritten, or at once when the consumer asks for the range
+ * with a non-matching pointer -- so the linked pair never loses items.  Only for edges whose ONLY reader is the linked
+ * consumer: any other reader of that host buffer (a second block on the same output, a probe) sees stale bytes; and the
+ * output buffer of a call must stay allocated until the producer's next call returns (the scheduler's buffers do). */
+DVBT2LL_API_EXPORT int dvbt2ll_link_lazy_host(dvbt2ll_handle *producer, int on);
+/* Number of late host writes `producer` had to do (0 in a flowgraph whose scheduler passes every buffer straight on). */
+DVBT2LL_API_EXPORT long long dvbt2ll_link_late_writes(const dvbt2ll_handle *producer);
 
 /* ---- ordered multi-GPU reassembly on one GPU ------------------------------------------------------
  * T2 frames shard across GPUs with no data-path collective; the one exchange is putting the ranks' finished frames

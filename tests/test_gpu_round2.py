@@ -222,6 +222,65 @@ def test_dropin_host_register_and_link(reflib):
         del bufs, ts_buf
 
 
+def test_dropin_link_lazy_host(reflib):
+    """dvbt2ll_link_lazy_host: intermediate host buffers are not written while the linked consumer takes every item
+    from HBM (the last block's output is still exact); what the consumer does not take is written late -- at the
+    producer's next call, or at once when the consumer asks for an overlapping range that is not resident."""
+    cfg = K.resolve("c1")
+    F = cfg["fecblocks"]
+    ts = K.make_ts(4 * F * 2000, seed=22)
+    rc = reflib.Chain(cfg)
+    refs = [rc.run_frame(ts) for _ in range(3)]
+    B = T.blocks_for(cfg)
+    order = [B["bb"], B["ldpc"], B["im"], B["fm"], B["pg"]]
+    bb, ldpc = order[0], order[1]
+    for i in range(4):
+        order[i].link_to(order[i + 1], lazy_host=True)
+    nfr = [F, F, F, 1, 1]
+    bufs = [np.empty(n * blk.output_multiple, dtype=blk.out_dtype) for blk, n in zip(order, nfr)]
+    need = bb.forecast(F * bb.output_multiple) + 400
+    nbch, nldpc = bb.output_multiple, ldpc.output_multiple
+    pos = 0
+    # A. every hand-off hits: the intermediate host buffers keep their sentinel, the baseband is exact
+    for b in bufs[:4]:
+        b.view(np.uint8)[:] = 0xA5
+    _, used = bb.work_into(ts[pos:pos + need].copy(), bufs[0], F)
+    pos += used
+    for i in range(1, 5):
+        order[i].work_into(bufs[i - 1], bufs[i], nfr[i])
+    assert mer_db(bufs[4], refs[0]["samples"]) >= MER_MIN_DB
+    assert all((b.view(np.uint8) == 0xA5).all() for b in bufs[:4])
+    assert sum(blk.link_hits for blk in order[1:]) == 4 and sum(blk.link_late_writes for blk in order[:4]) == 0
+    # B. (a fresh BB -> LDPC pair with only that edge lazy, so the LDPC block's own output goes to the host)
+    #    the consumer takes only the first half of frame 1 from HBM; the producer's next call (into another buffer)
+    #    first writes the record it is about to lose to the host buffer it stands for
+    del order, bb, ldpc
+    B2 = T.blocks_for(cfg)
+    bb, ldpc = B2["bb"], B2["ldpc"]
+    bb.link_to(ldpc, lazy_host=True)
+    first = np.empty_like(bufs[0])                 # stays alive: a lazy record may be written to its buffer later
+    bb.work_into(ts[:need].copy(), first, F)       # frame 0 again: same stream position as above
+    _, used = bb.work_into(ts[pos:pos + need].copy(), bufs[0], F)
+    pos += used
+    assert (bufs[0] == 0xA5).all()
+    half = np.empty((F // 2) * nldpc, np.uint8)
+    ldpc.work_into(bufs[0][:(F // 2) * nbch], half, F // 2)
+    assert bits_equal(half, refs[1]["fec"][:half.size]) and (bufs[0] == 0xA5).all()
+    assert bb.link_late_writes == 1 and bits_equal(first, refs[0]["bch"])       # frame 0 was never taken
+    big = np.full((F + 1) * nbch + 4096, 0xA5, np.uint8)
+    rec = big[128:128 + F * nbch]
+    _, used = bb.work_into(ts[pos:pos + need].copy(), rec, F)
+    assert bb.link_late_writes == 2 and bits_equal(bufs[0], refs[1]["bch"]) and (big == 0xA5).all()
+    # C. the consumer asks for a range that overlaps the record without lying inside it (one FECFRAME further on):
+    #    not resident, so the record is written back at once and the items come from the host as usual
+    big[128 + F * nbch:128 + (F + 1) * nbch] = refs[2]["bch"][:nbch]
+    out = np.empty(F * nldpc, np.uint8)
+    ldpc.work_into(big[128 + nbch:128 + (F + 1) * nbch], out, F)
+    assert bb.link_late_writes == 3 and bits_equal(rec, refs[2]["bch"])
+    assert bits_equal(out[:(F - 1) * nldpc], refs[2]["fec"][nldpc:]) and bits_equal(out[(F - 1) * nldpc:], refs[2]["fec"][:nldpc])
+    del B, B2, bb, ldpc
+
+
 def _run_gather(devices, cfg_name="c1", nch_total=5, nfr=2, steps=5, sink=0):
     """`len(devices)` ranks in ONE process (rank r on devices[r]): every step each rank runs its channels and the
     parts are reassembled in order on rank 0's device. Returns (list of per-step slots as host arrays, expected)."""

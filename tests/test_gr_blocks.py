@@ -20,7 +20,7 @@ def test_wrappers_are_built_and_export_make():
     syms = subprocess.run(["nm", "-DC", lib], capture_output=True, text=True).stdout
     for blk in ("bbheaderbch_bb", "interleavermod_bc", "framemapperfint_cc", "pilotgenp1insert_cc", "ldpc_bb"):
         assert "gr::dvbt2ll::%s::make(" % blk in syms
-    assert "gr::dvbt2ll::link(gr::block*, gr::block*)" in syms
+    assert "gr::dvbt2ll::link(gr::block*, gr::block*, bool)" in syms
 
 
 def test_cmake_overlay_configures():
@@ -48,13 +48,13 @@ def test_cmake_overlay_configures():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["plain", "link"])
+@pytest.mark.parametrize("mode", ["plain", "link", "link-lazy"])
 def test_flowgraph_demo_matches_oracle(mode):
     """apps/vv009-4kshort.grc parameters, 2 T2 frames through make()/forecast()/general_work() of the five gr::block
-    classes (the LDPC stage is this module's ldpc_bb); "link": adjacent blocks hand their items over in HBM."""
+    classes (the LDPC stage is this module's ldpc_bb); "link": adjacent blocks hand their items over in HBM; "link-lazy": and skip the host copies of the edges."""
     if not os.path.exists(DEMO):
         pytest.skip("gr_flowgraph_demo not built")
-    out = subprocess.run([DEMO, "2"] + (["link"] if mode == "link" else []), capture_output=True, text=True, timeout=300)
+    out = subprocess.run([DEMO, "2"] + ([mode] if mode != "plain" else []), capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr
     got = float(re.search(r"sum \|x\| = ([0-9.]+)", out.stdout).group(1))
     assert "TS consumed so far 24704 bytes" in out.stdout

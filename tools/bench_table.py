@@ -55,8 +55,10 @@ def main():
     d = one.get("dropin_e2e", {})
     if "pageable" in d:
         out.append("Drop-in per-block path (five `dvbt2ll_work` handles, one c3 T2 frame per round): %.0f Msamples/s on pageable buffers, "
-                   "%.0f with the buffers registered on first sight, %.0f with the device-resident hand-off as well." % (
-                       d["pageable"]["value"], d["host_register"]["value"], d["host_register+link"]["value"]))
+                   "%.0f with the buffers registered on first sight, %.0f with the device-resident hand-off as well%s." % (
+                       d["pageable"]["value"], d["host_register"]["value"], d["host_register+link"]["value"],
+                       ", %.0f with the host copies of the linked edges left out" % d["host_register+link_lazy_host"]["value"]
+                       if "host_register+link_lazy_host" in d else ""))
     multi = sorted([x for x in lines if x.get("n_gpus", 1) > 1], key=lambda x: x["n_gpus"])
     if multi:
         out.append("")
