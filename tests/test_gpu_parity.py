@@ -151,13 +151,15 @@ def test_chain_matches_reference(reflib, name):
 
 
 def _fuzz_configs():
-    """The committed random parameter sets (tools/make_fuzz_configs.py: seed 20261018 x 16 and seed 777 x 40), or the
-    file named by DVBT2LL_FUZZ."""
+    """The committed random parameter sets (tools/make_fuzz_configs.py: seed 20261018 x 16, seed 777 x 40 and the `wide`
+    draw seed 4242 x 24, which adds MISO / T2-Lite preambles, MISO group, PAPR signalling modes, reserved-bias bits and
+    bandwidths), or the file named by DVBT2LL_FUZZ."""
     import json
     import os
     here = os.path.join(os.path.dirname(__file__), "golden")
     paths = [os.environ["DVBT2LL_FUZZ"]] if os.environ.get("DVBT2LL_FUZZ") else [os.path.join(here, "fuzz_configs.json"),
-                                                                                os.path.join(here, "fuzz_configs_r2.json")]
+                                                                                os.path.join(here, "fuzz_configs_r2.json"),
+                                                                                os.path.join(here, "fuzz_configs_r2w.json")]
     out = []
     for p in paths:
         with open(p) as f:
@@ -165,11 +167,11 @@ def _fuzz_configs():
     return out
 
 
-@pytest.mark.parametrize("idx", range(int(os.environ.get("DVBT2LL_FUZZ_N", "56"))))
+@pytest.mark.parametrize("idx", range(int(os.environ.get("DVBT2LL_FUZZ_N", "80"))))
 def test_chain_random_configs(reflib, idx):
-    """56 random valid parameter sets (tools/make_fuzz_configs.py: FFT / guard interval / pilot pattern per EN 302 755,
+    """80 random valid parameter sets (tools/make_fuzz_configs.py: FFT / guard interval / pilot pattern per EN 302 755,
     all constellations, rotation, both frame sizes, L1 modulations, reserved tones, in-band, both input modes, inverse
-    sinc, extended carriers, v1.1.1 / v1.3.1) against the reference flowgraph, two channels x three T2 frames."""
+    sinc, extended carriers, v1.1.1 / v1.3.1; the last 24 also MISO / T2-Lite, PAPR modes, reserved-bias bits, bandwidths) against the reference flowgraph, two channels x three T2 frames."""
     cfg = K.resolve(_fuzz_configs()[idx])
     nch, nframes = 2, 3
     ch = T.Chain(cfg, max_frames=nch * nframes)

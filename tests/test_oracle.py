@@ -108,6 +108,31 @@ def test_oracle_frame_and_pilot_variants(reflib):
         assert max_err_over_rms(pg.work(y), rp.work(y, 1)[0]) < 1e-6
 
 
+def _wide_configs():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "fuzz_configs_r2w.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("idx", [0, 2, 3, 5, 9, 13, 19, 22])
+def test_oracle_wide_parameter_sets(reflib, idx):
+    """MISO / T2-Lite preambles, MISO group 2, all PAPR signalling modes, reserved-bias bits, every bandwidth
+    (tools/make_fuzz_configs.py ... wide): frame mapper bit-exact and pilot generator within 1e-6 of RMS of the
+    reference for eight of the committed random sets (the GPU sweep runs all 24 through the chain)."""
+    rng = np.random.default_rng(40 + idx)
+    cfg = K.resolve(_wide_configs()[idx])
+    fm, rf = O.FrameMapper(cfg), reflib.framemapper(*fm_args(cfg))
+    assert fm.mapped_items == rf.output_multiple
+    y = None
+    for _ in range(cfg["t2frames"] + 1):
+        x = (rng.standard_normal(fm.stream_items) + 1j * rng.standard_normal(fm.stream_items)).astype(np.complex64)
+        y = fm.work(x)
+        assert cells_equal(y, rf.work(x, 1)[0])
+    pg, rp = O.PilotGen(cfg), reflib.pilotgen(*pg_args(cfg))
+    assert max_err_over_rms(pg.work(y), rp.work(y, 1)[0]) < 1e-6
+
+
 # ---- known answers that do not depend on the reference code ------------------------------------------
 def test_bch_codewords_divisible_by_generator():
     rng = np.random.default_rng(5)

@@ -37,6 +37,9 @@ def ok(cfg):
         return False
 
 
+WIDE = False      # also draw MISO / T2-Lite preambles, the MISO group, PAPR signalling modes, reserved-bias bits, bandwidth
+
+
 def draw(rng):
     fft = rng.choice(list(ALLOWED))
     gi = rng.choice(list(ALLOWED[fft]))
@@ -51,6 +54,14 @@ def draw(rng):
                version=rng.choice((K.VERSION_111, K.VERSION_131)), inband=rng.choice((0, 1)), inputmode=rng.choice((0, 1)),
                misogroup=0, preamble=K.PREAMBLE_T2_SISO, equalization=rng.choice((0, 1)), t2frames=rng.choice((2, 3, 4)),
                numdatasyms=rng.choice((3, 5, 8, 12)) if fft in (K.FFTSIZE_16K, K.FFTSIZE_32K) else rng.choice((6, 10, 20, 40)))
+    if WIDE:
+        cfg["preamble"] = rng.choice((K.PREAMBLE_T2_SISO, K.PREAMBLE_T2_MISO, K.PREAMBLE_T2_LITE_SISO, K.PREAMBLE_T2_LITE_MISO))
+        if cfg["preamble"] in (K.PREAMBLE_T2_LITE_SISO, K.PREAMBLE_T2_LITE_MISO):
+            cfg["version"] = K.VERSION_131
+        cfg["misogroup"] = rng.choice((K.MISO_TX1, K.MISO_TX2))
+        cfg["paprmode"] = rng.choice((K.PAPR_OFF, K.PAPR_ACE, K.PAPR_TR, K.PAPR_BOTH))
+        cfg["reservedbiasbits"] = rng.choice((0, 1)) if cfg["version"] == K.VERSION_131 else 0
+        cfg["bandwidth"] = rng.choice(range(6))
     if cfg["version"] == K.VERSION_111:
         cfg["l1scrambled"] = 0
     else:
@@ -72,7 +83,9 @@ def draw(rng):
 
 
 def main():
-    # usage: make_fuzz_configs.py [seed [count [output.json]]]
+    # usage: make_fuzz_configs.py [seed [count [output.json [wide]]]]
+    global WIDE
+    WIDE = len(sys.argv) > 4 and sys.argv[4] == "wide"
     seed = int(sys.argv[1]) if len(sys.argv) > 1 else 20261018
     count = int(sys.argv[2]) if len(sys.argv) > 2 else 16
     path = sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, "tests", "golden", "fuzz_configs.json")
