@@ -3,9 +3,12 @@
 // framemapper -> pilotgen) through their gr::block interface (make / forecast / general_work), with the
 // parameters of that flowgraph (4K, short FECFRAME, 256QAM rotated, CR 4/5, PP7, GI 1/32).  The LDPC stage,
 // which the flowgraph takes from GNU Radio's gr-dtv, is this module's own ldpc_bb block here.
-// Usage: gr_flowgraph_demo [n_t2_frames] [link|link-lazy]   -- prints a checksum of the baseband; needs a CUDA device.
+// Usage: gr_flowgraph_demo [n_t2_frames] [plain|link|link-lazy] [tpb]   -- prints a checksum of the baseband; needs a CUDA device.
 // With "link" adjacent blocks hand their items over in HBM (dvbt2ll/cuda_link.h); the buffers between the blocks
 // are then kept at fixed addresses, as the scheduler's are.
+// With "tpb" the blocks run the way GNU Radio's thread-per-block scheduler runs them: one thread per block, the edges
+// are rings of three T2-frame slots at fixed addresses, a block works as soon as it has a frame of input and a free
+// output slot -- so adjacent blocks overlap and a producer can be two frames ahead of its consumer.
 #include <dvbt2ll/bbheaderbch_bb.h>
 #include <dvbt2ll/cuda_link.h>
 #include <dvbt2ll/ldpc_bb.h>
@@ -16,7 +19,11 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include "../../../include/dvbt2ll_cuda.h"
@@ -38,9 +45,45 @@ static void run_block(gr::block &b, const std::vector<In> &in, size_t &in_pos, s
   in_pos += b.last_consumed();
 }
 
+// one edge of the thread-per-block run: SLOTS buffers of one T2 frame's items each, reused round robin
+struct Edge {
+  enum { SLOTS = 3 };
+  std::vector<unsigned char> mem;
+  size_t slot_bytes;
+  std::mutex m;
+  std::condition_variable cv;
+  long long produced, consumed;
+  explicit Edge(size_t bytes) : mem(bytes * SLOTS + 64), slot_bytes(bytes), produced(0), consumed(0) {}
+  void *slot(long long k) { return mem.data() + 64 + (size_t)(k % SLOTS) * slot_bytes; }
+  void wait_space() { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return produced - consumed < SLOTS; }); }
+  void wait_item(long long k) { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return produced > k; }); }
+  void push() { { std::lock_guard<std::mutex> l(m); produced++; } cv.notify_all(); }
+  void pop() { { std::lock_guard<std::mutex> l(m); consumed++; } cv.notify_all(); }
+};
+
+// the body of one block's thread: frame f of the input edge -> frame f of the output edge
+static void block_thread(gr::block *b, Edge *in, int in_items, int in_item_size, Edge *out, int noutput, int nframes,
+                         const unsigned char *ts, size_t ts_bytes, size_t *ts_pos)
+{
+  (void)in_item_size;
+  for (int f = 0; f < nframes; f++) {
+    if (in) in->wait_item(f);
+    out->wait_space();
+    gr_vector_int nin(1, in ? in_items : (int)(ts_bytes - *ts_pos));
+    gr_vector_const_void_star ins(1, in ? (const void *)in->slot(f) : (const void *)(ts + *ts_pos));
+    gr_vector_void_star outs(1, out->slot(f));
+    const int produced = b->general_work(noutput, nin, ins, outs);
+    if (produced != noutput) { fprintf(stderr, "block produced %d of %d items\n", produced, noutput); exit(1); }
+    if (in) in->pop();
+    else *ts_pos += b->last_consumed();
+    out->push();
+  }
+}
+
 int main(int argc, char **argv)
 {
   const int nframes = argc > 1 ? atoi(argv[1]) : 2;
+  const bool tpb = argc > 3 && !strcmp(argv[3], "tpb");
   const bool lazy = argc > 2 && !strcmp(argv[2], "link-lazy");
   const bool linked = lazy || (argc > 2 && !strcmp(argv[2], "link"));
   const int fecblocks = 8;
@@ -66,9 +109,36 @@ int main(int argc, char **argv)
 
   size_t ts_pos = 0;
   double acc = 0.0;
+  if (tpb) {
+    Edge e_bch((size_t)fecblocks * 12600), e_fec((size_t)fecblocks * 16200), e_cells((size_t)fecblocks * 2025 * sizeof(gr_complex)),
+         e_mapped((size_t)18866 * sizeof(gr_complex)), e_samples((size_t)31616 * sizeof(gr_complex));
+    std::thread t0(block_thread, bb.get(), (Edge *)0, 0, 1, &e_bch, fecblocks * 12600, nframes, ts.data(), ts.size(), &ts_pos);
+    std::thread t1(block_thread, ldpc.get(), &e_bch, fecblocks * 12600, 1, &e_fec, fecblocks * 16200, nframes, (const unsigned char *)0, (size_t)0, (size_t *)0);
+    std::thread t2(block_thread, im.get(), &e_fec, fecblocks * 16200, 1, &e_cells, fecblocks * 2025, nframes, (const unsigned char *)0, (size_t)0, (size_t *)0);
+    std::thread t3(block_thread, fm.get(), &e_cells, fecblocks * 2025, 8, &e_mapped, 18866, nframes, (const unsigned char *)0, (size_t)0, (size_t *)0);
+    std::thread t4(block_thread, pg.get(), &e_mapped, 18866, 8, &e_samples, 31616, nframes, (const unsigned char *)0, (size_t)0, (size_t *)0);
+    std::chrono::steady_clock::time_point t_first;
+    for (int f = 0; f < nframes; f++) {           // the sink
+      e_samples.wait_item(f);
+      if (f == 0) t_first = std::chrono::steady_clock::now();
+      const gr_complex *sm = (const gr_complex *)e_samples.slot(f);
+      for (int i = 0; i < 31616; i++) acc += (f + 1) * (double)std::abs(sm[i]);       // frame-weighted: order matters
+      e_samples.pop();
+    }
+    t0.join(); t1.join(); t2.join(); t3.join(); t4.join();
+    if (nframes > 1)
+      printf("steady state: %.3f ms per T2 frame (thread per block)\n",
+             std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_first).count() / (nframes - 1));
+    printf("T2 frame %d: %d samples, TS consumed so far %zu bytes\n", nframes - 1, 31616, ts_pos);
+    printf("sum (f+1)|x| = %.6f, kernel launches = %lld\n", acc, dvbt2ll_kernel_launches());
+    bb.reset(); ldpc.reset(); im.reset(); fm.reset(); pg.reset();      // before the edges' buffers go
+    return 0;
+  }
   std::vector<unsigned char> bch, fec;
   std::vector<gr_complex> cells, mapped, samples;
+  std::chrono::steady_clock::time_point t_first;
   for (int f = 0; f < nframes; f++) {
+    if (f == 1) t_first = std::chrono::steady_clock::now();
     size_t p = 0;
     run_block(*bb, ts, ts_pos, bch, fecblocks * 12600);
     run_block(*ldpc, bch, p, fec, fecblocks * 16200);
@@ -78,10 +148,13 @@ int main(int argc, char **argv)
     run_block(*fm, cells, p, mapped, 18866);
     p = 0;
     run_block(*pg, mapped, p, samples, 31616);
-    for (size_t i = 0; i < samples.size(); i++) acc += std::abs(samples[i]);
+    for (size_t i = 0; i < samples.size(); i++) acc += (f + 1) * (double)std::abs(samples[i]);
     printf("T2 frame %d: %zu samples, TS consumed so far %zu bytes\n", f, samples.size(), ts_pos);
   }
-  printf("sum |x| = %.6f, kernel launches = %lld\n", acc, dvbt2ll_kernel_launches());
+  if (nframes > 1)
+    printf("steady state: %.3f ms per T2 frame (one thread)\n",
+           std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_first).count() / (nframes - 1));
+  printf("sum (f+1)|x| = %.6f, kernel launches = %lld\n", acc, dvbt2ll_kernel_launches());
   // the blocks (and with them the registrations of these buffers) go before the buffers do
   bb.reset(); ldpc.reset(); im.reset(); fm.reset(); pg.reset();
   return 0;

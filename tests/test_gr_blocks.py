@@ -48,20 +48,23 @@ def test_cmake_overlay_configures():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["plain", "link", "link-lazy"])
+@pytest.mark.parametrize("mode", ["plain", "link", "link-lazy", "plain tpb", "link tpb", "link-lazy tpb"])
 def test_flowgraph_demo_matches_oracle(mode):
     """apps/vv009-4kshort.grc parameters, 2 T2 frames through make()/forecast()/general_work() of the five gr::block
-    classes (the LDPC stage is this module's ldpc_bb); "link": adjacent blocks hand their items over in HBM; "link-lazy": and skip the host copies of the edges."""
+    classes (the LDPC stage is this module's ldpc_bb); "link": adjacent blocks hand their items over in HBM; "link-lazy": and skip the host copies of the edges;
+    "tpb": one thread per block over three-slot rings, as GNU Radio's thread-per-block scheduler runs them."""
     if not os.path.exists(DEMO):
         pytest.skip("gr_flowgraph_demo not built")
-    out = subprocess.run([DEMO, "2"] + ([mode] if mode != "plain" else []), capture_output=True, text=True, timeout=300)
+    nfr = 7 if "tpb" in mode else 2          # thread per block: enough frames for the rings to wrap and the blocks to overlap
+    out = subprocess.run([DEMO, str(nfr)] + mode.split(), capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr
-    got = float(re.search(r"sum \|x\| = ([0-9.]+)", out.stdout).group(1))
-    assert "TS consumed so far 24704 bytes" in out.stdout
+    got = float(re.search(r"sum \(f\+1\)\|x\| = ([0-9.]+)", out.stdout).group(1))
+    assert "TS consumed so far %d bytes" % (nfr * 12352) in out.stdout
     from oracle import t2oracle as O
     cfg = K.resolve("c1")
-    ts = K.make_ts(2 * 12352 + 1000)
-    want = float(np.abs(O.chain(cfg, ts, 2)["samples"].astype(np.complex128)).sum())
+    ts = K.make_ts(nfr * 12352 + 1000)
+    mag = np.abs(O.chain(cfg, ts, nfr)["samples"].astype(np.complex128)).reshape(nfr, -1).sum(axis=1)
+    want = float((mag * (1 + np.arange(nfr))).sum())         # frame-weighted, so a frame out of order shows
     assert abs(got - want) <= 2e-5 * want
 
 
