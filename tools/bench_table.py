@@ -62,15 +62,17 @@ def main():
     multi = sorted([x for x in lines if x.get("n_gpus", 1) > 1], key=lambda x: x["n_gpus"])
     if multi:
         out.append("")
-        out.append("| GPUs (64 channels in total, 64 / N each) | Msamples/s with the ordered reassembly on GPU 0 (`value`) | ms / step | NVLink ingest of GPU 0, GB/s (bound 770) | same step without the reassembly | reassembly with the int16 sink | e2e host buffers Msamples/s (PCIe GB/s of ceiling) |")
-        out.append("|---|---|---|---|---|---|---|")
-        out.append("| 1 | %.0f | %.3f | - | %.0f | - | %.0f (%.0f of %.0f) |" % (
+        out.append("| GPUs (64 channels in total, 64 / N each) | Msamples/s with the ordered reassembly on GPU 0 (`value`) | ms / step | NVLink ingest of GPU 0, GB/s (bound 770) | same step without the reassembly | reassembly with the int16 sink | reassembly with root-weighted shares (channels on GPU 0) | e2e host buffers Msamples/s (PCIe GB/s of ceiling) |")
+        out.append("|---|---|---|---|---|---|---|---|")
+        out.append("| 1 | %.0f | %.3f | - | %.0f | - | - | %.0f (%.0f of %.0f) |" % (
             one["value"], one["ms_per_step"], one["value"], one["e2e"]["value"], one["e2e"]["pcie_gbs_achieved"], one["e2e"]["pcie_ceiling_gbs"]))
         for m in multi:
             mg = m["multi_gpu"]
-            out.append("| %d | %.0f | %.3f | %.0f | %.0f | %.0f | %.0f (%.0f of %.0f) |" % (
+            rw = mg.get("reassembly_root_weighted")
+            out.append("| %d | %.0f | %.3f | %.0f | %.0f | %.0f | %s | %.0f (%.0f of %.0f) |" % (
                 m["n_gpus"], m["value"], m["ms_per_step"], mg["reassembly"]["ingest_gbs_achieved"], mg["compute_only"]["value"],
-                mg["reassembly_int16_sink"]["value"], m["e2e"]["value"], m["e2e"]["pcie_gbs_achieved"], m["e2e"]["pcie_ceiling_gbs"]))
+                mg["reassembly_int16_sink"]["value"], "%.0f (%d)" % (rw["value"], rw["channels_per_gpu"][0]) if rw else "-",
+                m["e2e"]["value"], m["e2e"]["pcie_gbs_achieved"], m["e2e"]["pcie_ceiling_gbs"]))
     text = "\n".join(out)
     p = os.path.join(ROOT, "README.md")
     s = open(p).read()
