@@ -72,7 +72,9 @@ std::vector<t2::cfloat> make_twiddles(int n, int count)
 } // namespace
 
 // Device-resident hand-off between two adjacent drop-in blocks (dvbt2ll_link): what the producer last wrote, on the
-// host and where the same items still sit in HBM.  Both blocks hold the mutex for the whole of their work() call.
+// host and where the same items still sit in HBM.  The mutex is held only around the look-up / update of the record and
+// the enqueueing of the consumer's kernels: the producer's next call orders its writes behind those kernels with an
+// event on its own stream, so adjacent blocks driven by different threads still overlap.
 // lazy (dvbt2ll_link_lazy_host): the producer leaves the host buffer unwritten; `pending` says the record's items
 // exist only in HBM, `taken_to` how far from the start the consumer has taken them.  Whatever was not taken is written
 // to the host buffer before the device copy is overwritten, and at once when the consumer asks for the range some
@@ -82,7 +84,9 @@ struct LinkRec {
   const uint8_t *host; size_t bytes; const uint8_t *dev;
   long long hits, misses, late_writes;
   bool lazy, pending; size_t taken_to;
-  LinkRec() : host(0), bytes(0), dev(0), hits(0), misses(0), late_writes(0), lazy(false), pending(false), taken_to(0) {}
+  cudaEvent_t taken_ev; bool taken_valid;      // recorded behind the consumer's kernels that read `dev` (see dvbt2ll_work)
+  LinkRec() : host(0), bytes(0), dev(0), hits(0), misses(0), late_writes(0), lazy(false), pending(false), taken_to(0), taken_ev(0), taken_valid(false) {}
+  ~LinkRec() { if (taken_ev) { cudaEventDestroy(taken_ev); cudaGetLastError(); } }
 };
 
 // Process-wide registry of host page ranges registered by this library (cudaHostRegister), shared by all handles.
@@ -1093,11 +1097,16 @@ int dvbt2ll_work(dvbt2ll_handle *h, const void *in, int ninput, void *out, int n
       if (L.pending && ip < L.host + L.bytes && ip + in_bytes > L.host && (r = write_back(L)) < 0) return r;
     }
   }
-  if (!resident) CK(d_in.ensure(prefix + in_bytes + 256));
   if (h->link_out) {
-    if ((r = write_back(*h->link_out)) < 0) return r;          // what the consumer did not take, before it is overwritten
-    h->link_out->dev = 0;                                      // about to be overwritten (and possibly reallocated)
+    LinkRec &L = *h->link_out;
+    if ((r = write_back(L)) < 0) return r;                     // what the consumer did not take, before it is overwritten
+    // the consumer's kernels may still be reading the device copy: this block's stream goes behind them
+    if (L.taken_valid) CK(cudaStreamWaitEvent(h->stream, L.taken_ev, 0));
+    L.dev = 0;                                                 // empty while this call works (and possibly reallocates)
+    lk_out.unlock();
   }
+  if (lk_in.owns_lock() && !resident) lk_in.unlock();
+  if (!resident) CK(d_in.ensure(prefix + in_bytes + 256));
   CK(d_out.ensure(out_bytes + 256));
   uint8_t *din = resident ? const_cast<uint8_t *>(resident) : d_in.as<uint8_t>() + prefix;
   cudaStream_t s = h->stream;
@@ -1117,7 +1126,15 @@ int dvbt2ll_work(dvbt2ll_handle *h, const void *in, int ninput, void *out, int n
   }
   else r = h->work_device(din, (int)need, d_out.p, nout, &used, s);
   if (r < 0) return r;
-  const bool lazy_out = h->link_out && h->link_out->lazy;
+  if (resident) {
+    // everything that reads the producer's device copy is enqueued: mark the point on this stream and let go of the record
+    LinkRec &L = *h->link_in;
+    if (!L.taken_ev) CK(cudaEventCreateWithFlags(&L.taken_ev, cudaEventDisableTiming));
+    CK(cudaEventRecord(L.taken_ev, s));
+    L.taken_valid = true;
+    lk_in.unlock();
+  }
+  const bool lazy_out = h->link_out && h->link_out->lazy;      // (only ever changed by this block's own thread)
   if (!lazy_out) CK(h->copy_host(out, d_out.p, out_bytes, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   if (b) {
@@ -1125,6 +1142,7 @@ int dvbt2ll_work(dvbt2ll_handle *h, const void *in, int ninput, void *out, int n
     b->note_consumed((const uint8_t *)in, used);
   }
   if (h->link_out) {
+    lk_out.lock();
     LinkRec &L = *h->link_out;
     L.host = (const uint8_t *)out; L.bytes = out_bytes; L.dev = d_out.as<uint8_t>();
     L.pending = lazy_out; L.taken_to = 0;
