@@ -71,22 +71,29 @@ std::vector<t2::cfloat> make_twiddles(int n, int count)
 
 } // namespace
 
-// Device-resident hand-off between two adjacent drop-in blocks (dvbt2ll_link): what the producer last wrote, on the
-// host and where the same items still sit in HBM.  The mutex is held only around the look-up / update of the record and
-// the enqueueing of the consumer's kernels: the producer's next call orders its writes behind those kernels with an
-// event on its own stream, so adjacent blocks driven by different threads still overlap.
-// lazy (dvbt2ll_link_lazy_host): the producer leaves the host buffer unwritten; `pending` says the record's items
-// exist only in HBM, `taken_to` how far from the start the consumer has taken them.  Whatever was not taken is written
-// to the host buffer before the device copy is overwritten, and at once when the consumer asks for the range some
-// other way (a miss), so the stream is never lost -- only late for readers other than the linked consumer.
+// Device-resident hand-off between two adjacent drop-in blocks (dvbt2ll_link): the producer's last NSLOT outputs, each
+// with the host range it stands for and the device buffer the same items still sit in.  A ring, not one record, because
+// a scheduler with a thread per block lets the producer run ahead of its consumer by as many calls as the host buffer
+// between them has room for.  The mutex is held only around the look-up / update of the records and the enqueueing of
+// the consumer's kernels: the producer's reuse of a slot is ordered behind those kernels by an event on its own
+// stream, so adjacent blocks driven by different threads still overlap.
+// lazy (dvbt2ll_link_lazy_host): the producer leaves the host buffer unwritten; `pending` says a slot's items exist only
+// in HBM, `taken_to` how far from the start the consumer has taken them.  Whatever was not taken is written to the host
+// buffer before the slot is reused, and at once when the consumer asks for the range some other way (a miss), so the
+// stream is never lost -- only late for readers other than the linked consumer.
 struct LinkRec {
+  enum { NSLOT = 4 };
+  struct Slot {
+    const uint8_t *host; size_t bytes; DevBuf buf; bool valid, pending; size_t taken_to;
+    cudaEvent_t taken_ev; bool taken_valid;      // recorded behind the consumer's kernels that read `buf`
+    Slot() : host(0), bytes(0), valid(false), pending(false), taken_to(0), taken_ev(0), taken_valid(false) {}
+    ~Slot() { if (taken_ev) { cudaEventDestroy(taken_ev); cudaGetLastError(); } }
+  } slot[NSLOT];
   std::mutex m;
-  const uint8_t *host; size_t bytes; const uint8_t *dev;
   long long hits, misses, late_writes;
-  bool lazy, pending; size_t taken_to;
-  cudaEvent_t taken_ev; bool taken_valid;      // recorded behind the consumer's kernels that read `dev` (see dvbt2ll_work)
-  LinkRec() : host(0), bytes(0), dev(0), hits(0), misses(0), late_writes(0), lazy(false), pending(false), taken_to(0), taken_ev(0), taken_valid(false) {}
-  ~LinkRec() { if (taken_ev) { cudaEventDestroy(taken_ev); cudaGetLastError(); } }
+  bool lazy;
+  int next;                                      // slot the producer's next call fills (the oldest)
+  LinkRec() : hits(0), misses(0), late_writes(0), lazy(false), next(0) {}
 };
 
 // Process-wide registry of host page ranges registered by this library (cudaHostRegister), shared by all handles.
@@ -186,7 +193,6 @@ struct dvbt2ll_handle {
   }
   virtual ~dvbt2ll_handle()
   {
-    if (link_out) { std::lock_guard<std::mutex> g(link_out->m); link_out->dev = 0; link_out->bytes = 0; link_out->pending = false; }
     if (!pinned.empty()) PinRegistry::get().release_all(this);
     if (bounce) cudaFreeHost(bounce);
     if (stream) cudaStreamDestroy(stream);
@@ -1064,48 +1070,72 @@ int dvbt2ll_work(dvbt2ll_handle *h, const void *in, int ninput, void *out, int n
   else need = (long long)h->forecast(nout);
   if (ninput < need) return fail(DVBT2LL_ERR_SHORT, "not enough input items for the requested output");
   if (ch && frames > ch->max_frames) return fail(DVBT2LL_ERR_INVALID, "chain: more frames requested than max_frames given at create");
-  DevBuf &d_in = h->stage_in, &d_out = h->stage_out;
+  DevBuf &d_in = h->stage_in;
   const size_t in_bytes = (size_t)need * h->in_item(), out_bytes = (size_t)nout * h->out_item();
   const size_t prefix = 192;
   // linked neighbours (dvbt2ll_link): upstream record first, then downstream -- one global lock order
   std::unique_lock<std::mutex> lk_in, lk_out;
   if (h->link_in) lk_in = std::unique_lock<std::mutex>(h->link_in->m);
   if (h->link_out) lk_out = std::unique_lock<std::mutex>(h->link_out->m);
-  // a lazily kept record goes to the host buffer it stands for (late, but before anyone can miss it)
-  auto write_back = [&](LinkRec &L) -> int {
-    if (L.pending && L.dev && L.bytes) {
-      CK(h->copy_host(const_cast<uint8_t *>(L.host), L.dev, L.bytes, cudaMemcpyDeviceToHost, h->stream));
+  // a lazily kept slot goes to the host buffer it stands for (late, but before anyone can miss it)
+  auto write_back = [&](LinkRec &L, LinkRec::Slot &S) -> int {
+    if (S.valid && S.pending && S.bytes) {
+      CK(h->copy_host(const_cast<uint8_t *>(S.host), S.buf.p, S.bytes, cudaMemcpyDeviceToHost, h->stream));
       CK(cudaStreamSynchronize(h->stream));
       L.late_writes++;
     }
-    L.pending = false;
+    S.pending = false;
     return 0;
   };
   const uint8_t *resident = 0;           // the input items, if the upstream block left them in HBM
+  LinkRec::Slot *taken = 0;
   if (h->link_in && !b) {
     LinkRec &L = *h->link_in;
     const uint8_t *ip = (const uint8_t *)in;
-    if (L.dev && ip >= L.host && ip + in_bytes <= L.host + L.bytes) {
-      resident = L.dev + (ip - L.host);
+    for (int k = 1; k <= LinkRec::NSLOT && !taken; k++) {         // newest first
+      LinkRec::Slot &S = L.slot[(L.next - k + LinkRec::NSLOT) % LinkRec::NSLOT];
+      if (S.valid && ip >= S.host && ip + in_bytes <= S.host + S.bytes) taken = &S;
+    }
+    if (taken) {
+      resident = taken->buf.as<uint8_t>() + (ip - taken->host);
       L.hits++;
-      const size_t o = (size_t)(ip - L.host);
-      if (o <= L.taken_to && o + in_bytes > L.taken_to) L.taken_to = o + in_bytes;
-      if (L.taken_to >= L.bytes) L.pending = false;            // taken in full: the host copy is never needed
+      const size_t o = (size_t)(ip - taken->host);
+      if (o <= taken->taken_to && o + in_bytes > taken->taken_to) taken->taken_to = o + in_bytes;
+      if (taken->taken_to >= taken->bytes) taken->pending = false;      // taken in full: the host copy is never needed
     }
     else {
       L.misses++;
-      if (L.pending && ip < L.host + L.bytes && ip + in_bytes > L.host && (r = write_back(L)) < 0) return r;
+      for (int k = 0; k < LinkRec::NSLOT; k++) {
+        LinkRec::Slot &S = L.slot[k];
+        if (S.valid && S.pending && ip < S.host + S.bytes && ip + in_bytes > S.host && (r = write_back(L, S)) < 0) return r;
+      }
     }
   }
+  LinkRec::Slot *mine = 0;               // where this call's output stays resident
   if (h->link_out) {
     LinkRec &L = *h->link_out;
-    if ((r = write_back(L)) < 0) return r;                     // what the consumer did not take, before it is overwritten
-    // the consumer's kernels may still be reading the device copy: this block's stream goes behind them
-    if (L.taken_valid) CK(cudaStreamWaitEvent(h->stream, L.taken_ev, 0));
-    L.dev = 0;                                                 // empty while this call works (and possibly reallocates)
+    mine = &L.slot[L.next];
+    if ((r = write_back(L, *mine)) < 0) return r;              // what the consumer did not take, before it is overwritten
+    // an older slot standing for (part of) the host range this call writes is dead: the scheduler only hands that
+    // range out again once its consumer is done with it
+    for (int k = 0; k < LinkRec::NSLOT; k++) {
+      LinkRec::Slot &S = L.slot[k];
+      if (&S != mine && S.valid && (const uint8_t *)out < S.host + S.bytes && (const uint8_t *)out + out_bytes > S.host) {
+        if ((r = write_back(L, S)) < 0) return r;
+        S.valid = false;
+      }
+    }
+    // the consumer's kernels may still be reading the slot: this block's stream goes behind them
+    if (mine->taken_valid) CK(cudaStreamWaitEvent(h->stream, mine->taken_ev, 0));
+    mine->valid = false;                                       // empty while this call works (and possibly reallocates)
+    // all empty slots get their device buffer now (first call of the link, or a larger request): later calls must
+    // not pay for an allocation each time they step to the next slot
+    for (int k = 0; k < LinkRec::NSLOT; k++)
+      if (!L.slot[k].valid) CK(L.slot[k].buf.ensure(out_bytes + 256));
     lk_out.unlock();
   }
   if (lk_in.owns_lock() && !resident) lk_in.unlock();
+  DevBuf &d_out = mine ? mine->buf : h->stage_out;
   if (!resident) CK(d_in.ensure(prefix + in_bytes + 256));
   CK(d_out.ensure(out_bytes + 256));
   uint8_t *din = resident ? const_cast<uint8_t *>(resident) : d_in.as<uint8_t>() + prefix;
@@ -1128,10 +1158,9 @@ int dvbt2ll_work(dvbt2ll_handle *h, const void *in, int ninput, void *out, int n
   if (r < 0) return r;
   if (resident) {
     // everything that reads the producer's device copy is enqueued: mark the point on this stream and let go of the record
-    LinkRec &L = *h->link_in;
-    if (!L.taken_ev) CK(cudaEventCreateWithFlags(&L.taken_ev, cudaEventDisableTiming));
-    CK(cudaEventRecord(L.taken_ev, s));
-    L.taken_valid = true;
+    if (!taken->taken_ev) CK(cudaEventCreateWithFlags(&taken->taken_ev, cudaEventDisableTiming));
+    CK(cudaEventRecord(taken->taken_ev, s));
+    taken->taken_valid = true;
     lk_in.unlock();
   }
   const bool lazy_out = h->link_out && h->link_out->lazy;      // (only ever changed by this block's own thread)
@@ -1141,11 +1170,12 @@ int dvbt2ll_work(dvbt2ll_handle *h, const void *in, int ninput, void *out, int n
     h->warnings = *b->h_err;         // mapped host counter, complete after the synchronize
     b->note_consumed((const uint8_t *)in, used);
   }
-  if (h->link_out) {
+  if (mine) {
     lk_out.lock();
     LinkRec &L = *h->link_out;
-    L.host = (const uint8_t *)out; L.bytes = out_bytes; L.dev = d_out.as<uint8_t>();
-    L.pending = lazy_out; L.taken_to = 0;
+    mine->host = (const uint8_t *)out; mine->bytes = out_bytes; mine->valid = true;
+    mine->pending = lazy_out; mine->taken_to = 0;
+    L.next = (L.next + 1) % LinkRec::NSLOT;
   }
   if (consumed) *consumed = used;
   return r;

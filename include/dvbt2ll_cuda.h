@@ -192,17 +192,18 @@ DVBT2LL_API_EXPORT void dvbt2ll_set_overfull_policy(int policy);
  * outlive the handle (the scheduler's do); default off, or DVBT2LL_HOST_REGISTER=1 in the environment. */
 DVBT2LL_API_EXPORT void dvbt2ll_set_host_register(dvbt2ll_handle *h, int on);
 /* Device-resident hand-off between adjacent drop-in blocks of one process: after dvbt2ll_work() the producer keeps
- * its output in HBM; a consumer linked to it takes its input from there when the host pointer/length it is handed
- * matches what the producer last wrote (the scheduler passes the very buffer on), skipping the D2H/H2D pair. */
+ * its last four outputs in HBM (a thread-per-block scheduler lets it run ahead of its consumer); a consumer linked to
+ * it takes its input from there when the host range it is handed lies inside one of them (the scheduler passes the
+ * very buffer on), skipping its host-to-device copy.  The blocks may be driven by different threads. */
 DVBT2LL_API_EXPORT int dvbt2ll_link(dvbt2ll_handle *producer, dvbt2ll_handle *consumer);
 /* Number of work() calls of `consumer` that found their input resident in HBM (tests, tuning). */
 DVBT2LL_API_EXPORT long long dvbt2ll_link_hits(const dvbt2ll_handle *consumer);
 /* Opt-in on top of dvbt2ll_link(): the producer no longer writes its host output buffer on every call; the items stay
  * in HBM for the linked consumer.  Whatever the consumer has not taken from HBM is written to the host buffer late --
- * at the producer's next call, before the device copy is overwritten, or at once when the consumer asks for the range
- * with a non-matching pointer -- so the linked pair never loses items.  Only for edges whose ONLY reader is the linked
+ * before the producer reuses that device copy (four calls later, or when it is handed the same host range again), or
+ * at once when the consumer asks for the range with a non-matching pointer -- so the linked pair never loses items.  Only for edges whose ONLY reader is the linked
  * consumer: any other reader of that host buffer (a second block on the same output, a probe) sees stale bytes; and the
- * output buffer of a call must stay allocated until the producer's next call returns (the scheduler's buffers do). */
+ * output buffer of a call must stay allocated for the producer's next four calls (the scheduler's buffers do). */
 DVBT2LL_API_EXPORT int dvbt2ll_link_lazy_host(dvbt2ll_handle *producer, int on);
 /* Number of late host writes `producer` had to do (0 in a flowgraph whose scheduler passes every buffer straight on). */
 DVBT2LL_API_EXPORT long long dvbt2ll_link_late_writes(const dvbt2ll_handle *producer);

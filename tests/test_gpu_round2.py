@@ -224,13 +224,13 @@ def test_dropin_host_register_and_link(reflib):
 
 def test_dropin_link_lazy_host(reflib):
     """dvbt2ll_link_lazy_host: intermediate host buffers are not written while the linked consumer takes every item
-    from HBM (the last block's output is still exact); what the consumer does not take is written late -- at the
-    producer's next call, or at once when the consumer asks for an overlapping range that is not resident."""
+    from HBM (the last block's output is still exact); what the consumer does not take is written late -- when the
+    producer reuses the slot, or at once when the consumer asks for an overlapping range that is not resident."""
     cfg = K.resolve("c1")
     F = cfg["fecblocks"]
-    ts = K.make_ts(4 * F * 2000, seed=22)
+    ts = K.make_ts(9 * F * 2000, seed=22)
     rc = reflib.Chain(cfg)
-    refs = [rc.run_frame(ts) for _ in range(3)]
+    refs = [rc.run_frame(ts) for _ in range(7)]
     B = T.blocks_for(cfg)
     order = [B["bb"], B["ldpc"], B["im"], B["fm"], B["pg"]]
     bb, ldpc = order[0], order[1]
@@ -252,32 +252,42 @@ def test_dropin_link_lazy_host(reflib):
     assert all((b.view(np.uint8) == 0xA5).all() for b in bufs[:4])
     assert sum(blk.link_hits for blk in order[1:]) == 4 and sum(blk.link_late_writes for blk in order[:4]) == 0
     # B. (a fresh BB -> LDPC pair with only that edge lazy, so the LDPC block's own output goes to the host)
-    #    the consumer takes only the first half of frame 1 from HBM; the producer's next call (into another buffer)
-    #    first writes the record it is about to lose to the host buffer it stands for
+    #    The producer keeps its last four outputs resident (a thread-per-block scheduler lets it run ahead); items the
+    #    consumer did not take are written to their host buffer when their slot is reused, four calls later.
     del order, bb, ldpc
     B2 = T.blocks_for(cfg)
     bb, ldpc = B2["bb"], B2["ldpc"]
     bb.link_to(ldpc, lazy_host=True)
-    first = np.empty_like(bufs[0])                 # stays alive: a lazy record may be written to its buffer later
-    bb.work_into(ts[:need].copy(), first, F)       # frame 0 again: same stream position as above
-    _, used = bb.work_into(ts[pos:pos + need].copy(), bufs[0], F)
-    pos += used
-    assert (bufs[0] == 0xA5).all()
+    outs = [np.full(F * nbch, 0xA5, np.uint8) for _ in range(6)]       # stay alive: lazy slots are written to them later
+    pos = 0
+    for k in range(2):
+        _, used = bb.work_into(ts[pos:pos + need].copy(), outs[k], F)
+        pos += used
+    assert all((o == 0xA5).all() for o in outs) and bb.link_late_writes == 0
+    # the consumer takes frame 0 in full (one frame behind the producer: found in the ring) and half of frame 1
+    fec0 = np.empty(F * nldpc, np.uint8)
+    ldpc.work_into(outs[0], fec0, F)
     half = np.empty((F // 2) * nldpc, np.uint8)
-    ldpc.work_into(bufs[0][:(F // 2) * nbch], half, F // 2)
-    assert bits_equal(half, refs[1]["fec"][:half.size]) and (bufs[0] == 0xA5).all()
-    assert bb.link_late_writes == 1 and bits_equal(first, refs[0]["bch"])       # frame 0 was never taken
+    ldpc.work_into(outs[1][:(F // 2) * nbch], half, F // 2)
+    assert ldpc.link_hits == 2 and bits_equal(fec0, refs[0]["fec"]) and bits_equal(half, refs[1]["fec"][:half.size])
+    assert all((o == 0xA5).all() for o in outs) and bb.link_late_writes == 0
+    for k in range(2, 6):          # calls 5 and 6 reuse the slots of frames 0 (taken in full: nothing to write) and 1
+        _, used = bb.work_into(ts[pos:pos + need].copy(), outs[k], F)
+        pos += used
+    assert bb.link_late_writes == 1 and (outs[0] == 0xA5).all() and bits_equal(outs[1], refs[1]["bch"])
+    assert all((o == 0xA5).all() for o in outs[2:])
+    # C. the consumer asks for a range that overlaps a resident output without lying inside it (one FECFRAME further
+    #    on): not resident, so that output is written back at once and the items come from the host as usual
     big = np.full((F + 1) * nbch + 4096, 0xA5, np.uint8)
     rec = big[128:128 + F * nbch]
-    _, used = bb.work_into(ts[pos:pos + need].copy(), rec, F)
-    assert bb.link_late_writes == 2 and bits_equal(bufs[0], refs[1]["bch"]) and (big == 0xA5).all()
-    # C. the consumer asks for a range that overlaps the record without lying inside it (one FECFRAME further on):
-    #    not resident, so the record is written back at once and the items come from the host as usual
-    big[128 + F * nbch:128 + (F + 1) * nbch] = refs[2]["bch"][:nbch]
+    _, used = bb.work_into(ts[pos:pos + need].copy(), rec, F)          # frame 6
+    assert (big == 0xA5).all()
+    big[128 + F * nbch:128 + (F + 1) * nbch] = refs[6]["bch"][:nbch]
     out = np.empty(F * nldpc, np.uint8)
+    late = bb.link_late_writes
     ldpc.work_into(big[128 + nbch:128 + (F + 1) * nbch], out, F)
-    assert bb.link_late_writes == 3 and bits_equal(rec, refs[2]["bch"])
-    assert bits_equal(out[:(F - 1) * nldpc], refs[2]["fec"][nldpc:]) and bits_equal(out[(F - 1) * nldpc:], refs[2]["fec"][:nldpc])
+    assert bb.link_late_writes == late + 1 and bits_equal(rec, refs[6]["bch"])
+    assert bits_equal(out[:(F - 1) * nldpc], refs[6]["fec"][nldpc:]) and bits_equal(out[(F - 1) * nldpc:], refs[6]["fec"][:nldpc])
     del B, B2, bb, ldpc
 
 

@@ -48,7 +48,7 @@ def test_cmake_overlay_configures():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["plain", "link", "link-lazy", "plain tpb", "link tpb", "link-lazy tpb"])
+@pytest.mark.parametrize("mode", ["plain", "link", "link-lazy", "plain tpb", "link tpb", "link-lazy tpb", "link-lazy tpb c3"])
 def test_flowgraph_demo_matches_oracle(mode):
     """apps/vv009-4kshort.grc parameters, 2 T2 frames through make()/forecast()/general_work() of the five gr::block
     classes (the LDPC stage is this module's ldpc_bb); "link": adjacent blocks hand their items over in HBM; "link-lazy": and skip the host copies of the edges;
@@ -56,13 +56,16 @@ def test_flowgraph_demo_matches_oracle(mode):
     if not os.path.exists(DEMO):
         pytest.skip("gr_flowgraph_demo not built")
     nfr = 7 if "tpb" in mode else 2          # thread per block: enough frames for the rings to wrap and the blocks to overlap
+    name, per_frame = ("c3", 1084740) if mode.endswith("c3") else ("c1", 12352)
+    if name == "c3":
+        nfr = 4
     out = subprocess.run([DEMO, str(nfr)] + mode.split(), capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr
     got = float(re.search(r"sum \(f\+1\)\|x\| = ([0-9.]+)", out.stdout).group(1))
-    assert "TS consumed so far %d bytes" % (nfr * 12352) in out.stdout
+    assert "TS consumed so far %d bytes" % (nfr * per_frame) in out.stdout
     from oracle import t2oracle as O
-    cfg = K.resolve("c1")
-    ts = K.make_ts(nfr * 12352 + 1000)
+    cfg = K.resolve(name)
+    ts = K.make_ts(nfr * per_frame + 1000)
     mag = np.abs(O.chain(cfg, ts, nfr)["samples"].astype(np.complex128)).reshape(nfr, -1).sum(axis=1)
     want = float((mag * (1 + np.arange(nfr))).sum())         # frame-weighted, so a frame out of order shows
     assert abs(got - want) <= 2e-5 * want

@@ -59,6 +59,10 @@ def main():
                        d["pageable"]["value"], d["host_register"]["value"], d["host_register+link"]["value"],
                        ", %.0f with the host copies of the linked edges left out" % d["host_register+link_lazy_host"]["value"]
                        if "host_register+link_lazy_host" in d else ""))
+        k1, k2 = "host_register+link, thread per block", "host_register+link_lazy_host, thread per block"
+        if k1 in d and k2 in d:
+            out.append("The same handles driven by one thread per block over three-slot rings (GNU Radio's scheduler model): %.0f Msamples/s "
+                       "linked, %.0f with lazy host output." % (d[k1]["value"], d[k2]["value"]))
     multi = sorted([x for x in lines if x.get("n_gpus", 1) > 1], key=lambda x: x["n_gpus"])
     if multi:
         out.append("")
