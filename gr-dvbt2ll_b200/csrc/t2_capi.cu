@@ -93,7 +93,36 @@ struct LinkRec {
   long long hits, misses, late_writes;
   bool lazy;
   int next;                                      // slot the producer's next call fills (the oldest)
-  LinkRec() : hits(0), misses(0), late_writes(0), lazy(false), next(0) {}
+  int item;                                      // bytes per item of the producer's output
+  LinkRec() : hits(0), misses(0), late_writes(0), lazy(false), next(0), item(0) {}
+};
+
+// Automatic hand-off (dvbt2ll_set_auto_link / DVBT2LL_AUTO_LINK=1): every drop-in block keeps its outputs resident and
+// registers its record here; a block that was not linked explicitly looks its input range up in the records of all the
+// others, so a flowgraph built by unchanged Python gets the device-resident hand-off without calling dvbt2ll_link.
+struct AutoLinks {
+  std::mutex m;
+  std::vector<std::weak_ptr<LinkRec> > recs;
+  int on;
+  AutoLinks() : on(-1) {}
+  static AutoLinks &get() { static AutoLinks a; return a; }
+  bool enabled()
+  {
+    std::lock_guard<std::mutex> g(m);
+    if (on < 0) { const char *e = std::getenv("DVBT2LL_AUTO_LINK"); on = (e && e[0] == '1') ? 1 : 0; }
+    return on == 1;
+  }
+  void add(const std::shared_ptr<LinkRec> &r) { std::lock_guard<std::mutex> g(m); recs.push_back(r); }
+  void snapshot(std::vector<std::shared_ptr<LinkRec> > &out)
+  {
+    std::lock_guard<std::mutex> g(m);
+    size_t w = 0;
+    for (size_t i = 0; i < recs.size(); i++) {
+      std::shared_ptr<LinkRec> p = recs[i].lock();
+      if (p) { out.push_back(p); recs[w++] = recs[i]; }
+    }
+    recs.resize(w);
+  }
 };
 
 // Process-wide registry of host page ranges registered by this library (cudaHostRegister), shared by all handles.
@@ -183,8 +212,10 @@ struct dvbt2ll_handle {
   struct Pinned { uintptr_t a0, a1; };
   std::vector<Pinned> pinned;   // page ranges this handle has already asked the registry for (lock-free fast path)
   bool pin_enabled;
-  std::shared_ptr<LinkRec> link_in, link_out;     // set by dvbt2ll_link
-  explicit dvbt2ll_handle(Kind k) : kind(k), stream(0), dev_ready(false), warnings(0), pin_enabled(false), bounce(0), bounce_cap(0), bounced_copies(0)
+  std::shared_ptr<LinkRec> link_in, link_out;     // set by dvbt2ll_link (link_out also by the automatic hand-off)
+  std::weak_ptr<LinkRec> auto_in;                 // automatic hand-off: where the input was found last time
+  long long auto_hits;
+  explicit dvbt2ll_handle(Kind k) : kind(k), stream(0), dev_ready(false), warnings(0), pin_enabled(false), auto_hits(0), bounce(0), bounce_cap(0), bounced_copies(0)
   {
     // opt-in (dvbt2ll_set_host_register or the environment): only safe when the caller's buffers outlive the handle,
     // as the GNU Radio scheduler's do -- a registration must never survive the munmap of its pages
@@ -1075,7 +1106,35 @@ int dvbt2ll_work(dvbt2ll_handle *h, const void *in, int ninput, void *out, int n
   const size_t prefix = 192;
   // linked neighbours (dvbt2ll_link): upstream record first, then downstream -- one global lock order
   std::unique_lock<std::mutex> lk_in, lk_out;
-  if (h->link_in) lk_in = std::unique_lock<std::mutex>(h->link_in->m);
+  const bool auto_link = !ch && AutoLinks::get().enabled();
+  if (auto_link && !h->link_out) {                 // every block is a producer under the automatic hand-off
+    h->link_out = std::make_shared<LinkRec>();
+    h->link_out->item = h->out_item();
+    AutoLinks::get().add(h->link_out);
+  }
+  std::shared_ptr<LinkRec> found_in = h->link_in;  // the record the input is looked up in (kept alive for the call)
+  if (!found_in && auto_link && !b) {
+    // not linked explicitly: try the record that matched last time, then every other block's (one lock at a time)
+    const uint8_t *ip = (const uint8_t *)in;
+    std::vector<std::shared_ptr<LinkRec> > cand;
+    if (std::shared_ptr<LinkRec> last = h->auto_in.lock()) cand.push_back(last);
+    const size_t tried_first = cand.size();
+    for (int pass = 0; pass < 2 && !found_in; pass++) {
+      if (pass == 1) AutoLinks::get().snapshot(cand);
+      for (size_t i = pass ? tried_first : 0; i < cand.size() && !found_in; i++) {
+        LinkRec &L = *cand[i];
+        if (cand[i] == h->link_out || L.item != h->in_item()) continue;
+        std::unique_lock<std::mutex> g(L.m);
+        for (int k = 0; k < LinkRec::NSLOT; k++) {
+          const LinkRec::Slot &S = L.slot[k];
+          if (S.valid && ip >= S.host && ip + (size_t)need * h->in_item() <= S.host + S.bytes) { found_in = cand[i]; break; }
+        }
+        if (found_in) lk_in = std::move(g);
+      }
+    }
+    if (found_in) h->auto_in = found_in;
+  }
+  else if (found_in) lk_in = std::unique_lock<std::mutex>(found_in->m);
   if (h->link_out) lk_out = std::unique_lock<std::mutex>(h->link_out->m);
   // a lazily kept slot goes to the host buffer it stands for (late, but before anyone can miss it)
   auto write_back = [&](LinkRec &L, LinkRec::Slot &S) -> int {
@@ -1089,8 +1148,8 @@ int dvbt2ll_work(dvbt2ll_handle *h, const void *in, int ninput, void *out, int n
   };
   const uint8_t *resident = 0;           // the input items, if the upstream block left them in HBM
   LinkRec::Slot *taken = 0;
-  if (h->link_in && !b) {
-    LinkRec &L = *h->link_in;
+  if (found_in && !b) {
+    LinkRec &L = *found_in;
     const uint8_t *ip = (const uint8_t *)in;
     for (int k = 1; k <= LinkRec::NSLOT && !taken; k++) {         // newest first
       LinkRec::Slot &S = L.slot[(L.next - k + LinkRec::NSLOT) % LinkRec::NSLOT];
@@ -1099,6 +1158,7 @@ int dvbt2ll_work(dvbt2ll_handle *h, const void *in, int ninput, void *out, int n
     if (taken) {
       resident = taken->buf.as<uint8_t>() + (ip - taken->host);
       L.hits++;
+      if (!h->link_in) h->auto_hits++;
       const size_t o = (size_t)(ip - taken->host);
       if (o <= taken->taken_to && o + in_bytes > taken->taken_to) taken->taken_to = o + in_bytes;
       if (taken->taken_to >= taken->bytes) taken->pending = false;      // taken in full: the host copy is never needed
@@ -1263,12 +1323,24 @@ int dvbt2ll_link(dvbt2ll_handle *producer, dvbt2ll_handle *consumer)
   if (consumer->kind == dvbt2ll_handle::BB || consumer->kind == dvbt2ll_handle::CHAIN)
     return fail(DVBT2LL_ERR_INVALID, "link: a TS-consuming block keeps stream history in front of its input and cannot be a consumer");
   std::shared_ptr<LinkRec> L = std::make_shared<LinkRec>();
+  L->item = producer->out_item();
   producer->link_out = L;
   consumer->link_in = L;
   return 0;
 }
 
-long long dvbt2ll_link_hits(const dvbt2ll_handle *consumer) { return (consumer && consumer->link_in) ? consumer->link_in->hits : 0; }
+long long dvbt2ll_link_hits(const dvbt2ll_handle *consumer)
+{
+  if (!consumer) return 0;
+  return consumer->link_in ? consumer->link_in->hits : consumer->auto_hits;
+}
+
+void dvbt2ll_set_auto_link(int on)
+{
+  AutoLinks &a = AutoLinks::get();
+  std::lock_guard<std::mutex> g(a.m);
+  a.on = on ? 1 : 0;
+}
 
 int dvbt2ll_link_lazy_host(dvbt2ll_handle *producer, int on)
 {

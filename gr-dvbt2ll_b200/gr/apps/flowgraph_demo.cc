@@ -3,7 +3,7 @@
 // framemapper -> pilotgen) through their gr::block interface (make / forecast / general_work), with the
 // parameters of that flowgraph (4K, short FECFRAME, 256QAM rotated, CR 4/5, PP7, GI 1/32).  The LDPC stage,
 // which the flowgraph takes from GNU Radio's gr-dtv, is this module's own ldpc_bb block here.
-// Usage: gr_flowgraph_demo [n_t2_frames] [plain|link|link-lazy] [tpb|seq] [c1|c3] [nocheck]   -- prints a checksum of the baseband; needs a CUDA device.
+// Usage: gr_flowgraph_demo [n_t2_frames] [plain|link|link-lazy|auto] [tpb|seq] [c1|c3] [nocheck]   -- prints a checksum of the baseband; needs a CUDA device.
 // c3 = BASELINE configuration 3 instead of the shipped flowgraph's: 32K extended, 256QAM rotated, CR 2/3, GI 1/128, PP7, 202 FECFRAMEs.
 // With "link" adjacent blocks hand their items over in HBM (dvbt2ll/cuda_link.h); the buffers between the blocks
 // are then kept at fixed addresses, as the scheduler's are.
@@ -93,6 +93,7 @@ int main(int argc, char **argv)
   const int nframes = argc > 1 ? atoi(argv[1]) : 2;
   const bool tpb = argc > 3 && !strcmp(argv[3], "tpb");
   const bool lazy = argc > 2 && !strcmp(argv[2], "link-lazy");
+  if (argc > 2 && !strcmp(argv[2], "auto")) dvbt2ll_set_auto_link(1);       // no link() calls: the blocks find each other's outputs
   const bool linked = lazy || (argc > 2 && !strcmp(argv[2], "link"));
   const bool c3 = argc > 4 && !strcmp(argv[4], "c3");
   const bool check = !(argc > 5 && !strcmp(argv[5], "nocheck"));      // timing runs skip the sink's checksum arithmetic

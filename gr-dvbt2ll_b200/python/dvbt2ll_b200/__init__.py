@@ -30,7 +30,7 @@ EXPORTED_SYMBOLS = [
     "dvbt2ll_chain_create", "dvbt2ll_chain_ts_bytes_per_frame", "dvbt2ll_chain_ts_bytes", "dvbt2ll_chain_samples_per_frame",
     "dvbt2ll_chain_fecframes_per_frame", "dvbt2ll_chain_run_device", "dvbt2ll_chain_run_host",
     "dvbt2ll_chain_tap", "dvbt2ll_chain_stage_ms", "dvbt2ll_chain_enable_timing", "dvbt2ll_chain_set_sink",
-    "dvbt2ll_set_overfull_policy", "dvbt2ll_set_host_register", "dvbt2ll_link", "dvbt2ll_link_hits", "dvbt2ll_link_lazy_host", "dvbt2ll_link_late_writes",
+    "dvbt2ll_set_overfull_policy", "dvbt2ll_set_host_register", "dvbt2ll_link", "dvbt2ll_link_hits", "dvbt2ll_link_lazy_host", "dvbt2ll_link_late_writes", "dvbt2ll_set_auto_link",
     "dvbt2ll_gather_last_error", "dvbt2ll_gather_create", "dvbt2ll_gather_export", "dvbt2ll_gather_connect",
     "dvbt2ll_gather_acquire", "dvbt2ll_gather_push", "dvbt2ll_gather_wait", "dvbt2ll_gather_release",
     "dvbt2ll_gather_side_stream", "dvbt2ll_gather_destroy",
@@ -102,6 +102,8 @@ def lib():
         L.dvbt2ll_link_hits.argtypes = [vp]
         L.dvbt2ll_link_hits.restype = cll
         L.dvbt2ll_link_lazy_host.argtypes = [vp, ci]
+        L.dvbt2ll_set_auto_link.argtypes = [ci]
+        L.dvbt2ll_set_auto_link.restype = None
         L.dvbt2ll_link_late_writes.argtypes = [vp]
         L.dvbt2ll_link_late_writes.restype = cll
         sz = C.c_size_t
@@ -494,6 +496,12 @@ def ts_fill(src, pos, nbytes):
     out = np.empty(nbytes, dtype=np.uint8)
     n = lib().dvbt2ll_ts_fill(out.ctypes.data, nbytes, src.ctypes.data, src.size, int(pos))
     return out, int(n)
+
+
+def set_auto_link(on=True):
+    """Process-wide: drop-in blocks keep their outputs resident and find their input among the other blocks' resident
+    outputs by host address -- the device-resident hand-off without link_to() (dvbt2ll_set_auto_link)."""
+    lib().dvbt2ll_set_auto_link(1 if on else 0)
 
 
 def set_overfull_policy(warn):

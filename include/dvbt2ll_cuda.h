@@ -196,6 +196,11 @@ DVBT2LL_API_EXPORT void dvbt2ll_set_host_register(dvbt2ll_handle *h, int on);
  * it takes its input from there when the host range it is handed lies inside one of them (the scheduler passes the
  * very buffer on), skipping its host-to-device copy.  The blocks may be driven by different threads. */
 DVBT2LL_API_EXPORT int dvbt2ll_link(dvbt2ll_handle *producer, dvbt2ll_handle *consumer);
+/* Automatic hand-off, process-wide (also DVBT2LL_AUTO_LINK=1 in the environment): every drop-in block keeps its last
+ * four outputs resident and a block that was not linked explicitly looks its input range up among the other blocks'
+ * resident outputs -- a flowgraph assembled by unchanged Python/GRC code gets the hand-off without calling
+ * dvbt2ll_link().  Host buffers are still written (never lazy).  Default off. */
+DVBT2LL_API_EXPORT void dvbt2ll_set_auto_link(int on);
 /* Number of work() calls of `consumer` that found their input resident in HBM (tests, tuning). */
 DVBT2LL_API_EXPORT long long dvbt2ll_link_hits(const dvbt2ll_handle *consumer);
 /* Opt-in on top of dvbt2ll_link(): the producer no longer writes its host output buffer on every call; the items stay

@@ -291,6 +291,41 @@ def test_dropin_link_lazy_host(reflib):
     del B, B2, bb, ldpc
 
 
+def test_dropin_auto_link(reflib):
+    """dvbt2ll_set_auto_link: no link() calls; every block finds its input among the other blocks' resident outputs by
+    host address (the producer may be a frame ahead), the items are the reference's."""
+    cfg = K.resolve("c1")
+    F = cfg["fecblocks"]
+    ts = K.make_ts(4 * F * 2000, seed=23)
+    rc = reflib.Chain(cfg)
+    refs = [rc.run_frame(ts) for _ in range(3)]
+    T.set_auto_link(True)
+    try:
+        B = T.blocks_for(cfg)
+        order = [B["bb"], B["ldpc"], B["im"], B["fm"], B["pg"]]
+        nfr = [F, F, F, 1, 1]
+        # two host slots per edge: the BB block runs one frame ahead of the rest
+        bufs = [[np.empty(n * blk.output_multiple, dtype=blk.out_dtype) for _ in range(2)] for blk, n in zip(order, nfr)]
+        need = B["bb"].forecast(F * B["bb"].output_multiple) + 400
+        pos = 0
+        _, used = order[0].work_into(ts[pos:pos + need].copy(), bufs[0][0], F)
+        pos += used
+        for fr in range(3):
+            if fr + 1 < 3:
+                _, used = order[0].work_into(ts[pos:pos + need].copy(), bufs[0][(fr + 1) % 2], F)
+                pos += used
+            for i in range(1, 5):
+                order[i].work_into(bufs[i - 1][fr % 2], bufs[i][fr % 2], nfr[i])
+            r = refs[fr]
+            assert bits_equal(bufs[0][fr % 2], r["bch"]) and bits_equal(bufs[1][fr % 2], r["fec"])
+            assert cells_equal(bufs[2][fr % 2], r["cells"]) and cells_equal(bufs[3][fr % 2], r["mapped"])
+            assert mer_db(bufs[4][fr % 2], r["samples"]) >= MER_MIN_DB
+        assert [blk.link_hits for blk in order] == [0, 3, 3, 3, 3]
+        del order, B
+    finally:
+        T.set_auto_link(False)
+
+
 def _run_gather(devices, cfg_name="c1", nch_total=5, nfr=2, steps=5, sink=0):
     """`len(devices)` ranks in ONE process (rank r on devices[r]): every step each rank runs its channels and the
     parts are reassembled in order on rank 0's device. Returns (list of per-step slots as host arrays, expected)."""

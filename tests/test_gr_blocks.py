@@ -48,7 +48,7 @@ def test_cmake_overlay_configures():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["plain", "link", "link-lazy", "plain tpb", "link tpb", "link-lazy tpb", "link-lazy tpb c3"])
+@pytest.mark.parametrize("mode", ["plain", "link", "link-lazy", "plain tpb", "link tpb", "link-lazy tpb", "auto", "auto tpb", "link-lazy tpb c3"])
 def test_flowgraph_demo_matches_oracle(mode):
     """apps/vv009-4kshort.grc parameters, 2 T2 frames through make()/forecast()/general_work() of the five gr::block
     classes (the LDPC stage is this module's ldpc_bb); "link": adjacent blocks hand their items over in HBM; "link-lazy": and skip the host copies of the edges;
