@@ -1105,6 +1105,7 @@ int dvbt2ll_work(dvbt2ll_handle *h, const void *in, int ninput, void *out, int n
   const size_t in_bytes = (size_t)need * h->in_item(), out_bytes = (size_t)nout * h->out_item();
   const size_t prefix = 192;
   // linked neighbours (dvbt2ll_link): upstream record first, then downstream -- one global lock order
+  std::shared_ptr<LinkRec> found_in = h->link_in;  // the record the input is looked up in (outlives the lock on it)
   std::unique_lock<std::mutex> lk_in, lk_out;
   const bool auto_link = !ch && AutoLinks::get().enabled();
   if (auto_link && !h->link_out) {                 // every block is a producer under the automatic hand-off
@@ -1112,7 +1113,6 @@ int dvbt2ll_work(dvbt2ll_handle *h, const void *in, int ninput, void *out, int n
     h->link_out->item = h->out_item();
     AutoLinks::get().add(h->link_out);
   }
-  std::shared_ptr<LinkRec> found_in = h->link_in;  // the record the input is looked up in (kept alive for the call)
   if (!found_in && auto_link && !b) {
     // not linked explicitly: try the record that matched last time, then every other block's (one lock at a time)
     const uint8_t *ip = (const uint8_t *)in;
