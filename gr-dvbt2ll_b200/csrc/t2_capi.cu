@@ -548,7 +548,7 @@ struct LdpcHandle : dvbt2ll_handle {
 // ================================================================================================
 struct MapHandle : dvbt2ll_handle {
   t2::MapPlan plan;
-  DevBuf d_bitsrc, d_lut, d_packed;
+  DevBuf d_bitsrc, d_lut, d_packed, d_qlut;
   MapHandle() : dvbt2ll_handle(MAP) {}
   int output_multiple() const { return plan.cell_size; }
   int in_item() const { return 1; }
@@ -558,6 +558,7 @@ struct MapHandle : dvbt2ll_handle {
   {
     CK(upload(d_bitsrc, plan.bit_src));
     CK(upload(d_lut, plan.lut));
+    if (!plan.qpsk_lut.empty()) CK(upload(d_qlut, plan.qpsk_lut));
     return 0;
   }
   void fill_args(t2k::MapArgs &a, const uint8_t *in, int in_pitch, float2 *out, int frames)
@@ -565,6 +566,7 @@ struct MapHandle : dvbt2ll_handle {
     a.in = in; a.in_pitch = in_pitch; a.out = out; a.frames = frames;
     a.nldpc = plan.fec.nldpc; a.mod = plan.mod; a.cell_size = plan.cell_size; a.cyclic_delay = plan.cyclic_delay;
     a.bit_src = d_bitsrc.as<uint16_t>(); a.lut = d_lut.as<float2>();
+    a.qpsk_lut = plan.qpsk_lut.empty() ? 0 : d_qlut.as<uint2>(); a.qpsk_lin_cells = a.qpsk_lut ? plan.qpsk_lin_cells : 0;
     a.ci_inv = 0; a.ci_inv4 = 0; a.ci_inv4_stride = 0; a.fec_shift = 0; a.fecblocks = 1; a.out16 = 0; a.out16_frame_stride = 0;
     a.in_len = (long long)frames * in_pitch; a.out_len = 0;
     a.ncol = plan.ncol;

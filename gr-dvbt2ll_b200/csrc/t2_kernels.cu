@@ -751,7 +751,24 @@ __device__ __forceinline__ void map_body(const MapArgs &a, const int f, const ui
   else if (mod == 2 && (Nc & 3) == 0) {
     // QPSK: four cells per step -- their eight source bit positions are one 16-byte load
     const uint8_t *ub = reinterpret_cast<const uint8_t *>(u);
-    for (int c = 4 * threadIdx.x; c < Nc; c += 4 * blockDim.x) {
+    // cells whose bits sit in place in the codeword (the info part; everything for the parity-interleaved codes): a
+    // 32-bit word is sixteen cells, each byte's four codes come from one 8-byte table entry
+#ifndef MAP_QPSK_GENERIC
+    const int lin = a.qpsk_lin_cells;
+    for (int wi = threadIdx.x; wi < (lin >> 4); wi += blockDim.x) {
+      const uint32_t W = u[wi];                      // raw byte order: byte k of the stream is bits 8k..8k+7
+      uint32_t *dst = reinterpret_cast<uint32_t *>(cw + 16 * wi + 2 * (wi >> 2));
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const uint2 cd = __ldg(a.qpsk_lut + ((W >> (8 * k)) & 255u));
+        dst[2 * k] = cd.x;
+        dst[2 * k + 1] = cd.y;
+      }
+    }
+#else
+    const int lin = 0;
+#endif
+    for (int c = lin + 4 * threadIdx.x; c < Nc; c += 4 * blockDim.x) {
       const uint4 pp = __ldg(reinterpret_cast<const uint4 *>(a.bit_src) + (c >> 2));
       const uint32_t w[4] = { pp.x, pp.y, pp.z, pp.w };
       uint32_t code[4];

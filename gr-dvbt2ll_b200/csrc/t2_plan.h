@@ -110,6 +110,10 @@ struct MapPlan {
   // single-table form of the constellation: Im lut[w] == Re lut[w~], w~ = (((w << 1) & im_mask_i) | ((w >> 1) & im_mask_q)) ^ im_flip
   int im_from_re;                     // 1 when that identity holds bit for bit for every word (checked at plan time)
   uint32_t im_mask_i, im_mask_q, im_flip;
+  // QPSK: cells [0, qpsk_lin_cells) take bits 2c, 2c+1 of the codeword as it arrives (a multiple of 16 cells: the info
+  // part, or everything for the parity-interleaved short codes); qpsk_lut[b] = the four cell codes of message byte b
+  int qpsk_lin_cells;
+  std::vector<uint32_t> qpsk_lut;     // [256][2]: codes of cells 0,1 | 2,3 of the byte (own word | w~ << 8)
 };
 bool build_map_plan(int framesize, int rate, int constellation, int rotation, MapPlan *p, std::string *err);
 

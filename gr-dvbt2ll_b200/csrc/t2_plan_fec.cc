@@ -412,6 +412,26 @@ bool build_map_plan(int framesize, int rate, int constellation, int rotation, Ma
       if (x != y) p->im_from_re = 0;
     }
   }
+  // ---- QPSK: the leading run of cells whose two bits sit where they are in the incoming codeword goes through a
+  // byte -> four cell codes table in the kernel (the general path extracts bit by bit through bit_src)
+  p->qpsk_lin_cells = 0;
+  p->qpsk_lut.clear();
+  if (constellation == MOD_QPSK) {
+    int n = 0;
+    while (n < N && p->bit_src[n] == (uint16_t)n) n++;
+    p->qpsk_lin_cells = (n / 32) * 16;
+    p->qpsk_lut.assign(512, 0);
+    for (int b = 0; b < 256; b++) {
+      uint32_t code[4];
+      for (int k = 0; k < 4; k++) {
+        const uint32_t v = ((uint32_t)b >> (6 - 2 * k)) & 3u;
+        const uint32_t vt = p->im_from_re ? ((((v << 1) & p->im_mask_i) | ((v >> 1) & p->im_mask_q)) ^ p->im_flip) & 0xFFu : v;
+        code[k] = v | (vt << 8);
+      }
+      p->qpsk_lut[2 * b] = code[0] | (code[1] << 16);
+      p->qpsk_lut[2 * b + 1] = code[2] | (code[3] << 16);
+    }
+  }
   return true;
 }
 
