@@ -1380,9 +1380,13 @@ __device__ __forceinline__ float2 w64(int k)
 // loads -- stored [quad][group][4] so that each load is contiguous across the warp
 int ofdm_table_index(int p, int log2_m)
 {
+#ifdef OFDM_4K_PLAIN_FILL
   if (log2_m != 14) return p;
+#else
+  if (log2_m != 14 && log2_m != 12) return p;       // the transforms whose fill carries a radix-16 first pass
+#endif
   const int g = p >> 4, q = (p >> 2) & 3, r = p & 3;
-  return ((q << 10) + g) * 4 + r;
+  return ((q << (log2_m - 4)) + g) * 4 + r;
 }
 
 int ofdm_position_of_bin(int m, int log2_m)
@@ -1433,7 +1437,12 @@ __device__ __forceinline__ void store_sample(short2 *p, int idx, float2 v)
 template <int LOG2M, int T>
 struct FillGeom {
   static constexpr int M = 1 << LOG2M;
+#ifdef OFDM_4K_PLAIN_FILL
   static constexpr int R0 = LOG2M == 14 ? 16 : 1 << (LOG2M & 3);   // first radix (1 = no first pass)
+#else
+  // 4K = 16 * 16 * 16: its first radix-16 pass (no twiddles) rides in the fill as well, like the 16K sub-transform's
+  static constexpr int R0 = (LOG2M == 14 || LOG2M == 12) ? 16 : 1 << (LOG2M & 3);   // first radix (1 = no first pass)
+#endif
   static constexpr int GROUPS = M / R0;             // first-pass butterflies
   static constexpr int INFL = LOG2M == 14 ? 16 : 8; // positions in flight per thread (16 where 128 registers are available)
   static constexpr int GPB0 = R0 >= INFL ? 1 : INFL / R0; // groups gathered per batch
@@ -1596,7 +1605,7 @@ __global__ void __launch_bounds__(T, (LOG2M == 14 ? 1 : 1024 / T)) k_ofdm(const 
     }
     __syncthreads();
   }
-  constexpr int R0 = 1 << (LOG2M & 3);       // first radix (1 = no first pass)
+  constexpr int R0 = FillGeom<LOG2M, T>::R0;       // first radix, done inside the fill (1 = no first pass)
   constexpr int NLAST = M / 16;              // NPREV of the last radix-16 pass
   const int N = a.fft_n;
   const int units = a.frames * a.num_symbols;
