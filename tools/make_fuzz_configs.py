@@ -30,9 +30,24 @@ SHORT_RATES = (K.C1_3, K.C2_5, K.C3_5, K.C2_3, K.C4_5)          # short 1/2, 3/4
 NORMAL_RATES = (K.C1_2, K.C3_5, K.C2_3, K.C3_4, K.C4_5, K.C5_6)
 
 
+def maps_consistent(cfg):
+    """The reference's carrier maps hold exactly the number of data carriers its own C_P2 / C_DATA / N_FC tables promise.
+    (For a few non-standard combinations they differ by one -- e.g. 16K extended, PP1, GI 1/4, reserved tones, MISO group
+    2: 12535 data carriers in one symbol against C_DATA = 12534 -- and the reference then reads one cell past its
+    input; the plan compiler refuses those, so they are not drawn.)"""
+    from oracle import t2oracle as O
+    pg = O.PilotGen(K.resolve(cfg))
+    d = pg.d
+    for l in range(d["L"]):
+        want = d["c_p2"] if l < d["n_p2"] else d["n_fc"] if (d["n_fc"] and l == d["L"] - 1) else d["c_data"]
+        if int((pg.carrier_map(l) == 1).sum()) != want:
+            return False
+    return True
+
+
 def ok(cfg):
     try:
-        return R.Chain(K.resolve(cfg)).fm.warnings == 0
+        return R.Chain(K.resolve(cfg)).fm.warnings == 0 and maps_consistent(cfg)
     except Exception:
         return False
 
