@@ -189,6 +189,35 @@ def test_chain_random_configs(reflib, idx):
             assert max_err_over_rms(s, refs[fr]["samples"]) <= MAX_ERR_OVER_RMS
 
 
+@pytest.mark.parametrize("idx", range(0, 80, 4))
+def test_blocks_random_configs(reflib, idx):
+    """Every fourth of the random parameter sets through the five per-block handles (the drop-in path proper), two T2
+    frames with state carried across: bits and cells bit-exact, baseband within the MER bar."""
+    cfg = K.resolve(_fuzz_configs()[idx])
+    nframes = 2
+    B = T.blocks_for(cfg)
+    F = cfg["fecblocks"]
+    n_ts = B["bb"].forecast(F * B["bb"].output_multiple)
+    ts = K.make_ts(nframes * n_ts + 2000, seed=K.TS_SEED + 7 * idx)
+    refs = _ref_frames(reflib, cfg, ts, nframes)
+    pos = 0
+    for fr in range(nframes):
+        r = refs[fr]
+        bch, used = B["bb"].work(ts[pos:pos + n_ts + 600], F)
+        pos += used
+        assert used == r["ts_used"]
+        assert bits_equal(bch, r["bch"]), "BCH codewords differ"
+        fec, _ = B["ldpc"].work(bch, F)
+        assert bits_equal(fec, r["fec"]), "LDPC codewords differ"
+        cells, _ = B["im"].work(fec, F)
+        assert cells_equal(cells, r["cells"]), "cells differ"
+        mapped, _ = B["fm"].work(cells, 1)
+        assert cells_equal(mapped, r["mapped"]), "frame mapper output differs"
+        samples, _ = B["pg"].work(mapped, 1)
+        assert mer_db(samples, r["samples"]) >= MER_MIN_DB
+        assert max_err_over_rms(samples, r["samples"]) <= MAX_ERR_OVER_RMS
+
+
 def test_chain_multichannel_and_offset(reflib):
     """c5-style batching: independent channels (seed + channel) in one launch, and a batch that starts at
     T2 frame 1 (stream history in front of the pointer) equals the tail of a batch that starts at frame 0."""
