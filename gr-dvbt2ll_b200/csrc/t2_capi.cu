@@ -567,6 +567,7 @@ struct MapHandle : dvbt2ll_handle {
     a.nldpc = plan.fec.nldpc; a.mod = plan.mod; a.cell_size = plan.cell_size; a.cyclic_delay = plan.cyclic_delay;
     a.bit_src = d_bitsrc.as<uint16_t>(); a.lut = d_lut.as<float2>();
     a.qpsk_lut = plan.qpsk_lut.empty() ? 0 : d_qlut.as<uint2>(); a.qpsk_lin_cells = a.qpsk_lut ? plan.qpsk_lin_cells : 0;
+    a.qpsk_par_q = a.qpsk_lut ? plan.qpsk_par_q : 0; a.qpsk_nbch = plan.qpsk_nbch;
     a.ci_inv = 0; a.ci_inv4 = 0; a.ci_inv4_stride = 0; a.fec_shift = 0; a.fecblocks = 1; a.out16 = 0; a.out16_frame_stride = 0;
     a.in_len = (long long)frames * in_pitch; a.out_len = 0;
     a.ncol = plan.ncol;
@@ -595,6 +596,7 @@ struct MapHandle : dvbt2ll_handle {
     std::string n(name);
     if (n == "map.bit_src") return copy_vec(plan.bit_src, out, cap);
     if (n == "map.lut") return copy_vec(plan.lut, out, cap);
+    if (n == "map.qpsk") { const int v[3] = { plan.qpsk_lin_cells, plan.qpsk_par_q, plan.qpsk_nbch }; return copy_out(v, sizeof(v), out, cap); }
     if (n == "map.im_from_re") { const int v[4] = { plan.im_from_re, (int)plan.im_mask_i, (int)plan.im_mask_q, (int)plan.im_flip }; return copy_out(v, sizeof(v), out, cap); }
     return -1;
   }

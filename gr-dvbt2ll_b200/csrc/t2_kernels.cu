@@ -673,6 +673,9 @@ __device__ __forceinline__ void map_setup(const MapArgs &a, float2 *lut, int *s_
 
 // Bit interleaver + demux + cell codes + output of FECFRAME f whose packed "u"-order codeword sits in shared memory
 // (raw byte order, zero slack words behind it).  The caller has synchronised the CTA on `u`; ends without a barrier.
+// QTR: the instantiation that carries the QPSK transposed-parity path (its 32-register tile would otherwise raise the
+// register count of every mapper launch)
+template <bool QTR>
 __device__ __forceinline__ void map_body(const MapArgs &a, const int f, const uint32_t *u, const float2 *lut, uint16_t *cw,
                                          const int *s_base, const int *s_twist, const int shift)
 {
@@ -768,7 +771,10 @@ __device__ __forceinline__ void map_body(const MapArgs &a, const int f, const ui
 #else
     const int lin = 0;
 #endif
-    for (int c = lin + 4 * threadIdx.x; c < Nc; c += 4 * blockDim.x) {
+    // cells [lin, gen_end) go bit by bit through bit_src; with the transposed parity path that is only the few info
+    // cells behind the last whole table word
+    const int gen_end = QTR && a.qpsk_par_q > 0 ? (a.qpsk_nbch >> 1) : Nc;
+    for (int c = lin + 4 * threadIdx.x; c < gen_end; c += 4 * blockDim.x) {
       const uint4 pp = __ldg(reinterpret_cast<const uint4 *>(a.bit_src) + (c >> 2));
       const uint32_t w[4] = { pp.x, pp.y, pp.z, pp.w };
       uint32_t code[4];
@@ -781,6 +787,55 @@ __device__ __forceinline__ void map_body(const MapArgs &a, const int f, const ui
       uint32_t *dst = reinterpret_cast<uint32_t *>(cw + c + 2 * (c >> 6));
       dst[0] = code[0] | (code[1] << 16);
       dst[1] = code[2] | (code[3] << 16);
+    }
+    if (QTR && a.qpsk_par_q > 0) {
+      // parity cells: natural parity bit q s + t is codeword bit nbch + 360 t + s, a q x 360 bit-matrix transpose.
+      // One thread per 32 x 32 tile: 32 row windows -> register transpose -> 32 column pieces; once every tile is in
+      // registers the (spent) info words of `u` become the natural-order parity stream, pieces OR-ed in at their bit
+      // offsets, and the byte table maps it like the info part.
+      const int q = a.qpsk_par_q, nbch = a.qpsk_nbch, par0 = nbch >> 1;
+      const int tr = (q + 31) >> 5;                      // tile rows; 12 tile columns (360 = 11.25 x 32)
+      const bool have = (int)threadIdx.x < tr * 12;
+      const int t0 = ((int)threadIdx.x / 12) << 5, s0 = ((int)threadIdx.x % 12) << 5;
+      uint32_t A[32];
+      if (have) {
+#pragma unroll
+        for (int y = 0; y < 32; y++) A[y] = t0 + y < q ? window32_be(u, nbch + 360 * (t0 + y) + s0) : 0u;
+        transpose32(A);                                   // A[i]: column s0 + i, row t0 + y at bit 31 - y
+      }
+      __syncthreads();                                    // everyone is done with the info words, all tiles are in registers
+      uint32_t *nat = const_cast<uint32_t *>(u);          // big-endian bit stream: natural parity bit P at word P / 32, bit 31 - P % 32
+      const int nat_words = ((q * 360 + 31) >> 5) + 1;
+      for (int i = threadIdx.x; i < nat_words; i += blockDim.x) nat[i] = 0u;
+      __syncthreads();
+      if (have) {
+        const int nv = min(32, q - t0);
+        const uint32_t vmask = nv >= 32 ? 0xFFFFFFFFu : ~(0xFFFFFFFFu >> nv);
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+          if (s0 + i < 360) {
+            const uint32_t word = A[i] & vmask;
+            const int P = q * (s0 + i) + t0, sh = P & 31;
+            atomicOr(nat + (P >> 5), word >> sh);
+            if (sh) atomicOr(nat + (P >> 5) + 1, word << (32 - sh));
+          }
+        }
+      }
+      __syncthreads();
+      const int npar = Nc - par0;                          // parity cells
+      for (int wi = threadIdx.x; wi < ((npar + 15) >> 4); wi += blockDim.x) {
+        const uint32_t W = nat[wi];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const int c = par0 + 16 * wi + 4 * k;
+          if (c < Nc) {
+            const uint2 cd = __ldg(a.qpsk_lut + ((W >> (24 - 8 * k)) & 255u));
+            uint32_t *dst = reinterpret_cast<uint32_t *>(cw + c + 2 * (c >> 6));
+            dst[0] = cd.x;
+            dst[1] = cd.y;
+          }
+        }
+      }
     }
     if (a.cyclic_delay) {
       __syncthreads();
@@ -892,7 +947,8 @@ __device__ __forceinline__ void map_body(const MapArgs &a, const int f, const ui
 __host__ __device__ inline int map_u_words(int nldpc) { return (((nldpc + 31) / 32) + 11) & ~3; }
 __host__ __device__ inline int map_cw_halfwords(int cell_size) { return ((cell_size + 127) & ~63) + 2 * (cell_size / 64 + 2); }
 
-__global__ void __launch_bounds__(MAP_THREADS) k_map(const MapArgs a)
+template <bool QTR>
+__device__ __forceinline__ void k_map_impl(const MapArgs &a)
 {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int nwords = (a.nldpc + 31) / 32;
@@ -919,9 +975,12 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map(const MapArgs a)
       if (threadIdx.x < 4) u[4 * n16 + threadIdx.x] = 0u;
     }
     __syncthreads();
-    map_body(a, f, u, lut, cw, s_base, s_twist, shift);
+    map_body<QTR>(a, f, u, lut, cw, s_base, s_twist, shift);
   }
 }
+__global__ void __launch_bounds__(MAP_THREADS) k_map(const MapArgs a) { k_map_impl<false>(a); }
+// QPSK with the transposed parity path: three CTAs per SM fit beside the 32400 cell codes of a normal FECFRAME
+__global__ void __launch_bounds__(MAP_THREADS, 3) k_map_qtr(const MapArgs a) { k_map_impl<true>(a); }
 
 // ================================================================================================
 // K2+K3 fused (chain mode): LDPC parity and bit interleaver / mapper of one FECFRAME per CTA.  The BCH codeword comes
@@ -1059,7 +1118,7 @@ __global__ void __launch_bounds__(MAP_THREADS, FEC_MIN_BLOCKS) k_fec(const LdpcA
       uint32_t *o = reinterpret_cast<uint32_t *>(fec_tap + (long long)f * fec_tap_pitch);
       for (int i = tid; i < (a.nldpc / 8 + 3) / 4; i += MAP_THREADS) o[i] = u[i];
     }
-    map_body(a, f, u, lut, cw, s_base, s_twist, shift);
+    map_body<false>(a, f, u, lut, cw, s_base, s_twist, shift);
   }
 }
 
@@ -1069,9 +1128,16 @@ void launch_map(const MapArgs &a, cudaStream_t s)
   // one FECFRAME per CTA: the hardware scheduler balances the tail at frame granularity
   const int blocks = a.frames;
   if (blocks < 1) return;
-  static bool attr[MAX_DEVICES];
+  static bool attr[MAX_DEVICES], attr_q[MAX_DEVICES];
   allow_smem(k_map, 100 * 1024, attr);      // QPSK normal: 32400 cell codes
-  k_map<<<blocks, MAP_THREADS, smem, s>>>(a);
+  allow_smem(k_map_qtr, 100 * 1024, attr_q);
+#ifdef MAP_QPSK_NO_TRANSPOSE
+  const bool qtr = false;
+#else
+  const bool qtr = a.qpsk_par_q > 0 && a.mod == 2 && a.ncol == 0 && (a.cell_size & 3) == 0;
+#endif
+  if (qtr) k_map_qtr<<<blocks, MAP_THREADS, smem, s>>>(a);
+  else k_map<<<blocks, MAP_THREADS, smem, s>>>(a);
   count_launch();
 }
 

@@ -64,6 +64,7 @@ struct MapArgs {
   const uint16_t *bit_src;   // nldpc (generic path, used when ncol == 0: QPSK)
   const uint2 *qpsk_lut;     // QPSK: four cell codes per codeword byte, for the first qpsk_lin_cells cells (see MapPlan)
   int qpsk_lin_cells;
+  int qpsk_par_q, qpsk_nbch; // > 0: parity cells through in-kernel bit transposes (see MapPlan), q rows of 360 bits behind bit nbch
   const float2 *lut;         // 1 << mod
   // QAM fast path: column-twist geometry; col_of_bit[p] = twist-matrix column feeding output bit p
   // (p = 0 is the MSB of the ncol-bit demux word), twist_of_col[c] = start row of column c

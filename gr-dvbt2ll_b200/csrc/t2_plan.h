@@ -113,6 +113,10 @@ struct MapPlan {
   // QPSK: cells [0, qpsk_lin_cells) take bits 2c, 2c+1 of the codeword as it arrives (a multiple of 16 cells: the info
   // part, or everything for the parity-interleaved short codes); qpsk_lut[b] = the four cell codes of message byte b
   int qpsk_lin_cells;
+  // QPSK without parity interleaving: the parity cells read the natural-order parity bits q s + t <- codeword bit
+  // nbch + 360 t + s; when qpsk_par_q > 0 the kernel rebuilds that natural order with 32 x 32 bit transposes (in the
+  // shared-memory words of the info part, which is spent by then) and maps it through the same table
+  int qpsk_par_q, qpsk_nbch;
   std::vector<uint32_t> qpsk_lut;     // [256][2]: codes of cells 0,1 | 2,3 of the byte (own word | w~ << 8)
 };
 bool build_map_plan(int framesize, int rate, int constellation, int rotation, MapPlan *p, std::string *err);

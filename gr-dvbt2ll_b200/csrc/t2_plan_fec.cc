@@ -415,11 +415,22 @@ bool build_map_plan(int framesize, int rate, int constellation, int rotation, Ma
   // ---- QPSK: the leading run of cells whose two bits sit where they are in the incoming codeword goes through a
   // byte -> four cell codes table in the kernel (the general path extracts bit by bit through bit_src)
   p->qpsk_lin_cells = 0;
+  p->qpsk_par_q = 0;
+  p->qpsk_nbch = nbch;
   p->qpsk_lut.clear();
   if (constellation == MOD_QPSK) {
     int n = 0;
     while (n < N && p->bit_src[n] == (uint16_t)n) n++;
+    if (n > nbch && n < N) n = nbch;           // (parity bit 0 sits in place in either order)
     p->qpsk_lin_cells = (n / 32) * 16;
+    // transposed parity: only where bit_src is exactly "info in place, parity bit q s + t <- nbch + 360 t + s", the
+    // natural parity stream fits the info part's words and one thread per 32 x 32 tile suffices
+    bool tr = n == nbch && nbch % 8 == 0 && N - nbch <= nbch && ((q + 31) / 32) * 12 <= 128;
+    for (int i = nbch; i < N && tr; i++) {
+      const int pidx = i - nbch;
+      if (p->bit_src[i] != (uint16_t)(nbch + 360 * (pidx % q) + pidx / q)) tr = false;
+    }
+    if (tr) p->qpsk_par_q = q;
     p->qpsk_lut.assign(512, 0);
     for (int b = 0; b < 256; b++) {
       uint32_t code[4];
