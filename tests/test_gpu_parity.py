@@ -370,6 +370,26 @@ def test_ldpc_and_mapper_modes(reflib, fs, rate, con, rot):
     assert cells_equal(cells, rim.work(want, nfr)[0])
 
 
+def test_qpsk_mapper_every_code(reflib):
+    """QPSK has three mapper paths (byte table for bits in place, transposed parity, bit by bit): every frame size /
+    code rate x rotation against the reference's interleavermod, three FECFRAMEs of random bits each."""
+    from oracle import t2oracle as O
+    rng = np.random.default_rng(77)
+    paths = set()
+    for fs, rates in ((1, (K.C1_2, K.C3_5, K.C2_3, K.C3_4, K.C4_5, K.C5_6)),
+                      (0, (K.C1_3, K.C2_5, K.C1_2, K.C3_5, K.C2_3, K.C3_4, K.C4_5, K.C5_6))):
+        for rate in rates:
+            N = O.fec_params(fs, rate)["nldpc"]
+            fec = rng.integers(0, 2, 3 * N, dtype=np.uint8)
+            for rot in (0, 1):
+                im = T.interleavermod_bc(fs, rate, K.MOD_QPSK, rot)
+                lin, par_q, _ = (int(v) for v in im.plan("map.qpsk", np.int32))
+                paths.add((lin > 0, par_q > 0))
+                cells, _ = im.work(fec, 3)
+                assert cells_equal(cells, reflib.interleavermod(fs, rate, K.MOD_QPSK, rot).work(fec, 3)[0]), (fs, rate, rot)
+    assert (True, True) in paths and (True, False) in paths      # both fast paths were exercised
+
+
 def test_ldpc_parity_check_independent():
     """Known-answer independent of the reference code: every parity check of the IRA code built straight
     from the address table (check j: XOR of the info bits hitting row j, p[j] and p[j-1]) is satisfied."""
