@@ -1695,6 +1695,19 @@ __global__ void __launch_bounds__(T, (LOG2M == 14 ? 1 : 1024 / T)) k_ofdm(const 
     tw_last = __ldg(a.tw + threadIdx.x);                        // last pass: W_M^{tid}; butterfly tid + 512 j adds exp(j 2 pi j / 32)
     if (SPLIT == 2) tw_rec = __fmul2_rn(__ldg(a.tw_split + threadIdx.x), make_float2(a.norm, a.norm));   // W_N^{tid} * norm
   }
+  // smaller transforms with at most one butterfly per thread and pass (M / 16 <= T): the thread's twiddle base of every
+  // pass is the same for every symbol -- loaded once here instead of at the head of each pass, where the load's
+  // latency was exposed (13 % of the 8K kernel's stall samples)
+  constexpr bool PRETW = !REGTW && (M / 16 <= T);
+  constexpr int NP1 = R0, NP2 = R0 * 16 < NLAST ? R0 * 16 : 1;       // NPREV of the middle passes (see below)
+  (void)NP1; (void)NP2;
+  if (PRETW) {
+#ifndef OFDM_NO_PRETW
+    tw_p1 = __ldg(a.tw + (threadIdx.x & (NP1 - 1)) * (M / (NP1 * 16)));
+    tw_p2 = __ldg(a.tw + (threadIdx.x & (NP2 - 1)) * (M / (NP2 * 16)));
+    tw_last = (int)threadIdx.x < NLAST ? __ldg(a.tw + threadIdx.x) : make_float2(1.f, 0.f);
+#endif
+  }
 
   // C16: the cells of symbol `u` go to the staging area by bulk asynchronous copies (TMA, cp.async.bulk): one copy
   // per run of consecutive source cells -- the enclosing 16-byte aligned span of the frame's cell memory -- spread over
@@ -1822,8 +1835,13 @@ __global__ void __launch_bounds__(T, (LOG2M == 14 ? 1 : 1024 / T)) k_ofdm(const 
 #endif
       }
       else {
+#ifndef OFDM_NO_PRETW
+        if (R0 * 16 < NLAST * 16 && R0 < NLAST) { fft_pass16<M, NP1, T, PRETW>(x, a.tw, tw_p1); __syncthreads(); }
+        if (R0 * 16 < NLAST) { fft_pass16<M, NP2, T, PRETW>(x, a.tw, tw_p2); __syncthreads(); }
+#else
         if (R0 * 16 < NLAST * 16 && R0 < NLAST) { fft_pass16<M, R0, T>(x, a.tw); __syncthreads(); }
         if (R0 * 16 < NLAST) { fft_pass16<M, (R0 * 16 < NLAST ? R0 * 16 : 1), T>(x, a.tw); __syncthreads(); }
+#endif
       }
       // ---- 3. last pass fused with scale + store (+ cyclic prefix, + 32K recombination)
       if constexpr (REGTW) {
@@ -1896,7 +1914,11 @@ __global__ void __launch_bounds__(T, (LOG2M == 14 ? 1 : 1024 / T)) k_ofdm(const 
 #pragma unroll 1
       for (int i = threadIdx.x; i < NLAST; i += T) {
         const float2 *xb = x + padx(i);
+#ifndef OFDM_NO_PRETW
+        const float2 w1 = PRETW ? tw_last : __ldg(a.tw + i);      // TW_STEP = M / (NLAST * 16) = 1
+#else
         const float2 w1 = __ldg(a.tw + i);      // TW_STEP = M / (NLAST * 16) = 1
+#endif
         float2 v[16];
 #pragma unroll
         for (int qd = 0; qd < 16; qd++) v[qd] = xb[padx(qd * NLAST)];
