@@ -343,6 +343,75 @@ def per_config_extras(torch, T, K, dev, stream, peak, peak_src, steps):
     return out
 
 
+def per_block_device_extras(torch, T, K, dev, stream, peak, peak_src, cfg_name, nframes, steps):
+    """The five drop-in blocks' own kernels, device-resident (dvbt2ll_work_device: the items already in HBM in the
+    reference's item types -- one byte per bit between the bit blocks, complex64 cells after the mapper), nframes T2 frames
+    per call, each block fed by the previous block's output.  Per block: ms per call, the bytes of its input and output
+    items over that time, and for the cell-domain stages SURVEY 8(d)'s algorithmic bytes against the measured HBM copy rate."""
+    cfg = K.resolve(cfg_name)
+    b = T.blocks_for(cfg)
+    F = cfg["fecblocks"]
+    nfec = nframes * F
+    nldpc = 64800 if cfg["framesize"] else 16200
+    sp = stream.cuda_stream
+    om = {k: v.output_multiple for k, v in b.items()}
+    n_out = {"bb": nfec * om["bb"], "ldpc": nfec * om["ldpc"], "im": nfec * om["im"], "fm": nframes * om["fm"], "pg": nframes * om["pg"]}
+    n_in = {"bb": None, "ldpc": n_out["bb"], "im": n_out["ldpc"], "fm": n_out["im"], "pg": n_out["fm"]}
+    item_in = {"bb": 1, "ldpc": 1, "im": 1, "fm": 8, "pg": 8}
+    item_out = {"bb": 1, "ldpc": 1, "im": 8, "fm": 8, "pg": 8}
+    # TS for the BB block: one stream; the block carries its packet phase from call to call, so every call is handed the
+    # (periodic) stream at the phase it expects: base + consumed % 188, with >= 187 bytes of history in front
+    need = b["bb"].forecast(n_out["bb"]) + 2 * 188
+    period = K.make_ts(188 * 64)
+    reps = (need + 188 + period.size - 1) // period.size + 1
+    d_ts = torch.zeros(256 + reps * period.size, dtype=torch.uint8, device=dev)
+    d_ts[256:] = torch.from_numpy(period).to(dev).repeat(reps)
+    n_in["bb"] = need
+    bufs = {"ts": d_ts[256:]}
+    for k in ("bb", "ldpc", "im", "fm", "pg"):
+        bufs[k] = torch.empty(n_out[k] * item_out[k] + 64, dtype=torch.uint8, device=dev)
+    src = {"bb": "ts", "ldpc": "bb", "im": "ldpc", "fm": "im", "pg": "fm"}
+    if n_in["fm"] < b["fm"].forecast(n_out["fm"]) or n_in["pg"] < b["pg"].forecast(n_out["pg"]):
+        raise RuntimeError("block item counts do not chain")
+    out = {"workload": "%d %s T2 frames (%d FECFRAMEs) per call, items resident in HBM, dvbt2ll_work_device" % (nframes, cfg_name, nfec),
+           "peak": peak, "peak_source": peak_src, "blocks": {}}
+    mapped, stream_items, samples = om["fm"], b["fm"].forecast(om["fm"]), om["pg"]
+    alg = {"im": ("mapper: Nldpc/8 packed bits in + 8 B per cell out, per FECFRAME", nfec * (nldpc // 8 + 8 * om["im"])),
+           "fm": ("frame mapper (cell + time interleaver, L1, frame, frequency interleaver): 8 B x (stream items + mapped items)", nframes * 8 * (stream_items + mapped)),
+           "pg": ("pilots + IFFT + guard interval + P1: 8 B x (mapped items + samples)", nframes * 8 * (b["pg"].forecast(samples) + samples))}
+    names = {"bb": "bbheaderbch_bb", "ldpc": "ldpc_bb", "im": "interleavermod_bc", "fm": "framemapperfint_cc", "pg": "pilotgenp1insert_cc"}
+    for k in ("bb", "ldpc", "im", "fm", "pg"):
+        blk, din, dout = b[k], bufs[src[k]], bufs[k]
+        consumed_total = [0]
+        def call():
+            ofs = consumed_total[0] % 188 if k == "bb" else 0
+            r, used = blk.work_device(din.data_ptr() + ofs, n_in[k], dout.data_ptr(), n_out[k], sp)
+            consumed_total[0] += used
+            if r != n_out[k]:
+                raise RuntimeError("%s produced %d of %d items" % (k, r, n_out[k]))
+            return used
+        used = 0
+        for _ in range(3):
+            used = call()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            call()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        api_bytes = used * item_in[k] + n_out[k] * item_out[k]
+        ent = {"ms_per_call": ms, "item_bytes_in_out": int(api_bytes), "item_gbs": api_bytes / (ms * 1e-3) / 1e9,
+               "item_frac_of_peak": api_bytes / (ms * 1e-3) / 1e9 / peak}
+        if k in alg:
+            ent["algorithmic"] = {"what": alg[k][0], "bytes": int(alg[k][1]), "gbs": alg[k][1] / (ms * 1e-3) / 1e9,
+                                  "frac_of_peak": alg[k][1] / (ms * 1e-3) / 1e9 / peak}
+        out["blocks"][names[k]] = ent
+    del bufs, d_ts, b
+    return out
+
+
 def dropin_extras(torch, T, K, cfg_name, frames_timed):
     """The reference-facing per-block path: one T2 frame per round through the five dvbt2ll_work() handles
     (bbheaderbch -> ldpc -> interleavermod -> framemapper -> pilotgen) on PAGEABLE host buffers -- what a GNU Radio
@@ -805,6 +874,11 @@ def run_ours(args):
             extras["dropin_e2e"] = dropin_extras(torch, T, K, args.config, 8)
         except Exception as e:      # pragma: no cover  (an extra must never cost the headline line)
             extras["dropin_e2e"] = {"error": str(e)[:300]}
+        try:
+            extras["per_block_device"] = per_block_device_extras(torch, T, K, dev, stream, peak, peak_src, args.config, 32, max(5, args.steps // 2))
+        except Exception as e:      # pragma: no cover
+            extras["per_block_device"] = {"error": str(e)[:300]}
+            torch.cuda.synchronize()
         try:
             extras["per_config"] = per_config_extras(torch, T, K, dev, stream, peak, peak_src, max(5, args.steps // 2))
         except Exception as e:      # pragma: no cover

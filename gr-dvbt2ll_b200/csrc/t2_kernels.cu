@@ -936,10 +936,25 @@ __device__ __forceinline__ void map_body(const MapArgs &a, const int f, const ui
     }
   }
   else {
-    for (int c = threadIdx.x; c < Nc; c += blockDim.x) {
+    // drop-in block: complex64 cells in natural order, two cells per 16-byte store (the first cell of a FECFRAME that
+    // starts on an odd cell and a last odd one go alone)
+    auto cell = [&](int c) -> float2 {
       const unsigned cd = code(c);
-      out[c] = make_float2(lut[cd & 255u].x, tilde ? lut[cd >> 8].x : lut[cd >> 8].y);
+      return make_float2(lut[cd & 255u].x, tilde ? lut[cd >> 8].x : lut[cd >> 8].y);
+    };
+    const int head = (int)(((long long)f * Nc) & 1);
+    const int npair = (Nc - head) >> 1;
+    if ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0) {
+      float4 *o4 = reinterpret_cast<float4 *>(out + head);
+      for (int pr = threadIdx.x; pr < npair; pr += blockDim.x) {
+        const float2 c0 = cell(head + 2 * pr), c1 = cell(head + 2 * pr + 1);
+        o4[pr] = make_float4(c0.x, c0.y, c1.x, c1.y);
+      }
+      if (threadIdx.x == 0 && head) out[0] = cell(0);
+      if (threadIdx.x == 32 && head + 2 * npair < Nc) out[Nc - 1] = cell(Nc - 1);
     }
+    else
+    for (int c = threadIdx.x; c < Nc; c += blockDim.x) out[c] = cell(c);
   }
 }
 
@@ -1206,6 +1221,118 @@ __global__ void k_pack_ldpc(const uint8_t *in, int nbch, int nldpc, int q, uint8
   }
 }
 
+// ---- the same conversions, vectorised (HBM-bound: 1 byte per bit on one side).  Frames are multiples of 8 bits, so with
+// 8-byte aligned buffers every 8 one-bit bytes are one aligned 8-byte access; the byte <-> 8 bytes conversion is a
+// multiply that moves each bit to its place (no carries: all partial products land on distinct bits).
+// eight one-bit bytes (first = most significant) -> one byte
+__device__ __forceinline__ uint32_t pack8(uint2 v)
+{
+  return ((((v.x & 0x01010101u) * 0x08040201u) >> 24) << 4) | (((v.y & 0x01010101u) * 0x08040201u) >> 24);
+}
+// one byte -> eight one-bit bytes (most significant bit first)
+__device__ __forceinline__ uint2 unpack8(uint32_t b)
+{
+  // nibble n = b0 b1 b2 b3: (n * 0x00204081) & 0x01010101 has b3, b2, b1, b0 in bytes 0..3; the byte permute reverses them
+  return make_uint2(__byte_perm(((b >> 4) * 0x00204081u) & 0x01010101u, 0u, 0x0123u),
+                    __byte_perm(((b & 15u) * 0x00204081u) & 0x01010101u, 0u, 0x0123u));
+}
+// pack / unpack of the first nbits (a multiple of 8) of a frame: a thread per packed byte, so that a warp's 8-byte
+// accesses on the one-bit side are 256 contiguous bytes (four independent ones in flight per thread)
+__device__ __forceinline__ void pack_span(const uint8_t *src, int nbits, uint8_t *dst)
+{
+  const int nb = nbits >> 3, T = blockDim.x;
+  const uint2 *s8 = reinterpret_cast<const uint2 *>(src);
+  int b = threadIdx.x;
+  for (; b + 3 * T < nb; b += 4 * T) {
+    const uint2 v0 = __ldg(s8 + b), v1 = __ldg(s8 + b + T), v2 = __ldg(s8 + b + 2 * T), v3 = __ldg(s8 + b + 3 * T);
+    dst[b] = (uint8_t)pack8(v0); dst[b + T] = (uint8_t)pack8(v1); dst[b + 2 * T] = (uint8_t)pack8(v2); dst[b + 3 * T] = (uint8_t)pack8(v3);
+  }
+  for (; b < nb; b += T) dst[b] = (uint8_t)pack8(__ldg(s8 + b));
+}
+__device__ __forceinline__ void unpack_span(const uint8_t *src, int nbits, uint8_t *dst)
+{
+  const int nb = nbits >> 3, T = blockDim.x;
+  uint2 *d8 = reinterpret_cast<uint2 *>(dst);
+  int b = threadIdx.x;
+  for (; b + 3 * T < nb; b += 4 * T) {
+    const uint32_t v0 = src[b], v1 = src[b + T], v2 = src[b + 2 * T], v3 = src[b + 3 * T];
+    d8[b] = unpack8(v0); d8[b + T] = unpack8(v1); d8[b + 2 * T] = unpack8(v2); d8[b + 3 * T] = unpack8(v3);
+  }
+  for (; b < nb; b += T) d8[b] = unpack8(src[b]);
+}
+
+__global__ void __launch_bounds__(256) k_pack_bits_v(const uint8_t *in, int nbits, uint8_t *out, int out_pitch, int frames)
+{
+  for (int f = blockIdx.x; f < frames; f += gridDim.x) pack_span(in + (long long)f * nbits, nbits, out + (long long)f * out_pitch);
+}
+
+__global__ void __launch_bounds__(256) k_unpack_bits_v(const uint8_t *in, int in_pitch, int nbits, uint8_t *out, int frames)
+{
+  for (int f = blockIdx.x; f < frames; f += gridDim.x) unpack_span(in + (long long)f * in_pitch, nbits, out + (long long)f * nbits);
+}
+
+// LDPC codeword, packed "u" order -> natural order, 1 bit per byte: the q x 360 parity bit matrix is transposed through
+// shared memory (packed rows in, eight consecutive natural-order bits = one 8-byte store out)
+__global__ void __launch_bounds__(256) k_unpack_ldpc_v(const uint8_t *in, int in_pitch, int nbch, int nldpc, int q, uint8_t *out, int frames)
+{
+  extern __shared__ __align__(16) uint8_t sm_fmt[];
+  const int npar = nldpc - nbch, ib = nbch >> 3;
+  for (int f = blockIdx.x; f < frames; f += gridDim.x) {
+    const uint8_t *src = in + (long long)f * in_pitch;
+    uint8_t *o = out + (long long)f * nldpc;
+    for (int b = threadIdx.x; b < (npar >> 3); b += blockDim.x) sm_fmt[b] = src[ib + b];
+    unpack_span(src, nbch, o);
+    __syncthreads();
+    for (int i = threadIdx.x; i < (npar >> 3); i += blockDim.x) {
+      int s = (8 * i) / q, t = 8 * i - s * q;       // natural parity index n = q s + t  <-  row t, bit s
+      uint32_t w[2] = { 0u, 0u };
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const uint32_t bit = (sm_fmt[45 * t + (s >> 3)] >> (7 - (s & 7))) & 1u;
+        w[j >> 2] |= bit << (8 * (j & 3));
+        if (++t == q) { t = 0; s++; }
+      }
+      *reinterpret_cast<uint2 *>(o + nbch + 8 * i) = make_uint2(w[0], w[1]);
+    }
+    __syncthreads();
+  }
+}
+
+// natural-order codeword, 1 bit per byte -> packed "u" order: parity bytes staged in shared memory by 8-byte loads, a
+// thread packs the eight bits of one byte of a parity row (lanes on consecutive rows: consecutive shared-memory bytes)
+__global__ void __launch_bounds__(256) k_pack_ldpc_v(const uint8_t *in, int nbch, int nldpc, int q, uint8_t *out, int out_pitch, int frames)
+{
+  extern __shared__ __align__(16) uint8_t sm_fmt[];
+  const int npar = nldpc - nbch, ib = nbch >> 3;
+  uint8_t *sp = sm_fmt, *so = sm_fmt + npar;
+  for (int f = blockIdx.x; f < frames; f += gridDim.x) {
+    const uint8_t *fr = in + (long long)f * nldpc;
+    uint8_t *o = out + (long long)f * out_pitch;
+    for (int i = threadIdx.x; i < (npar >> 3); i += blockDim.x)
+      reinterpret_cast<uint2 *>(sp)[i] = __ldg(reinterpret_cast<const uint2 *>(fr + nbch) + i);
+    pack_span(fr, nbch, o);
+    __syncthreads();
+    for (int i = threadIdx.x; i < q * 45; i += blockDim.x) {
+      const int k = i / q, t = i - k * q;
+      const uint8_t *col = sp + q * 8 * k + t;
+      uint32_t v = 0;
+#pragma unroll
+      for (int j = 0; j < 8; j++) v = (v << 1) | (col[q * j] & 1u);
+      so[45 * t + k] = (uint8_t)v;
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < q * 45; b += blockDim.x) o[ib + b] = so[b];
+    __syncthreads();
+  }
+}
+
+static inline bool aligned8(const void *a, const void *b) { return ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 7) == 0; }
+static inline int frame_grid(int frames)
+{
+  const int cap = sm_count() * 16;
+  return frames < cap ? frames : cap;
+}
+
 static inline int grid_for(long long total, int threads)
 {
   long long b = (total + threads - 1) / threads;
@@ -1218,24 +1345,37 @@ static inline int grid_for(long long total, int threads)
 void launch_pack_bits(const uint8_t *in, int nbits, uint8_t *out, int out_pitch, int frames, cudaStream_t s)
 {
   if (frames < 1) return;
+  if ((nbits & 7) == 0 && (out_pitch & 3) == 0 && aligned8(in, out)) k_pack_bits_v<<<frame_grid(frames), 256, 0, s>>>(in, nbits, out, out_pitch, frames);
+  else
   k_pack_bits<<<grid_for((long long)frames * ((nbits + 7) / 8), 256), 256, 0, s>>>(in, nbits, out, out_pitch, frames);
   count_launch();
 }
 void launch_unpack_bits(const uint8_t *in, int in_pitch, int nbits, uint8_t *out, int frames, cudaStream_t s)
 {
   if (frames < 1) return;
+  if ((nbits & 7) == 0 && (in_pitch & 3) == 0 && aligned8(in, out)) k_unpack_bits_v<<<frame_grid(frames), 256, 0, s>>>(in, in_pitch, nbits, out, frames);
+  else
   k_unpack_bits<<<grid_for((long long)frames * nbits, 256), 256, 0, s>>>(in, in_pitch, nbits, out, frames);
   count_launch();
 }
 void launch_unpack_ldpc(const uint8_t *in, int in_pitch, int nbch, int nldpc, int q, uint8_t *out, int frames, cudaStream_t s)
 {
   if (frames < 1) return;
+  const bool shape_ok = (nbch & 7) == 0 && (nldpc & 7) == 0 && nldpc - nbch == 360 * q && (nldpc - nbch) / 8 <= 40 * 1024;
+  if (shape_ok && (in_pitch & 3) == 0 && aligned8(in, out))
+    k_unpack_ldpc_v<<<frame_grid(frames), 256, (size_t)(nldpc - nbch) / 8, s>>>(in, in_pitch, nbch, nldpc, q, out, frames);
+  else
   k_unpack_ldpc<<<grid_for((long long)frames * nldpc, 256), 256, 0, s>>>(in, in_pitch, nbch, nldpc, q, out, frames);
   count_launch();
 }
 void launch_pack_ldpc(const uint8_t *in, int nbch, int nldpc, int q, uint8_t *out, int out_pitch, int frames, cudaStream_t s)
 {
   if (frames < 1) return;
+  const int npar = nldpc - nbch;
+  const bool shape_ok = (nbch & 7) == 0 && (nldpc & 7) == 0 && npar == 360 * q && npar + npar / 8 <= 44 * 1024;
+  if (shape_ok && (out_pitch & 3) == 0 && aligned8(in, out))
+    k_pack_ldpc_v<<<frame_grid(frames), 256, (size_t)npar + npar / 8, s>>>(in, nbch, nldpc, q, out, out_pitch, frames);
+  else
   k_pack_ldpc<<<grid_for((long long)frames * (nldpc / 8), 256), 256, 0, s>>>(in, nbch, nldpc, q, out, out_pitch, frames);
   count_launch();
 }
@@ -1252,21 +1392,77 @@ __device__ __forceinline__ float2 fetch_cell(int code, const float2 *__restrict_
   return __ldg(pool + idx);
 }
 
+// address of the cell a code stands for (the load itself is left to the caller, so that a thread's loads are independent)
+__device__ __forceinline__ const float2 *cell_ptr(int code, const float2 *__restrict__ cells, const float2 *__restrict__ pool,
+                                                 int l1post_base, int l1post_cells, int variant)
+{
+  if (code >= 0) return cells + code;
+  int idx = -(code + 1);
+  if ((unsigned)(idx - l1post_base) < (unsigned)l1post_cells) idx += variant * l1post_cells;
+  return pool + idx;
+}
+
+// One thread: two consecutive output cells of FPB T2 frames.  The code pair is one 8-byte load shared by the FPB frames,
+// the 2 * FPB gathers (random 8-byte reads: the composed cell / time / frequency interleavers leave no locality) are all
+// in flight before the first store, and a store is 16 bytes (V16: frames start on even cells).  Frames are walked in
+// chunks of FPB by blockIdx.y, so the input cells of the chunk in flight (FPB x 13 MB for c3) stay in L2 while their
+// four cells per 32-byte sector are picked up.
+template <int FPB, bool V16>
 __global__ void __launch_bounds__(256) k_gather(const GatherArgs a)
 {
-  const long long total = (long long)a.frames * a.n;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int f = (int)(i / a.n), j = (int)(i - (long long)f * a.n);
-    const int variant = (a.frame_idx0 + f) % a.l1post_variants;
-    a.out[(long long)f * a.out_stride + j] =
-        fetch_cell(__ldg(a.code + j), a.in + (long long)f * a.in_stride, a.pool, a.l1post_base, a.l1post_cells, variant);
+  const int npair = a.n >> 1;
+  for (int f0 = blockIdx.y * FPB; f0 < a.frames; f0 += gridDim.y * FPB) {
+    for (int pr = blockIdx.x * 256 + threadIdx.x; pr < npair; pr += gridDim.x * 256) {
+      const int2 cd = __ldg(reinterpret_cast<const int2 *>(a.code) + pr);
+      float2 v0[FPB], v1[FPB];
+#pragma unroll
+      for (int k = 0; k < FPB; k++) {
+        const int f = f0 + k;
+        if (f < a.frames) {
+          const int variant = (a.frame_idx0 + f) % a.l1post_variants;
+          const float2 *in = a.in + (long long)f * a.in_stride;
+          BND(cd.x < a.in_stride && cd.y < a.in_stride);
+          v0[k] = __ldg(cell_ptr(cd.x, in, a.pool, a.l1post_base, a.l1post_cells, variant));
+          v1[k] = __ldg(cell_ptr(cd.y, in, a.pool, a.l1post_base, a.l1post_cells, variant));
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < FPB; k++) {
+        const int f = f0 + k;
+        if (f < a.frames) {
+          float2 *o = a.out + (long long)f * a.out_stride + 2 * pr;
+          if (V16) __stcs(reinterpret_cast<float4 *>(o), make_float4(v0[k].x, v0[k].y, v1[k].x, v1[k].y));
+          else { __stcs(o, v0[k]); __stcs(o + 1, v1[k]); }
+        }
+      }
+    }
+    // odd cell count: the last cell of each frame of the chunk
+    if ((a.n & 1) && blockIdx.x == 0 && (int)threadIdx.x < FPB && f0 + (int)threadIdx.x < a.frames) {
+      const int f = f0 + threadIdx.x, j = a.n - 1;
+      const int variant = (a.frame_idx0 + f) % a.l1post_variants;
+      a.out[(long long)f * a.out_stride + j] =
+          fetch_cell(__ldg(a.code + j), a.in + (long long)f * a.in_stride, a.pool, a.l1post_base, a.l1post_cells, variant);
+    }
   }
 }
 
 void launch_gather(const GatherArgs &a, cudaStream_t s)
 {
-  if (a.frames < 1) return;
-  k_gather<<<grid_for((long long)a.frames * a.n, 256), 256, 0, s>>>(a);
+  if (a.frames < 1 || a.n < 1) return;
+#ifndef GATHER_FPB
+#define GATHER_FPB 4
+#endif
+  constexpr int FPB = GATHER_FPB;
+  const int npair = a.n >> 1;
+  int gx = (npair + 255) / 256;
+  if (gx < 1) gx = 1;
+  int gy = (a.frames + FPB - 1) / FPB;
+  if (gy > 65535) gy = 65535;
+  const dim3 grid(gx, gy);
+  // 16-byte stores need every frame to start on a 16-byte boundary
+  const bool v16 = (a.out_stride & 1) == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0;
+  if (v16) k_gather<FPB, true><<<grid, 256, 0, s>>>(a);
+  else k_gather<FPB, false><<<grid, 256, 0, s>>>(a);
   count_launch();
 }
 

@@ -272,6 +272,16 @@ class _Block(object):
             raise RuntimeError("dvbt2ll_work failed (%d): %s" % (r, last_error()))
         return r, consumed.value
 
+    def work_device(self, d_in, n_in, d_out, n_out, stream=None):
+        """general_work() on DEVICE buffers (raw pointers, item counts), asynchronous on `stream` (a raw cudaStream_t;
+        None = the handle's own stream followed by a synchronize). Returns (items produced, consumed)."""
+        consumed = C.c_int(0)
+        r = lib().dvbt2ll_work_device(self._h, C.c_void_p(d_in), int(n_in), C.c_void_p(d_out), int(n_out), C.byref(consumed),
+                                      C.c_void_p(stream) if stream else None)
+        if r < 0:
+            raise RuntimeError("dvbt2ll_work_device failed (%d): %s" % (r, last_error()))
+        return r, consumed.value
+
     def set_host_register(self, on=True):
         """Register the host buffers handed to work() with CUDA on first sight (only for long-lived buffers)."""
         lib().dvbt2ll_set_host_register(self._h, 1 if on else 0)

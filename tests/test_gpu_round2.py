@@ -457,3 +457,40 @@ def test_ldpc_both_accumulation_schemes(monkeypatch):
             monkeypatch.setenv("DVBT2LL_LDPC_MODE", mode)
             fec, _ = T.ldpc_bb(fs, rate).work(info, 3)
             assert bits_equal(fec, want), (fs, rate, mode)
+
+
+@pytest.mark.parametrize("name", ["c1", "c3"])
+def test_dropin_blocks_device_resident_any_alignment(name):
+    """dvbt2ll_work_device on the four blocks behind the BB stage, items resident in HBM: the vectorised kernels (8-byte
+    bit-format conversions, 16-byte cell stores, paired frame-mapper gathers) taken with aligned buffers and the scalar
+    ones taken with byte- / cell-misaligned buffers both reproduce the host-buffer path (which the other tests tie to the
+    reference) bit for bit."""
+    cfg = K.resolve(name)
+    b = T.blocks_for(cfg)
+    F = cfg["fecblocks"]
+    nfr = 2
+    rng = np.random.default_rng(5)
+    nbch = b["bb"].output_multiple
+    bits = rng.integers(0, 2, size=nfr * F * nbch, dtype=np.uint8)
+    # host path = the checker here (itself bit-exact against the reference in test_blocks_match_reference)
+    fec, _ = b["ldpc"].work(bits, nfr * F)
+    cells, _ = b["im"].work(fec, nfr * F)
+    mapped, _ = b["fm"].work(cells.view(np.complex64), nfr)
+    stages = (("ldpc", bits, fec, 1, 1, nfr * F), ("im", fec, cells.view(np.complex64), 1, 8, nfr * F),
+              ("fm", cells.view(np.complex64), mapped.view(np.complex64), 8, 8, nfr))
+    for k, x, want, isz, osz, n in stages:
+        blk = T.blocks_for(cfg)[k]          # fresh block: the frame mapper carries its T2 frame counter
+        for in_ofs, out_ofs in ((0, 0), (isz, osz), (0, osz), (isz, 0)):
+            if in_ofs or out_ofs:
+                blk = T.blocks_for(cfg)[k]
+            raw = np.ascontiguousarray(x).view(np.uint8)
+            d_in = T.DeviceBuffer(raw.size + 64, data=np.concatenate([np.zeros(in_ofs, np.uint8), raw]))
+            nout = n * blk.output_multiple
+            d_out = T.DeviceBuffer(nout * osz + 64)
+            r, used = blk.work_device(d_in.ptr + in_ofs, raw.size // isz, d_out.ptr + out_ofs, nout, None)
+            assert r == nout and used == raw.size // isz
+            got = np.empty(nout * osz + 64, np.uint8)
+            T.copy_to_host(got, d_out.ptr)
+            got = got[out_ofs:out_ofs + nout * osz]
+            assert np.array_equal(got, np.ascontiguousarray(want).view(np.uint8)[:nout * osz]), (k, in_ofs, out_ofs)
+            d_in.free(); d_out.free()
