@@ -203,6 +203,7 @@ __global__ void __launch_bounds__(BB_MAX_WARPS * 32) k_bb_bch(const BbArgs a)
       }
       if (lane < 2) buf[10 + lane] = src[lane];
       const int w_end = (10 + Dj) >> 2;                    // words [3, w_end) lie completely inside the payload
+#ifdef BB_STAGE_OLD
       for (int w0 = 3 + lane; w0 < w_end; w0 += 128) {     // four loads in flight per lane
         uint32_t d[4];
 #pragma unroll
@@ -210,6 +211,31 @@ __global__ void __launch_bounds__(BB_MAX_WARPS * 32) k_bb_bch(const BbArgs a)
 #pragma unroll
         for (int u = 0; u < 4; u++) if (w0 + 32 * u < w_end) bufw[w0 + 32 * u] = d[u];
       }
+#else
+      {
+        // buffer word w = payload bytes 4 w - 10 .. 4 w - 7: the payload's misalignment is the same for every word of the
+        // frame, so a word is a funnel shift of two ALIGNED global words.  All eight loads of a batch are issued
+        // unconditionally (indices clamped to the last valid word) before the first is used: as predicated unaligned loads
+        // the compiler waited for each pair in turn, and that wait was a quarter of the kernel's stall samples.
+        const uintptr_t ad = reinterpret_cast<uintptr_t>(src + 2);            // address of buffer word 3
+        const uint32_t *wp = reinterpret_cast<const uint32_t *>(ad & ~(uintptr_t)3);
+        const int sh = (int)(ad & 3) * 8;
+        const int last = w_end - 4;                                           // index (from word 3) of the last whole word
+        if (last >= 0)
+        for (int w0 = lane; w0 <= last; w0 += 128) {
+          uint32_t lo[4], hi[4];
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const int k = min(w0 + 32 * u, last);
+            lo[u] = __ldg(wp + k);
+            hi[u] = __ldg(wp + k + (sh ? 1 : 0));
+          }
+#pragma unroll
+          for (int u = 0; u < 4; u++)
+            if (w0 + 32 * u <= last) bufw[3 + w0 + 32 * u] = __funnelshift_r(lo[u], hi[u], sh);
+        }
+      }
+#endif
       for (int i = 4 * w_end - 10 + lane; i < Dj; i += 32) buf[10 + i] = src[i];
       // the 187 bytes before the frame (previous packet's tail) for the first CRC-8; missing history reads as 0,
       // which leaves a zero CRC state unchanged
@@ -491,18 +517,46 @@ __global__ void __launch_bounds__(LDPC_WARPS * 32, 8) k_ldpc(const LdpcArgs a, i
     {
       uint32_t *ow = reinterpret_cast<uint32_t *>(out);
       const int nw = info_bytes >> 2;
+#ifdef LDPC_LOADS_OLD
       for (int i = lane; i < nw; i += 32) ow[i] = __ldg(cw + i);
+#else
+      for (int i = lane; i < nw; i += 256) {           // eight loads in flight per lane (their latency was 13 % of the stall samples)
+        uint32_t v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) v[u] = __ldg(cw + min(i + 32 * u, nw - 1));
+#pragma unroll
+        for (int u = 0; u < 8; u++) if (i + 32 * u < nw) ow[i + 32 * u] = v[u];
+      }
+#endif
       for (int b = (nw << 2) + lane; b < info_bytes; b += 32) out[b] = __ldg(in + b);
     }
     // ---- wrap-extended groups: 13 words = circular bits [0, 416) of each 360-bit group.  A group is 45 bytes, so
     // word w is the big-endian 32-bit value at byte 45 g + 4 w (w <= 10), bytes {44, 0, 1, 2} (w = 11) or bytes 3..6
     // (w = 12): unaligned loads by byte permute (bytes past the group only land in positions that are masked off)
+#ifdef LDPC_LOADS_OLD
     for (int idx = lane; idx < G * 13; idx += 32) {
       const int g = idx / 13, w = idx - g * 13;
       uint32_t v = be32_at(cw, 45 * g + (w == 12 ? 3 : 4 * w));
       if (w == 11) v = (v & 0xFF000000u) | (be32_at(cw, 45 * g) >> 8);
       ext[idx] = v;
     }
+#else
+    for (int idx0 = lane; idx0 < G * 13; idx0 += 128) {      // four words (twelve loads) in flight per lane
+      uint32_t v[4], h[4];
+      int wsel[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int idx = min(idx0 + 32 * u, G * 13 - 1);
+        const int g = idx / 13, w = idx - g * 13;
+        wsel[u] = w;
+        v[u] = be32_at(cw, 45 * g + (w == 12 ? 3 : 4 * w));
+        h[u] = be32_at(cw, 45 * g);                          // head of the group: completes word 11
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (idx0 + 32 * u < G * 13) ext[idx0 + 32 * u] = wsel[u] == 11 ? (v[u] & 0xFF000000u) | (h[u] >> 8) : v[u];
+    }
+#endif
     __syncwarp();
     // ---- pre-accumulator parity rows: R_t = XOR of rotated info groups
     if (a.lane_per_row) {
@@ -535,7 +589,22 @@ __global__ void __launch_bounds__(LDPC_WARPS * 32, 8) k_ldpc(const LdpcArgs a, i
       const int t = idx / 12, w = idx - t * 12;
       uint32_t acc = 0;
       const int e1 = a.row_ptr[t + 1];
-      for (int e = a.row_ptr[t]; e < e1; e++) {
+      int e = a.row_ptr[t];
+#ifndef LDPC_LOADS_OLD
+      for (; e + 4 <= e1; e += 4) {                          // four table entries and their windows in flight
+        uint32_t en[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) en[u] = __ldg(a.entries + e + u);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          int p = 32 * w - (int)(en[u] >> 16);
+          if (p < 0) p += 360;
+          BND((int)(en[u] & 0xffffu) < G && (en[u] >> 16) < 360u && p >= 0 && p < 360);
+          acc ^= window32(ext + (en[u] & 0xffffu) * 13, p);
+        }
+      }
+#endif
+      for (; e < e1; e++) {
         const uint32_t en = __ldg(a.entries + e);
         int p = 32 * w - (int)(en >> 16);
         if (p < 0) p += 360;
@@ -973,22 +1042,27 @@ __device__ __forceinline__ void k_map_impl(const MapArgs &a)
   // word under the cyclic Q delay, the cell's own otherwise.  Padded: cell c at index c + 2 (c / 64).
   uint16_t *cw = reinterpret_cast<uint16_t *>(lut + (1 << a.mod));
   __shared__ int s_base[16], s_twist[16];
+  // packed codeword into shared memory as raw bytes with 16-byte asynchronous copies (frames are 16-byte pitched)
+  const int n16 = (nwords + 3) >> 2;
+  auto fetch = [&](int f) {
+    const uint8_t *in = a.in + (long long)f * a.in_pitch;
+    const unsigned dst0 = (unsigned)__cvta_generic_to_shared(u);
+    for (int i = threadIdx.x; i < n16; i += MAP_THREADS)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst0 + 16u * i), "l"(in + 16 * i));
+    asm volatile("cp.async.commit_group;\n" ::);
+  };
+  // the CTA's first codeword is requested before the tables are set up: one exposed global round trip instead of two
+  if ((int)blockIdx.x < a.frames) fetch(blockIdx.x);
   map_setup(a, lut, s_base, s_twist);
 
   for (int f = blockIdx.x; f < a.frames; f += gridDim.x) {
-    const uint32_t *in = reinterpret_cast<const uint32_t *>(a.in + (long long)f * a.in_pitch);
     const int shift = a.fec_shift ? __ldg(a.fec_shift + f % a.fecblocks) : 0;     // requested early: used by the last stage
-    __syncthreads();
-    {
-      // packed codeword into shared memory as raw bytes with 16-byte asynchronous copies (frames are 16-byte pitched)
-      const int n16 = (nwords + 3) >> 2;
-      const unsigned dst0 = (unsigned)__cvta_generic_to_shared(u);
-      for (int i = threadIdx.x; i < n16; i += MAP_THREADS)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst0 + 16u * i), "l"(reinterpret_cast<const uint8_t *>(in) + 16 * i));
-      asm volatile("cp.async.commit_group;\n" ::);
-      asm volatile("cp.async.wait_group 0;\n" ::);
-      if (threadIdx.x < 4) u[4 * n16 + threadIdx.x] = 0u;
+    if (f != (int)blockIdx.x) {
+      __syncthreads();                    // the previous frame's body has finished with u
+      fetch(f);
     }
+    asm volatile("cp.async.wait_group 0;\n" ::);
+    if (threadIdx.x < 4) u[4 * n16 + threadIdx.x] = 0u;
     __syncthreads();
     map_body<QTR>(a, f, u, lut, cw, s_base, s_twist, shift);
   }
@@ -1271,29 +1345,29 @@ __global__ void __launch_bounds__(256) k_unpack_bits_v(const uint8_t *in, int in
   for (int f = blockIdx.x; f < frames; f += gridDim.x) unpack_span(in + (long long)f * in_pitch, nbits, out + (long long)f * nbits);
 }
 
-// LDPC codeword, packed "u" order -> natural order, 1 bit per byte: the q x 360 parity bit matrix is transposed through
-// shared memory (packed rows in, eight consecutive natural-order bits = one 8-byte store out)
+// LDPC codeword, packed "u" order -> natural order, 1 bit per byte.  The q x 360 parity bit matrix is transposed through
+// shared memory: a thread takes one packed byte (row t, columns 8 k .. 8 k + 7), expands it with one multiply per nibble
+// and writes the eight one-bit bytes to their natural places q (8 k + j) + t of a shared-memory image of the parity part
+// (lanes on consecutive rows: consecutive bytes); the image then leaves with 8-byte stores.
 __global__ void __launch_bounds__(256) k_unpack_ldpc_v(const uint8_t *in, int in_pitch, int nbch, int nldpc, int q, uint8_t *out, int frames)
 {
   extern __shared__ __align__(16) uint8_t sm_fmt[];
   const int npar = nldpc - nbch, ib = nbch >> 3;
+  uint8_t *sp = sm_fmt;                      // npar one-bit bytes, natural order
   for (int f = blockIdx.x; f < frames; f += gridDim.x) {
     const uint8_t *src = in + (long long)f * in_pitch;
     uint8_t *o = out + (long long)f * nldpc;
-    for (int b = threadIdx.x; b < (npar >> 3); b += blockDim.x) sm_fmt[b] = src[ib + b];
+    for (int i = threadIdx.x; i < q * 45; i += blockDim.x) {
+      const int k = i / q, t = i - k * q;
+      const uint2 e = unpack8(src[ib + 45 * t + k]);
+      uint8_t *d = sp + q * 8 * k + t;
+      d[0] = (uint8_t)e.x; d[q] = (uint8_t)(e.x >> 8); d[2 * q] = (uint8_t)(e.x >> 16); d[3 * q] = (uint8_t)(e.x >> 24);
+      d[4 * q] = (uint8_t)e.y; d[5 * q] = (uint8_t)(e.y >> 8); d[6 * q] = (uint8_t)(e.y >> 16); d[7 * q] = (uint8_t)(e.y >> 24);
+    }
     unpack_span(src, nbch, o);
     __syncthreads();
-    for (int i = threadIdx.x; i < (npar >> 3); i += blockDim.x) {
-      int s = (8 * i) / q, t = 8 * i - s * q;       // natural parity index n = q s + t  <-  row t, bit s
-      uint32_t w[2] = { 0u, 0u };
-#pragma unroll
-      for (int j = 0; j < 8; j++) {
-        const uint32_t bit = (sm_fmt[45 * t + (s >> 3)] >> (7 - (s & 7))) & 1u;
-        w[j >> 2] |= bit << (8 * (j & 3));
-        if (++t == q) { t = 0; s++; }
-      }
-      *reinterpret_cast<uint2 *>(o + nbch + 8 * i) = make_uint2(w[0], w[1]);
-    }
+    uint2 *d8 = reinterpret_cast<uint2 *>(o + nbch);
+    for (int i = threadIdx.x; i < (npar >> 3); i += blockDim.x) d8[i] = reinterpret_cast<const uint2 *>(sp)[i];
     __syncthreads();
   }
 }
@@ -1308,8 +1382,17 @@ __global__ void __launch_bounds__(256) k_pack_ldpc_v(const uint8_t *in, int nbch
   for (int f = blockIdx.x; f < frames; f += gridDim.x) {
     const uint8_t *fr = in + (long long)f * nldpc;
     uint8_t *o = out + (long long)f * out_pitch;
-    for (int i = threadIdx.x; i < (npar >> 3); i += blockDim.x)
-      reinterpret_cast<uint2 *>(sp)[i] = __ldg(reinterpret_cast<const uint2 *>(fr + nbch) + i);
+    {
+      const uint2 *s8 = reinterpret_cast<const uint2 *>(fr + nbch);
+      uint2 *d8 = reinterpret_cast<uint2 *>(sp);
+      const int n8 = npar >> 3, T = blockDim.x;
+      int i = threadIdx.x;
+      for (; i + 3 * T < n8; i += 4 * T) {         // four loads in flight per thread
+        const uint2 v0 = __ldg(s8 + i), v1 = __ldg(s8 + i + T), v2 = __ldg(s8 + i + 2 * T), v3 = __ldg(s8 + i + 3 * T);
+        d8[i] = v0; d8[i + T] = v1; d8[i + 2 * T] = v2; d8[i + 3 * T] = v3;
+      }
+      for (; i < n8; i += T) d8[i] = __ldg(s8 + i);
+    }
     pack_span(fr, nbch, o);
     __syncthreads();
     for (int i = threadIdx.x; i < q * 45; i += blockDim.x) {
@@ -1361,9 +1444,9 @@ void launch_unpack_bits(const uint8_t *in, int in_pitch, int nbits, uint8_t *out
 void launch_unpack_ldpc(const uint8_t *in, int in_pitch, int nbch, int nldpc, int q, uint8_t *out, int frames, cudaStream_t s)
 {
   if (frames < 1) return;
-  const bool shape_ok = (nbch & 7) == 0 && (nldpc & 7) == 0 && nldpc - nbch == 360 * q && (nldpc - nbch) / 8 <= 40 * 1024;
+  const bool shape_ok = (nbch & 7) == 0 && (nldpc & 7) == 0 && nldpc - nbch == 360 * q && nldpc - nbch <= 44 * 1024;
   if (shape_ok && (in_pitch & 3) == 0 && aligned8(in, out))
-    k_unpack_ldpc_v<<<frame_grid(frames), 256, (size_t)(nldpc - nbch) / 8, s>>>(in, in_pitch, nbch, nldpc, q, out, frames);
+    k_unpack_ldpc_v<<<frame_grid(frames), 256, (size_t)(nldpc - nbch), s>>>(in, in_pitch, nbch, nldpc, q, out, frames);
   else
   k_unpack_ldpc<<<grid_for((long long)frames * nldpc, 256), 256, 0, s>>>(in, in_pitch, nbch, nldpc, q, out, frames);
   count_launch();

@@ -63,6 +63,16 @@ def main():
         if k1 in d and k2 in d:
             out.append("The same handles driven by one thread per block over three-slot rings (GNU Radio's scheduler model): %.0f Msamples/s "
                        "linked, %.0f with lazy host output." % (d[k1]["value"], d[k2]["value"]))
+    pb = one.get("per_block_device", {})
+    if "blocks" in pb:
+        parts = []
+        for name, e in pb["blocks"].items():
+            t = "`%s` %.3f ms (%.0f GB/s of items" % (name, e["ms_per_call"], e["item_gbs"])
+            if "algorithmic" in e:
+                t += "; SURVEY 8(d) bytes at %.2f of the copy rate" % e["algorithmic"]["frac_of_peak"]
+            parts.append(t + ")")
+        out.append("The five drop-in blocks on device-resident items (`dvbt2ll_work_device`, %s): %s." % (
+            pb["workload"].split(",")[0], ", ".join(parts)))
     multi = sorted([x for x in lines if x.get("n_gpus", 1) > 1], key=lambda x: x["n_gpus"])
     if multi:
         out.append("")
