@@ -726,7 +726,9 @@ __device__ __forceinline__ void transpose32(uint32_t (&A)[32])
 // of the column that feeds it and that column's twist; plus the constellation table
 __device__ __forceinline__ void map_setup(const MapArgs &a, float2 *lut, int *s_base, int *s_twist)
 {
-  for (int i = threadIdx.x; i < (1 << a.mod); i += blockDim.x) lut[i] = a.lut[i];
+  // (the constellation table is only read by the complex64 output of the drop-in block: the chain's 16-bit codes skip it)
+  if (!a.out16)
+    for (int i = threadIdx.x; i < (1 << a.mod); i += blockDim.x) lut[i] = a.lut[i];
   if (threadIdx.x < 16) {
     const int rho = threadIdx.x;
     int col = 0;

@@ -27,7 +27,7 @@ for l in dis[start+1:]:
         if lines: break
     m=re.search(r'//## File "([^"]+)", line (\d+)(.*)',l)
     if m:
-        cur=int(m.group(2)); 
+        cur=(m.group(1).split("/")[-1], int(m.group(2)))
         continue
     m2=re.match(r'\s+/\*([0-9a-f]{4,})\*/\s+(.*?);',l)
     if m2: lines.append((cur,m2.group(2)))
@@ -44,4 +44,5 @@ for k in range(n):
 src=open("/root/repo/gr-dvbt2ll_b200/csrc/t2_kernels.cu").read().splitlines()
 print("total samples",tot_s,"total inst",tot_i)
 for ln,a in sorted(agg.items(), key=lambda x:-x[1][0])[:int(sys.argv[4]) if len(sys.argv)>4 else 40]:
-    print("%5s samp %5.1f%% inst %5.1f%% smemwf %9d exc %9d | %s" % (ln, 100*a[0]/tot_s, 100*a[1]/tot_i, a[2], a[3], src[ln-1].strip()[:110] if ln else ""))
+    own = ln and ln[0] == "t2_kernels.cu"
+    print("%22s samp %5.1f%% inst %5.1f%% smemwf %9d exc %9d | %s" % ("%s:%d" % ln if ln else "?", 100*a[0]/tot_s, 100*a[1]/tot_i, a[2], a[3], src[ln[1]-1].strip()[:100] if own else ""))
