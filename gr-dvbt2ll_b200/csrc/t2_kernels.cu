@@ -958,15 +958,30 @@ __device__ __forceinline__ void map_body(const MapArgs &a, const int f, const ui
         const int k = yv & 3;                                 // source phase of every group
         const uint2 *ci4 = reinterpret_cast<const uint2 *>(a.ci_inv4 + (long long)k * a.ci_inv4_stride + (yv - k));
         uint2 *ov = reinterpret_cast<uint2 *>(o16 + yv + dofs);
-#pragma unroll 2
-        for (int g = threadIdx.x; g < ngrp; g += MAP_THREADS) {
-          // the shifted copies hold the PADDED index c + 2 (c / 64) of each cell: no index arithmetic per look-up
-          const uint2 ci = __ldg(ci4 + g);
+        // the shifted copies hold the PADDED index c + 2 (c / 64) of each cell: no index arithmetic per look-up
+        auto emit4 = [&](int g, const uint2 ci) {
           const unsigned c0 = ci.x & 0xFFFFu, c1 = ci.x >> 16, c2 = ci.y & 0xFFFFu, c3 = ci.y >> 16;
           BND((int)c0 < Nc + 2 * (Nc >> 6) + 2 && (int)c1 < Nc + 2 * (Nc >> 6) + 2 && (int)c2 < Nc + 2 * (Nc >> 6) + 2 && (int)c3 < Nc + 2 * (Nc >> 6) + 2);
           BND(a.out_len == 0 || (a0 + yv + dofs + 4ll * g >= 0 && a0 + yv + dofs + 4ll * g + 4 <= a.out_len));
           ov[g] = make_uint2((unsigned)cw[c0] | ((unsigned)cw[c1] << 16), (unsigned)cw[c2] | ((unsigned)cw[c3] << 16));
+        };
+        // the permutation entries come from L2 (the CTAs' shared memory leaves almost no L1).  The QPSK instantiation
+        // (three CTAs per SM: little else to hide the round trip behind) keeps four requests in flight per thread
+        // (c2: mapper 0.071 -> 0.064 ms); with eight CTAs per SM the same batching is 5 % SLOWER (c3: 0.137 -> 0.144), so
+        // the QAM instantiation keeps the two-deep unrolled loop
+        int g = threadIdx.x;
+#ifndef MAP_PERM_BATCH_OLD
+        if (QTR)
+        for (; g + 3 * MAP_THREADS < ngrp; g += 4 * MAP_THREADS) {
+          uint2 ci[4];
+#pragma unroll
+          for (int k4 = 0; k4 < 4; k4++) ci[k4] = __ldg(ci4 + g + k4 * MAP_THREADS);
+#pragma unroll
+          for (int k4 = 0; k4 < 4; k4++) emit4(g + k4 * MAP_THREADS, ci[k4]);
         }
+#endif
+#pragma unroll 2
+        for (; g < ngrp; g += MAP_THREADS) emit4(g, __ldg(ci4 + g));
         // ragged ends: up to 3 cells before and after the aligned part
         const int tail0 = yv + 4 * ngrp;
         const int nrag = (yv - y_beg) + (y_end - tail0);
