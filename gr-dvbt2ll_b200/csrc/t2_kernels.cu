@@ -746,7 +746,10 @@ __device__ __forceinline__ void map_setup(const MapArgs &a, float2 *lut, int *s_
 // (raw byte order, zero slack words behind it).  The caller has synchronised the CTA on `u`; ends without a barrier.
 // QTR: the instantiation that carries the QPSK transposed-parity path (its 32-register tile would otherwise raise the
 // register count of every mapper launch)
-template <bool QTR>
+// NCOL > 0: the column count of the twist matrix as a compile-time constant -- which rows of the bit tile are empty is
+// then known to the compiler (the transposes shrink for 8 and 12 columns) and the per-bit geometry comes from the
+// kernel-parameter constant bank (a.base_of_bit / a.twist_of_bit, compile-time indices) instead of shared memory.
+template <bool QTR, int NCOL = 0>
 __device__ __forceinline__ void map_body(const MapArgs &a, const int f, const uint32_t *u, const float2 *lut, uint16_t *cw,
                                          const int *s_base, const int *s_twist, const int shift)
 {
@@ -756,8 +759,9 @@ __device__ __forceinline__ void map_body(const MapArgs &a, const int f, const ui
   const uint32_t tI = a.im_mask_i * 0x01010101u, tQ = a.im_mask_q * 0x01010101u, tF = a.im_flip * 0x01010101u;
   auto tilde4 = [&](uint32_t w) -> uint32_t { return tilde ? ((((w << 1) & tI) | ((w >> 1) & tQ)) ^ tF) : w; };   // four packed cell words
   auto tilde1 = [&](uint32_t w) -> uint32_t { return tilde4(w) & 0xFFu; };
-  if (a.ncol) {
-    const int rows = a.nldpc / a.ncol;
+  const int ncol = NCOL ? NCOL : a.ncol;
+  if (ncol) {
+    const int rows = a.nldpc / ncol;
     const int groups = (rows + 31) >> 5;
     for (int g = threadIdx.x; g < groups; g += blockDim.x) {
       const int d0 = g << 5;
@@ -766,11 +770,11 @@ __device__ __forceinline__ void map_body(const MapArgs &a, const int f, const ui
       for (int y = 0; y < 32; y++) A[y] = 0;
 #pragma unroll
       for (int y = 16; y < 32; y++) {
-        const int rho = y - (32 - a.ncol);     // output bit (0 = MSB of the ncol-bit demux word) held by row y
+        const int rho = y - (32 - ncol);       // output bit (0 = MSB of the ncol-bit demux word) held by row y
         if (rho >= 0) {
-          int s0 = d0 - s_twist[rho];
+          int s0 = d0 - (NCOL ? a.twist_of_bit[NCOL ? y - (32 - NCOL) : 0] : s_twist[rho]);
           if (s0 < 0) s0 += rows;
-          const int base = s_base[rho];
+          const int base = NCOL ? a.base_of_bit[NCOL ? y - (32 - NCOL) : 0] : s_base[rho];
           const int n1 = rows - s0;
           uint32_t w = window32_be(u, base + s0);
           if (n1 < 32) w = (w & ~(0xFFFFFFFFu >> n1)) | (window32_be(u, base) >> n1);
@@ -788,7 +792,7 @@ __device__ __forceinline__ void map_body(const MapArgs &a, const int f, const ui
       // X = the four words supplying the imaginary parts (as w~): the previous cell's under the Q delay, else the own
       const int xs = a.cyclic_delay ? 8 : 0;
       uint32_t wprev = 0;
-      if (a.ncol == 2 * mod) {
+      if (ncol == 2 * mod) {
         uint32_t *dst = reinterpret_cast<uint32_t *>(cw + 2 * d0 + 2 * g);      // 64 cells + 1 pad word per thread
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
@@ -815,7 +819,7 @@ __device__ __forceinline__ void map_body(const MapArgs &a, const int f, const ui
     if (a.cyclic_delay) {
       // first cell of every thread's run: the imaginary part comes from the last cell of the previous run
       __syncthreads();
-      const int run = a.ncol == 2 * mod ? 64 : 32;
+      const int run = ncol == 2 * mod ? 64 : 32;
       for (int c = threadIdx.x * run; c < Nc; c += blockDim.x * run) {
         const int pc = c == 0 ? Nc - 1 : c - 1;
         reinterpret_cast<uint8_t *>(cw)[2 * (c + 2 * (c >> 6)) + 1] = (uint8_t)tilde1(cw[pc + 2 * (pc >> 6)]);
@@ -1048,7 +1052,7 @@ __device__ __forceinline__ void map_body(const MapArgs &a, const int f, const ui
 __host__ __device__ inline int map_u_words(int nldpc) { return (((nldpc + 31) / 32) + 11) & ~3; }
 __host__ __device__ inline int map_cw_halfwords(int cell_size) { return ((cell_size + 127) & ~63) + 2 * (cell_size / 64 + 2); }
 
-template <bool QTR>
+template <bool QTR, int NCOL = 0>
 __device__ __forceinline__ void k_map_impl(const MapArgs &a)
 {
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -1081,10 +1085,13 @@ __device__ __forceinline__ void k_map_impl(const MapArgs &a)
     asm volatile("cp.async.wait_group 0;\n" ::);
     if (threadIdx.x < 4) u[4 * n16 + threadIdx.x] = 0u;
     __syncthreads();
-    map_body<QTR>(a, f, u, lut, cw, s_base, s_twist, shift);
+    map_body<QTR, NCOL>(a, f, u, lut, cw, s_base, s_twist, shift);
   }
 }
 __global__ void __launch_bounds__(MAP_THREADS) k_map(const MapArgs a) { k_map_impl<false>(a); }
+// 8, 12 or 16 twist-matrix columns as a compile-time constant (16QAM / short 256QAM, 64QAM, normal 256QAM)
+template <int NCOL>
+__global__ void __launch_bounds__(MAP_THREADS) k_map_n(const MapArgs a) { k_map_impl<false, NCOL>(a); }
 // QPSK with the transposed parity path: three CTAs per SM fit beside the 32400 cell codes of a normal FECFRAME
 __global__ void __launch_bounds__(MAP_THREADS, 3) k_map_qtr(const MapArgs a) { k_map_impl<true>(a); }
 
@@ -1241,6 +1248,23 @@ void launch_map(const MapArgs &a, cudaStream_t s)
   const bool qtr = false;
 #else
   const bool qtr = a.qpsk_par_q > 0 && a.mod == 2 && a.ncol == 0 && (a.cell_size & 3) == 0;
+#endif
+#ifndef MAP_NO_NCOL_TEMPLATE
+  if (!qtr && (a.ncol == 8 || a.ncol == 12 || a.ncol == 16)) {
+    MapArgs b = a;
+    const int rows = a.nldpc / a.ncol;
+    for (int rho = 0; rho < 16; rho++) {
+      const int col = rho < a.ncol ? a.col_of_bit[rho] : 0;
+      b.base_of_bit[rho] = rows * col;
+      b.twist_of_bit[rho] = a.twist_of_col[col];
+    }
+    static bool attr_n[3][MAX_DEVICES];
+    if (a.ncol == 8) { allow_smem(k_map_n<8>, 100 * 1024, attr_n[0]); k_map_n<8><<<blocks, MAP_THREADS, smem, s>>>(b); }
+    else if (a.ncol == 12) { allow_smem(k_map_n<12>, 100 * 1024, attr_n[1]); k_map_n<12><<<blocks, MAP_THREADS, smem, s>>>(b); }
+    else { allow_smem(k_map_n<16>, 100 * 1024, attr_n[2]); k_map_n<16><<<blocks, MAP_THREADS, smem, s>>>(b); }
+    count_launch();
+    return;
+  }
 #endif
   if (qtr) k_map_qtr<<<blocks, MAP_THREADS, smem, s>>>(a);
   else k_map<<<blocks, MAP_THREADS, smem, s>>>(a);

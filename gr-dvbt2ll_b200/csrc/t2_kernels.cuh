@@ -71,6 +71,9 @@ struct MapArgs {
   int ncol;                  // 0 = use bit_src
   uint8_t col_of_bit[16];
   uint8_t twist_of_col[16];
+  // the same geometry per output bit (filled by launch_map): first codeword bit and twist of the column feeding bit p --
+  // constant-bank operands of the instantiations whose column count is a template parameter
+  int base_of_bit[16], twist_of_bit[16];
   // optional fused cell interleaver (chain mode): out[(perm[c] + shift_r) % cell_size] = cell c of FEC block r
   uint16_t *out16;           // chain mode: 16-bit cell codes (own word | imaginary-part word << 8) instead of `out`
   long long out16_frame_stride;   // cells between T2 frames in out16 (multiple of 4: frames stay 8-byte aligned)
