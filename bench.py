@@ -54,6 +54,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip per_config / dropin_e2e (N = 1 extras)")
     ap.add_argument("--no-parity", action="store_true", help="skip the untimed per-rank parity check")
+    ap.add_argument("--deadline", type=int, default=-1, help="seconds after which a run without a result reports where it stopped and exits "
+                                                             "(default: 300 for N > 1, 1500 for N = 1; 0 = never)")
     return ap.parse_args()
 
 
@@ -529,6 +531,30 @@ def dropin_extras(torch, T, K, cfg_name, frames_timed):
     return res
 
 
+STAGE = {"name": "start"}
+
+
+def stage(name):
+    """Where the run is (reported by the watchdog if the run stops making progress)."""
+    STAGE["name"] = name
+
+
+def start_watchdog(seconds, rank, world):
+    """A multi-rank run that stops making progress (a lost peer, a device-side wait that is never satisfied) must not hang the
+    caller silently: after `seconds` rank 0 prints a line that says where the run was, and every rank exits."""
+    if seconds <= 0:
+        return
+
+    def fire():
+        time.sleep(seconds)
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": 0.0, "unit": UNIT, "n_gpus": world, "higher_is_better": True,
+                              "error": "bench.py: no result after %d s; the run was in stage '%s' -- value 0 = not measured" % (seconds, STAGE["name"])}))
+            sys.stdout.flush()
+        os._exit(4)
+    threading.Thread(target=fire, daemon=True).start()
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -543,9 +569,12 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    start_watchdog(args.deadline if args.deadline >= 0 else (300 if world > 1 else 1500), rank, world)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        stage("process group init")
         dist.init_process_group("nccl", device_id=dev)
+    stage("plan + synthetic TS")
 
     cfg = K.resolve(args.config)
     nfr = args.frames
@@ -584,6 +613,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    stage("parity check against the checker")
     # ---- untimed: every rank checks one of its OWN channels (its last) against the checker
     parity = {"ok": None}
     if not args.no_parity and nch > 0:
@@ -606,6 +636,7 @@ def run_ours(args):
     part_bytes = nfr * S * 8
     offs, sizes, slot_bytes = shard.slot_layout(counts, part_bytes)
     if world > 1:
+        stage("reassembly: connect")
         G = T.Gather(rank, world, 0, local, slot_bytes, sizes[rank], n_slots=2)
         blobs = [None] * world
         dist.all_gather_object(blobs, G.export())
@@ -648,23 +679,35 @@ def run_ours(args):
     clocks = ClockSampler(local)
     clocks.start()
     chain.enable_timing(False)
+    stage("warm-up")
     main_step = gather_step if G is not None else plain_step
     t_w, n_w = time.perf_counter(), 0
-    while n_w < max(3, args.warmup) or time.perf_counter() - t_w < 0.4:
-        main_step()
-        n_w += 1
-        if n_w % 8 == 0:
-            torch.cuda.synchronize()
-    if world > 1:       # every rank does the same number of warm-up steps (the step counter must agree)
-        t = torch.tensor([n_w], device=dev, dtype=torch.int64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        for _ in range(int(t.item()) - n_w):
+    if world == 1:
+        while n_w < max(3, args.warmup) or time.perf_counter() - t_w < 0.4:
             main_step()
-        n_w = int(t.item())
+            n_w += 1
+            if n_w % 8 == 0:
+                torch.cuda.synchronize()
+    else:
+        # Every rank must issue the SAME steps between two host synchronisations: a rank that runs ahead of the root by
+        # more than the ring's depth and then synchronises waits for slot releases the root only issues with its own later
+        # steps -- if the root has meanwhile left a time-based loop for a collective, both wait for ever (seen once at
+        # N = 4).  So: chunks of 8 steps, and the decision to stop is itself collective.
+        while True:
+            for _ in range(8):
+                main_step()
+            n_w += 8
+            torch.cuda.synchronize()
+            done = 1 if (n_w >= max(3, args.warmup) and time.perf_counter() - t_w >= 0.4) else 0
+            t = torch.tensor([done], device=dev, dtype=torch.int64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            if int(t.item()):
+                break
     barrier()
 
     # ---- timed region: K steps, CUDA events on the launching streams, max over ranks
     chain.enable_timing(True)
+    stage("timed region")
     launches0 = T.kernel_launches()
     if G is None:
         end_stream = None
@@ -681,6 +724,7 @@ def run_ours(args):
 
     # ---- N > 1 extras: the same step without the reassembly, the int16-sink reassembly, weak scaling
     multi = None
+    stage("extras after the timed region")
     if G is not None:
         # the gathered slot must be what the ranks produced: the root compares every rank's last channel of the final
         # slot with the checker (untimed)
@@ -710,6 +754,7 @@ def run_ours(args):
         int16_ms = timed(lambda: gather_step(4), args.steps, end_stream)
         chain.set_sink(0, 1.0)
         # weak scaling: 64 channels on every GPU, no reassembly (round-1 headline, kept for continuity)
+        stage("extras: weak scaling")
         wts = torch.empty((weak_nch, pitch), dtype=torch.uint8)
         wnp = wts.numpy()
         for c in range(weak_nch):
@@ -726,6 +771,7 @@ def run_ours(args):
         # root-weighted shares: GPU 0 computes as many channels itself as it can in the time the others' channels take to
         # arrive over its NVLink ingest (its own channels cost no transfer); the rest is spread over the other GPUs.
         # c1 = one channel's compute time in a full batch (from the 64-channel step above), t_in = its transfer time.
+        stage("extras: root-weighted reassembly")
         c1 = weak_ms / weak_nch
         t_in = part_bytes / (NVLINK_PEER_GBS * 1e9) * 1e3
         n_root = max(1, min(args.channels - (world - 1), int(args.channels * t_in / (c1 + t_in) + 0.5)))
@@ -796,6 +842,7 @@ def run_ours(args):
             "limiter": "one GPU's NVLink ingest: all but 1/N of every step's samples must enter GPU 0",
         }
 
+    stage("e2e through host buffers")
     # ---- e2e: HOST TS in, HOST samples out through the C ABI (pinned buffers), copies inside the timed region
     out_host = torch.empty((max(nch, 1), nfr * S), dtype=torch.complex64).pin_memory()
     out_np = out_host.numpy()
@@ -869,6 +916,7 @@ def run_ours(args):
     roofline["traffic_source"] = traffic_src
 
     extras = {}
+    stage("N = 1 extras / cpu baseline")
     if world == 1 and not args.no_extras:
         try:
             extras["dropin_e2e"] = dropin_extras(torch, T, K, args.config, 8)
