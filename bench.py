@@ -55,7 +55,7 @@ def parse():
     ap.add_argument("--no-extras", action="store_true", help="skip per_config / dropin_e2e (N = 1 extras)")
     ap.add_argument("--no-parity", action="store_true", help="skip the untimed per-rank parity check")
     ap.add_argument("--deadline", type=int, default=-1, help="seconds after which a run without a result reports where it stopped and exits "
-                                                             "(default: 300 for N > 1, 1500 for N = 1; 0 = never)")
+                                                             "(default: 420 for N > 1, 1500 for N = 1; 0 = never)")
     return ap.parse_args()
 
 
@@ -569,7 +569,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    start_watchdog(args.deadline if args.deadline >= 0 else (300 if world > 1 else 1500), rank, world)
+    start_watchdog(args.deadline if args.deadline >= 0 else (420 if world > 1 else 1500), rank, world)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         stage("process group init")
