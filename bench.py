@@ -689,20 +689,13 @@ def run_ours(args):
             if n_w % 8 == 0:
                 torch.cuda.synchronize()
     else:
-        # Every rank must issue the SAME steps between two host synchronisations: a rank that runs ahead of the root by
-        # more than the ring's depth and then synchronises waits for slot releases the root only issues with its own later
-        # steps -- if the root has meanwhile left a time-based loop for a collective, both wait for ever (seen once at
-        # N = 4).  So: chunks of 8 steps, and the decision to stop is itself collective.
-        while True:
-            for _ in range(8):
-                main_step()
-            n_w += 8
-            torch.cuda.synchronize()
-            done = 1 if (n_w >= max(3, args.warmup) and time.perf_counter() - t_w >= 0.4) else 0
-            t = torch.tensor([done], device=dev, dtype=torch.int64)
+        # every rank issues the same steps between two host synchronisations, and the decision to stop is collective
+        # (shard.collective_warmup: a time-based loop per rank deadlocked one N = 4 run)
+        def any_rank(flag):
+            t = torch.tensor([1 if flag else 0], device=dev, dtype=torch.int64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            if int(t.item()):
-                break
+            return bool(int(t.item()))
+        n_w = shard.collective_warmup(main_step, torch.cuda.synchronize, any_rank, max(3, args.warmup), 0.4)
     barrier()
 
     # ---- timed region: K steps, CUDA events on the launching streams, max over ranks

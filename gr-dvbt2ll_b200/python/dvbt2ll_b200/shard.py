@@ -75,3 +75,21 @@ def gather_frames(local, dst=0, group=None):
     if rank != dst:
         return None
     return torch.cat([b[:n] for b, n in zip(bufs, sizes)])
+
+
+def collective_warmup(step, sync, any_rank, min_steps, min_seconds, chunk=8):
+    """Warm-up for a job whose ranks are coupled only through the reassembly ring's device-side counters: every rank must
+    issue the SAME steps between two host synchronisations (a rank that runs ahead of the root by more than the ring's
+    depth and then synchronises waits for slot releases the root only issues with its own later steps).  So the steps go
+    in chunks of `chunk`, each followed by `sync()`, and the decision to stop is collective: `any_rank(flag)` must return
+    the OR of the ranks' flags (an all-reduce).  Returns the number of steps issued -- the same on every rank."""
+    import time
+    t0, n = time.perf_counter(), 0
+    while True:
+        for _ in range(chunk):
+            step()
+        n += chunk
+        sync()
+        done = n >= min_steps and time.perf_counter() - t0 >= min_seconds
+        if any_rank(bool(done)):
+            return n

@@ -81,3 +81,49 @@ def test_ordered_gather_gloo_world2(n_channels):
         assert p.exitcode == 0
     want = np.array([[complex(c, k) for k in range(5)] for c in range(n_channels)], dtype=np.complex64).reshape(-1)
     assert np.array_equal(out, want)
+
+
+def _warmup_worker(rank, world, port, q):
+    import time
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    if rank == 1:
+        time.sleep(0.3)              # skewed clocks: this rank's timer starts late and its steps are slower
+    issued = []
+
+    def step():
+        issued.append(len(issued))
+        time.sleep(0.002 * (1 + rank))
+
+    def any_rank(flag):
+        t = torch.tensor([1 if flag else 0])
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return bool(int(t.item()))
+    n = shard.collective_warmup(step, lambda: None, any_rank, min_steps=3, min_seconds=0.1)
+    q.put((rank, n, len(issued)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_collective_warmup_issues_the_same_steps_on_every_rank():
+    """bench.py's multi-rank warm-up: ranks with skewed clocks and different step times still issue the same number of
+    steps (a multiple of the chunk), because the stop decision is an all-reduce -- the property whose absence let a rank
+    wait for slot releases the root never issued."""
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_warmup_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    assert got[0][1] == got[1][1] == got[0][2] == got[1][2]
+    assert got[0][1] % 8 == 0 and got[0][1] >= 8
